@@ -1,0 +1,688 @@
+// Device code of the deFuse DP hot path for sm_100a.
+//
+// Replaces (batch form, bit-exact):
+//   SplitReadAligner::FillMatrix / Align / FindMaxRowEntry / GetAlignments
+//       /root/reference tools/SplitReadAligner.cpp:24-75, 77-89, 91-122, 156-298
+//   SimpleAligner::Align
+//       tools/SimpleAligner.cpp:23-63
+//
+// Design: no DP matrix is ever stored.  A group of G lanes owns G*S read
+// rows (S per lane, in registers) and sweeps the reference one column per step as a skewed
+// wavefront; lane g hands the last row of its strip to lane g+1 with one SHFL per step.
+// In the s16x2 kernel every 32-bit register holds TWO independent DPs (low/high half),
+// advanced by DPX instructions (VIADDMNMX.S16x2, VIMNMX.U16x2): per register-pair of cells
+// the loop issues LOP3, VIMNMX, IMAD, VIADDMNMX, VIADDMNMX, VIADDMNMX -- the six issues
+// SURVEY.md 8(d) counts as the algorithmic work of a cell vector.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dfb
+{
+
+// ------------------------------------------------------------------------------------------
+// HBM layout of sequences
+// ------------------------------------------------------------------------------------------
+// Every sequence (already in the orientation its DP consumes it) is stored 16 bases per
+// "word":   pool[w] = { codes: 16 x 2 bit (A,C,G,T = 0..3, base n at bits 2n..2n+1),
+//                       mask : bit n set  <=>  base n is NOT one of ACGT (exception plane) }
+// and, for the exception plane only, obytes[16*w + n] keeps the raw byte so that equality is
+// exact for every byte value (the reference compares raw bytes: SplitReadAligner.cpp:51,
+// SimpleAligner.cpp:50).  A sequence starts on a word boundary.
+
+struct PackItem
+{
+	int64_t src;       // offset of the first byte in the raw upload
+	uint32_t len;      // bases
+	uint32_t dst_word; // first pool word
+	uint32_t flags;    // bit0: store reversed
+	uint32_t pad;
+};
+
+enum
+{
+	PACK_REVERSE = 1
+};
+
+// One thread per 16-base output word.  HBM-bound: reads 16 B, writes 8 B + 16 B.
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ raw, const PackItem* __restrict__ items,
+                                                    int n_items, uint32_t total_words, uint2* __restrict__ pool,
+                                                    uint8_t* __restrict__ obytes)
+{
+	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total_words; w += gridDim.x * blockDim.x)
+	{
+		// last item whose dst_word <= w (items are laid out back to back, ascending)
+		int lo = 0, hi = n_items;
+		while (hi - lo > 1)
+		{
+			int mid = (lo + hi) >> 1;
+			if (__ldg(&items[mid].dst_word) <= w) lo = mid; else hi = mid;
+		}
+		const PackItem it = items[lo];
+		const uint32_t first = (w - it.dst_word) * 16u;
+		uint32_t codes = 0, mask = 0;
+		uint32_t ob[4] = {0, 0, 0, 0};
+#pragma unroll
+		for (int n = 0; n < 16; n++)
+		{
+			uint32_t p = first + n;
+			uint32_t byte = 0;
+			if (p < it.len)
+			{
+				uint32_t sp = (it.flags & PACK_REVERSE) ? (it.len - 1 - p) : p;
+				byte = __ldg(raw + it.src + sp);
+				uint32_t code = 0, exc = 0;
+				switch (byte)
+				{
+					case 'A': code = 0; break;
+					case 'C': code = 1; break;
+					case 'G': code = 2; break;
+					case 'T': code = 3; break;
+					default: exc = 1; break;
+				}
+				codes |= code << (2 * n);
+				mask |= exc << n;
+			}
+			ob[n >> 2] |= byte << (8 * (n & 3));
+		}
+		pool[w] = make_uint2(codes, mask);
+		reinterpret_cast<uint4*>(obytes)[w] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// s16x2 wavefront kernel
+// ------------------------------------------------------------------------------------------
+
+// Two DPs ("halves") that travel in the low and high 16 bits of every register.
+struct JobPair
+{
+	uint32_t ref_w[2];  // first pool word of each half's reference (already oriented)
+	uint32_t read_w[2]; // first pool word of each half's read (already oriented)
+	uint16_t R[2];      // reference lengths
+	uint16_t L[2];      // read lengths
+	int32_t out0;       // SIMPLE: task index of half 0 (-1: none).  SPLIT: task index
+	int32_t out1;       // SIMPLE: task index of half 1 (-1: none).  SPLIT: minScore
+};
+
+struct Event
+{
+	int32_t task;
+	int32_t half_row; // (half << 30) | row
+	int32_t col;      // matrix column index i (1-based over the oriented reference)
+	int32_t score;    // the row maximum this column attains
+};
+
+enum
+{
+	MODE_SIMPLE = 0, // SimpleAligner::Align: best interior cell
+	MODE_SPLIT = 1,  // SplitReadAligner first sweep: per-row maxima -> best split -> probe queue
+	MODE_PROBE = 2   // second sweep of the winning tasks: every column attaining a winning row max
+};
+
+struct FastParams
+{
+	const uint2* pool;
+	const uint8_t* obytes;
+	const JobPair* jobs;
+	int n_jobs;
+	int* cursor; // work queue position (SIMPLE/SPLIT: over jobs; PROBE: over hitq)
+	// scoring, pre-packed for the two halves
+	int m;           // match
+	uint32_t bias;   // B: stored value = H - m*j + B, kept in [8, B]
+	uint32_t xm;     // (mismatch - match) as a 32-bit multiplier of the 0/1 mismatch indicator
+	uint32_t g2;     // gap in both halves
+	uint32_t gm2;    // gap - match in both halves
+	int min_split;   // SPLIT: minSplitScore
+	// outputs
+	int32_t* out;    // SIMPLE: score per task.  SPLIT: best per task
+	int* hit_count;  // SPLIT (write) / PROBE (read): number of queued tasks
+	int* hitq;       // job index per queue slot
+	uint32_t* ntg;   // [slot][S][G] negated row-max targets (or "row disabled")
+	Event* events;
+	unsigned long long* ev_count;
+	unsigned long long ev_cap;
+	uint32_t ck[32]; // SIMPLE: m*(k+1) in both halves
+};
+
+__device__ __forceinline__ uint32_t decode_base(uint2 w, uint32_t word_index, int n, const uint8_t* __restrict__ obytes)
+{
+	if ((w.y >> n) & 1u)
+	{
+		return __ldg(obytes + (size_t)word_index * 16 + n); // exception plane: raw byte
+	}
+	return (0x54474341u >> (8 * ((w.x >> (2 * n)) & 3u))) & 0xFFu; // "ACGT"
+}
+
+#define DFB_READ_PAD 0x7FFEu // read rows beyond L: never equals a reference field
+#define DFB_REF_PAD 0xFFFFu  // reference columns beyond R: never equals a read field; bit 15 doubles as the row-max mask
+
+template <int G, int S, int MODE>
+__global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ FastParams p)
+{
+	constexpr int NG = 32 / G;      // job pairs per warp
+	constexpr int CH = 8 * G;       // reference ring: block of CH columns, two blocks resident
+	constexpr int RING = 2 * CH;
+	constexpr int ROWS = G * S;
+	constexpr int RDW = (ROWS + 15) / 16;
+	constexpr int HG = G / 2;       // lanes that feed one half of the ring
+	static_assert(G >= 4 && (G & (G - 1)) == 0 && G <= 32, "group size");
+	static_assert(S >= 1 && S <= 32, "strip height");
+
+	__shared__ uint32_t s_ring[4][NG][RING];
+	__shared__ uint32_t s_rows[4][NG][ROWS + 1];
+
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int q = lane / G;
+	const int g = lane % G;
+	uint32_t* ring = s_ring[warp][q];
+	uint32_t* rows = s_rows[warp][q];
+	uint16_t* ring16 = reinterpret_cast<uint16_t*>(ring);
+	uint16_t* rows16 = reinterpret_cast<uint16_t*>(rows);
+
+	const uint32_t B = p.bias;
+	const uint32_t Bp = B | (B << 16);
+
+	int n_items = p.n_jobs;
+	if (MODE == MODE_PROBE) n_items = *p.hit_count;
+
+	for (;;)
+	{
+		int base = 0;
+		if (lane == 0) base = atomicAdd(p.cursor, NG);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= n_items) break;
+		const int item = base + q;
+		const bool have = item < n_items;
+		int jid = 0;
+		JobPair jp;
+		jp.ref_w[0] = jp.ref_w[1] = jp.read_w[0] = jp.read_w[1] = 0;
+		jp.R[0] = jp.R[1] = jp.L[0] = jp.L[1] = 0;
+		jp.out0 = jp.out1 = -1;
+		if (have)
+		{
+			jid = (MODE == MODE_PROBE) ? p.hitq[item] : item;
+			jp = p.jobs[jid];
+		}
+
+		// ---- stage the reads: pool words -> 16-bit fields -> S registers per lane ----
+		__syncwarp();
+		for (int w = g; w < 2 * RDW; w += G)
+		{
+			const int h = w / RDW;
+			const int wi = w % RDW;
+			const uint32_t len = jp.L[h];
+			uint2 pw = make_uint2(0, 0);
+			const uint32_t widx = jp.read_w[h] + wi;
+			if ((uint32_t)wi * 16u < len) pw = __ldg(p.pool + widx);
+#pragma unroll
+			for (int n = 0; n < 16; n++)
+			{
+				const int pos = wi * 16 + n;
+				if (pos < ROWS)
+				{
+					uint32_t f = DFB_READ_PAD;
+					if ((uint32_t)pos < len) f = decode_base(pw, widx, n, p.obytes);
+					rows16[2 * pos + h] = (uint16_t)f;
+				}
+			}
+		}
+		__syncwarp();
+		uint32_t rd[S], F[S], X[S];
+		const int j0 = g * S; // rows owned: j0+1 .. j0+S
+#pragma unroll
+		for (int k = 0; k < S; k++)
+		{
+			rd[k] = rows[j0 + k];
+			// column i = 0: H(0,j) = j*gap  ->  stored value B + j*(gap - match)
+			const uint32_t v = B + (uint32_t)(j0 + k + 1) * (p.gm2 & 0xFFFFu) & 0xFFFFu;
+			F[k] = v | (v << 16);
+			X[k] = 0;
+		}
+		if (MODE == MODE_PROBE)
+		{
+#pragma unroll
+			for (int k = 0; k < S; k++)
+			{
+				X[k] = have ? p.ntg[((size_t)item * S + k) * G + g] : 0x80018001u;
+			}
+		}
+		__syncwarp();
+
+		// ---- reference ring: two blocks of CH columns resident, next block prefetched ----
+		const int h_mine = g / HG;
+		const int sub = g % HG;
+		const uint32_t Rh = jp.R[h_mine];
+		auto load_block = [&](int blk) -> uint2 {
+			const uint32_t wi = (uint32_t)blk * HG + sub;
+			if (wi * 16u < Rh) return __ldg(p.pool + jp.ref_w[h_mine] + wi);
+			return make_uint2(0, 0);
+		};
+		auto fill_block = [&](int blk, uint2 pw) {
+			const uint32_t wi = (uint32_t)blk * HG + sub;
+			const uint32_t widx = jp.ref_w[h_mine] + wi;
+#pragma unroll
+			for (int n = 0; n < 16; n++)
+			{
+				const uint32_t b = wi * 16u + n;
+				uint32_t f = DFB_REF_PAD;
+				if (b < Rh) f = decode_base(pw, widx, n, p.obytes);
+				ring16[2 * (b & (RING - 1)) + h_mine] = (uint16_t)f;
+			}
+		};
+		int Rg = max((int)jp.R[0], (int)jp.R[1]);
+		int Rw = Rg;
+#pragma unroll
+		for (int o = 16; o >= 1; o >>= 1) Rw = max(Rw, __shfl_xor_sync(0xffffffffu, Rw, o));
+
+		fill_block(0, load_block(0));
+		fill_block(1, load_block(1));
+		uint2 pf = load_block(2);
+		int blk_next = 2;
+		int next_refill = CH + G - 1;
+		__syncwarp();
+
+		// left boundary of the strip: lane 0 sees row 0 (H = 0 -> stored B); other lanes
+		// start from column 0 of row j0.
+		const uint32_t v0 = (B + (uint32_t)j0 * (p.gm2 & 0xFFFFu)) & 0xFFFFu;
+		uint32_t prev = v0 | (v0 << 16); // stored value of (i-1, j0)
+		uint32_t Flast = F[S - 1];
+		uint32_t acc = 0x80008000u;
+		const int T = Rw + G - 1;
+
+		for (int tau = 0; tau < T; tau++)
+		{
+			if (tau == next_refill)
+			{
+				__syncwarp();
+				fill_block(blk_next, pf);
+				blk_next++;
+				pf = load_block(blk_next);
+				next_refill += CH;
+				__syncwarp();
+			}
+			uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G);
+			if (g == 0) recv = Bp;
+			const int b = tau - g;
+			if (b >= 0 && b < Rg)
+			{
+				const uint32_t rf = ring[b & (RING - 1)];
+				uint32_t left = recv;
+				uint32_t dg_in = prev;
+				uint32_t pen = 0;
+				if (MODE == MODE_SPLIT) pen = rf & 0x80008000u;
+				if (MODE == MODE_PROBE) acc = 0x80008000u;
+#pragma unroll
+				for (int k = 0; k < S; k++)
+				{
+					const uint32_t d = __vminu2(rd[k] ^ rf, 0x00010001u); // 1 per half on mismatch
+					const uint32_t dg = d * p.xm + dg_in;                  // diagonal: + (match ? 0 : x - m)
+					dg_in = F[k];
+					const uint32_t e = __viaddmax_s16x2(F[k], p.g2, dg);   // max(up + gap, diagonal)
+					left = __viaddmax_s16x2(left, p.gm2, e);               // max(left + gap - m, e)
+					F[k] = left;
+					if (MODE == MODE_SPLIT) X[k] = __viaddmax_s16x2(left, pen, X[k]);
+					if (MODE == MODE_SIMPLE) acc = __viaddmax_s16x2(left, p.ck[k], acc);
+					if (MODE == MODE_PROBE) acc = __viaddmax_s16x2(left, X[k], acc);
+				}
+				prev = recv;
+				Flast = left;
+				if (MODE == MODE_PROBE)
+				{
+					// a half of acc is >= 0 only when some enabled row reached its target here
+					if ((~acc) & 0x80008000u)
+					{
+#pragma unroll
+						for (int k = 0; k < S; k++)
+						{
+#pragma unroll
+							for (int h = 0; h < 2; h++)
+							{
+								const int f = (int)((F[k] >> (16 * h)) & 0xFFFFu);
+								const int t = (int)(short)((X[k] >> (16 * h)) & 0xFFFFu);
+								const int j = j0 + k + 1;
+								if (f + t == 0 && b < (int)jp.R[h] && j <= (int)jp.L[h])
+								{
+									const unsigned long long idx = atomicAdd(p.ev_count, 1ull);
+									if (idx < p.ev_cap)
+									{
+										Event ev;
+										ev.task = jp.out0;
+										ev.half_row = (h << 30) | j;
+										ev.col = b + 1;
+										ev.score = f - (int)B + p.m * j;
+										p.events[idx] = ev;
+									}
+								}
+							}
+						}
+					}
+				}
+			}
+		}
+
+		// ---- epilogues ----
+		if (MODE == MODE_SIMPLE)
+		{
+			int lo = (int)(short)(acc & 0xFFFFu);
+			int hi = (int)(short)(acc >> 16);
+			lo = lo - (int)B + p.m * j0;
+			hi = hi - (int)B + p.m * j0;
+#pragma unroll
+			for (int o = G / 2; o >= 1; o >>= 1)
+			{
+				lo = max(lo, __shfl_xor_sync(0xffffffffu, lo, o, G));
+				hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o, G));
+			}
+			if (g == 0 && have)
+			{
+				if (jp.out0 >= 0) p.out[jp.out0] = max(lo, 0);
+				if (jp.out1 >= 0) p.out[jp.out1] = max(hi, 0);
+			}
+		}
+		if (MODE == MODE_SPLIT)
+		{
+			const int L = jp.L[0];
+			__syncwarp();
+			// FindMaxRowEntry (SplitReadAligner.cpp:91-102): keep a row max only if >= minSplitScore and > 0
+#pragma unroll
+			for (int k = 0; k < S; k++)
+			{
+				const int j = j0 + k + 1;
+				int v1 = (int)(X[k] & 0xFFFFu) - (int)B + p.m * j;
+				int v2 = (int)(X[k] >> 16) - (int)B + p.m * j;
+				if (!(v1 >= p.min_split && v1 > 0)) v1 = 0;
+				if (!(v2 >= p.min_split && v2 > 0)) v2 = 0;
+				rows[j] = (uint32_t)v1 | ((uint32_t)v2 << 16);
+			}
+			if (g == 0) rows[0] = 0;
+			__syncwarp();
+			// best split total over a = 0..L (SplitReadAligner.cpp:194-222)
+			int best = 0;
+#pragma unroll
+			for (int k = 0; k < S; k++)
+			{
+				const int j = j0 + k + 1;
+				if (j <= L) best = max(best, (int)(rows[j] & 0xFFFFu) + (int)(rows[L - j] >> 16));
+			}
+			if (g == 0) best = max(best, (int)(rows[L] >> 16)); // a = 0
+#pragma unroll
+			for (int o = G / 2; o >= 1; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o, G));
+			const int min_score = jp.out1;
+			const bool hit = have && best >= min_score && best > 0;
+			// rows that tie for the best AND have a non-empty column set on both sides need the
+			// second sweep (SplitReadAligner.cpp:233-269); the others emit nothing.
+			bool en_any = false;
+			uint32_t ntg[S];
+#pragma unroll
+			for (int k = 0; k < S; k++)
+			{
+				const int j = j0 + k + 1;
+				uint32_t tlo = 0x8001u, thi = 0x8001u;
+				if (hit && j <= L)
+				{
+					const int a1 = (int)(rows[j] & 0xFFFFu), a2 = (int)(rows[L - j] >> 16);     // this row as matrix-1 row a=j
+					const int b1 = (int)(rows[L - j] & 0xFFFFu), b2 = (int)(rows[j] >> 16);     // this row as matrix-2 row, a=L-j
+					if (a1 > 0 && a2 > 0 && a1 + a2 == best) { tlo = (0u - (X[k] & 0xFFFFu)) & 0xFFFFu; en_any = true; }
+					if (b1 > 0 && b2 > 0 && b1 + b2 == best) { thi = (0u - (X[k] >> 16)) & 0xFFFFu; en_any = true; }
+				}
+				ntg[k] = tlo | (thi << 16);
+			}
+			const uint32_t ballot = __ballot_sync(0xffffffffu, en_any);
+			const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (q * G));
+			const bool group_en = (ballot & gmask) != 0;
+			int slot = -1;
+			if (g == 0 && have)
+			{
+				p.out[jp.out0] = hit ? best : 0;
+				if (group_en)
+				{
+					slot = atomicAdd(p.hit_count, 1);
+					p.hitq[slot] = jid;
+				}
+			}
+			slot = __shfl_sync(0xffffffffu, slot, q * G);
+			if (group_en && have)
+			{
+#pragma unroll
+				for (int k = 0; k < S; k++) p.ntg[((size_t)slot * S + k) * G + g] = ntg[k];
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// s32 generic kernels: any scoring triple (positive gaps, endGaps, minSplitScore <= 0 ...),
+// any read / reference length.  One warp per DP, 8 rows per lane, the read tiled 256 rows at
+// a time with the tile boundary row kept in a per-warp HBM scratch line.  Same wavefront as
+// above, plain 32-bit max/add, H stored directly.  Rarely selected (see host dispatch);
+// exactness over speed.
+// ------------------------------------------------------------------------------------------
+
+struct GenJob
+{
+	uint32_t ref_w;  // first pool word of the (oriented) reference
+	uint32_t read_w; // first pool word of the (oriented) read
+	uint32_t R;
+	uint32_t L;
+	int32_t task;    // output index
+	int32_t half;    // SPLIT/PROBE: 0 = matrix 1, 1 = matrix 2
+	int64_t row_off; // SPLIT/PROBE: first entry of this DP's row arrays (L + 1 entries)
+};
+
+struct GenParams
+{
+	const uint8_t* obytes;
+	const GenJob* jobs;
+	int n_jobs;
+	int* cursor;
+	int m, x, g, end_gaps;
+	int32_t* out;          // SIMPLE: score per task
+	int32_t* rowmax;       // SPLIT: raw row maxima over i = 0..R     PROBE: target per row
+	const uint8_t* row_en; // PROBE: 1 = enumerate the columns of this row
+	const int* probe_flag; // PROBE: per task (jobs 2t, 2t+1): 0 = nothing to enumerate, skip
+	int32_t* bnd;          // per-warp scratch: 2 * bnd_stride ints
+	int64_t bnd_stride;
+	Event* events;
+	unsigned long long* ev_count;
+	unsigned long long ev_cap;
+};
+
+#define DFB_GEN_S 8
+#define DFB_GEN_TILE (32 * DFB_GEN_S)
+
+__device__ __forceinline__ void emit_event(const GenParams& p, int task, int half, int row, int col, int score)
+{
+	const unsigned long long idx = atomicAdd(p.ev_count, 1ull);
+	if (idx < p.ev_cap)
+	{
+		Event ev;
+		ev.task = task;
+		ev.half_row = (half << 30) | row;
+		ev.col = col;
+		ev.score = score;
+		p.events[idx] = ev;
+	}
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) dp_generic_kernel(const __grid_constant__ GenParams p)
+{
+	constexpr int S = DFB_GEN_S;
+	const int lane = threadIdx.x & 31;
+	const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	int32_t* bnd_a = p.bnd + (int64_t)gwarp * 2 * p.bnd_stride;
+	int32_t* bnd_b = bnd_a + p.bnd_stride;
+	const int col0_step = p.end_gaps ? 0 : p.g; // H(0,j) = j * col0_step  (SplitReadAligner.cpp:44-48)
+
+	for (;;)
+	{
+		int jid = 0;
+		if (lane == 0) jid = atomicAdd(p.cursor, 1);
+		jid = __shfl_sync(0xffffffffu, jid, 0);
+		if (jid >= p.n_jobs) break;
+		if (MODE == MODE_PROBE && p.probe_flag[jid >> 1] == 0) continue;
+		const GenJob job = p.jobs[jid];
+		const int R = (int)job.R, L = (int)job.L;
+		const uint8_t* refb = p.obytes + (size_t)job.ref_w * 16;
+		const uint8_t* readb = p.obytes + (size_t)job.read_w * 16;
+		int best = INT32_MIN; // SIMPLE: max over interior cells
+
+		if (MODE == MODE_PROBE)
+		{
+			// row 0 is H(i,0) = 0 for every i
+			if (p.row_en[job.row_off] && p.rowmax[job.row_off] == 0)
+			{
+				for (int i = lane; i <= R; i += 32) emit_event(p, job.task, job.half, 0, i, 0);
+			}
+		}
+		if (MODE == MODE_SPLIT)
+		{
+			if (lane == 0) p.rowmax[job.row_off] = 0;
+		}
+
+		const int n_tiles = (L + DFB_GEN_TILE - 1) / DFB_GEN_TILE;
+		for (int tile = 0; tile < n_tiles; tile++)
+		{
+			const int jbase = tile * DFB_GEN_TILE; // rows jbase+1 .. jbase+256
+			const int j0 = jbase + lane * S;
+			const bool first_tile = tile == 0;
+			const bool last_tile = tile == n_tiles - 1;
+			const int32_t* bin = (tile & 1) ? bnd_b : bnd_a;  // row jbase of every column (written by the previous tile)
+			int32_t* bout = (tile & 1) ? bnd_a : bnd_b;
+			int rd[S], H[S], X[S], tg[S];
+			bool en[S];
+#pragma unroll
+			for (int k = 0; k < S; k++)
+			{
+				const int j = j0 + k + 1;
+				rd[k] = (j <= L) ? (int)readb[j - 1] : -1;
+				H[k] = j * col0_step;
+				X[k] = H[k];
+				tg[k] = 0;
+				en[k] = false;
+				if (MODE == MODE_PROBE && j <= L)
+				{
+					en[k] = p.row_en[job.row_off + j] != 0;
+					tg[k] = p.rowmax[job.row_off + j];
+					if (en[k] && H[k] == tg[k]) emit_event(p, job.task, job.half, j, 0, tg[k]); // column i = 0
+				}
+			}
+			int prev = j0 * col0_step; // H(0, j0); for lane 0 of tile 0 this is H(0,0) = 0
+			int Hlast = H[S - 1];
+			const int T = R + 31;
+			__syncwarp();
+			for (int tau = 0; tau < T; tau++)
+			{
+				int recv = __shfl_up_sync(0xffffffffu, Hlast, 1);
+				const int b = tau - lane;
+				if (lane == 0) recv = (first_tile || b >= R) ? 0 : __ldcg(bin + b + 1);
+				if (b >= 0 && b < R)
+				{
+					const int rf = (int)refb[b];
+					int left = recv;
+					int dg_in = prev;
+#pragma unroll
+					for (int k = 0; k < S; k++)
+					{
+						const int dg = dg_in + ((rd[k] == rf) ? p.m : p.x);
+						dg_in = H[k];
+						const int e = max(H[k] + p.g, dg);
+						left = max(left + p.g, e);
+						H[k] = left;
+						const int j = j0 + k + 1;
+						if (MODE == MODE_SIMPLE) { if (j <= L) best = max(best, left); }
+						if (MODE == MODE_SPLIT) X[k] = max(X[k], left);
+						if (MODE == MODE_PROBE) { if (en[k] && left == tg[k]) emit_event(p, job.task, job.half, j, b + 1, left); }
+					}
+					prev = recv;
+					Hlast = left;
+					if (lane == 31 && !last_tile) bout[b + 1] = left;
+				}
+			}
+			if (MODE == MODE_SPLIT)
+			{
+#pragma unroll
+				for (int k = 0; k < S; k++)
+				{
+					const int j = j0 + k + 1;
+					if (j <= L) p.rowmax[job.row_off + j] = X[k];
+				}
+			}
+			__syncwarp();
+			__threadfence_block();
+		}
+		if (MODE == MODE_SIMPLE)
+		{
+#pragma unroll
+			for (int o = 16; o >= 1; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+			if (lane == 0) p.out[job.task] = max(best, 0);
+		}
+	}
+}
+
+// Per split task (generic path): turn the raw row maxima of both matrices into the best split
+// total and the per-row probe targets.  One thread per task; rows are few thousand at most.
+struct GenReduceParams
+{
+	const GenJob* jobs; // two consecutive jobs per task: matrix 1, matrix 2
+	int n_tasks;
+	const int32_t* task_min_score; // indexed by jobs[2t].task
+	int min_split;
+	int32_t* rowmax;  // in: raw maxima; out: FindMaxRowEntry value (0 when not accepted)
+	uint8_t* row_en;  // out
+	int32_t* out_best;
+	int* probe_flag;  // out per task pair index: 1 = needs the probe sweep
+};
+
+__global__ void __launch_bounds__(128) split_reduce_generic_kernel(const GenReduceParams p)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= p.n_tasks) return;
+	const GenJob j1 = p.jobs[2 * t], j2 = p.jobs[2 * t + 1];
+	const int L = (int)j1.L;
+	int32_t* r1 = p.rowmax + j1.row_off;
+	int32_t* r2 = p.rowmax + j2.row_off;
+	uint8_t* e1 = p.row_en + j1.row_off;
+	uint8_t* e2 = p.row_en + j2.row_off;
+	// FindMaxRowEntry (SplitReadAligner.cpp:91-102): values below minSplitScore or not above 0 give 0
+	for (int j = 0; j <= L; j++)
+	{
+		int v1 = r1[j], v2 = r2[j];
+		if (!(v1 >= p.min_split && v1 > 0)) v1 = 0;
+		if (!(v2 >= p.min_split && v2 > 0)) v2 = 0;
+		r1[j] = v1;
+		r2[j] = v2;
+		e1[j] = 0;
+		e2[j] = 0;
+	}
+	const int min_score = p.task_min_score[j1.task];
+	int best = 0;
+	for (int a = 0; a <= L; a++)
+	{
+		const int tot = r1[a] + r2[L - a];
+		if (tot >= min_score && tot > best) best = tot;
+	}
+	p.out_best[j1.task] = best;
+	int need = 0;
+	if (best != 0)
+	{
+		// a row with maximum 0 still has columns when 0 >= minSplitScore (the == branch of
+		// SplitReadAligner.cpp:111-121 with max == 0)
+		const bool zero_ok = p.min_split <= 0;
+		for (int a = 0; a <= L; a++)
+		{
+			if (r1[a] + r2[L - a] == best && (r1[a] > 0 || zero_ok) && (r2[L - a] > 0 || zero_ok))
+			{
+				e1[a] = 1;
+				e2[L - a] = 1;
+				need = 1;
+			}
+		}
+	}
+	p.probe_flag[t] = need;
+}
+
+}  // namespace dfb

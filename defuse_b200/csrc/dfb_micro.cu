@@ -1,0 +1,209 @@
+// Integer / DPX issue-rate microbenchmark: the measured denominator of the DP roofline
+// (roofline_CUPS = P_int * cells_per_vector / 6).  Each kernel runs eight
+// independent dependency chains per thread of ONE instruction kind (rotating three registers
+// so that nothing folds), on every SM at full occupancy, and reports warp-instructions / s.
+#include "../../include/defuse_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace
+{
+
+constexpr int kChains = 8;
+constexpr int kUnroll = 16; // rotations per loop iteration; 3 instructions per rotation per chain
+
+template <int KIND>
+__device__ __forceinline__ void rot(uint32_t& a, uint32_t& b, uint32_t& c)
+{
+	if (KIND == 0)
+	{
+		a = __viaddmax_s16x2(b, c, a);
+		b = __viaddmax_s16x2(c, a, b);
+		c = __viaddmax_s16x2(a, b, c);
+	}
+	else if (KIND == 1)
+	{
+		a = __vminu2(b, c);
+		b = __vmaxu2(c, a);
+		c = __vminu2(a, b) ^ 0u;
+	}
+	else if (KIND == 2)
+	{
+		a = __vimax3_s16x2(a, b, c);
+		b = __vimin3_s16x2(b, c, a);
+		c = __vimax3_s16x2(c, a, b);
+	}
+	else if (KIND == 3)
+	{
+		a = (a ^ b) | (c & a);
+		b = (b & c) ^ (a | b);
+		c = (c | a) & (b ^ c);
+	}
+	else if (KIND == 4)
+	{
+		a = a * b + c;
+		b = b * c + a;
+		c = c * a + b;
+	}
+	else if (KIND == 5)
+	{
+		a = a + b + c;
+		b = b + c + a;
+		c = c + a + b;
+	}
+	else if (KIND == 6)
+	{
+		a = __byte_perm(a, b, c);
+		b = __byte_perm(b, c, a);
+		c = __byte_perm(c, a, b);
+	}
+	else if (KIND == 8)
+	{
+		a = __shfl_up_sync(0xffffffffu, a, 1);
+		b = __shfl_up_sync(0xffffffffu, b, 1);
+		c = __shfl_up_sync(0xffffffffu, c, 1);
+	}
+	else if (KIND == 9)
+	{
+		a = (uint32_t)__viaddmax_s32((int)b, (int)c, (int)a);
+		b = (uint32_t)__viaddmax_s32((int)c, (int)a, (int)b);
+		c = (uint32_t)__viaddmax_s32((int)a, (int)b, (int)c);
+	}
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) issue_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int iters)
+{
+	uint32_t a[kChains], b[kChains], c[kChains];
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+	for (int k = 0; k < kChains; k++)
+	{
+		a[k] = in[(tid + k) & 1023];
+		b[k] = in[(tid + 3 * k + 1) & 1023];
+		c[k] = in[(tid + 5 * k + 2) & 1023];
+	}
+	for (int it = 0; it < iters; it++)
+	{
+#pragma unroll
+		for (int u = 0; u < kUnroll; u++)
+		{
+#pragma unroll
+			for (int k = 0; k < kChains; k++) rot<KIND>(a[k], b[k], c[k]);
+		}
+	}
+	uint32_t r = 0;
+#pragma unroll
+	for (int k = 0; k < kChains; k++) r ^= a[k] ^ b[k] ^ c[k];
+	out[tid] = r;
+}
+
+// KIND 7: the s16x2 DP cell body exactly as dp_fast_kernel issues it (S = 8 rows per lane,
+// one column per iteration): LOP3, VIMNMX.U16x2, IMAD, VIADDMNMX, VIADDMNMX, VIADDMNMX per row.
+__global__ void __launch_bounds__(256) cell_body_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int iters,
+                                                         uint32_t xm, uint32_t g2, uint32_t gm2)
+{
+	constexpr int S = 8;
+	uint32_t rd[S], F[S], X[S];
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+	for (int k = 0; k < S; k++)
+	{
+		rd[k] = in[(tid + k) & 1023] & 0x00030003u;
+		F[k] = 0x40004000u;
+		X[k] = 0;
+	}
+	uint32_t rf = in[tid & 1023] & 0x00030003u;
+	uint32_t prev = 0x40004000u;
+	for (int it = 0; it < iters * 6; it++)
+	{
+		uint32_t left = prev;
+		uint32_t dg_in = prev;
+		const uint32_t pen = rf & 0x80008000u;
+#pragma unroll
+		for (int k = 0; k < S; k++)
+		{
+			const uint32_t d = __vminu2(rd[k] ^ rf, 0x00010001u);
+			const uint32_t dg = d * xm + dg_in;
+			dg_in = F[k];
+			const uint32_t e = __viaddmax_s16x2(F[k], g2, dg);
+			left = __viaddmax_s16x2(left, gm2, e);
+			F[k] = left;
+			X[k] = __viaddmax_s16x2(left, pen, X[k]);
+		}
+		prev = left;
+		rf = (rf + 0x00010001u) & 0x00030003u;
+	}
+	uint32_t r = 0;
+#pragma unroll
+	for (int k = 0; k < S; k++) r ^= F[k] ^ X[k];
+	out[tid] = r;
+}
+
+}  // namespace
+
+extern "C" int dfb_microbench_issue_rate(dfb_ctx* ctx, int kind, int iters, double* warp_instr_per_s, double* elapsed_ms)
+{
+	if (!ctx || !warp_instr_per_s || kind < 0 || kind > 9 || iters <= 0) return DFB_ERR_ARG;
+	dfb_device_info info;
+	int rc = dfb_ctx_device_info(ctx, &info);
+	if (rc) return rc;
+	if (cudaSetDevice(info.ordinal) != cudaSuccess) return DFB_ERR_CUDA;
+	const int blocks = info.sm_count * 8;
+	const int threads = 256;
+	uint32_t* d_in = nullptr;
+	uint32_t* d_out = nullptr;
+	if (cudaMalloc(&d_in, 1024 * sizeof(uint32_t)) != cudaSuccess) return DFB_ERR_NOMEM;
+	if (cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(uint32_t)) != cudaSuccess)
+	{
+		cudaFree(d_in);
+		return DFB_ERR_NOMEM;
+	}
+	uint32_t h_in[1024];
+	uint32_t s = 12345u;
+	for (int k = 0; k < 1024; k++)
+	{
+		s = s * 1664525u + 1013904223u;
+		h_in[k] = (s >> 4) & 0x0FFF0FFFu;
+	}
+	cudaMemcpy(d_in, h_in, sizeof(h_in), cudaMemcpyHostToDevice);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	float best_ms = 1e30f;
+	for (int rep = 0; rep < 4; rep++) // first repetition is the warm-up
+	{
+		cudaEventRecord(e0, 0);
+		switch (kind)
+		{
+			case 0: issue_kernel<0><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 1: issue_kernel<1><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 2: issue_kernel<2><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 3: issue_kernel<3><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 4: issue_kernel<4><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 5: issue_kernel<5><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 6: issue_kernel<6><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 7: cell_body_kernel<<<blocks, threads>>>(d_in, d_out, iters, 0xFFFFFFFDu, 0xFFFEFFFEu, 0xFFFCFFFCu); break;
+			case 8: issue_kernel<8><<<blocks, threads>>>(d_in, d_out, iters); break;
+			default: issue_kernel<9><<<blocks, threads>>>(d_in, d_out, iters); break;
+		}
+		cudaEventRecord(e1, 0);
+		if (cudaEventSynchronize(e1) != cudaSuccess) break;
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if (rep > 0 && ms < best_ms) best_ms = ms;
+	}
+	cudaError_t e = cudaDeviceSynchronize();
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d_in);
+	cudaFree(d_out);
+	if (e != cudaSuccess || best_ms > 1e29f) return DFB_ERR_CUDA;
+	const double warps = (double)blocks * threads / 32.0;
+	// kind 7 counts one "body" = the 6 instructions of one register-pair of cells
+	const double per_thread = (kind == 7) ? (double)iters * 6 * 8 : (double)iters * kUnroll * kChains * 3;
+	*warp_instr_per_s = warps * per_thread / (best_ms * 1e-3);
+	if (elapsed_ms) *elapsed_ms = best_ms;
+	return DFB_OK;
+}

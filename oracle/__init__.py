@@ -141,6 +141,24 @@ def split_align(read, ref1, ref2, min_score, match=2, mismatch=-1, gap=-2, end_g
         cap = int(n)
 
 
+def split_align_count(read, ref1, ref2, min_score, match=2, mismatch=-1, gap=-2, end_gaps=False, min_split_score=8,
+                      impl="port"):
+    """Number of alignments GetAlignments would emit and the winning total (0 if none), without
+    materialising them (tie-heavy inputs emit millions)."""
+    read, ref1, ref2 = bytes(read), bytes(ref1), bytes(ref2)
+    lib = _lib(impl)
+    out = np.zeros((1, 7), dtype=np.int32)
+    if impl == "ref":
+        n = lib.ref_split_align(match, mismatch, gap, int(end_gaps), min_split_score,
+                                read, len(read), ref1, len(ref1), ref2, len(ref2), min_score, _p(out, _c_i32p), 1)
+    else:
+        a, b, c = _u8(read), _u8(ref1), _u8(ref2)
+        n = lib.dpo_split_align(_p(a, _c_u8p), len(read), _p(b, _c_u8p), len(ref1), _p(c, _c_u8p), len(ref2),
+                                match, mismatch, gap, int(end_gaps), min_split_score, min_score,
+                                _p(out, _c_i32p), 1, None, None)
+    return int(n), (int(out[0, 4]) if n else 0)
+
+
 def split_rowmax(read, ref1, ref2, match=2, mismatch=-1, gap=-2, end_gaps=False, min_split_score=8):
     """FindMaxRowEntry of every row of both matrices (port only): two (L+1,) int32 arrays."""
     read, ref1, ref2 = bytes(read), bytes(ref1), bytes(ref2)

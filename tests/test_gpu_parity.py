@@ -1,0 +1,180 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+Bit-exact: scores, split positions, column sets, emission order."""
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _tables(refs, seqs):
+    import defuse_b200 as d
+    return d.SeqTable.from_list(refs), d.SeqTable.from_list(seqs)
+
+
+def _check_simple(oracle, ctx, refs, seqs, task_ref, task_seq, m, x, g):
+    import defuse_b200 as d
+    rt, st = _tables(refs, seqs)
+    got = d.SimpleAligner(m, x, g, ctx=ctx).align_batch(rt, st, task_ref, task_seq)
+    want = oracle.simple_align_batch(m, x, g, rt.data, rt.off, st.data, st.off, task_ref, task_seq)
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, "first mismatch task %d: got %d want %d (R=%d L=%d)" % (
+        bad[0], got[bad[0]], want[bad[0]], len(refs[task_ref[bad[0]]]), len(seqs[task_seq[bad[0]]]))
+
+
+def _check_split(oracle, ctx, refs, reads, task_cluster, task_read, min_score, params=(2, -1, -2, False, 8)):
+    import defuse_b200 as d
+    rt, st = _tables(refs, reads)
+    m, x, g, eg, ms = params
+    res = d.SplitReadAligner(m, x, g, eg, ms, ctx=ctx).align_batch(rt, st, task_cluster, task_read, min_score)
+    cnt, want = oracle.split_align_batch(rt.data, rt.off, st.data, st.off, task_cluster, task_read, min_score,
+                                         m, x, g, eg, ms)
+    pos = np.concatenate([[0], np.cumsum(cnt)])
+    for t in range(len(task_cluster)):
+        w = want[pos[t]:pos[t + 1]]
+        a = res.alignments(t)
+        assert a.shape == w.shape and (a == w).all(), "task %d: got\n%s\nwant\n%s" % (t, a[:8], w[:8])
+        assert res.best[t] == (w[0, 4] if len(w) else res.best[t])
+        rec = res.records(t)
+        wrec = oracle.split_dedupe(w)
+        assert rec.shape == wrec.shape and (rec == wrec).all()
+    return res
+
+
+@pytest.mark.parametrize("scoring", [(10, -5, -5), (2, -1, -2), (1, 0, 0), (5, -3, -2), (3, 0, -1)])
+def test_simple_random(oracle_mod, gpu_ctx, scoring):
+    rng = np.random.default_rng(11)
+    refs, seqs, tr, ts = util.simple_batch(rng, 40, 600, (1, 700), (1, 260))
+    _check_simple(oracle_mod, gpu_ctx, refs, seqs, tr, ts, *scoring)
+
+
+def test_simple_localalign_shape(oracle_mod, gpu_ctx):
+    rng = np.random.default_rng(12)
+    refs, seqs, tr, ts = util.simple_batch(rng, 8, 300, 2001, (90, 110))
+    _check_simple(oracle_mod, gpu_ctx, refs, seqs, tr, ts, 10, -5, -5)
+
+
+def test_simple_long_reads(oracle_mod, gpu_ctx):
+    rng = np.random.default_rng(13)
+    refs, seqs, tr, ts = util.simple_batch(rng, 6, 60, (800, 1500), (250, 1024))
+    _check_simple(oracle_mod, gpu_ctx, refs, seqs, tr, ts, 2, -1, -2)
+
+
+def test_simple_edge_cases(oracle_mod, gpu_ctx):
+    refs = [b"", b"A", b"ACGTN", b"ACGT", b"acgtacgtNNNNacgt", b"A" * 300, bytes(range(1, 200)), b"GATTACA" * 30]
+    seqs = [b"", b"A", b"GTN", b"acgt", b"NNNN", b"A" * 120, bytes(range(50, 120)), b"TACAGATT", b"N" * 17, b"ACGT" * 70]
+    tr, ts = np.meshgrid(np.arange(len(refs)), np.arange(len(seqs)))
+    for sc in [(10, -5, -5), (2, -1, -2)]:
+        _check_simple(oracle_mod, gpu_ctx, refs, seqs, tr.ravel().astype(np.int32), ts.ravel().astype(np.int32), *sc)
+
+
+@pytest.mark.parametrize("scoring", [(1, -1, 1), (0, 0, 0), (-1, -2, -3), (2, 1, -1), (300, -200, -250), (2, -1, 0),
+                                     (3, 3, 3)])
+def test_simple_generic_scoring(oracle_mod, gpu_ctx, scoring):
+    rng = np.random.default_rng(14)
+    refs, seqs, tr, ts = util.simple_batch(rng, 10, 120, (1, 300), (1, 300))
+    _check_simple(oracle_mod, gpu_ctx, refs, seqs, tr, ts, *scoring)
+
+
+def test_simple_generic_very_long(oracle_mod, gpu_ctx):
+    rng = np.random.default_rng(15)
+    refs, seqs, tr, ts = util.simple_batch(rng, 3, 8, (1500, 3000), (1025, 2100))
+    _check_simple(oracle_mod, gpu_ctx, refs, seqs, tr, ts, 10, -5, -5)
+
+
+def test_split_planted(oracle_mod, gpu_ctx):
+    import defuse_b200 as d
+    rng = np.random.default_rng(21)
+    refs, reads, tc, trd = util.split_batch(rng, 30, 12, 100, 280, 420)
+    ms = np.array([d.split_min_score(len(reads[r])) for r in trd], np.int32)
+    res = _check_split(oracle_mod, gpu_ctx, refs, reads, tc, trd, ms)
+    assert (res.best > 0).sum() > 50  # the planted junctions are found
+
+
+def test_split_varied_lengths(oracle_mod, gpu_ctx):
+    import defuse_b200 as d
+    rng = np.random.default_rng(22)
+    refs, reads, tc, trd = util.split_batch(rng, 25, 10, (20, 260), 60, 700, sub=0.03, indel=0.01, n_rate=0.01)
+    ms = np.array([d.split_min_score(len(reads[r])) for r in trd], np.int32)
+    _check_split(oracle_mod, gpu_ctx, refs, reads, tc, trd, ms)
+
+
+def test_split_zero_threshold_ties(oracle_mod, gpu_ctx):
+    rng = np.random.default_rng(23)
+    refs, reads, tc, trd = util.split_batch(rng, 12, 6, (8, 60), 10, 90, sub=0.05)
+    _check_split(oracle_mod, gpu_ctx, refs, reads, tc, trd, np.zeros(len(tc), np.int32))
+
+
+def test_split_edge_cases(oracle_mod, gpu_ctx):
+    import defuse_b200 as d
+    polyA = b"A" * 120
+    refs = [polyA, polyA,                       # poly-A vs poly-A windows: huge tie sets
+            b"ACGT" * 40, b"TTGCA" * 30,        # tandem repeats
+            b"", b"ACGTACGTAC",                 # empty reference 1
+            b"ACGTTGCANNNNACGT" * 10, b"acgtNNNNACGTTTGA" * 9,  # N and lowercase
+            b"GATTACAGATTACA", b"CATCATCAT"]    # windows shorter than the read
+    reads = [b"A" * 60, b"ACGT" * 10 + b"TTGCA" * 8, b"", b"ACGTNNNNACGTacgtNNNNACGT", b"GATTACA" * 5, b"N" * 30,
+             b"ACGTACGTACGTAAAAAAAAAAAAAAAAAAAA", b"T"]
+    tc, trd = np.meshgrid(np.arange(len(refs) // 2), np.arange(len(reads)))
+    tc, trd = tc.ravel().astype(np.int32), trd.ravel().astype(np.int32)
+    for ms in (np.zeros(len(tc), np.int32), np.array([d.split_min_score(len(reads[r])) for r in trd], np.int32)):
+        _check_split(oracle_mod, gpu_ctx, refs, reads, tc, trd, ms)
+
+
+@pytest.mark.parametrize("params", [(2, -1, -2, True, 8), (2, -1, -2, False, 0), (2, -1, -2, False, -3),
+                                    (1, -1, 1, False, 4), (3, 1, -2, True, 0), (300, -200, -250, False, 1200),
+                                    (0, 0, 0, False, 0)])
+def test_split_generic_params(oracle_mod, gpu_ctx, params):
+    rng = np.random.default_rng(24)
+    refs, reads, tc, trd = util.split_batch(rng, 6, 5, (5, 40), 8, 70, sub=0.05)
+    m = params[0]
+    ms = np.array([int(0.9 * m * len(reads[r])) for r in trd], np.int32)
+    _check_split(oracle_mod, gpu_ctx, refs, reads, tc, trd, ms, params)
+    _check_split(oracle_mod, gpu_ctx, refs, reads, tc, trd, np.zeros(len(tc), np.int32), params)
+
+
+def test_split_generic_long_read(oracle_mod, gpu_ctx):
+    import defuse_b200 as d
+    rng = np.random.default_rng(25)
+    refs, reads, tc, trd = util.split_batch(rng, 2, 2, (1030, 1200), 1300, 1500)
+    ms = np.array([d.split_min_score(len(reads[r])) for r in trd], np.int32)
+    _check_split(oracle_mod, gpu_ctx, refs, reads, tc, trd, ms)
+
+
+def test_staged_plan_matches_one_call(oracle_mod, gpu_ctx):
+    import defuse_b200 as d
+    rng = np.random.default_rng(26)
+    refs, seqs, tr, ts = util.simple_batch(rng, 10, 500, (300, 600), (80, 120))
+    rt, st = _tables(refs, seqs)
+    al = d.SimpleAligner(10, -5, -5, ctx=gpu_ctx)
+    plan = al.plan(rt, st, tr, ts)
+    for _ in range(3):  # re-running a resident plan overwrites its outputs
+        plan.run()
+    got = plan.fetch()
+    want = oracle_mod.simple_align_batch(10, -5, -5, rt.data, rt.off, st.data, st.off, tr, ts)
+    assert (got == want).all()
+    st_ = plan.stats()
+    assert st_["cells"] == sum(len(refs[a]) * len(seqs[b]) for a, b in zip(tr, ts))
+    assert st_["kernel_launches"] >= 1 and st_["fast_jobs"] > 0
+    plan.close()
+
+
+def test_event_buffer_overflow_is_recovered(oracle_mod, gpu_ctx):
+    """poly-A windows give ~R arg-max columns per row and ~L tie rows: far more than the default
+    event buffer share; the fetch must notice, re-size and re-sweep."""
+    polyA = b"A" * 700
+    refs = [polyA, polyA]
+    reads = [b"A" * 200] * 24
+    tc = np.zeros(len(reads), np.int32)
+    trd = np.arange(len(reads), dtype=np.int32)
+    import defuse_b200 as d
+    rt, st = _tables(refs, reads)
+    res = d.SplitReadAligner(ctx=gpu_ctx).align_batch(rt, st, tc, trd, np.full(len(reads), 360, np.int32))
+    n_want, best_want = oracle_mod.split_align_count(reads[0], refs[0], refs[1], 360)
+    # compare the factorised form (the expansion is ~R*R*L tuples)
+    for t in (0, len(reads) - 1):
+        rows = res.rows[res.rows["task"] == t]
+        assert res.best[t] == best_want
+        assert sum(int(r["n1"]) * int(r["n2"]) for r in rows) == n_want
+    assert len(res.cols) > (1 << 20)  # more events than the initial buffer held
