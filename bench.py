@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- split-read DP throughput (GCUPS, tasks/s) of the B200 path, with the reference's
+CPU implementation timed beside it.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches N ranks)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU aligner on host cores
+
+Workload (BASELINE.json configs[2], the split-read metric's own config, per GPU):
+dosplitalign-shaped batch of 20 000 candidate clusters x 100 candidate reads = 2.0 M
+SplitReadAligner tasks, 100-bp reads against ~340-bp breakpoint window pairs, scoring 2/-1/-2,
+minSplitScore 8, minScore = floor(1.8 L).  Weak scaling: every rank aligns its own shard of that
+size (work is partitioned by cluster, no collective on the data path).
+
+A "step" = one pass of the hot path over the batch.  `value` times the step with the batch resident
+in HBM (first sweep + probe sweep kernels); `e2e` times the C-ABI call with pinned HOST buffers
+(H2D copy, pack, both sweeps, D2H, host assembly of the winning rows).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "split_read_dp_gcups"
+UNIT = "GCUPS"
+
+
+def workload_params(args):
+    return dict(n_clusters=args.clusters, tasks_per_cluster=args.tasks_per_cluster, L=100, R_lo=320, R_hi=360)
+
+
+def config_dict(args, n_gpus):
+    return {
+        "workload": "BASELINE.json configs[2]: dosplitalign split-read DP shard, %d clusters x %d candidate reads "
+                    "= %d SplitReadAligner tasks per GPU, L=100, R1,R2 in [320,360], scoring 2/-1/-2, "
+                    "minSplitScore 8, minScore floor(1.8L); planted junctions, 1%% substitutions, 0.1%% N"
+                    % (args.clusters, args.tasks_per_cluster, args.clusters * args.tasks_per_cluster),
+        "tasks_per_gpu": args.clusters * args.tasks_per_cluster,
+        "partitioning": "by cluster, %d shard(s), no collective" % n_gpus,
+        "l2_policy": "inputs larger than L2 (packed pool + job list + outputs ~ 0.6 GB per step vs 126 MB L2)",
+        "seed": args.seed,
+    }
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            top = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
+            out.update(sm_mhz=float(np.median(top)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference's own aligner (oracle/_ref, compiled from /root/reference) or the C port
+# --------------------------------------------------------------------------------------------
+
+def cpu_split_throughput(w, n_tasks, threads):
+    """Times SplitReadAligner::Align + GetAlignments on `n_tasks` tasks of the workload with `threads`
+    host threads (one aligner object per thread, like one dosplitalign process per core).
+    Returns (gcups, tasks_per_s, seconds, kind)."""
+    import oracle  # cpu_baseline leg: the one place bench.py may execute oracle/
+    kind = "reference" if oracle.have_ref() else "port"
+    impl = "ref" if kind == "reference" else "port"
+    n_tasks = min(n_tasks, w["n_tasks"])
+    bounds = np.linspace(0, n_tasks, threads + 1).astype(int)
+    cells = int((w["L"] * ((w["ref_off"][2 * w["task_cluster"][:n_tasks].astype(np.int64) + 2]
+                            - w["ref_off"][2 * w["task_cluster"][:n_tasks].astype(np.int64)]))).sum())
+
+    def run(k):
+        a, b = bounds[k], bounds[k + 1]
+        if b > a:
+            oracle.split_align_batch(w["ref_bytes"], w["ref_off"], w["read_bytes"], w["read_off"],
+                                     w["task_cluster"][a:b], w["task_read"][a:b], w["min_score"][a:b], impl=impl)
+
+    oracle._lib(impl)
+    ths = [threading.Thread(target=run, args=(k,)) for k in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return cells / dt / 1e9, n_tasks / dt, dt, kind
+
+
+def run_reference_arm(args):
+    import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    per_step = args.ref_tasks_per_core * threads
+    n_clusters = max(1, min(args.clusters, (per_step * (args.steps + args.warmup)) // args.tasks_per_cluster + 1))
+    w = synth.split_workload(args.seed, n_clusters, args.tasks_per_cluster, 100, 320, 360)
+    sub = dict(w)
+    times, gc, tps, kind = [], [], [], "port"
+    for s in range(args.warmup + args.steps):
+        a = (s * per_step) % max(1, w["n_tasks"] - per_step + 1)
+        for key in ("task_cluster", "task_read", "min_score"):
+            sub[key] = w[key][a:a + per_step]
+        sub["n_tasks"] = len(sub["task_cluster"])
+        g, t, dt, kind = cpu_split_throughput(sub, per_step, threads)
+        if s >= args.warmup:
+            times.append(dt)
+            gc.append(g)
+            tps.append(t)
+    value = float(np.mean(gc))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": config_dict(args, args.gpus), "tasks_per_s": float(np.mean(tps)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": "%d tasks per step (%d per host thread) of the same workload" % (per_step, args.ref_tasks_per_core)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+
+def pinned(arr):
+    import torch
+    t = torch.empty(arr.shape, dtype=getattr(torch, str(arr.dtype)), pin_memory=True)
+    out = t.numpy()
+    out[...] = arr
+    return out, t
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import defuse_b200 as d
+    import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the DP path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ctx = d.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    info = ctx.device_info()
+
+    # every rank owns a different shard of clusters (seed offset), same size: weak scaling
+    w = synth.split_workload(args.seed + 1000 * rank, **workload_params(args))
+    keep = []
+    host = {}
+    for k in ("ref_bytes", "ref_off", "read_bytes", "read_off", "task_cluster", "task_read", "min_score"):
+        host[k], t = pinned(w[k])
+        keep.append(t)
+    refs = d.SeqTable(host["ref_bytes"], host["ref_off"])
+    reads = d.SeqTable(host["read_bytes"], host["read_off"])
+    aligner = d.SplitReadAligner(2, -1, -2, False, 8, ctx=ctx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident: inputs already packed in HBM ----
+    plan = aligner.plan(refs, reads, host["task_cluster"], host["task_read"], host["min_score"])
+    plan.set_timing(True)
+    for _ in range(max(args.warmup, 3)):
+        plan.run()
+    plan.sync()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sweep_ms, probe_ms = [], []
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        plan.run()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    plan.sync()
+    st = plan.stats()
+    sweep_ms.append(st["ms_sweep"])
+    probe_ms.append(st["ms_probe"])
+    res = plan.fetch()
+    st = plan.stats()
+    n_hit = int((res.best > 0).sum())
+    n_rows = len(res.rows)
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e_ms = []
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for s in range(1 + e2e_steps):  # first one is the warm-up
+        barrier()
+        t0 = time.perf_counter()
+        r2 = aligner.align_batch(refs, reads, host["task_cluster"], host["task_read"], host["min_score"])
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        if s > 0:
+            e2e_ms.append(dt)
+    assert (r2.best == res.best).all() and len(r2.rows) == n_rows
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms_total, float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_mean = float(t[0]), float(t[1])
+    cells_rank = st["cells"]
+    tc = torch.tensor([float(cells_rank), float(st["n_tasks"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+    cells_all, tasks_all = float(tc[0]), float(tc[1])
+    ms_step = ms_total / args.steps
+
+    if rank == 0:
+        value = cells_all / (ms_step * 1e-3) / 1e9
+        # roofline of the dominant kernel (first sweep, dp_fast_kernel<8,13,SPLIT>): integer/DPX issue bound.
+        rate, _ = ctx.microbench_issue_rate(0, 2000)   # VIADDMNMX.S16x2 warp-instructions/s, measured now
+        p_int_lane = rate * 32.0
+        peak_gcups = p_int_lane * 2.0 / 6.0 / 1e9      # 6 INT issues per s16x2 vector of 2 cells
+        k_ms = float(np.mean(sweep_ms))
+        achieved = cells_rank / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dp_fast_kernel_split_bytes_per_launch")
+            except Exception:
+                traffic = None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        pack_bytes = st["raw_bytes"] + st["packed_bytes"] * 3   # read raw; write 8 B codes+mask and 16 B raw copy per 16 bases
+        pack_gbs = pack_bytes / (st["ms_pack"] * 1e-3) / 1e9 if st["ms_pack"] > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "s16x2 (int16 pairs, DPX)", "data": "synthetic", "config": config_dict(args, world),
+            "tasks_per_s": tasks_all / (ms_step * 1e-3),
+            "e2e": {"value": cells_all / (e2e_mean * 1e-3) / 1e9, "unit": UNIT,
+                    "tasks_per_s": tasks_all / (e2e_mean * 1e-3), "ms_per_step": e2e_mean,
+                    "h2d_bytes_per_step": st["h2d_bytes"] + 3 * 4 * st["n_tasks"],
+                    "d2h_bytes_per_step": st["d2h_bytes"], "steps": e2e_steps},
+            "gpu_launches": int(st["kernel_launches"]) * args.steps,
+            "roofline": {"bound": "int_issue", "kernel": "dp_fast_kernel<8,13,SPLIT> (first sweep)",
+                         "achieved": achieved, "peak": peak_gcups, "unit": UNIT, "frac": achieved / peak_gcups,
+                         "traffic": traffic,
+                         "peak_source": "measured now: VIADDMNMX.S16x2 issue rate %.1f Gwarp-instr/s x 32 lanes x 2 cells / 6 issues"
+                                        % (rate / 1e9),
+                         "kernel_ms": k_ms, "probe_sweep_ms": float(np.mean(probe_ms)),
+                         "step_frac_incl_probe": value / world / peak_gcups},
+            "roofline_staging": {"bound": "hbm", "kernel": "pack_kernel", "achieved": pack_gbs, "peak": hbm_peak,
+                                 "unit": "GB/s", "frac": (pack_gbs / hbm_peak) if pack_gbs else None,
+                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                                 "bytes": pack_bytes, "ms": st["ms_pack"]},
+            "clocks": clocks,
+            "results": {"tasks_with_split": n_hit, "winning_rows": n_rows, "probe_jobs": int(st["probe_jobs"]),
+                        "events": int(st["events"])},
+            "device": info["name"],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n = args.ref_tasks_per_core * threads
+            g, tps, dt, kind = cpu_split_throughput(w, n, threads)
+            line["cpu_baseline"] = {"value": g, "unit": UNIT, "cores": threads, "kind": kind, "tasks_per_s": tps,
+                                    "seconds": dt,
+                                    "sample": "first %d tasks of the same workload (%d per host thread)" % (n, args.ref_tasks_per_core)}
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clusters", type=int, default=20000)
+    ap.add_argument("--tasks-per-cluster", type=int, default=100)
+    ap.add_argument("--seed", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-tasks-per-core", type=int, default=2000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

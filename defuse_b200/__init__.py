@@ -53,7 +53,8 @@ class _SplitParams(ctypes.Structure):
 class _PlanStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in
                 ("n_tasks", "cells", "fast_jobs", "generic_jobs", "probe_jobs", "events", "kernel_launches",
-                 "h2d_bytes", "d2h_bytes", "packed_bytes", "raw_bytes")]
+                 "h2d_bytes", "d2h_bytes", "packed_bytes", "raw_bytes")] + \
+               [(n, ctypes.c_double) for n in ("ms_pack", "ms_sweep", "ms_probe")]
 
 
 class _DeviceInfo(ctypes.Structure):
@@ -103,6 +104,7 @@ def load_library():
         "dfb_split_plan_create": ([vp, P(_SplitParams), P(_SeqTable), P(_SeqTable), vp, vp, vp, i64, P(vp)], ctypes.c_int),
         "dfb_plan_run": ([vp], ctypes.c_int),
         "dfb_plan_sync": ([vp], ctypes.c_int),
+        "dfb_plan_set_timing": ([vp, ctypes.c_int], ctypes.c_int),
         "dfb_simple_plan_fetch": ([vp, vp], ctypes.c_int),
         "dfb_split_plan_fetch": ([vp, vp, P(i64), P(i64)], ctypes.c_int),
         "dfb_split_plan_copy": ([vp, vp, vp], ctypes.c_int),
@@ -122,6 +124,7 @@ ABI_SYMBOLS = (
     "dfb_abi_version", "dfb_device_count", "dfb_ctx_create", "dfb_ctx_destroy", "dfb_last_error", "dfb_ctx_set_stream",
     "dfb_ctx_device_info", "dfb_simple_align_batch", "dfb_split_align_batch", "dfb_split_result_size",
     "dfb_split_result_copy", "dfb_simple_plan_create", "dfb_split_plan_create", "dfb_plan_run", "dfb_plan_sync",
+    "dfb_plan_set_timing",
     "dfb_simple_plan_fetch", "dfb_split_plan_fetch", "dfb_split_plan_copy", "dfb_plan_get_stats", "dfb_plan_destroy",
     "dfb_microbench_issue_rate",
 )
@@ -235,6 +238,10 @@ class _Plan:
 
     def sync(self):
         self.ctx._check(self.ctx._lib.dfb_plan_sync(self._h))
+
+    def set_timing(self, enable=True):
+        """Bracket the kernel groups of run() with CUDA events (stats: ms_sweep, ms_probe)."""
+        self.ctx._check(self.ctx._lib.dfb_plan_set_timing(self._h, int(bool(enable))))
 
     def stats(self):
         st = _PlanStats()

@@ -247,6 +247,10 @@ struct dfb_plan
 	std::vector<dfb_split_row> rows;
 	std::vector<int32_t> cols;
 	bool ran = false, fetched = false;
+	bool timing = false;
+	bool pack_timed = false;
+	bool run_timed = false;
+	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 	dfb_plan_stats stats{};
 };
 
@@ -286,6 +290,8 @@ extern "C" void dfb_plan_destroy(dfb_plan* plan)
 	dfree(plan->d_gen_bnd);
 	dfree(plan->d_gen_probe_flag);
 	dfree(plan->d_task_min_score);
+	for (int k = 0; k < 3; k++)
+		if (plan->ev[k]) cudaEventDestroy(plan->ev[k]);
 	delete plan;
 }
 
@@ -366,8 +372,12 @@ static int upload_and_pack(dfb_plan* pl, const dfb_seq_table* a, const dfb_seq_t
 	if (lay.total_words && n_items)
 	{
 		int grid = (int)std::min<uint32_t>((lay.total_words + 255) / 256, 148 * 16);
+		for (int k = 0; k < 3; k++) CK(ctx, cudaEventCreate(&pl->ev[k]));
+		CK(ctx, cudaEventRecord(pl->ev[0], ctx->stream));
 		pack_kernel<<<grid, 256, 0, ctx->stream>>>(pl->d_raw, pl->d_items, (int)n_items, lay.total_words, pl->d_pool, pl->d_obytes);
 		CK(ctx, cudaGetLastError());
+		CK(ctx, cudaEventRecord(pl->ev[1], ctx->stream));
+		pl->pack_timed = true;
 	}
 	pl->stats.h2d_bytes += na + nb + (int64_t)(n_items * sizeof(PackItem));
 	pl->stats.raw_bytes = na + nb;
@@ -546,6 +556,11 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 		pl->sp.gap = params->gap;
 		cudaError_t e = cudaStreamSynchronize(ctx->stream);
 		if (e != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "plan upload/pack failed: %s", cudaGetErrorString(e));
+		if (!rc && pl->pack_timed)
+		{
+			float ms = 0;
+			if (cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]) == cudaSuccess) pl->stats.ms_pack = ms;
+		}
 	}
 	if (rc)
 	{
@@ -690,6 +705,11 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 				fill_fast_params(pl, c, params->match, params->mismatch, params->gap, params->min_split_score);
 		cudaError_t e = cudaStreamSynchronize(ctx->stream);
 		if (e != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "plan upload/pack failed: %s", cudaGetErrorString(e));
+		if (!rc && pl->pack_timed)
+		{
+			float ms = 0;
+			if (cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]) == cudaSuccess) pl->stats.ms_pack = ms;
+		}
 	}
 	if (rc)
 	{
@@ -762,6 +782,13 @@ extern "C" int dfb_plan_run(dfb_plan* pl)
 	const int sm = ctx->prop.multiProcessorCount;
 	pl->stats.kernel_launches = 0;
 	pl->fetched = false;
+	pl->run_timed = false;
+	if (pl->timing)
+	{
+		for (int k = 0; k < 3; k++)
+			if (!pl->ev[k]) CK(ctx, cudaEventCreate(&pl->ev[k]));
+		CK(ctx, cudaEventRecord(pl->ev[0], ctx->stream));
+	}
 	for (int c = 0; c < kNumClasses; c++)
 	{
 		ClassWork& cw = pl->cls[c];
@@ -800,10 +827,16 @@ extern "C" int dfb_plan_run(dfb_plan* pl)
 			pl->stats.kernel_launches++;
 		}
 	}
+	if (pl->timing) CK(ctx, cudaEventRecord(pl->ev[1], ctx->stream));
 	if (pl->split)
 	{
 		int rc = run_probe(pl);
 		if (rc) return rc;
+	}
+	if (pl->timing)
+	{
+		CK(ctx, cudaEventRecord(pl->ev[2], ctx->stream));
+		pl->run_timed = true;
 	}
 	pl->ran = true;
 	return DFB_OK;
@@ -815,6 +848,21 @@ extern "C" int dfb_plan_sync(dfb_plan* pl)
 	dfb_ctx* ctx = pl->ctx;
 	CK(ctx, cudaSetDevice(ctx->device));
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	if (pl->run_timed)
+	{
+		float a = 0, b = 0;
+		CK(ctx, cudaEventElapsedTime(&a, pl->ev[0], pl->ev[1]));
+		CK(ctx, cudaEventElapsedTime(&b, pl->ev[1], pl->ev[2]));
+		pl->stats.ms_sweep = a;
+		pl->stats.ms_probe = b;
+	}
+	return DFB_OK;
+}
+
+extern "C" int dfb_plan_set_timing(dfb_plan* pl, int enable)
+{
+	if (!pl) return DFB_ERR_ARG;
+	pl->timing = enable != 0;
 	return DFB_OK;
 }
 

@@ -120,6 +120,11 @@ typedef struct dfb_plan_stats
 	int64_t d2h_bytes;        /* bytes copied device->host by the last fetch */
 	int64_t packed_bytes;     /* bytes of packed sequence data resident in HBM */
 	int64_t raw_bytes;        /* bytes of raw sequence data the pack kernel read */
+	/* CUDA-event timings on the context's stream, in ms; valid after dfb_plan_sync when
+	 * dfb_plan_set_timing(plan, 1) was called, else 0 */
+	double ms_pack;           /* the pack kernel at plan creation (always measured) */
+	double ms_sweep;          /* first-sweep DP kernels of the last run (all classes) */
+	double ms_probe;          /* probe-sweep kernels of the last run */
 } dfb_plan_stats;
 
 typedef struct dfb_device_info
@@ -191,6 +196,8 @@ DFB_API int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* params,
 /* Enqueues every DP kernel of the plan on the context's stream and returns without
  * synchronising.  May be called repeatedly (outputs are overwritten). */
 DFB_API int dfb_plan_run(dfb_plan* plan);
+/* With enable != 0, dfb_plan_run brackets its kernel groups with CUDA events (ms_sweep, ms_probe). */
+DFB_API int dfb_plan_set_timing(dfb_plan* plan, int enable);
 /* Waits for the stream and reports any kernel failure. */
 DFB_API int dfb_plan_sync(dfb_plan* plan);
 DFB_API int dfb_simple_plan_fetch(dfb_plan* plan, int32_t* out_score);

@@ -1,0 +1,104 @@
+"""Synthetic RNA-seq style workloads for bench.py and the tests: there is no
+network, so reads are drawn from random window pairs with a planted fusion junction.
+Vectorised numpy; seeded; no reference code involved."""
+import numpy as np
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def _mutate(rng, reads, sub, n_rate):
+    """In-place substitutions and N's on a (n, L) uint8 matrix."""
+    if sub > 0:
+        mask = rng.random(reads.shape) < sub
+        reads[mask] = ACGT[rng.integers(0, 4, int(mask.sum()))]
+    if n_rate > 0:
+        mask = rng.random(reads.shape) < n_rate
+        reads[mask] = ord("N")
+
+
+def split_workload(seed, n_clusters, tasks_per_cluster, L=100, R_lo=320, R_hi=360, sub=0.01, n_rate=0.001,
+                   indel_frac=0.1, span_frac=0.5, unrelated_frac=0.05, zipf=None, match=2):
+    """dosplitalign-shaped batch (configs 1/3/5 of BASELINE.json): n_clusters window pairs of R_lo..R_hi
+    bases with a planted junction; per task a read of L bases that spans the junction (span_frac), lies
+    wholly in one window, or is unrelated.  Returns CSR tables + task arrays + minScore per task."""
+    rng = np.random.default_rng(seed)
+    R1 = rng.integers(R_lo, R_hi + 1, n_clusters)
+    R2 = rng.integers(R_lo, R_hi + 1, n_clusters)
+    Rmax = int(R_hi)
+    win1 = ACGT[rng.integers(0, 4, (n_clusters, Rmax))]
+    win2 = ACGT[rng.integers(0, 4, (n_clusters, Rmax))]
+    bp1 = rng.integers(R1 // 3, R1 - 4)          # fusion = win1[:bp1] + win2[bp2:R2]
+    bp2 = rng.integers(4, 2 * R2 // 3)
+    # fusion sequence per cluster, padded
+    flen = bp1 + (R2 - bp2)
+    fus = np.zeros((n_clusters, 2 * Rmax), dtype=np.uint8)
+    col = np.arange(2 * Rmax)[None, :]
+    left = col < bp1[:, None]
+    fus[:, :Rmax][left[:, :Rmax]] = win1[left[:, :Rmax]]
+    src2 = col - bp1[:, None] + bp2[:, None]
+    right = (~left) & (src2 < R2[:, None])
+    fus[right] = win2[np.nonzero(right)[0], src2[right]]
+
+    if zipf:
+        w = 1.0 / np.arange(1, n_clusters + 1) ** zipf
+        w /= w.sum()
+        n_tasks = n_clusters * tasks_per_cluster
+        task_cluster = np.sort(rng.choice(n_clusters, n_tasks, p=w)).astype(np.int32)
+    else:
+        task_cluster = np.repeat(np.arange(n_clusters, dtype=np.int32), tasks_per_cluster)
+    n_tasks = task_cluster.size
+    c = task_cluster
+    kind = rng.random(n_tasks)
+    # start positions in the fusion sequence
+    lo_span = np.maximum(0, bp1[c] - L + 4)
+    hi_span = np.maximum(lo_span, np.minimum(bp1[c] - 4, flen[c] - L))
+    start_span = lo_span + (rng.random(n_tasks) * (hi_span - lo_span + 1)).astype(np.int64)
+    start_any = (rng.random(n_tasks) * np.maximum(1, flen[c] - L + 1)).astype(np.int64)
+    start = np.where(kind < span_frac, start_span, start_any)
+    idx = start[:, None] + np.arange(L)[None, :]
+    idx = np.minimum(idx, 2 * Rmax - 1)
+    reads = fus[c[:, None], idx]
+    unrelated = kind > 1.0 - unrelated_frac
+    reads[unrelated] = ACGT[rng.integers(0, 4, (int(unrelated.sum()), L))]
+    _mutate(rng, reads, sub, n_rate)
+    # crude single-base deletions: shift the tail left and append a random base
+    dele = np.nonzero(rng.random(n_tasks) < indel_frac)[0]
+    if dele.size:
+        pos = rng.integers(1, L - 1, dele.size)
+        for t, p in zip(dele[:20000], pos[:20000]):
+            reads[t, p:-1] = reads[t, p + 1:]
+            reads[t, -1] = ACGT[rng.integers(0, 4)]
+
+    ref_len = np.empty(2 * n_clusters, dtype=np.int64)
+    ref_len[0::2] = R1
+    ref_len[1::2] = R2
+    ref_off = np.zeros(2 * n_clusters + 1, dtype=np.int64)
+    ref_off[1:] = np.cumsum(ref_len)
+    ref_bytes = np.zeros(int(ref_off[-1]), dtype=np.uint8)
+    both = np.stack([win1, win2], axis=1).reshape(2 * n_clusters, Rmax)
+    keep = np.arange(Rmax)[None, :] < ref_len[:, None]
+    ref_bytes[:] = both[keep]
+    read_off = np.arange(n_tasks + 1, dtype=np.int64) * L
+    task_read = np.arange(n_tasks, dtype=np.int32)
+    min_score = np.full(n_tasks, int(np.float64(np.float32(np.float32(L) * np.float32(match))) * 0.90), dtype=np.int32)
+    cells = int((L * (R1[c] + R2[c])).sum())
+    return {"ref_bytes": ref_bytes, "ref_off": ref_off, "read_bytes": np.ascontiguousarray(reads).reshape(-1),
+            "read_off": read_off, "task_cluster": task_cluster, "task_read": task_read, "min_score": min_score,
+            "cells": cells, "n_tasks": int(n_tasks), "L": int(L)}
+
+
+def local_workload(seed, n_refs, n_tasks, R=2001, L=100, sub=0.02, unrelated_frac=0.2):
+    """localalign-shaped batch (config 2): n_refs references of R bases; each task picks one and a
+    L-base substring with substitutions, or an unrelated random sequence."""
+    rng = np.random.default_rng(seed)
+    refs = ACGT[rng.integers(0, 4, (n_refs, R))]
+    task_ref = rng.integers(0, n_refs, n_tasks).astype(np.int32)
+    start = rng.integers(0, R - L + 1, n_tasks)
+    seqs = refs[task_ref[:, None], start[:, None] + np.arange(L)[None, :]]
+    unrelated = rng.random(n_tasks) < unrelated_frac
+    seqs[unrelated] = ACGT[rng.integers(0, 4, (int(unrelated.sum()), L))]
+    _mutate(rng, seqs, sub, 0.0)
+    return {"ref_bytes": np.ascontiguousarray(refs).reshape(-1), "ref_off": np.arange(n_refs + 1, dtype=np.int64) * R,
+            "seq_bytes": np.ascontiguousarray(seqs).reshape(-1), "seq_off": np.arange(n_tasks + 1, dtype=np.int64) * L,
+            "task_ref": task_ref, "task_seq": np.arange(n_tasks, dtype=np.int32),
+            "cells": int(n_tasks) * R * L, "n_tasks": int(n_tasks), "L": int(L)}
