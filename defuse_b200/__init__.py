@@ -64,7 +64,8 @@ class _DeviceInfo(ctypes.Structure):
 
 
 SPLIT_ROW_DTYPE = np.dtype([("task", "<i4"), ("read_split", "<i4"), ("score1", "<i4"), ("score2", "<i4"),
-                            ("col1_begin", "<i8"), ("col2_begin", "<i8"), ("n1", "<i4"), ("n2", "<i4")])
+                            ("col_begin", "<i8"), ("n1", "<i4"), ("n2", "<i4")])
+assert SPLIT_ROW_DTYPE.itemsize == 32
 
 _lib = None
 
@@ -100,6 +101,8 @@ def load_library():
         "dfb_split_align_batch": ([vp, P(_SplitParams), P(_SeqTable), P(_SeqTable), vp, vp, vp, i64, vp], ctypes.c_int),
         "dfb_split_result_size": ([vp, P(i64), P(i64)], ctypes.c_int),
         "dfb_split_result_copy": ([vp, vp, vp], ctypes.c_int),
+        "dfb_split_result_view": ([vp, P(vp), P(i64), P(vp), P(i64)], ctypes.c_int),
+        "dfb_split_plan_view": ([vp, P(vp), P(i64), P(vp), P(i64)], ctypes.c_int),
         "dfb_simple_plan_create": ([vp, P(_SimpleParams), P(_SeqTable), P(_SeqTable), vp, vp, i64, P(vp)], ctypes.c_int),
         "dfb_split_plan_create": ([vp, P(_SplitParams), P(_SeqTable), P(_SeqTable), vp, vp, vp, i64, P(vp)], ctypes.c_int),
         "dfb_plan_run": ([vp], ctypes.c_int),
@@ -123,7 +126,7 @@ def load_library():
 ABI_SYMBOLS = (
     "dfb_abi_version", "dfb_device_count", "dfb_ctx_create", "dfb_ctx_destroy", "dfb_last_error", "dfb_ctx_set_stream",
     "dfb_ctx_device_info", "dfb_simple_align_batch", "dfb_split_align_batch", "dfb_split_result_size",
-    "dfb_split_result_copy", "dfb_simple_plan_create", "dfb_split_plan_create", "dfb_plan_run", "dfb_plan_sync",
+    "dfb_split_result_copy", "dfb_split_result_view", "dfb_split_plan_view", "dfb_simple_plan_create", "dfb_split_plan_create", "dfb_plan_run", "dfb_plan_sync",
     "dfb_plan_set_timing",
     "dfb_simple_plan_fetch", "dfb_split_plan_fetch", "dfb_split_plan_copy", "dfb_plan_get_stats", "dfb_plan_destroy",
     "dfb_microbench_issue_rate",
@@ -286,8 +289,8 @@ class SplitResult:
         L = int(self._read_len[task])
         R2 = int(self._ref2_len[task])
         for r in self.rows[self._row_start[task]:self._row_start[task + 1]]:
-            c1 = self.cols[r["col1_begin"]:r["col1_begin"] + r["n1"]]
-            c2 = self.cols[r["col2_begin"]:r["col2_begin"] + r["n2"]]
+            c1 = self.cols[r["col_begin"]:r["col_begin"] + r["n1"]]
+            c2 = self.cols[r["col_begin"] + r["n1"]:r["col_begin"] + r["n1"] + r["n2"]]
             a = int(r["read_split"])
             for i1 in c1:
                 for i2 in c2:
@@ -310,21 +313,38 @@ class SplitResult:
         return np.array(out, dtype=np.int32).reshape(-1, 5)
 
 
+def _view_arrays(rows_p, n_rows, cols_p, n_cols, copy):
+    """numpy arrays over (or copied from) the library-owned result buffers."""
+    if n_rows:
+        rows = np.frombuffer((ctypes.c_char * (n_rows * SPLIT_ROW_DTYPE.itemsize)).from_address(rows_p), dtype=SPLIT_ROW_DTYPE)
+    else:
+        rows = np.zeros(0, dtype=SPLIT_ROW_DTYPE)
+    if n_cols:
+        cols = np.frombuffer((ctypes.c_char * (n_cols * 4)).from_address(cols_p), dtype=np.int32)
+    else:
+        cols = np.zeros(0, dtype=np.int32)
+    if copy:
+        rows, cols = rows.copy(), cols.copy()
+    return rows, cols
+
+
 class SplitPlan(_Plan):
     def __init__(self, ctx, handle, n_tasks, read_len, ref2_len):
         super().__init__(ctx, handle, n_tasks)
         self._read_len = read_len
         self._ref2_len = ref2_len
 
-    def fetch(self):
+    def fetch(self, copy=True):
+        """Results of the last run.  copy=False returns views into library memory that stay valid until the
+        next fetch on this plan."""
         best = np.zeros(self.n_tasks, dtype=np.int32)
         n_rows = ctypes.c_int64()
         n_cols = ctypes.c_int64()
-        self.ctx._check(self.ctx._lib.dfb_split_plan_fetch(self._h, best.ctypes.data, ctypes.byref(n_rows), ctypes.byref(n_cols)))
-        rows = np.zeros(n_rows.value, dtype=SPLIT_ROW_DTYPE)
-        cols = np.zeros(n_cols.value, dtype=np.int32)
-        self.ctx._check(self.ctx._lib.dfb_split_plan_copy(self._h, rows.ctypes.data if n_rows.value else None,
-                                                          cols.ctypes.data if n_cols.value else None))
+        lib = self.ctx._lib
+        self.ctx._check(lib.dfb_split_plan_fetch(self._h, best.ctypes.data, ctypes.byref(n_rows), ctypes.byref(n_cols)))
+        rp, cp = ctypes.c_void_p(), ctypes.c_void_p()
+        self.ctx._check(lib.dfb_split_plan_view(self._h, ctypes.byref(rp), ctypes.byref(n_rows), ctypes.byref(cp), ctypes.byref(n_cols)))
+        rows, cols = _view_arrays(rp.value, n_rows.value, cp.value, n_cols.value, copy)
         return SplitResult(best, rows, cols, self._read_len, self._ref2_len)
 
 
@@ -391,9 +411,10 @@ class SplitReadAligner:
         read_len, ref2_len = self._lens(refs, reads, task_cluster, task_read)
         return SplitPlan(self.ctx, h, task_cluster.size, read_len, ref2_len)
 
-    def align_batch(self, refs, reads, task_cluster, task_read, task_min_score):
+    def align_batch(self, refs, reads, task_cluster, task_read, task_min_score, copy=True):
         """Batch of Align + GetAlignments(minScore, forceSplits=True, firstOnly=False) through
-        dfb_split_align_batch; cluster c uses refs[2c] / refs[2c+1]."""
+        dfb_split_align_batch; cluster c uses refs[2c] / refs[2c+1].  copy=False returns views into
+        library memory that stay valid until the next split call on this context."""
         task_cluster, task_read, task_min_score = _i32(task_cluster), _i32(task_read), _i32(task_min_score)
         best = np.zeros(task_cluster.size, dtype=np.int32)
         rt, st = refs.c_struct(), reads.c_struct()
@@ -402,11 +423,10 @@ class SplitReadAligner:
                                                   task_cluster.ctypes.data, task_read.ctypes.data, task_min_score.ctypes.data,
                                                   task_cluster.size, best.ctypes.data))
         n_rows, n_cols = ctypes.c_int64(), ctypes.c_int64()
-        self.ctx._check(lib.dfb_split_result_size(self.ctx._h, ctypes.byref(n_rows), ctypes.byref(n_cols)))
-        rows = np.zeros(n_rows.value, dtype=SPLIT_ROW_DTYPE)
-        cols = np.zeros(n_cols.value, dtype=np.int32)
-        self.ctx._check(lib.dfb_split_result_copy(self.ctx._h, rows.ctypes.data if n_rows.value else None,
-                                                  cols.ctypes.data if n_cols.value else None))
+        rp, cp = ctypes.c_void_p(), ctypes.c_void_p()
+        self.ctx._check(lib.dfb_split_result_view(self.ctx._h, ctypes.byref(rp), ctypes.byref(n_rows), ctypes.byref(cp),
+                                                  ctypes.byref(n_cols)))
+        rows, cols = _view_arrays(rp.value, n_rows.value, cp.value, n_cols.value, copy)
         read_len, ref2_len = self._lens(refs, reads, task_cluster, task_read)
         return SplitResult(best, rows, cols, read_len, ref2_len)
 

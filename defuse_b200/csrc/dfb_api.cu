@@ -1,6 +1,15 @@
 // Host side of the C ABI in include/defuse_b200.h: context, plan building (packing,
 // length-bucketed job lists), kernel dispatch and result assembly.  No CPU implementation
 // of the DP exists in this library: without a GPU every entry point fails.
+//
+// Host-path design (it bounds the end-to-end number once the kernels run at TCUPS rates):
+//  * device memory comes from the stream-ordered pool (cudaMallocAsync, nothing released
+//    back to the driver between batches); host-built arrays are written straight into a
+//    grow-only pinned staging buffer, results land in another one;
+//  * jobs are ordered by one counting sort (kernel class, reference length), O(n);
+//  * the probe sweep leaves its arg-max columns in fixed 64-byte regions per winning task,
+//    so the host only has to order a handful of entries per task; that assembly is
+//    spread over host threads.
 #include "../../include/defuse_b200.h"
 #include "dfb_kernels.cuh"
 
@@ -10,6 +19,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace dfb;
@@ -18,6 +28,29 @@ using namespace dfb;
 // context
 // ------------------------------------------------------------------------------------------
 
+struct PinnedBuf
+{
+	void* p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t n)
+	{
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 4 + 4096;
+		cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release()
+	{
+		if (p) cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
 struct dfb_ctx
 {
 	int device = 0;
@@ -25,10 +58,34 @@ struct dfb_ctx
 	cudaStream_t stream = nullptr;
 	cudaDeviceProp prop;
 	mutable std::string err;
+	PinnedBuf h_in;  // host-built descriptors and job lists, on their way to the device
+	PinnedBuf h_out; // results on their way back
 	dfb_plan* last_split = nullptr; // result holder of dfb_split_align_batch
+	int host_threads = 1;
 };
 
 static thread_local std::string g_create_err;
+
+// DFB_TRACE=1: phase timings of the host path on stderr
+#include <chrono>
+static bool trace_on()
+{
+	static int on = -1;
+	if (on < 0) { const char* e = getenv("DFB_TRACE"); on = (e && *e && *e != '0') ? 1 : 0; }
+	return on == 1;
+}
+struct Trace
+{
+	std::chrono::steady_clock::time_point t0;
+	Trace() : t0(std::chrono::steady_clock::now()) {}
+	void lap(const char* what)
+	{
+		if (!trace_on()) return;
+		auto t1 = std::chrono::steady_clock::now();
+		fprintf(stderr, "[dfb] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		t0 = t1;
+	}
+};
 
 static int set_err(const dfb_ctx* ctx, int code, const char* fmt, ...)
 {
@@ -103,6 +160,15 @@ extern "C" int dfb_ctx_create(int device_ordinal, dfb_ctx** out)
 		return set_err(nullptr, DFB_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(e));
 	}
 	ctx->stream = ctx->own_stream;
+	// keep freed blocks in the stream-ordered pool: a batch re-uses the previous batch's memory
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, device_ordinal) == cudaSuccess)
+	{
+		unsigned long long keep = ~0ull;
+		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+	}
+	unsigned hc = std::thread::hardware_concurrency();
+	ctx->host_threads = (int)std::max(1u, std::min(hc ? hc : 1u, 16u));
 	*out = ctx;
 	return DFB_OK;
 }
@@ -112,6 +178,9 @@ extern "C" void dfb_ctx_destroy(dfb_ctx* ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->last_split) dfb_plan_destroy(ctx->last_split);
+	cudaStreamSynchronize(ctx->stream);
+	ctx->h_in.release();
+	ctx->h_out.release();
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
@@ -161,6 +230,7 @@ static const ClassDef kClasses[] = {DFB_CLASSES(X)};
 #undef X
 static const int kNumClasses = (int)(sizeof(kClasses) / sizeof(kClasses[0]));
 static const int kMaxFastRows = 1024;
+static const int kRBins = 1024; // job order inside a class: reference length / 16, longest first
 
 template <int G, int S, int MODE>
 static cudaError_t launch_fast_t(const FastParams& p, int sm_count, cudaStream_t stream, int n_items_bound)
@@ -202,10 +272,13 @@ static cudaError_t launch_fast(int cls, int mode, const FastParams& p, int sm_co
 
 struct ClassWork
 {
-	std::vector<JobPair> jobs;
-	JobPair* d_jobs = nullptr;
-	int* d_ctrl = nullptr; // [0] cursor, [1] hit_count, [2] probe cursor
+	int64_t n_jobs = 0;
+	JobPair* d_jobs = nullptr; // inside the plan's staged upload
+	int* d_ctrl = nullptr;     // [0] cursor, [1] hit_count, [2] probe cursor (inside plan->d_ctrl)
 	int* d_hitq = nullptr;
+	int32_t* d_slot_task = nullptr;
+	int* d_slot_n = nullptr;
+	uint2* d_slot_ev = nullptr;
 	uint32_t* d_ntg = nullptr;
 	FastParams fp;
 };
@@ -221,16 +294,17 @@ struct dfb_plan
 
 	// device
 	uint8_t* d_raw = nullptr;
-	PackItem* d_items = nullptr;
+	uint8_t* d_stage = nullptr; // descriptors + fast jobs + generic jobs (one upload)
 	uint2* d_pool = nullptr;
 	uint8_t* d_obytes = nullptr;
 	int32_t* d_out = nullptr; // score / best per task
+	int* d_ctrl = nullptr;    // all classes' control words
 	Event* d_events = nullptr;
 	unsigned long long* d_ev_count = nullptr;
 	unsigned long long ev_cap = 0;
 	ClassWork cls[kNumClasses];
 	// generic path
-	std::vector<GenJob> gen_jobs;
+	int64_t n_gen_jobs = 0;
 	GenJob* d_gen_jobs = nullptr;
 	int* d_gen_ctrl = nullptr; // [0] cursor pass 1, [1] cursor probe
 	int32_t* d_gen_rowmax = nullptr;
@@ -243,7 +317,7 @@ struct dfb_plan
 	int64_t gen_rows_total = 0;
 
 	// host
-	std::vector<int32_t> task_L;      // read length per task (split)
+	std::vector<int32_t> task_L; // read length per task (split)
 	std::vector<dfb_split_row> rows;
 	std::vector<int32_t> cols;
 	bool ran = false, fetched = false;
@@ -254,11 +328,48 @@ struct dfb_plan
 	dfb_plan_stats stats{};
 };
 
-template <class T>
-static void dfree(T*& p)
+static cudaError_t dalloc(dfb_ctx* ctx, void** p, size_t bytes)
 {
-	if (p) cudaFree(p);
+	return cudaMallocAsync(p, std::max<size_t>(bytes, 256), ctx->stream);
+}
+#define DALLOC(ctx, ptr, bytes) CK(ctx, dalloc(ctx, (void**)&(ptr), (bytes)))
+
+template <class T>
+static void dfree(dfb_ctx* ctx, T*& p)
+{
+	if (p) cudaFreeAsync(p, ctx->stream);
 	p = nullptr;
+}
+
+static void release_device(dfb_plan* plan)
+{
+	dfb_ctx* ctx = plan->ctx;
+	dfree(ctx, plan->d_raw);
+	dfree(ctx, plan->d_stage);
+	dfree(ctx, plan->d_pool);
+	dfree(ctx, plan->d_obytes);
+	dfree(ctx, plan->d_out);
+	dfree(ctx, plan->d_ctrl);
+	dfree(ctx, plan->d_events);
+	dfree(ctx, plan->d_ev_count);
+	for (int c = 0; c < kNumClasses; c++)
+	{
+		ClassWork& cw = plan->cls[c];
+		cw.d_jobs = nullptr;
+		cw.d_ctrl = nullptr;
+		dfree(ctx, cw.d_hitq);
+		dfree(ctx, cw.d_slot_task);
+		dfree(ctx, cw.d_slot_n);
+		dfree(ctx, cw.d_slot_ev);
+		dfree(ctx, cw.d_ntg);
+	}
+	plan->d_gen_jobs = nullptr;
+	dfree(ctx, plan->d_gen_ctrl);
+	dfree(ctx, plan->d_gen_rowmax);
+	dfree(ctx, plan->d_gen_row_en);
+	dfree(ctx, plan->d_gen_bnd);
+	dfree(ctx, plan->d_gen_probe_flag);
+	dfree(ctx, plan->d_task_min_score);
 }
 
 extern "C" void dfb_plan_destroy(dfb_plan* plan)
@@ -268,28 +379,8 @@ extern "C" void dfb_plan_destroy(dfb_plan* plan)
 	{
 		cudaSetDevice(plan->ctx->device);
 		if (plan->ctx->last_split == plan) plan->ctx->last_split = nullptr;
+		release_device(plan);
 	}
-	dfree(plan->d_raw);
-	dfree(plan->d_items);
-	dfree(plan->d_pool);
-	dfree(plan->d_obytes);
-	dfree(plan->d_out);
-	dfree(plan->d_events);
-	dfree(plan->d_ev_count);
-	for (int c = 0; c < kNumClasses; c++)
-	{
-		dfree(plan->cls[c].d_jobs);
-		dfree(plan->cls[c].d_ctrl);
-		dfree(plan->cls[c].d_hitq);
-		dfree(plan->cls[c].d_ntg);
-	}
-	dfree(plan->d_gen_jobs);
-	dfree(plan->d_gen_ctrl);
-	dfree(plan->d_gen_rowmax);
-	dfree(plan->d_gen_row_en);
-	dfree(plan->d_gen_bnd);
-	dfree(plan->d_gen_probe_flag);
-	dfree(plan->d_task_min_score);
 	for (int k = 0; k < 3; k++)
 		if (plan->ev[k]) cudaEventDestroy(plan->ev[k]);
 	delete plan;
@@ -302,8 +393,9 @@ static int check_table(const dfb_ctx* ctx, const dfb_seq_table* t, const char* w
 	if (t->off[0] != 0) return set_err(ctx, DFB_ERR_ARG, "%s: off[0] must be 0", what);
 	for (int64_t k = 0; k < t->n; k++)
 	{
-		if (t->off[k + 1] < t->off[k]) return set_err(ctx, DFB_ERR_ARG, "%s: offsets decrease at %lld", what, (long long)k);
-		if (t->off[k + 1] - t->off[k] > 0x7fffffffLL) return set_err(ctx, DFB_ERR_ARG, "%s: sequence %lld too long", what, (long long)k);
+		const int64_t len = t->off[k + 1] - t->off[k];
+		if (len < 0) return set_err(ctx, DFB_ERR_ARG, "%s: offsets decrease at %lld", what, (long long)k);
+		if (len > 0x7fffff00LL) return set_err(ctx, DFB_ERR_ARG, "%s: sequence %lld too long", what, (long long)k);
 	}
 	return DFB_OK;
 }
@@ -334,97 +426,100 @@ static int class_for_rows(int L)
 
 static uint32_t pack2(int v) { return ((uint32_t)v & 0xFFFFu) | ((uint32_t)v << 16); }
 
-struct SeqLayout
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Everything the host builds for one batch, laid out in the pinned staging buffer and
+// uploaded with a single copy: [table A descs][table B descs][fast jobs, class by class][generic jobs]
+struct Staging
 {
-	std::vector<PackItem> items;
-	uint32_t total_words = 0;
-	// adds one stored sequence, returns its first pool word
-	uint32_t add(int64_t src, uint32_t len, uint32_t flags)
-	{
-		PackItem it;
-		it.src = src;
-		it.len = len;
-		it.dst_word = total_words;
-		it.flags = flags;
-		it.pad = 0;
-		items.push_back(it);
-		uint32_t w = total_words;
-		total_words += (len + 15) / 16;
-		return w;
-	}
+	size_t off_desc_a = 0, off_desc_b = 0, off_jobs = 0, off_gen = 0, total = 0;
+	SeqDesc* desc_a = nullptr;
+	SeqDesc* desc_b = nullptr;
+	JobPair* jobs = nullptr;
+	GenJob* gen = nullptr;
 };
 
-static int upload_and_pack(dfb_plan* pl, const dfb_seq_table* a, const dfb_seq_table* b, SeqLayout& lay)
+static cudaError_t stage_layout(dfb_ctx* ctx, Staging& st, int64_t na, int64_t nb, int64_t n_fast, int64_t n_gen)
+{
+	st.off_desc_a = 0;
+	st.off_desc_b = align_up(st.off_desc_a + (size_t)na * sizeof(SeqDesc), 256);
+	st.off_jobs = align_up(st.off_desc_b + (size_t)nb * sizeof(SeqDesc), 256);
+	st.off_gen = align_up(st.off_jobs + (size_t)n_fast * sizeof(JobPair), 256);
+	st.total = align_up(st.off_gen + (size_t)n_gen * sizeof(GenJob), 256) + 256;
+	cudaError_t e = ctx->h_in.ensure(st.total);
+	if (e != cudaSuccess) return e;
+	uint8_t* base = (uint8_t*)ctx->h_in.p;
+	st.desc_a = (SeqDesc*)(base + st.off_desc_a);
+	st.desc_b = (SeqDesc*)(base + st.off_desc_b);
+	st.jobs = (JobPair*)(base + st.off_jobs);
+	st.gen = (GenJob*)(base + st.off_gen);
+	return cudaSuccess;
+}
+
+// word layout of the two tables; returns total words
+static uint32_t layout_words(const dfb_seq_table* a, int mode_a, const dfb_seq_table* b, int mode_b, SeqDesc* da,
+                             SeqDesc* db, uint32_t* words_a_end, bool* overflow)
+{
+	uint64_t w = 0;
+	const int64_t b_src_base = a->off[a->n];
+	for (int64_t k = 0; k < a->n; k++)
+	{
+		const uint32_t len = (uint32_t)(a->off[k + 1] - a->off[k]);
+		da[k].src = 16 + a->off[k];
+		da[k].len = len;
+		da[k].word = (uint32_t)w;
+		w += (uint64_t)((len + 15) / 16) * (mode_a == PACK_BOTH ? 2 : 1);
+	}
+	*words_a_end = (uint32_t)w;
+	for (int64_t k = 0; k < b->n; k++)
+	{
+		const uint32_t len = (uint32_t)(b->off[k + 1] - b->off[k]);
+		db[k].src = 16 + b_src_base + b->off[k];
+		db[k].len = len;
+		db[k].word = (uint32_t)w;
+		w += (uint64_t)((len + 15) / 16) * (mode_b == PACK_BOTH ? 2 : 1);
+	}
+	*overflow = w >= 0xFFFFFFF0ull;
+	return (uint32_t)w;
+}
+
+static int upload_and_pack(dfb_plan* pl, const dfb_seq_table* a, int mode_a, const dfb_seq_table* b, int mode_b,
+                           const Staging& st, uint32_t words_a_end, uint32_t total_words)
 {
 	dfb_ctx* ctx = pl->ctx;
 	const int64_t na = a->off[a->n], nb = b->off[b->n];
-	CK(ctx, cudaMalloc(&pl->d_raw, (size_t)std::max<int64_t>(na + nb, 16)));
-	if (na) CK(ctx, cudaMemcpyAsync(pl->d_raw, a->bytes, (size_t)na, cudaMemcpyHostToDevice, ctx->stream));
-	if (nb) CK(ctx, cudaMemcpyAsync(pl->d_raw + na, b->bytes, (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
-	const size_t n_items = lay.items.size();
-	// one spare word so that an empty batch still has valid pointers
-	const uint32_t words = lay.total_words + 1;
-	CK(ctx, cudaMalloc(&pl->d_items, std::max<size_t>(n_items, 1) * sizeof(PackItem)));
-	CK(ctx, cudaMalloc(&pl->d_pool, (size_t)words * sizeof(uint2)));
-	CK(ctx, cudaMalloc(&pl->d_obytes, (size_t)words * 16));
-	if (n_items)
-		CK(ctx, cudaMemcpyAsync(pl->d_items, lay.items.data(), n_items * sizeof(PackItem), cudaMemcpyHostToDevice, ctx->stream));
-	if (lay.total_words && n_items)
-	{
-		int grid = (int)std::min<uint32_t>((lay.total_words + 255) / 256, 148 * 16);
-		for (int k = 0; k < 3; k++) CK(ctx, cudaEventCreate(&pl->ev[k]));
-		CK(ctx, cudaEventRecord(pl->ev[0], ctx->stream));
-		pack_kernel<<<grid, 256, 0, ctx->stream>>>(pl->d_raw, pl->d_items, (int)n_items, lay.total_words, pl->d_pool, pl->d_obytes);
-		CK(ctx, cudaGetLastError());
-		CK(ctx, cudaEventRecord(pl->ev[1], ctx->stream));
-		pl->pack_timed = true;
-	}
-	pl->stats.h2d_bytes += na + nb + (int64_t)(n_items * sizeof(PackItem));
-	pl->stats.raw_bytes = na + nb;
-	pl->stats.packed_bytes = (int64_t)lay.total_words * 8;
-	return DFB_OK;
-}
-
-static int upload_jobs(dfb_plan* pl, bool split)
-{
-	dfb_ctx* ctx = pl->ctx;
-	for (int c = 0; c < kNumClasses; c++)
-	{
-		ClassWork& cw = pl->cls[c];
-		if (cw.jobs.empty()) continue;
-		const size_t n = cw.jobs.size();
-		CK(ctx, cudaMalloc(&cw.d_jobs, n * sizeof(JobPair)));
-		CK(ctx, cudaMemcpyAsync(cw.d_jobs, cw.jobs.data(), n * sizeof(JobPair), cudaMemcpyHostToDevice, ctx->stream));
-		CK(ctx, cudaMalloc(&cw.d_ctrl, 4 * sizeof(int)));
-		pl->stats.h2d_bytes += (int64_t)(n * sizeof(JobPair));
-		pl->stats.fast_jobs += (int64_t)n;
-		if (split)
-		{
-			CK(ctx, cudaMalloc(&cw.d_hitq, n * sizeof(int)));
-			CK(ctx, cudaMalloc(&cw.d_ntg, n * (size_t)kClasses[c].G * kClasses[c].S * sizeof(uint32_t)));
-		}
-	}
-	if (!pl->gen_jobs.empty())
-	{
-		const size_t n = pl->gen_jobs.size();
-		CK(ctx, cudaMalloc(&pl->d_gen_jobs, n * sizeof(GenJob)));
-		CK(ctx, cudaMemcpyAsync(pl->d_gen_jobs, pl->gen_jobs.data(), n * sizeof(GenJob), cudaMemcpyHostToDevice, ctx->stream));
-		CK(ctx, cudaMalloc(&pl->d_gen_ctrl, 4 * sizeof(int)));
-		uint32_t maxR = 0;
-		for (const GenJob& j : pl->gen_jobs) maxR = std::max(maxR, j.R);
-		pl->gen_bnd_stride = (int64_t)maxR + 2;
-		pl->gen_grid = (int)std::min<size_t>((n + 3) / 4, (size_t)ctx->prop.multiProcessorCount * 4);
-		CK(ctx, cudaMalloc(&pl->d_gen_bnd, (size_t)pl->gen_grid * 4 * 2 * pl->gen_bnd_stride * sizeof(int32_t)));
-		if (split)
-		{
-			CK(ctx, cudaMalloc(&pl->d_gen_rowmax, (size_t)std::max<int64_t>(pl->gen_rows_total, 1) * sizeof(int32_t)));
-			CK(ctx, cudaMalloc(&pl->d_gen_row_en, (size_t)std::max<int64_t>(pl->gen_rows_total, 1)));
-			CK(ctx, cudaMemsetAsync(pl->d_gen_row_en, 0, (size_t)std::max<int64_t>(pl->gen_rows_total, 1), ctx->stream));
-			CK(ctx, cudaMalloc(&pl->d_gen_probe_flag, (n / 2 + 1) * sizeof(int)));
-		}
-		pl->stats.h2d_bytes += (int64_t)(n * sizeof(GenJob));
-		pl->stats.generic_jobs += (int64_t)n;
-	}
+	// raw bytes: 16 bytes of slack in front, 32 behind (the pack kernel reads whole 16-byte windows)
+	DALLOC(ctx, pl->d_raw, (size_t)(na + nb + 48));
+	if (na) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16, a->bytes, (size_t)na, cudaMemcpyHostToDevice, ctx->stream));
+	if (nb) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16 + na, b->bytes, (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+	DALLOC(ctx, pl->d_stage, st.total);
+	CK(ctx, cudaMemcpyAsync(pl->d_stage, ctx->h_in.p, st.total, cudaMemcpyHostToDevice, ctx->stream));
+	DALLOC(ctx, pl->d_pool, ((size_t)total_words + 2) * sizeof(uint2));
+	DALLOC(ctx, pl->d_obytes, ((size_t)total_words + 2) * 16);
+	for (int k = 0; k < 3; k++)
+		if (!pl->ev[k]) CK(ctx, cudaEventCreate(&pl->ev[k]));
+	CK(ctx, cudaEventRecord(pl->ev[0], ctx->stream));
+	const SeqDesc* d_da = (const SeqDesc*)(pl->d_stage + st.off_desc_a);
+	const SeqDesc* d_db = (const SeqDesc*)(pl->d_stage + st.off_desc_b);
+	const int max_grid = ctx->prop.multiProcessorCount * 16;
+	auto launch = [&](int mode, const SeqDesc* d, int64_t n, uint32_t w0, uint32_t w1) -> cudaError_t {
+		if (n == 0 || w1 <= w0) return cudaSuccess;
+		const int grid = (int)std::min<uint32_t>((w1 - w0 + 255) / 256, (uint32_t)max_grid);
+		if (mode == PACK_FWD)
+			pack_kernel<PACK_FWD><<<grid, 256, 0, ctx->stream>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
+		else if (mode == PACK_REV_ODD)
+			pack_kernel<PACK_REV_ODD><<<grid, 256, 0, ctx->stream>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
+		else
+			pack_kernel<PACK_BOTH><<<grid, 256, 0, ctx->stream>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
+		return cudaGetLastError();
+	};
+	CK(ctx, launch(mode_a, d_da, a->n, 0, words_a_end));
+	CK(ctx, launch(mode_b, d_db, b->n, words_a_end, total_words));
+	CK(ctx, cudaEventRecord(pl->ev[1], ctx->stream));
+	pl->pack_timed = true;
+	pl->stats.h2d_bytes += na + nb + (int64_t)st.total;
+	pl->stats.raw_bytes = na * (mode_a == PACK_BOTH ? 2 : 1) + nb * (mode_b == PACK_BOTH ? 2 : 1);
+	pl->stats.packed_bytes = (int64_t)total_words * 8;
 	return DFB_OK;
 }
 
@@ -436,7 +531,7 @@ static void fill_fast_params(dfb_plan* pl, int c, int m, int x, int g, int min_s
 	fp.pool = pl->d_pool;
 	fp.obytes = pl->d_obytes;
 	fp.jobs = cw.d_jobs;
-	fp.n_jobs = (int)cw.jobs.size();
+	fp.n_jobs = (int)cw.n_jobs;
 	fp.m = m;
 	fp.bias = pl->bias[c];
 	fp.xm = (uint32_t)(x - m);
@@ -444,13 +539,74 @@ static void fill_fast_params(dfb_plan* pl, int c, int m, int x, int g, int min_s
 	fp.gm2 = pack2(g - m);
 	fp.min_split = min_split;
 	fp.out = pl->d_out;
-	fp.hit_count = cw.d_ctrl ? cw.d_ctrl + 1 : nullptr;
+	fp.hit_count = cw.d_ctrl + 1;
 	fp.hitq = cw.d_hitq;
+	fp.slot_task = cw.d_slot_task;
+	fp.slot_ev = cw.d_slot_ev;
+	fp.slot_n = cw.d_slot_n;
 	fp.ntg = cw.d_ntg;
 	fp.events = pl->d_events;
 	fp.ev_count = pl->d_ev_count;
 	fp.ev_cap = pl->ev_cap;
 	for (int k = 0; k < 32; k++) fp.ck[k] = pack2(m * (k + 1));
+}
+
+// device-side bookkeeping common to both plan kinds, after the job counts are known
+static int alloc_work(dfb_plan* pl, const Staging& st, const int64_t* n_jobs_cls, bool split, uint32_t gen_max_R)
+{
+	dfb_ctx* ctx = pl->ctx;
+	DALLOC(ctx, pl->d_ctrl, kNumClasses * 4 * sizeof(int));
+	int64_t first = 0;
+	for (int c = 0; c < kNumClasses; c++)
+	{
+		ClassWork& cw = pl->cls[c];
+		cw.n_jobs = n_jobs_cls[c];
+		cw.d_jobs = (JobPair*)(pl->d_stage + st.off_jobs) + first;
+		cw.d_ctrl = pl->d_ctrl + 4 * c;
+		first += cw.n_jobs;
+		pl->stats.fast_jobs += cw.n_jobs;
+		if (split && cw.n_jobs)
+		{
+			const size_t n = (size_t)cw.n_jobs;
+			DALLOC(ctx, cw.d_hitq, n * sizeof(int));
+			DALLOC(ctx, cw.d_slot_task, n * sizeof(int32_t));
+			DALLOC(ctx, cw.d_slot_n, n * sizeof(int));
+			DALLOC(ctx, cw.d_slot_ev, n * DFB_SLOT_EVENTS * sizeof(uint2));
+			DALLOC(ctx, cw.d_ntg, n * (size_t)kClasses[c].G * kClasses[c].S * sizeof(uint32_t));
+		}
+	}
+	if (pl->n_gen_jobs)
+	{
+		const size_t n = (size_t)pl->n_gen_jobs;
+		pl->d_gen_jobs = (GenJob*)(pl->d_stage + st.off_gen);
+		DALLOC(ctx, pl->d_gen_ctrl, 4 * sizeof(int));
+		pl->gen_bnd_stride = (int64_t)gen_max_R + 2;
+		pl->gen_grid = (int)std::min<size_t>((n + 3) / 4, (size_t)ctx->prop.multiProcessorCount * 4);
+		DALLOC(ctx, pl->d_gen_bnd, (size_t)pl->gen_grid * 4 * 2 * pl->gen_bnd_stride * sizeof(int32_t));
+		if (split)
+		{
+			DALLOC(ctx, pl->d_gen_rowmax, (size_t)std::max<int64_t>(pl->gen_rows_total, 1) * sizeof(int32_t));
+			DALLOC(ctx, pl->d_gen_row_en, (size_t)std::max<int64_t>(pl->gen_rows_total, 1));
+			CK(ctx, cudaMemsetAsync(pl->d_gen_row_en, 0, (size_t)std::max<int64_t>(pl->gen_rows_total, 1), ctx->stream));
+			DALLOC(ctx, pl->d_gen_probe_flag, (n / 2 + 1) * sizeof(int));
+		}
+		pl->stats.generic_jobs += (int64_t)n;
+	}
+	DALLOC(ctx, pl->d_out, (size_t)std::max<int64_t>(pl->n_tasks, 1) * sizeof(int32_t));
+	CK(ctx, cudaMemsetAsync(pl->d_out, 0, (size_t)std::max<int64_t>(pl->n_tasks, 1) * sizeof(int32_t), ctx->stream));
+	return DFB_OK;
+}
+
+static int finish_create(dfb_plan* pl)
+{
+	dfb_ctx* ctx = pl->ctx;
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	if (pl->pack_timed)
+	{
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]) == cudaSuccess) pl->stats.ms_pack = ms;
+	}
+	return DFB_OK;
 }
 
 // ---- SimpleAligner plan ------------------------------------------------------------------
@@ -465,12 +621,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 	*out = nullptr;
 	int rc;
 	if ((rc = check_table(ctx, refs, "refs")) || (rc = check_table(ctx, seqs, "seqs"))) return rc;
-	if (n_tasks > 0x7fffffffLL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
-	for (int64_t t = 0; t < n_tasks; t++)
-	{
-		if (task_ref[t] < 0 || task_ref[t] >= refs->n || task_seq[t] < 0 || task_seq[t] >= seqs->n)
-			return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)t);
-	}
+	if (n_tasks > 0x7fffff00LL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
 	CK(ctx, cudaSetDevice(ctx->device));
 	dfb_plan* pl = new (std::nothrow) dfb_plan();
 	if (!pl) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
@@ -478,89 +629,121 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 	pl->split = false;
 	pl->n_tasks = n_tasks;
 	pl->stats.n_tasks = n_tasks;
+	pl->sp.match = params->match;
+	pl->sp.mismatch = params->mismatch;
+	pl->sp.gap = params->gap;
 	classify_params(pl, params->match, params->mismatch, params->gap, true);
 
-	SeqLayout lay;
-	std::vector<uint32_t> ref_word((size_t)refs->n), seq_word((size_t)seqs->n);
-	for (int64_t k = 0; k < refs->n; k++) ref_word[k] = lay.add(refs->off[k], (uint32_t)(refs->off[k + 1] - refs->off[k]), 0);
-	const int64_t seq_base = refs->off[refs->n];
-	for (int64_t k = 0; k < seqs->n; k++) seq_word[k] = lay.add(seq_base + seqs->off[k], (uint32_t)(seqs->off[k + 1] - seqs->off[k]), 0);
-
-	// bucket by kernel class, longest reference first inside a bucket, pair neighbours
-	struct Key
-	{
-		uint64_t key;
-		int32_t task;
-	};
-	std::vector<Key> keys;
-	keys.reserve((size_t)n_tasks);
+	// pass 1: classify every task, count per (class, reference-length bin)
+	std::vector<int32_t> bin_of((size_t)n_tasks);
+	std::vector<int64_t> bin_pos((size_t)kNumClasses * kRBins, 0);
+	int64_t n_gen = 0;
+	uint32_t gen_max_R = 0;
 	for (int64_t t = 0; t < n_tasks; t++)
 	{
-		const int64_t R = refs->off[task_ref[t] + 1] - refs->off[task_ref[t]];
-		const int64_t L = seqs->off[task_seq[t] + 1] - seqs->off[task_seq[t]];
-		pl->stats.cells += R * L;
-		if (R == 0 || L == 0) continue; // no interior cell: score 0 (d_out is zero-initialised)
-		int c = (L <= kMaxFastRows && R <= 65535) ? class_for_rows((int)L) : -1;
-		if (c >= 0 && !pl->fast_ok[c]) c = -1;
-		if (c < 0)
+		const int32_t r = task_ref[t], s = task_seq[t];
+		if (r < 0 || r >= refs->n || s < 0 || s >= seqs->n)
 		{
-			GenJob j;
-			j.ref_w = ref_word[task_ref[t]];
-			j.read_w = seq_word[task_seq[t]];
-			j.R = (uint32_t)R;
-			j.L = (uint32_t)L;
+			delete pl;
+			return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)t);
+		}
+		const int64_t R = refs->off[r + 1] - refs->off[r];
+		const int64_t L = seqs->off[s + 1] - seqs->off[s];
+		pl->stats.cells += R * L;
+		int32_t bin = -1; // no interior cell: score 0 (d_out is zero-initialised)
+		if (R > 0 && L > 0)
+		{
+			int c = (L <= kMaxFastRows && R <= 65535) ? class_for_rows((int)L) : -1;
+			if (c >= 0 && !pl->fast_ok[c]) c = -1;
+			if (c < 0)
+			{
+				bin = -2;
+				n_gen++;
+				gen_max_R = std::max<uint32_t>(gen_max_R, (uint32_t)R);
+			}
+			else
+			{
+				bin = c * kRBins + (kRBins - 1 - (int)std::min<int64_t>(R >> 4, kRBins - 1));
+				bin_pos[bin]++;
+			}
+		}
+		bin_of[t] = bin;
+	}
+	// two tasks share a job (low / high half): task position p inside its class -> job p/2, half p%2
+	int64_t n_jobs_cls[kNumClasses], job_base[kNumClasses];
+	int64_t n_fast_jobs = 0;
+	for (int c = 0; c < kNumClasses; c++)
+	{
+		int64_t tasks_c = 0;
+		for (int b = 0; b < kRBins; b++)
+		{
+			const int64_t cnt = bin_pos[(size_t)c * kRBins + b];
+			bin_pos[(size_t)c * kRBins + b] = tasks_c;
+			tasks_c += cnt;
+		}
+		job_base[c] = n_fast_jobs;
+		n_jobs_cls[c] = (tasks_c + 1) / 2;
+		n_fast_jobs += n_jobs_cls[c];
+	}
+
+	Staging st;
+	cudaError_t e = stage_layout(ctx, st, refs->n, seqs->n, n_fast_jobs, n_gen);
+	if (e != cudaSuccess)
+	{
+		delete pl;
+		return set_err(ctx, DFB_ERR_NOMEM, "pinned staging buffer: %s", cudaGetErrorString(e));
+	}
+	uint32_t words_a_end = 0;
+	bool overflow = false;
+	const uint32_t total_words = layout_words(refs, PACK_FWD, seqs, PACK_FWD, st.desc_a, st.desc_b, &words_a_end, &overflow);
+	if (overflow)
+	{
+		delete pl;
+		return set_err(ctx, DFB_ERR_ARG, "batch too large: more than 2^32 packed words; split it");
+	}
+	// pass 2: place every task into its job slot
+	for (int64_t j = 0; j < n_fast_jobs; j++)
+	{
+		JobPair& jp = st.jobs[j];
+		memset(&jp, 0, sizeof(jp));
+		jp.out0 = jp.out1 = -1;
+	}
+	int64_t gi = 0;
+	for (int64_t t = 0; t < n_tasks; t++)
+	{
+		const int32_t bin = bin_of[t];
+		if (bin == -1) continue;
+		const int32_t r = task_ref[t], s = task_seq[t];
+		if (bin == -2)
+		{
+			GenJob& j = st.gen[gi++];
+			j.ref_w = st.desc_a[r].word;
+			j.read_w = st.desc_b[s].word;
+			j.R = st.desc_a[r].len;
+			j.L = st.desc_b[s].len;
 			j.task = (int32_t)t;
 			j.half = 0;
 			j.row_off = 0;
-			pl->gen_jobs.push_back(j);
 			continue;
 		}
-		Key k;
-		k.key = ((uint64_t)c << 48) | ((uint64_t)(65535 - R) << 24) | (uint64_t)(0xFFFFFF - L);
-		k.task = (int32_t)t;
-		keys.push_back(k);
+		const int64_t p = bin_pos[bin]++;
+		JobPair& jp = st.jobs[job_base[bin / kRBins] + (p >> 1)];
+		const int h = (int)(p & 1);
+		jp.ref_w[h] = st.desc_a[r].word;
+		jp.read_w[h] = st.desc_b[s].word;
+		jp.R[h] = (uint16_t)st.desc_a[r].len;
+		jp.L[h] = (uint16_t)st.desc_b[s].len;
+		if (h == 0) jp.out0 = (int32_t)t; else jp.out1 = (int32_t)t;
 	}
-	std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.key < b.key || (a.key == b.key && a.task < b.task); });
-	for (size_t i = 0; i < keys.size();)
-	{
-		const int c = (int)(keys[i].key >> 48);
-		JobPair jp;
-		memset(&jp, 0, sizeof(jp));
-		jp.out0 = jp.out1 = -1;
-		for (int h = 0; h < 2 && i < keys.size() && (int)(keys[i].key >> 48) == c; h++, i++)
-		{
-			const int32_t t = keys[i].task;
-			jp.ref_w[h] = ref_word[task_ref[t]];
-			jp.read_w[h] = seq_word[task_seq[t]];
-			jp.R[h] = (uint16_t)(refs->off[task_ref[t] + 1] - refs->off[task_ref[t]]);
-			jp.L[h] = (uint16_t)(seqs->off[task_seq[t] + 1] - seqs->off[task_seq[t]]);
-			if (h == 0) jp.out0 = t; else jp.out1 = t;
-		}
-		pl->cls[c].jobs.push_back(jp);
-	}
+	pl->n_gen_jobs = n_gen;
 
-	rc = upload_and_pack(pl, refs, seqs, lay);
-	if (!rc) rc = upload_jobs(pl, false);
-	if (!rc)
-	{
-		cudaError_t e = cudaMalloc(&pl->d_out, (size_t)std::max<int64_t>(n_tasks, 1) * sizeof(int32_t));
-		if (e == cudaSuccess) e = cudaMemsetAsync(pl->d_out, 0, (size_t)std::max<int64_t>(n_tasks, 1) * sizeof(int32_t), ctx->stream);
-		if (e != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "output allocation failed: %s", cudaGetErrorString(e));
-	}
+	rc = upload_and_pack(pl, refs, PACK_FWD, seqs, PACK_FWD, st, words_a_end, total_words);
+	if (!rc) rc = alloc_work(pl, st, n_jobs_cls, false, gen_max_R);
 	if (!rc)
 	{
 		for (int c = 0; c < kNumClasses; c++)
-			if (!pl->cls[c].jobs.empty()) fill_fast_params(pl, c, params->match, params->mismatch, params->gap, 0);
-		pl->sp.match = params->match;
-		pl->sp.mismatch = params->mismatch;
-		pl->sp.gap = params->gap;
-		cudaError_t e = cudaStreamSynchronize(ctx->stream);
-		if (e != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "plan upload/pack failed: %s", cudaGetErrorString(e));
-		if (!rc && pl->pack_timed)
-		{
-			float ms = 0;
-			if (cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]) == cudaSuccess) pl->stats.ms_pack = ms;
-		}
+			if (pl->cls[c].n_jobs) fill_fast_params(pl, c, params->match, params->mismatch, params->gap, 0);
+		rc = finish_create(pl);
 	}
 	if (rc)
 	{
@@ -584,13 +767,8 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 	int rc;
 	if ((rc = check_table(ctx, refs, "refs")) || (rc = check_table(ctx, reads, "reads"))) return rc;
 	if (refs->n & 1) return set_err(ctx, DFB_ERR_ARG, "refs must hold two windows per cluster (n is odd)");
-	if (n_tasks > 0x7fffffffLL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
+	if (n_tasks > 0x7fffff00LL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
 	const int64_t n_clusters = refs->n / 2;
-	for (int64_t t = 0; t < n_tasks; t++)
-	{
-		if (task_cluster[t] < 0 || task_cluster[t] >= n_clusters || task_read[t] < 0 || task_read[t] >= reads->n)
-			return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)t);
-	}
 	CK(ctx, cudaSetDevice(ctx->device));
 	dfb_plan* pl = new (std::nothrow) dfb_plan();
 	if (!pl) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
@@ -601,115 +779,142 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 	pl->stats.n_tasks = n_tasks;
 	classify_params(pl, params->match, params->mismatch, params->gap, params->end_gaps == 0 && params->min_split_score >= 1);
 
-	// reference 1 of every cluster forward, reference 2 reversed (SplitReadAligner.cpp:80-81);
-	// every read forward and reversed (:84-85)
-	SeqLayout lay;
-	std::vector<uint32_t> ref_word((size_t)refs->n), read_word((size_t)reads->n * 2);
-	for (int64_t k = 0; k < refs->n; k++)
-		ref_word[k] = lay.add(refs->off[k], (uint32_t)(refs->off[k + 1] - refs->off[k]), (k & 1) ? PACK_REVERSE : 0);
-	const int64_t read_base = refs->off[refs->n];
-	for (int64_t k = 0; k < reads->n; k++)
-	{
-		const uint32_t len = (uint32_t)(reads->off[k + 1] - reads->off[k]);
-		read_word[2 * k] = lay.add(read_base + reads->off[k], len, 0);
-		read_word[2 * k + 1] = lay.add(read_base + reads->off[k], len, PACK_REVERSE);
-	}
-
-	struct Key
-	{
-		uint64_t key;
-		int32_t task;
-	};
-	std::vector<Key> keys;
-	keys.reserve((size_t)n_tasks);
+	Trace tr;
+	std::vector<int32_t> bin_of((size_t)n_tasks);
+	std::vector<int64_t> bin_pos((size_t)kNumClasses * kRBins, 0);
 	pl->task_L.resize((size_t)n_tasks);
-	std::vector<int32_t> gen_tasks;
+	int64_t n_gen_tasks = 0;
+	uint32_t gen_max_R = 0;
 	for (int64_t t = 0; t < n_tasks; t++)
 	{
-		const int64_t c2 = 2 * (int64_t)task_cluster[t];
+		const int32_t c0 = task_cluster[t], rd = task_read[t];
+		if (c0 < 0 || c0 >= n_clusters || rd < 0 || rd >= reads->n)
+		{
+			delete pl;
+			return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)t);
+		}
+		const int64_t c2 = 2 * (int64_t)c0;
 		const int64_t R1 = refs->off[c2 + 1] - refs->off[c2];
 		const int64_t R2 = refs->off[c2 + 2] - refs->off[c2 + 1];
-		const int64_t L = reads->off[task_read[t] + 1] - reads->off[task_read[t]];
+		const int64_t L = reads->off[rd + 1] - reads->off[rd];
 		pl->task_L[t] = (int32_t)L;
 		pl->stats.cells += (R1 + R2) * L;
-		if (L == 0) continue; // every row maximum is 0: no split (SplitReadAligner.cpp:224-227)
-		int c = (L <= kMaxFastRows && R1 <= 65535 && R2 <= 65535) ? class_for_rows((int)L) : -1;
-		if (c >= 0 && !pl->fast_ok[c]) c = -1;
-		if (c < 0)
+		int32_t bin = -1; // empty read: every row maximum is 0, no split (SplitReadAligner.cpp:224-227)
+		if (L > 0)
 		{
-			gen_tasks.push_back((int32_t)t);
-			continue;
+			int c = (L <= kMaxFastRows && R1 <= 65535 && R2 <= 65535) ? class_for_rows((int)L) : -1;
+			if (c >= 0 && !pl->fast_ok[c]) c = -1;
+			if (c < 0)
+			{
+				bin = -2;
+				n_gen_tasks++;
+				gen_max_R = std::max<uint32_t>(gen_max_R, (uint32_t)std::max(R1, R2));
+			}
+			else
+			{
+				bin = c * kRBins + (kRBins - 1 - (int)std::min<int64_t>(std::max(R1, R2) >> 4, kRBins - 1));
+				bin_pos[bin]++;
+			}
 		}
-		Key k;
-		k.key = ((uint64_t)c << 48) | ((uint64_t)(65535 - std::max(R1, R2)) << 24);
-		k.task = (int32_t)t;
-		keys.push_back(k);
+		bin_of[t] = bin;
 	}
-	std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.key < b.key || (a.key == b.key && a.task < b.task); });
-	for (const Key& k : keys)
+	int64_t n_jobs_cls[kNumClasses];
+	int64_t n_fast_jobs = 0;
+	for (int c = 0; c < kNumClasses; c++)
 	{
-		const int32_t t = k.task;
-		const int c = (int)(k.key >> 48);
-		const int64_t c2 = 2 * (int64_t)task_cluster[t];
-		JobPair jp;
-		jp.ref_w[0] = ref_word[c2];
-		jp.ref_w[1] = ref_word[c2 + 1];
-		jp.read_w[0] = read_word[2 * (int64_t)task_read[t]];
-		jp.read_w[1] = read_word[2 * (int64_t)task_read[t] + 1];
-		jp.R[0] = (uint16_t)(refs->off[c2 + 1] - refs->off[c2]);
-		jp.R[1] = (uint16_t)(refs->off[c2 + 2] - refs->off[c2 + 1]);
-		jp.L[0] = jp.L[1] = (uint16_t)pl->task_L[t];
-		jp.out0 = t;
-		jp.out1 = task_min_score[t];
-		pl->cls[c].jobs.push_back(jp);
-	}
-	for (int32_t t : gen_tasks)
-	{
-		const int64_t c2 = 2 * (int64_t)task_cluster[t];
-		for (int h = 0; h < 2; h++)
+		int64_t in_class = 0;
+		for (int b = 0; b < kRBins; b++)
 		{
-			GenJob j;
-			j.ref_w = ref_word[c2 + h];
-			j.read_w = read_word[2 * (int64_t)task_read[t] + h];
-			j.R = (uint32_t)(refs->off[c2 + h + 1] - refs->off[c2 + h]);
-			j.L = (uint32_t)pl->task_L[t];
-			j.task = t;
-			j.half = h;
-			j.row_off = pl->gen_rows_total;
-			pl->gen_rows_total += (int64_t)j.L + 1;
-			pl->gen_jobs.push_back(j);
+			const int64_t cnt = bin_pos[(size_t)c * kRBins + b];
+			bin_pos[(size_t)c * kRBins + b] = n_fast_jobs + in_class;
+			in_class += cnt;
 		}
+		n_jobs_cls[c] = in_class;
+		n_fast_jobs += in_class;
 	}
 
-	rc = upload_and_pack(pl, refs, reads, lay);
+	tr.lap("split.create: classify");
+	Staging st;
+	cudaError_t e = stage_layout(ctx, st, refs->n, reads->n, n_fast_jobs, 2 * n_gen_tasks);
+	if (e != cudaSuccess)
+	{
+		delete pl;
+		return set_err(ctx, DFB_ERR_NOMEM, "pinned staging buffer: %s", cudaGetErrorString(e));
+	}
+	// reference 1 of every cluster forward, reference 2 reversed (SplitReadAligner.cpp:80-81);
+	// every read forward and reversed (:84-85)
+	uint32_t words_a_end = 0;
+	bool overflow = false;
+	const uint32_t total_words = layout_words(refs, PACK_REV_ODD, reads, PACK_BOTH, st.desc_a, st.desc_b, &words_a_end, &overflow);
+	if (overflow)
+	{
+		delete pl;
+		return set_err(ctx, DFB_ERR_ARG, "batch too large: more than 2^32 packed words; split it");
+	}
+	tr.lap("split.create: layout");
+	int64_t gi = 0;
+	for (int64_t t = 0; t < n_tasks; t++)
+	{
+		const int32_t bin = bin_of[t];
+		if (bin == -1) continue;
+		const int64_t c2 = 2 * (int64_t)task_cluster[t];
+		const SeqDesc& rdd = st.desc_b[task_read[t]];
+		const uint32_t rev_w = rdd.word + (rdd.len + 15) / 16;
+		if (bin == -2)
+		{
+			for (int h = 0; h < 2; h++)
+			{
+				GenJob& j = st.gen[gi++];
+				j.ref_w = st.desc_a[c2 + h].word;
+				j.read_w = h ? rev_w : rdd.word;
+				j.R = st.desc_a[c2 + h].len;
+				j.L = rdd.len;
+				j.task = (int32_t)t;
+				j.half = h;
+				j.row_off = pl->gen_rows_total;
+				pl->gen_rows_total += (int64_t)j.L + 1;
+			}
+			continue;
+		}
+		JobPair& jp = st.jobs[bin_pos[bin]++];
+		jp.ref_w[0] = st.desc_a[c2].word;
+		jp.ref_w[1] = st.desc_a[c2 + 1].word;
+		jp.read_w[0] = rdd.word;
+		jp.read_w[1] = rev_w;
+		jp.R[0] = (uint16_t)st.desc_a[c2].len;
+		jp.R[1] = (uint16_t)st.desc_a[c2 + 1].len;
+		jp.L[0] = jp.L[1] = (uint16_t)rdd.len;
+		jp.out0 = (int32_t)t;
+		jp.out1 = task_min_score[t];
+	}
+	pl->n_gen_jobs = 2 * n_gen_tasks;
+	tr.lap("split.create: jobs");
+
+	rc = upload_and_pack(pl, refs, PACK_REV_ODD, reads, PACK_BOTH, st, words_a_end, total_words);
+	tr.lap("split.create: enqueue h2d+pack");
 	if (!rc)
 	{
-		pl->ev_cap = (unsigned long long)std::max<int64_t>(8 * n_tasks, 1 << 20);
-		cudaError_t e = cudaMalloc(&pl->d_events, (size_t)pl->ev_cap * sizeof(Event));
-		if (e == cudaSuccess) e = cudaMalloc(&pl->d_ev_count, sizeof(unsigned long long));
-		if (e == cudaSuccess) e = cudaMalloc(&pl->d_out, (size_t)std::max<int64_t>(n_tasks, 1) * sizeof(int32_t));
-		if (e == cudaSuccess) e = cudaMemsetAsync(pl->d_out, 0, (size_t)std::max<int64_t>(n_tasks, 1) * sizeof(int32_t), ctx->stream);
-		if (e == cudaSuccess && !pl->gen_jobs.empty())
+		pl->ev_cap = (unsigned long long)std::max<int64_t>(n_tasks, 1 << 20);
+		cudaError_t e2 = dalloc(ctx, (void**)&pl->d_events, (size_t)pl->ev_cap * sizeof(Event));
+		if (e2 == cudaSuccess) e2 = dalloc(ctx, (void**)&pl->d_ev_count, sizeof(unsigned long long));
+		if (e2 == cudaSuccess && n_gen_tasks)
 		{
-			e = cudaMalloc(&pl->d_task_min_score, (size_t)n_tasks * sizeof(int32_t));
-			if (e == cudaSuccess)
-				e = cudaMemcpyAsync(pl->d_task_min_score, task_min_score, (size_t)n_tasks * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+			e2 = dalloc(ctx, (void**)&pl->d_task_min_score, (size_t)n_tasks * sizeof(int32_t));
+			if (e2 == cudaSuccess)
+				e2 = cudaMemcpyAsync(pl->d_task_min_score, task_min_score, (size_t)n_tasks * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+			pl->stats.h2d_bytes += n_tasks * (int64_t)sizeof(int32_t);
 		}
-		if (e != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "output allocation failed: %s", cudaGetErrorString(e));
+		if (e2 != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "output allocation failed: %s", cudaGetErrorString(e2));
 	}
-	if (!rc) rc = upload_jobs(pl, true);
+	if (!rc) rc = alloc_work(pl, st, n_jobs_cls, true, gen_max_R);
 	if (!rc)
 	{
 		for (int c = 0; c < kNumClasses; c++)
-			if (!pl->cls[c].jobs.empty())
+			if (pl->cls[c].n_jobs)
 				fill_fast_params(pl, c, params->match, params->mismatch, params->gap, params->min_split_score);
-		cudaError_t e = cudaStreamSynchronize(ctx->stream);
-		if (e != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "plan upload/pack failed: %s", cudaGetErrorString(e));
-		if (!rc && pl->pack_timed)
-		{
-			float ms = 0;
-			if (cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]) == cudaSuccess) pl->stats.ms_pack = ms;
-		}
+		tr.lap("split.create: alloc");
+		rc = finish_create(pl);
+		tr.lap("split.create: sync");
 	}
 	if (rc)
 	{
@@ -726,9 +931,10 @@ static GenParams gen_params(dfb_plan* pl, int cursor_slot)
 {
 	GenParams gp;
 	memset(&gp, 0, sizeof(gp));
+	gp.pool = pl->d_pool;
 	gp.obytes = pl->d_obytes;
 	gp.jobs = pl->d_gen_jobs;
-	gp.n_jobs = (int)pl->gen_jobs.size();
+	gp.n_jobs = (int)pl->n_gen_jobs;
 	gp.cursor = pl->d_gen_ctrl + cursor_slot;
 	gp.m = pl->sp.match;
 	gp.x = pl->sp.mismatch;
@@ -754,16 +960,17 @@ static int run_probe(dfb_plan* pl)
 	for (int c = 0; c < kNumClasses; c++)
 	{
 		ClassWork& cw = pl->cls[c];
-		if (cw.jobs.empty()) continue;
+		if (!cw.n_jobs) continue;
 		CK(ctx, cudaMemsetAsync(cw.d_ctrl + 2, 0, sizeof(int), ctx->stream));
+		CK(ctx, cudaMemsetAsync(cw.d_slot_n, 0, (size_t)cw.n_jobs * sizeof(int), ctx->stream));
 		FastParams fp = cw.fp;
 		fp.cursor = cw.d_ctrl + 2;
 		fp.events = pl->d_events;
 		fp.ev_cap = pl->ev_cap;
-		CK(ctx, launch_fast(c, MODE_PROBE, fp, sm, ctx->stream, (int)cw.jobs.size()));
+		CK(ctx, launch_fast(c, MODE_PROBE, fp, sm, ctx->stream, (int)cw.n_jobs));
 		pl->stats.kernel_launches++;
 	}
-	if (!pl->gen_jobs.empty())
+	if (pl->n_gen_jobs)
 	{
 		CK(ctx, cudaMemsetAsync(pl->d_gen_ctrl + 1, 0, sizeof(int), ctx->stream));
 		GenParams gp = gen_params(pl, 1);
@@ -778,6 +985,7 @@ extern "C" int dfb_plan_run(dfb_plan* pl)
 {
 	if (!pl) return DFB_ERR_ARG;
 	dfb_ctx* ctx = pl->ctx;
+	if (!pl->d_pool) return set_err(ctx, DFB_ERR_STATE, "plan's device buffers were released");
 	CK(ctx, cudaSetDevice(ctx->device));
 	const int sm = ctx->prop.multiProcessorCount;
 	pl->stats.kernel_launches = 0;
@@ -789,17 +997,17 @@ extern "C" int dfb_plan_run(dfb_plan* pl)
 			if (!pl->ev[k]) CK(ctx, cudaEventCreate(&pl->ev[k]));
 		CK(ctx, cudaEventRecord(pl->ev[0], ctx->stream));
 	}
+	CK(ctx, cudaMemsetAsync(pl->d_ctrl, 0, kNumClasses * 4 * sizeof(int), ctx->stream));
 	for (int c = 0; c < kNumClasses; c++)
 	{
 		ClassWork& cw = pl->cls[c];
-		if (cw.jobs.empty()) continue;
-		CK(ctx, cudaMemsetAsync(cw.d_ctrl, 0, 4 * sizeof(int), ctx->stream));
+		if (!cw.n_jobs) continue;
 		FastParams fp = cw.fp;
 		fp.cursor = cw.d_ctrl;
-		CK(ctx, launch_fast(c, pl->split ? MODE_SPLIT : MODE_SIMPLE, fp, sm, ctx->stream, (int)cw.jobs.size()));
+		CK(ctx, launch_fast(c, pl->split ? MODE_SPLIT : MODE_SIMPLE, fp, sm, ctx->stream, (int)cw.n_jobs));
 		pl->stats.kernel_launches++;
 	}
-	if (!pl->gen_jobs.empty())
+	if (pl->n_gen_jobs)
 	{
 		CK(ctx, cudaMemsetAsync(pl->d_gen_ctrl, 0, 4 * sizeof(int), ctx->stream));
 		GenParams gp = gen_params(pl, 0);
@@ -809,7 +1017,7 @@ extern "C" int dfb_plan_run(dfb_plan* pl)
 			CK(ctx, cudaGetLastError());
 			GenReduceParams rp;
 			rp.jobs = pl->d_gen_jobs;
-			rp.n_tasks = (int)(pl->gen_jobs.size() / 2);
+			rp.n_tasks = (int)(pl->n_gen_jobs / 2);
 			rp.task_min_score = pl->d_task_min_score;
 			rp.min_split = pl->sp.min_split_score;
 			rp.rowmax = pl->d_gen_rowmax;
@@ -882,6 +1090,55 @@ extern "C" int dfb_simple_plan_fetch(dfb_plan* pl, int32_t* out_score)
 	return DFB_OK;
 }
 
+// ---- split result assembly ---------------------------------------------------------------------
+
+namespace
+{
+struct Chunk
+{
+	std::vector<dfb_split_row> rows;
+	std::vector<int32_t> cols;
+};
+
+inline uint64_t wide_key(int half, int row, int col) { return ((uint64_t)half << 62) | ((uint64_t)row << 31) | (uint64_t)col; }
+inline int key_row(uint64_t k) { return (int)((k >> 31) & 0x7fffffff); }
+
+// rows of one task from its events sorted by (matrix, row, column): the nested loops of
+// SplitReadAligner.cpp:233-269 walk tie rows, then columns1, then columns2, all ascending
+void emit_task_rows(int task, int L, const uint64_t* key, const int32_t* score, int n, Chunk& out)
+{
+	int n0 = 0;
+	while (n0 < n && (key[n0] >> 62) == 0) n0++;
+	int i = 0;
+	while (i < n0)
+	{
+		const int a = key_row(key[i]);
+		int i_end = i;
+		while (i_end < n0 && key_row(key[i_end]) == a) i_end++;
+		const int want = L - a;
+		int j = n0;
+		while (j < n && key_row(key[j]) != want) j++;
+		if (j < n)
+		{
+			int j_end = j;
+			while (j_end < n && key_row(key[j_end]) == want) j_end++;
+			dfb_split_row row;
+			row.task = task;
+			row.read_split = a;
+			row.score1 = score[i];
+			row.score2 = score[j];
+			row.col_begin = (int64_t)out.cols.size();
+			row.n1 = i_end - i;
+			row.n2 = j_end - j;
+			for (int k = i; k < i_end; k++) out.cols.push_back((int32_t)(key[k] & 0x7fffffff));
+			for (int k = j; k < j_end; k++) out.cols.push_back((int32_t)(key[k] & 0x7fffffff));
+			out.rows.push_back(row);
+		}
+		i = i_end;
+	}
+}
+}  // namespace
+
 extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols)
 {
 	if (!pl) return DFB_ERR_ARG;
@@ -889,94 +1146,187 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 	if (!pl->split) return set_err(ctx, DFB_ERR_STATE, "dfb_split_plan_fetch on a simple plan");
 	if (!pl->ran) return set_err(ctx, DFB_ERR_STATE, "dfb_split_plan_fetch before dfb_plan_run");
 	CK(ctx, cudaSetDevice(ctx->device));
-	unsigned long long n_ev = 0;
+	Trace tr;
+
+	// 1. counters: overflow-list length and winning tasks per class
+	int h_ctrl[kNumClasses * 4];
+	unsigned long long n_ov = 0;
 	for (int attempt = 0;; attempt++)
 	{
-		CK(ctx, cudaMemcpyAsync(&n_ev, pl->d_ev_count, sizeof(n_ev), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(&n_ov, pl->d_ev_count, sizeof(n_ov), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(h_ctrl, pl->d_ctrl, sizeof(h_ctrl), cudaMemcpyDeviceToHost, ctx->stream));
 		CK(ctx, cudaStreamSynchronize(ctx->stream));
-		if (n_ev <= pl->ev_cap) break;
+		if (n_ov <= pl->ev_cap) break;
 		if (attempt >= 2) return set_err(ctx, DFB_ERR_STATE, "event buffer overflow persists");
-		// the probe sweep found more arg-max columns than the buffer holds: size it exactly and redo the sweep
-		dfree(pl->d_events);
-		pl->ev_cap = n_ev + 1024;
-		cudaError_t e = cudaMalloc(&pl->d_events, (size_t)pl->ev_cap * sizeof(Event));
+		// the probe sweep found more arg-max columns than the overflow list holds: size it exactly, redo the sweep
+		dfree(ctx, pl->d_events);
+		pl->ev_cap = n_ov + 1024;
+		cudaError_t e = dalloc(ctx, (void**)&pl->d_events, (size_t)pl->ev_cap * sizeof(Event));
 		if (e != cudaSuccess) return set_err(ctx, DFB_ERR_NOMEM, "event buffer of %llu entries: %s", pl->ev_cap, cudaGetErrorString(e));
 		int rc = run_probe(pl);
 		if (rc) return rc;
 	}
-	std::vector<Event> ev((size_t)n_ev);
-	if (n_ev) CK(ctx, cudaMemcpyAsync(ev.data(), pl->d_events, (size_t)n_ev * sizeof(Event), cudaMemcpyDeviceToHost, ctx->stream));
-	if (out_best && pl->n_tasks)
-		CK(ctx, cudaMemcpyAsync(out_best, pl->d_out, (size_t)pl->n_tasks * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-	int probe_jobs = 0;
+	int64_t hits_cls[kNumClasses], slot_base[kNumClasses], n_slots = 0;
 	for (int c = 0; c < kNumClasses; c++)
 	{
-		if (pl->cls[c].jobs.empty()) continue;
-		int h = 0;
-		CK(ctx, cudaMemcpyAsync(&h, pl->cls[c].d_ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-		CK(ctx, cudaStreamSynchronize(ctx->stream));
-		probe_jobs += h;
+		hits_cls[c] = pl->cls[c].n_jobs ? h_ctrl[4 * c + 1] : 0;
+		slot_base[c] = n_slots;
+		n_slots += hits_cls[c];
 	}
-	CK(ctx, cudaStreamSynchronize(ctx->stream));
-	pl->stats.d2h_bytes = (int64_t)(n_ev * sizeof(Event)) + pl->n_tasks * (int64_t)sizeof(int32_t);
-	pl->stats.events = (int64_t)n_ev;
-	pl->stats.probe_jobs = probe_jobs;
 
-	// order: task, then matrix (half), then row, then column -- the nested loops of
-	// SplitReadAligner.cpp:233-269 walk rows and columns ascending
-	std::sort(ev.begin(), ev.end(), [](const Event& a, const Event& b) {
+	tr.lap("split.fetch: wait kernels");
+	// 2. bulk copy into pinned staging: best | slot_task | slot_n | slot_ev | overflow events
+	const size_t off_best = 0;
+	const size_t off_task = align_up(off_best + (size_t)pl->n_tasks * 4, 256);
+	const size_t off_n = align_up(off_task + (size_t)n_slots * 4, 256);
+	const size_t off_ev = align_up(off_n + (size_t)n_slots * 4, 256);
+	const size_t off_ov = align_up(off_ev + (size_t)n_slots * DFB_SLOT_EVENTS * sizeof(uint2), 256);
+	const size_t total = off_ov + (size_t)n_ov * sizeof(Event) + 256;
+	{
+		cudaError_t e = ctx->h_out.ensure(total);
+		if (e != cudaSuccess) return set_err(ctx, DFB_ERR_NOMEM, "pinned result buffer: %s", cudaGetErrorString(e));
+	}
+	uint8_t* hb = (uint8_t*)ctx->h_out.p;
+	int32_t* h_best = (int32_t*)(hb + off_best);
+	int32_t* h_task = (int32_t*)(hb + off_task);
+	int32_t* h_n = (int32_t*)(hb + off_n);
+	uint2* h_ev = (uint2*)(hb + off_ev);
+	Event* h_ov = (Event*)(hb + off_ov);
+	if (pl->n_tasks) CK(ctx, cudaMemcpyAsync(h_best, pl->d_out, (size_t)pl->n_tasks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	for (int c = 0; c < kNumClasses; c++)
+	{
+		if (!hits_cls[c]) continue;
+		const ClassWork& cw = pl->cls[c];
+		CK(ctx, cudaMemcpyAsync(h_task + slot_base[c], cw.d_slot_task, (size_t)hits_cls[c] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(h_n + slot_base[c], cw.d_slot_n, (size_t)hits_cls[c] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(h_ev + slot_base[c] * DFB_SLOT_EVENTS, cw.d_slot_ev,
+		                        (size_t)hits_cls[c] * DFB_SLOT_EVENTS * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	if (n_ov) CK(ctx, cudaMemcpyAsync(h_ov, pl->d_events, (size_t)n_ov * sizeof(Event), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	pl->stats.d2h_bytes = (int64_t)(total - 256);
+	pl->stats.probe_jobs = n_slots;
+	tr.lap("split.fetch: d2h");
+
+	if (out_best && pl->n_tasks) memcpy(out_best, h_best, (size_t)pl->n_tasks * 4);
+
+	// 3. overflow list (tie-heavy tasks, generic-path tasks): order by task, then (matrix,row,col)
+	std::sort(h_ov, h_ov + n_ov, [](const Event& a, const Event& b) {
 		if (a.task != b.task) return a.task < b.task;
 		if (a.half_row != b.half_row) return a.half_row < b.half_row;
 		return a.col < b.col;
 	});
-	pl->rows.clear();
-	pl->cols.clear();
-	pl->cols.reserve(ev.size());
-	size_t i = 0;
-	struct Run
+
+	// 4. slot of every task; per-thread assembly over contiguous task ranges (rows come out in task order)
+	std::vector<int32_t> slot_of((size_t)pl->n_tasks, -1);
+	int64_t n_events = (int64_t)n_ov;
+	for (int64_t s = 0; s < n_slots; s++)
 	{
-		int row, score;
-		size_t begin, n;
-	};
-	std::vector<Run> r1, r2;
-	while (i < ev.size())
-	{
-		const int task = ev[i].task;
-		r1.clear();
-		r2.clear();
-		while (i < ev.size() && ev[i].task == task)
-		{
-			const int hr = ev[i].half_row;
-			Run r;
-			r.row = hr & 0x3fffffff;
-			r.score = ev[i].score;
-			r.begin = i;
-			while (i < ev.size() && ev[i].task == task && ev[i].half_row == hr) i++;
-			r.n = i - r.begin;
-			((hr >> 30) ? r2 : r1).push_back(r);
-		}
-		const int L = pl->task_L[task];
-		for (const Run& a : r1) // ascending read_split
-		{
-			const int want = L - a.row;
-			const Run* b = nullptr;
-			for (const Run& c : r2)
-				if (c.row == want) { b = &c; break; }
-			if (!b) continue;
-			dfb_split_row row;
-			row.task = task;
-			row.read_split = a.row;
-			row.score1 = a.score;
-			row.score2 = b->score;
-			row.col1_begin = (int64_t)pl->cols.size();
-			row.n1 = (int32_t)a.n;
-			for (size_t k = 0; k < a.n; k++) pl->cols.push_back(ev[a.begin + k].col);
-			row.col2_begin = (int64_t)pl->cols.size();
-			row.n2 = (int32_t)b->n;
-			for (size_t k = 0; k < b->n; k++) pl->cols.push_back(ev[b->begin + k].col);
-			pl->rows.push_back(row);
-		}
+		slot_of[h_task[s]] = (int32_t)s;
+		n_events += std::min<int32_t>(h_n[s], DFB_SLOT_EVENTS);
 	}
+	pl->stats.events = n_events;
+	tr.lap("split.fetch: slot map");
+	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->host_threads, pl->n_tasks / 4096 + 1));
+	std::vector<Chunk> chunks((size_t)T);
+	auto work = [&](int tid) {
+		const int64_t t0 = pl->n_tasks * tid / T, t1 = pl->n_tasks * (tid + 1) / T;
+		Chunk& out = chunks[tid];
+		const Event* ov_begin = h_ov;
+		const Event* ov_end = h_ov + n_ov;
+		const Event* ov = std::lower_bound(ov_begin, ov_end, (int32_t)t0, [](const Event& e, int32_t t) { return e.task < t; });
+		std::vector<uint64_t> key, k2;
+		std::vector<int32_t> score, s2;
+		std::vector<int> order;
+		for (int64_t t = t0; t < t1; t++)
+		{
+			const int32_t s = slot_of[t];
+			const bool has_ov = ov < ov_end && ov->task == (int32_t)t;
+			if (s < 0 && !has_ov) continue;
+			key.clear();
+			score.clear();
+			if (s >= 0)
+			{
+				const int n = std::min<int32_t>(h_n[s], DFB_SLOT_EVENTS);
+				const uint2* e = h_ev + (size_t)s * DFB_SLOT_EVENTS;
+				for (int k = 0; k < n; k++)
+				{
+					key.push_back(wide_key((int)(e[k].x >> 27), (int)((e[k].x >> 16) & 0x7ff), (int)(e[k].x & 0xffff)));
+					score.push_back((int32_t)e[k].y);
+				}
+			}
+			while (ov < ov_end && ov->task == (int32_t)t)
+			{
+				key.push_back(wide_key(ov->half_row >> 30, ov->half_row & 0x3fffffff, ov->col));
+				score.push_back(ov->score);
+				ov++;
+			}
+			const int n = (int)key.size();
+			order.resize(n);
+			for (int k = 0; k < n; k++) order[k] = k;
+			if (n <= 32)
+			{
+				for (int a = 1; a < n; a++) // few entries: insertion sort
+				{
+					const int v = order[a];
+					int b = a - 1;
+					while (b >= 0 && key[order[b]] > key[v]) { order[b + 1] = order[b]; b--; }
+					order[b + 1] = v;
+				}
+			}
+			else
+			{
+				std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+			}
+			k2.resize(n);
+			s2.resize(n);
+			for (int k = 0; k < n; k++) { k2[k] = key[order[k]]; s2[k] = score[order[k]]; }
+			emit_task_rows((int)t, pl->task_L[t], k2.data(), s2.data(), n, out);
+		}
+	};
+	if (T == 1)
+	{
+		work(0);
+	}
+	else
+	{
+		std::vector<std::thread> th;
+		for (int k = 0; k < T; k++) th.emplace_back(work, k);
+		for (auto& x : th) x.join();
+	}
+	tr.lap("split.fetch: assemble");
+	// 5. concatenate
+	size_t tot_rows = 0, tot_cols = 0;
+	std::vector<size_t> row_base((size_t)T), col_base((size_t)T);
+	for (int k = 0; k < T; k++)
+	{
+		row_base[k] = tot_rows;
+		col_base[k] = tot_cols;
+		tot_rows += chunks[k].rows.size();
+		tot_cols += chunks[k].cols.size();
+	}
+	pl->rows.resize(tot_rows);
+	pl->cols.resize(tot_cols);
+	auto merge = [&](int k) {
+		for (size_t r = 0; r < chunks[k].rows.size(); r++)
+		{
+			dfb_split_row row = chunks[k].rows[r];
+			row.col_begin += (int64_t)col_base[k];
+			pl->rows[row_base[k] + r] = row;
+		}
+		if (!chunks[k].cols.empty()) memcpy(pl->cols.data() + col_base[k], chunks[k].cols.data(), chunks[k].cols.size() * 4);
+	};
+	if (T == 1)
+	{
+		merge(0);
+	}
+	else
+	{
+		std::vector<std::thread> th;
+		for (int k = 0; k < T; k++) th.emplace_back(merge, k);
+		for (auto& x : th) x.join();
+	}
+	tr.lap("split.fetch: concatenate");
 	if (n_rows) *n_rows = (int64_t)pl->rows.size();
 	if (n_cols) *n_cols = (int64_t)pl->cols.size();
 	pl->fetched = true;
@@ -989,6 +1339,18 @@ extern "C" int dfb_split_plan_copy(const dfb_plan* pl, dfb_split_row* rows, int3
 	if (!pl->fetched || !pl->split) return set_err(pl->ctx, DFB_ERR_STATE, "dfb_split_plan_copy before dfb_split_plan_fetch");
 	if (rows && !pl->rows.empty()) memcpy(rows, pl->rows.data(), pl->rows.size() * sizeof(dfb_split_row));
 	if (cols && !pl->cols.empty()) memcpy(cols, pl->cols.data(), pl->cols.size() * sizeof(int32_t));
+	return DFB_OK;
+}
+
+extern "C" int dfb_split_plan_view(const dfb_plan* pl, const dfb_split_row** rows, int64_t* n_rows, const int32_t** cols,
+                                   int64_t* n_cols)
+{
+	if (!pl) return DFB_ERR_ARG;
+	if (!pl->fetched || !pl->split) return set_err(pl->ctx, DFB_ERR_STATE, "dfb_split_plan_view before dfb_split_plan_fetch");
+	if (rows) *rows = pl->rows.data();
+	if (n_rows) *n_rows = (int64_t)pl->rows.size();
+	if (cols) *cols = pl->cols.data();
+	if (n_cols) *n_cols = (int64_t)pl->cols.size();
 	return DFB_OK;
 }
 
@@ -1034,7 +1396,8 @@ extern "C" int dfb_split_align_batch(dfb_ctx* ctx, const dfb_split_params* param
 		dfb_plan_destroy(pl);
 		return rc;
 	}
-	// keep only the host-side result; device memory can go
+	// only the host-side rows are kept; the device buffers go back to the pool now
+	release_device(pl);
 	ctx->last_split = pl;
 	return DFB_OK;
 }
@@ -1053,4 +1416,12 @@ extern "C" int dfb_split_result_copy(const dfb_ctx* ctx, dfb_split_row* rows, in
 	if (!ctx) return DFB_ERR_ARG;
 	if (!ctx->last_split) return set_err(ctx, DFB_ERR_STATE, "no split result on this context");
 	return dfb_split_plan_copy(ctx->last_split, rows, cols);
+}
+
+extern "C" int dfb_split_result_view(const dfb_ctx* ctx, const dfb_split_row** rows, int64_t* n_rows, const int32_t** cols,
+                                     int64_t* n_cols)
+{
+	if (!ctx) return DFB_ERR_ARG;
+	if (!ctx->last_split) return set_err(ctx, DFB_ERR_STATE, "no split result on this context");
+	return dfb_split_plan_view(ctx->last_split, rows, n_rows, cols, n_cols);
 }

@@ -31,63 +31,92 @@ namespace dfb
 // exact for every byte value (the reference compares raw bytes: SplitReadAligner.cpp:51,
 // SimpleAligner.cpp:50).  A sequence starts on a word boundary.
 
-struct PackItem
+struct SeqDesc
 {
-	int64_t src;       // offset of the first byte in the raw upload
-	uint32_t len;      // bases
-	uint32_t dst_word; // first pool word
-	uint32_t flags;    // bit0: store reversed
-	uint32_t pad;
+	int64_t src;   // offset of the first byte in the raw upload
+	uint32_t len;  // bases
+	uint32_t word; // first pool word of this sequence's (first) stored copy
 };
 
 enum
 {
-	PACK_REVERSE = 1
+	PACK_FWD = 0,     // one forward copy per sequence
+	PACK_REV_ODD = 1, // even table entries forward, odd entries reversed (reference2 of each cluster)
+	PACK_BOTH = 2     // forward copy at `word`, reversed copy right behind it (reads of the split aligner)
 };
 
-// One thread per 16-base output word.  HBM-bound: reads 16 B, writes 8 B + 16 B.
-__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ raw, const PackItem* __restrict__ items,
-                                                    int n_items, uint32_t total_words, uint2* __restrict__ pool,
-                                                    uint8_t* __restrict__ obytes)
+// One thread per 16-base output word: binary-search the owning sequence, fetch the 16-byte
+// source window with five aligned 32-bit loads, emit 2-bit codes + exception mask (8 B).
+// The raw copy of a word is written only when it has an exception.  The raw upload is padded
+// by 16 bytes in front and 32 behind so that the window never leaves the allocation.
+template <int MODE>
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ raw, const SeqDesc* __restrict__ descs,
+                                                    int n_seqs, uint32_t word_begin, uint32_t word_end,
+                                                    uint2* __restrict__ pool, uint8_t* __restrict__ obytes)
 {
-	for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total_words; w += gridDim.x * blockDim.x)
+	for (uint32_t w = word_begin + blockIdx.x * blockDim.x + threadIdx.x; w < word_end; w += gridDim.x * blockDim.x)
 	{
-		// last item whose dst_word <= w (items are laid out back to back, ascending)
-		int lo = 0, hi = n_items;
+		int lo = 0, hi = n_seqs; // last sequence whose first word <= w
 		while (hi - lo > 1)
 		{
-			int mid = (lo + hi) >> 1;
-			if (__ldg(&items[mid].dst_word) <= w) lo = mid; else hi = mid;
+			const int mid = (lo + hi) >> 1;
+			if (__ldg(&descs[mid].word) <= w) lo = mid; else hi = mid;
 		}
-		const PackItem it = items[lo];
-		const uint32_t first = (w - it.dst_word) * 16u;
+		const SeqDesc sd = descs[lo];
+		uint32_t local = w - sd.word;
+		bool rev = false;
+		if (MODE == PACK_REV_ODD) rev = (lo & 1) != 0;
+		if (MODE == PACK_BOTH)
+		{
+			const uint32_t nw = (sd.len + 15u) >> 4;
+			if (local >= nw) { rev = true; local -= nw; }
+		}
+		const uint32_t first = local * 16u;
+		const uint32_t n_valid = min(16u, sd.len - first);
+		// source window: forward bytes [first, first+16); reversed bytes [len-first-16, len-first) read backwards
+		const int64_t win = sd.src + (rev ? (int64_t)sd.len - (int64_t)first - 16 : (int64_t)first);
+		const uint8_t* wp = raw + win;
+		const uintptr_t addr = reinterpret_cast<uintptr_t>(wp);
+		const uint32_t* ap = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+		const uint32_t sh = (uint32_t)(addr & 3u) * 8u;
+		uint32_t a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2), a3 = __ldg(ap + 3), a4 = __ldg(ap + 4);
+		uint32_t b[4];
+		b[0] = __funnelshift_r(a0, a1, sh);
+		b[1] = __funnelshift_r(a1, a2, sh);
+		b[2] = __funnelshift_r(a2, a3, sh);
+		b[3] = __funnelshift_r(a3, a4, sh);
+		if (rev)
+		{
+			const uint32_t r0 = __byte_perm(b[3], 0, 0x0123), r1 = __byte_perm(b[2], 0, 0x0123);
+			const uint32_t r2 = __byte_perm(b[1], 0, 0x0123), r3 = __byte_perm(b[0], 0, 0x0123);
+			b[0] = r0; b[1] = r1; b[2] = r2; b[3] = r3;
+		}
 		uint32_t codes = 0, mask = 0;
-		uint32_t ob[4] = {0, 0, 0, 0};
 #pragma unroll
 		for (int n = 0; n < 16; n++)
 		{
-			uint32_t p = first + n;
-			uint32_t byte = 0;
-			if (p < it.len)
-			{
-				uint32_t sp = (it.flags & PACK_REVERSE) ? (it.len - 1 - p) : p;
-				byte = __ldg(raw + it.src + sp);
-				uint32_t code = 0, exc = 0;
-				switch (byte)
-				{
-					case 'A': code = 0; break;
-					case 'C': code = 1; break;
-					case 'G': code = 2; break;
-					case 'T': code = 3; break;
-					default: exc = 1; break;
-				}
-				codes |= code << (2 * n);
-				mask |= exc << n;
-			}
-			ob[n >> 2] |= byte << (8 * (n & 3));
+			const uint32_t byte = (b[n >> 2] >> (8 * (n & 3))) & 0xFFu;
+			// A=0x41 C=0x43 G=0x47 T=0x54: bits 2..1 are 00 01 11 10 -> a 2-bit code; exact iff it decodes back
+			const uint32_t gray = (byte >> 1) & 3u;
+			const uint32_t code = gray ^ (gray >> 1);                   // 00 01 11 10 -> A0 C1 G2 T3
+			const uint32_t back = (0x54474341u >> (8 * code)) & 0xFFu;  // 'A','C','G','T'
+			const bool in_seq = (uint32_t)n < n_valid;
+			const bool ok = back == byte;
+			codes |= ((ok && in_seq) ? code : 0u) << (2 * n);
+			mask |= ((!ok && in_seq) ? 1u : 0u) << n;
 		}
 		pool[w] = make_uint2(codes, mask);
-		reinterpret_cast<uint4*>(obytes)[w] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+		if (mask)
+		{
+#pragma unroll
+			for (int q = 0; q < 4; q++)
+			{
+				// zero the bytes beyond the sequence end
+				const int keep = (int)n_valid - 4 * q;
+				if (keep < 4) b[q] = keep <= 0 ? 0u : (b[q] & (0xFFFFFFFFu >> (8 * (4 - keep))));
+			}
+			reinterpret_cast<uint4*>(obytes)[w] = make_uint4(b[0], b[1], b[2], b[3]);
+		}
 	}
 }
 
@@ -140,11 +169,16 @@ struct FastParams
 	int* hit_count;  // SPLIT (write) / PROBE (read): number of queued tasks
 	int* hitq;       // job index per queue slot
 	uint32_t* ntg;   // [slot][S][G] negated row-max targets (or "row disabled")
-	Event* events;
+	int32_t* slot_task; // SPLIT (write): task index per queue slot
+	uint2* slot_ev;     // PROBE: [slot][DFB_SLOT_EVENTS] {key = half<<27 | row<<16 | col, score}
+	int* slot_n;        // PROBE: events found per slot (may exceed DFB_SLOT_EVENTS: the rest is in `events`)
+	Event* events;      // PROBE: overflow list
 	unsigned long long* ev_count;
 	unsigned long long ev_cap;
 	uint32_t ck[32]; // SIMPLE: m*(k+1) in both halves
 };
+
+#define DFB_SLOT_EVENTS 8
 
 __device__ __forceinline__ uint32_t decode_base(uint2 w, uint32_t word_index, int n, const uint8_t* __restrict__ obytes)
 {
@@ -345,15 +379,25 @@ __global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ Fa
 								const int j = j0 + k + 1;
 								if (f + t == 0 && b < (int)jp.R[h] && j <= (int)jp.L[h])
 								{
-									const unsigned long long idx = atomicAdd(p.ev_count, 1ull);
-									if (idx < p.ev_cap)
+									const int score = f - (int)B + p.m * j;
+									const int n = atomicAdd(p.slot_n + item, 1);
+									if (n < DFB_SLOT_EVENTS)
 									{
-										Event ev;
-										ev.task = jp.out0;
-										ev.half_row = (h << 30) | j;
-										ev.col = b + 1;
-										ev.score = f - (int)B + p.m * j;
-										p.events[idx] = ev;
+										p.slot_ev[(size_t)item * DFB_SLOT_EVENTS + n] =
+										    make_uint2(((uint32_t)h << 27) | ((uint32_t)j << 16) | (uint32_t)(b + 1), (uint32_t)score);
+									}
+									else
+									{
+										const unsigned long long idx = atomicAdd(p.ev_count, 1ull);
+										if (idx < p.ev_cap)
+										{
+											Event ev;
+											ev.task = jp.out0;
+											ev.half_row = (h << 30) | j;
+											ev.col = b + 1;
+											ev.score = score;
+											p.events[idx] = ev;
+										}
 									}
 								}
 							}
@@ -441,6 +485,7 @@ __global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ Fa
 				{
 					slot = atomicAdd(p.hit_count, 1);
 					p.hitq[slot] = jid;
+					p.slot_task[slot] = jp.out0;
 				}
 			}
 			slot = __shfl_sync(0xffffffffu, slot, q * G);
@@ -474,6 +519,7 @@ struct GenJob
 
 struct GenParams
 {
+	const uint2* pool;
 	const uint8_t* obytes;
 	const GenJob* jobs;
 	int n_jobs;
@@ -526,8 +572,10 @@ __global__ void __launch_bounds__(128) dp_generic_kernel(const __grid_constant__
 		if (MODE == MODE_PROBE && p.probe_flag[jid >> 1] == 0) continue;
 		const GenJob job = p.jobs[jid];
 		const int R = (int)job.R, L = (int)job.L;
-		const uint8_t* refb = p.obytes + (size_t)job.ref_w * 16;
-		const uint8_t* readb = p.obytes + (size_t)job.read_w * 16;
+		auto base_at = [&](uint32_t first_word, int pos) -> int {
+			const uint32_t widx = first_word + ((uint32_t)pos >> 4);
+			return (int)decode_base(__ldg(p.pool + widx), widx, pos & 15, p.obytes);
+		};
 		int best = INT32_MIN; // SIMPLE: max over interior cells
 
 		if (MODE == MODE_PROBE)
@@ -558,7 +606,7 @@ __global__ void __launch_bounds__(128) dp_generic_kernel(const __grid_constant__
 			for (int k = 0; k < S; k++)
 			{
 				const int j = j0 + k + 1;
-				rd[k] = (j <= L) ? (int)readb[j - 1] : -1;
+				rd[k] = (j <= L) ? base_at(job.read_w, j - 1) : -1;
 				H[k] = j * col0_step;
 				X[k] = H[k];
 				tg[k] = 0;
@@ -581,7 +629,7 @@ __global__ void __launch_bounds__(128) dp_generic_kernel(const __grid_constant__
 				if (lane == 0) recv = (first_tile || b >= R) ? 0 : __ldcg(bin + b + 1);
 				if (b >= 0 && b < R)
 				{
-					const int rf = (int)refb[b];
+					const int rf = base_at(job.ref_w, b);
 					int left = recv;
 					int dg_in = prev;
 #pragma unroll

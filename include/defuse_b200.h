@@ -90,7 +90,7 @@ typedef struct dfb_split_params
 /* One winning split row of one task: the factorised form of what
  * SplitReadAligner::GetAlignments emits (tools/SplitReadAligner.cpp:229-297).  For a task the
  * rows come in ascending read_split; GetAlignments' output for the task is, in order,
- *   for row in rows(task): for i1 in cols[col1_begin .. +n1): for i2 in cols[col2_begin .. +n2):
+ *   for row in rows(task): for i1 in cols[col_begin .. +n1): for i2 in cols[col_begin+n1 .. +n2):
  *     refSplit  = (i1, len(reference2) - i2 - 1)      readSplit = (read_split, len(read) - read_split)
  *     score = score1 + score2,  score1,  score2
  * Rows whose column set is empty on either side emit nothing in the reference and are omitted. */
@@ -100,8 +100,8 @@ typedef struct dfb_split_row
 	int32_t read_split; /* alignedToRef1 (tools/SplitReadAligner.cpp:196) */
 	int32_t score1;     /* row maximum of matrix 1 at read_split */
 	int32_t score2;     /* row maximum of matrix 2 at len(read) - read_split */
-	int64_t col1_begin; /* into the column pool; ascending matrix-1 column indices i1 */
-	int64_t col2_begin; /* ascending matrix-2 column indices i2 (of the REVERSED reference2) */
+	int64_t col_begin;  /* into the column pool: n1 ascending matrix-1 columns i1, then n2 ascending
+	                       matrix-2 columns i2 (columns of the REVERSED reference2) */
 	int32_t n1;
 	int32_t n2;
 } dfb_split_row;
@@ -179,6 +179,10 @@ DFB_API int dfb_split_align_batch(dfb_ctx* ctx, const dfb_split_params* params,
                           int32_t* out_best);
 DFB_API int dfb_split_result_size(const dfb_ctx* ctx, int64_t* n_rows, int64_t* n_cols);
 DFB_API int dfb_split_result_copy(const dfb_ctx* ctx, dfb_split_row* rows, int32_t* cols);
+/* Zero-copy alternative: pointers into library-owned host memory, valid until the next split
+ * call on this context (or its destruction). */
+DFB_API int dfb_split_result_view(const dfb_ctx* ctx, const dfb_split_row** rows, int64_t* n_rows,
+                                  const int32_t** cols, int64_t* n_cols);
 
 /* ---- staged form: the same work with the batch resident in HBM -------------------------- */
 
@@ -205,6 +209,9 @@ DFB_API int dfb_simple_plan_fetch(dfb_plan* plan, int32_t* out_score);
  * with a larger event buffer if it overflowed).  Then use dfb_split_plan_copy. */
 DFB_API int dfb_split_plan_fetch(dfb_plan* plan, int32_t* out_best, int64_t* n_rows, int64_t* n_cols);
 DFB_API int dfb_split_plan_copy(const dfb_plan* plan, dfb_split_row* rows, int32_t* cols);
+/* Zero-copy alternative, valid until the next fetch on this plan (or its destruction). */
+DFB_API int dfb_split_plan_view(const dfb_plan* plan, const dfb_split_row** rows, int64_t* n_rows,
+                                const int32_t** cols, int64_t* n_cols);
 DFB_API int dfb_plan_get_stats(const dfb_plan* plan, dfb_plan_stats* stats);
 DFB_API void dfb_plan_destroy(dfb_plan* plan);
 

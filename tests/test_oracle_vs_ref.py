@@ -1,0 +1,45 @@
+"""The C restatement against the unmodified reference compiled here (oracle/_ref).  Runs wherever
+oracle/_ref/libref_aligners.so exists (it is built in the build container and shipped with the snapshot)."""
+import numpy as np
+import pytest
+
+import util
+
+
+@pytest.fixture(scope="module")
+def ref(oracle_mod):
+    if not oracle_mod.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    return oracle_mod
+
+
+def test_simple_random_vs_ref(ref):
+    rng = np.random.default_rng(5)
+    for scoring in [(10, -5, -5), (2, -1, -2), (1, -1, 1), (0, 0, 0), (-2, -3, -1), (7, 2, -3)]:
+        refs, seqs, tr, ts = util.simple_batch(rng, 8, 60, (0, 200), (0, 120))
+        import defuse_b200 as d
+        rt, st = d.SeqTable.from_list(refs), d.SeqTable.from_list(seqs)
+        a = ref.simple_align_batch(*scoring, rt.data, rt.off, st.data, st.off, tr, ts, impl="port")
+        b = ref.simple_align_batch(*scoring, rt.data, rt.off, st.data, st.off, tr, ts, impl="ref")
+        assert (a == b).all()
+
+
+@pytest.mark.parametrize("params", [(2, -1, -2, False, 8), (2, -1, -2, True, 8), (2, -1, -2, False, 0), (1, -1, 1, False, 3),
+                                    (5, -4, -3, False, -2), (0, 0, 0, False, 0)])
+def test_split_random_vs_ref(ref, params):
+    import defuse_b200 as d
+    rng = np.random.default_rng(6)
+    refs, reads, tc, trd = util.split_batch(rng, 10, 6, (0, 90), 0, 200, sub=0.03, indel=0.01, n_rate=0.01)
+    rt, st = d.SeqTable.from_list(refs), d.SeqTable.from_list(reads)
+    m, x, g, eg, ms = params
+    for thr in (np.zeros(len(tc), np.int32), np.array([int(0.9 * m * len(reads[r])) for r in trd], np.int32)):
+        ca, aa = ref.split_align_batch(rt.data, rt.off, st.data, st.off, tc, trd, thr, m, x, g, eg, ms, impl="port")
+        cb, ab = ref.split_align_batch(rt.data, rt.off, st.data, st.off, tc, trd, thr, m, x, g, eg, ms, impl="ref")
+        assert (ca == cb).all() and (aa == ab).all()
+
+
+def test_reverse_complement_vs_ref(ref):
+    rng = np.random.default_rng(7)
+    for _ in range(50):
+        s = bytes(rng.integers(32, 127, int(rng.integers(0, 60))).astype(np.uint8))
+        assert ref.reverse_complement(s, impl="port") == ref.reverse_complement(s, impl="ref")
