@@ -280,6 +280,10 @@ struct ClassWork
 	int* d_slot_n = nullptr;
 	uint2* d_slot_ev = nullptr;
 	uint32_t* d_ntg = nullptr;
+	uint32_t* d_ckpt = nullptr;    // wavefront checkpoints of the first sweep (probe windows resume from them)
+	uint32_t* d_slot_rng = nullptr;
+	int ckpt_blocks = 0;
+	uint32_t max_R = 0;            // longest reference in the class
 	FastParams fp;
 };
 
@@ -362,6 +366,8 @@ static void release_device(dfb_plan* plan)
 		dfree(ctx, cw.d_slot_n);
 		dfree(ctx, cw.d_slot_ev);
 		dfree(ctx, cw.d_ntg);
+		dfree(ctx, cw.d_ckpt);
+		dfree(ctx, cw.d_slot_rng);
 	}
 	plan->d_gen_jobs = nullptr;
 	dfree(ctx, plan->d_gen_ctrl);
@@ -545,6 +551,9 @@ static void fill_fast_params(dfb_plan* pl, int c, int m, int x, int g, int min_s
 	fp.slot_ev = cw.d_slot_ev;
 	fp.slot_n = cw.d_slot_n;
 	fp.ntg = cw.d_ntg;
+	fp.ckpt = cw.d_ckpt;
+	fp.ckpt_blocks = cw.ckpt_blocks;
+	fp.slot_rng = cw.d_slot_rng;
 	fp.events = pl->d_events;
 	fp.ev_count = pl->d_ev_count;
 	fp.ev_cap = pl->ev_cap;
@@ -573,6 +582,15 @@ static int alloc_work(dfb_plan* pl, const Staging& st, const int64_t* n_jobs_cls
 			DALLOC(ctx, cw.d_slot_n, n * sizeof(int));
 			DALLOC(ctx, cw.d_slot_ev, n * DFB_SLOT_EVENTS * sizeof(uint2));
 			DALLOC(ctx, cw.d_ntg, n * (size_t)kClasses[c].G * kClasses[c].S * sizeof(uint32_t));
+			DALLOC(ctx, cw.d_slot_rng, n * sizeof(uint32_t));
+			// checkpoints every CH = 8G steps of the wavefront (R + G - 1 steps)
+			const int G = kClasses[c].G, CH = 8 * G;
+			cw.ckpt_blocks = (int)(((int64_t)cw.max_R + G - 2) / CH);
+			const size_t ck_bytes = n * (size_t)cw.ckpt_blocks * (size_t)(kClasses[c].S + 2) * G * sizeof(uint32_t);
+			if (cw.ckpt_blocks > 0 && cw.max_R + G - 1 <= 255u * CH && ck_bytes <= (size_t)ctx->prop.totalGlobalMem / 4)
+				DALLOC(ctx, cw.d_ckpt, ck_bytes);
+			else
+				cw.ckpt_blocks = 0;
 		}
 	}
 	if (pl->n_gen_jobs)
@@ -814,6 +832,7 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 			{
 				bin = c * kRBins + (kRBins - 1 - (int)std::min<int64_t>(std::max(R1, R2) >> 4, kRBins - 1));
 				bin_pos[bin]++;
+				pl->cls[c].max_R = std::max<uint32_t>(pl->cls[c].max_R, (uint32_t)std::max(R1, R2));
 			}
 		}
 		bin_of[t] = bin;

@@ -169,6 +169,9 @@ struct FastParams
 	int* hit_count;  // SPLIT (write) / PROBE (read): number of queued tasks
 	int* hitq;       // job index per queue slot
 	uint32_t* ntg;   // [slot][S][G] negated row-max targets (or "row disabled")
+	uint32_t* ckpt;  // [job][ckpt_blocks][S+2][G] wavefront state (F[S], prev, Flast) in front of every CH-th step (null: off)
+	int ckpt_blocks; // checkpoints per job in this launch
+	uint32_t* slot_rng; // per queue slot: checkpoint blocks to re-sweep, first/last per half
 	int32_t* slot_task; // SPLIT (write): task index per queue slot
 	uint2* slot_ev;     // PROBE: [slot][DFB_SLOT_EVENTS] {key = half<<27 | row<<16 | col, score}
 	int* slot_n;        // PROBE: events found per slot (may exceed DFB_SLOT_EVENTS: the rest is in `events`)
@@ -192,11 +195,20 @@ __device__ __forceinline__ uint32_t decode_base(uint2 w, uint32_t word_index, in
 #define DFB_READ_PAD 0x7FFEu // read rows beyond L: never equals a reference field
 #define DFB_REF_PAD 0xFFFFu  // reference columns beyond R: never equals a read field; bit 15 doubles as the row-max mask
 
+// registers per thread the mode needs (arrays of S) decide how many CTAs we ask ptxas to fit per SM
+template <int S, int MODE>
+struct FastOcc
+{
+	static constexpr int kArrays = (MODE == MODE_SPLIT) ? 5 : (MODE == MODE_PROBE ? 3 : 2);
+	static constexpr int kEst = kArrays * S + 48;
+	static constexpr int kMinBlocks = kEst <= 128 ? 4 : (kEst <= 168 ? 3 : (kEst <= 255 ? 2 : 1));
+};
+
 template <int G, int S, int MODE>
-__global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ FastParams p)
+__global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_kernel(const __grid_constant__ FastParams p)
 {
 	constexpr int NG = 32 / G;      // job pairs per warp
-	constexpr int CH = 8 * G;       // reference ring: block of CH columns, two blocks resident
+	constexpr int CH = 8 * G;       // reference ring: block of CH columns, two blocks resident; also the checkpoint interval
 	constexpr int RING = 2 * CH;
 	constexpr int ROWS = G * S;
 	constexpr int RDW = (ROWS + 15) / 16;
@@ -218,6 +230,7 @@ __global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ Fa
 
 	const uint32_t B = p.bias;
 	const uint32_t Bp = B | (B << 16);
+	const uint32_t gm16 = p.gm2 & 0xFFFFu;
 
 	int n_items = p.n_jobs;
 	if (MODE == MODE_PROBE) n_items = *p.hit_count;
@@ -271,64 +284,99 @@ __global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ Fa
 		{
 			rd[k] = rows[j0 + k];
 			// column i = 0: H(0,j) = j*gap  ->  stored value B + j*(gap - match)
-			const uint32_t v = B + (uint32_t)(j0 + k + 1) * (p.gm2 & 0xFFFFu) & 0xFFFFu;
+			const uint32_t v = (B + (uint32_t)(j0 + k + 1) * gm16) & 0xFFFFu;
 			F[k] = v | (v << 16);
 			X[k] = 0;
 		}
+		const uint32_t v0 = (B + (uint32_t)j0 * gm16) & 0xFFFFu;
+		uint32_t prev = v0 | (v0 << 16); // stored value of (i-1, j0); lane 0: row 0 is H = 0 -> B
+		__syncwarp();
+
+		// ---- step window.  SIMPLE/SPLIT: the whole wavefront, steps u = 0 .. R+G-2, lane g at column
+		//      u-g.  PROBE: only the checkpoint blocks (CH steps each) in which a winning row reaches
+		//      its maximum; unless a window starts at step 0 the wavefront state is restored from the
+		//      checkpoint in front of it, separately for the two halves ----
+		constexpr int PRE = (G <= 16) ? 16 : 32;      // ring columns kept in front of a resumed window (>= G-1, whole words)
+		uint32_t off0 = 0, off1 = 0;                  // absolute column of relative column 0, per half
+		int pre = 0;                                  // PROBE resumed: ring index = relative column + PRE
+		int Rg = max((int)jp.R[0], (int)jp.R[1]);     // columns (from step 0) or steps (resumed) to run
+		uint32_t Flast = F[S - 1];
+		bool resumed = false;
 		if (MODE == MODE_PROBE)
 		{
+			const uint32_t rng = have ? p.slot_rng[item] : 0u;
+			const int f0 = rng & 0xFF, l0 = (rng >> 8) & 0xFF, f1 = (rng >> 16) & 0xFF, l1 = rng >> 24;
 #pragma unroll
-			for (int k = 0; k < S; k++)
+			for (int k = 0; k < S; k++) X[k] = have ? p.ntg[((size_t)item * S + k) * G + g] : 0x80018001u;
+			if (f0 > 0 && f1 > 0)
 			{
-				X[k] = have ? p.ntg[((size_t)item * S + k) * G + g] : 0x80018001u;
+				resumed = true;
+				pre = PRE;
+				off0 = (uint32_t)f0 * CH;
+				off1 = (uint32_t)f1 * CH;
+				Rg = max(l0 - f0 + 1, l1 - f1 + 1) * CH; // steps
+				const size_t cb0 = ((size_t)jid * p.ckpt_blocks + (size_t)(f0 - 1)) * (S + 2);
+				const size_t cb1 = ((size_t)jid * p.ckpt_blocks + (size_t)(f1 - 1)) * (S + 2);
+#pragma unroll
+				for (int k = 0; k < S; k++)
+					F[k] = (p.ckpt[(cb0 + k) * G + g] & 0x0000FFFFu) | (p.ckpt[(cb1 + k) * G + g] & 0xFFFF0000u);
+				prev = (p.ckpt[(cb0 + S) * G + g] & 0x0000FFFFu) | (p.ckpt[(cb1 + S) * G + g] & 0xFFFF0000u);
+				Flast = (p.ckpt[(cb0 + S + 1) * G + g] & 0x0000FFFFu) | (p.ckpt[(cb1 + S + 1) * G + g] & 0xFFFF0000u);
+			}
+			else
+			{
+				// from step 0: columns up to the end of the last needed block (lane g is at column u-g)
+				Rg = have ? max(min((int)jp.R[0], (l0 + 1) * CH), min((int)jp.R[1], (l1 + 1) * CH)) : 0;
 			}
 		}
-		__syncwarp();
+		// steps this warp runs: the longest of its groups (every lane takes part in the shuffles)
+		int T = resumed ? Rg : Rg + G - 1;
+#pragma unroll
+		for (int o = 16; o >= 1; o >>= 1) T = max(T, __shfl_xor_sync(0xffffffffu, T, o));
+		const bool ck_on = p.ckpt != nullptr && T <= 255 * CH;
 
 		// ---- reference ring: two blocks of CH columns resident, next block prefetched ----
 		const int h_mine = g / HG;
 		const int sub = g % HG;
 		const uint32_t Rh = jp.R[h_mine];
+		const uint32_t offw = ((h_mine ? off1 : off0) - (uint32_t)pre) >> 4; // first ring column, in pool words
 		auto load_block = [&](int blk) -> uint2 {
-			const uint32_t wi = (uint32_t)blk * HG + sub;
+			const uint32_t wi = offw + (uint32_t)blk * HG + sub;
 			if (wi * 16u < Rh) return __ldg(p.pool + jp.ref_w[h_mine] + wi);
 			return make_uint2(0, 0);
 		};
 		auto fill_block = [&](int blk, uint2 pw) {
-			const uint32_t wi = (uint32_t)blk * HG + sub;
-			const uint32_t widx = jp.ref_w[h_mine] + wi;
+			const uint32_t wrel = (uint32_t)blk * HG + sub;
+			const uint32_t widx = jp.ref_w[h_mine] + offw + wrel;
 #pragma unroll
 			for (int n = 0; n < 16; n++)
 			{
-				const uint32_t b = wi * 16u + n;
+				const uint32_t t = wrel * 16u + n;            // ring column
 				uint32_t f = DFB_REF_PAD;
-				if (b < Rh) f = decode_base(pw, widx, n, p.obytes);
-				ring16[2 * (b & (RING - 1)) + h_mine] = (uint16_t)f;
+				if ((offw + wrel) * 16u + n < Rh) f = decode_base(pw, widx, n, p.obytes);
+				ring16[2 * (t & (RING - 1)) + h_mine] = (uint16_t)f;
 			}
 		};
-		int Rg = max((int)jp.R[0], (int)jp.R[1]);
-		int Rw = Rg;
-#pragma unroll
-		for (int o = 16; o >= 1; o >>= 1) Rw = max(Rw, __shfl_xor_sync(0xffffffffu, Rw, o));
-
 		fill_block(0, load_block(0));
 		fill_block(1, load_block(1));
 		uint2 pf = load_block(2);
 		int blk_next = 2;
+		// one refill schedule for every group of the warp (valid for pre = 0 and pre = PRE: G-1+PRE <= CH)
+		static_assert(G - 1 + PRE <= CH, "ring refill schedule");
 		int next_refill = CH + G - 1;
 		__syncwarp();
 
-		// left boundary of the strip: lane 0 sees row 0 (H = 0 -> stored B); other lanes
-		// start from column 0 of row j0.
-		const uint32_t v0 = (B + (uint32_t)j0 * (p.gm2 & 0xFFFFu)) & 0xFFFFu;
-		uint32_t prev = v0 | (v0 << 16); // stored value of (i-1, j0)
-		uint32_t Flast = F[S - 1];
 		uint32_t acc = 0x80008000u;
-		const int T = Rw + G - 1;
-
-		for (int tau = 0; tau < T; tau++)
+		uint32_t Y[(MODE == MODE_SPLIT) ? S : 1];    // SPLIT: row maxima inside the current checkpoint block
+		uint32_t info[(MODE == MODE_SPLIT) ? S : 1]; // SPLIT: first/last block attaining X, per half: f_lo | l_lo<<8 | f_hi<<16 | l_hi<<24
+		if (MODE == MODE_SPLIT)
 		{
-			if (tau == next_refill)
+#pragma unroll
+			for (int k = 0; k < S; k++) { Y[k] = 0; info[k] = 0; }
+		}
+		for (int u = 0; u < T; u++)
+		{
+			if (u == next_refill)
 			{
 				__syncwarp();
 				fill_block(blk_next, pf);
@@ -337,12 +385,28 @@ __global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ Fa
 				next_refill += CH;
 				__syncwarp();
 			}
+			if (MODE == MODE_SPLIT)
+			{
+				// checkpoint: the wavefront state in front of every CH-th step (same step for all lanes)
+				if (ck_on && (u & (CH - 1)) == 0 && u > 0)
+				{
+					const size_t cb = ((size_t)jid * p.ckpt_blocks + (size_t)(u / CH - 1)) * (S + 2);
+					if (have)
+					{
+#pragma unroll
+						for (int k = 0; k < S; k++) p.ckpt[(cb + k) * G + g] = F[k];
+						p.ckpt[(cb + S) * G + g] = prev;
+						p.ckpt[(cb + S + 1) * G + g] = Flast;
+					}
+				}
+			}
 			uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G);
 			if (g == 0) recv = Bp;
-			const int b = tau - g;
-			if (b >= 0 && b < Rg)
+			const int b = u - g; // relative column; absolute column = off + b
+			const bool active = resumed ? (u < Rg) : (b >= 0 && b < Rg);
+			if (active)
 			{
-				const uint32_t rf = ring[b & (RING - 1)];
+				const uint32_t rf = ring[(b + pre) & (RING - 1)];
 				uint32_t left = recv;
 				uint32_t dg_in = prev;
 				uint32_t pen = 0;
@@ -357,7 +421,7 @@ __global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ Fa
 					const uint32_t e = __viaddmax_s16x2(F[k], p.g2, dg);   // max(up + gap, diagonal)
 					left = __viaddmax_s16x2(left, p.gm2, e);               // max(left + gap - m, e)
 					F[k] = left;
-					if (MODE == MODE_SPLIT) X[k] = __viaddmax_s16x2(left, pen, X[k]);
+					if (MODE == MODE_SPLIT) Y[k] = __viaddmax_s16x2(left, pen, Y[k]);
 					if (MODE == MODE_SIMPLE) acc = __viaddmax_s16x2(left, p.ck[k], acc);
 					if (MODE == MODE_PROBE) acc = __viaddmax_s16x2(left, X[k], acc);
 				}
@@ -377,14 +441,15 @@ __global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ Fa
 								const int f = (int)((F[k] >> (16 * h)) & 0xFFFFu);
 								const int t = (int)(short)((X[k] >> (16 * h)) & 0xFFFFu);
 								const int j = j0 + k + 1;
-								if (f + t == 0 && b < (int)jp.R[h] && j <= (int)jp.L[h])
+								const int col = (int)(h ? off1 : off0) + b; // 0-based column in the reference
+								if (f + t == 0 && col >= 0 && col < (int)jp.R[h] && j <= (int)jp.L[h])
 								{
 									const int score = f - (int)B + p.m * j;
 									const int n = atomicAdd(p.slot_n + item, 1);
 									if (n < DFB_SLOT_EVENTS)
 									{
 										p.slot_ev[(size_t)item * DFB_SLOT_EVENTS + n] =
-										    make_uint2(((uint32_t)h << 27) | ((uint32_t)j << 16) | (uint32_t)(b + 1), (uint32_t)score);
+										    make_uint2(((uint32_t)h << 27) | ((uint32_t)j << 16) | (uint32_t)(col + 1), (uint32_t)score);
 									}
 									else
 									{
@@ -394,7 +459,7 @@ __global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ Fa
 											Event ev;
 											ev.task = jp.out0;
 											ev.half_row = (h << 30) | j;
-											ev.col = b + 1;
+											ev.col = col + 1;
 											ev.score = score;
 											p.events[idx] = ev;
 										}
@@ -402,6 +467,30 @@ __global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ Fa
 								}
 							}
 						}
+					}
+				}
+			}
+			if (MODE == MODE_SPLIT)
+			{
+				// end of a checkpoint block (or of the sweep), same step for all lanes: fold the block
+				// maxima into the row maxima and remember in which blocks each row maximum occurs
+				if ((u & (CH - 1)) == CH - 1 || u == T - 1)
+				{
+					const uint32_t blk = (uint32_t)(u / CH) & 0xFFu;
+#pragma unroll
+					for (int k = 0; k < S; k++)
+					{
+						const uint32_t xn = __vmaxs2(X[k], Y[k]);
+						const uint32_t grew = X[k] ^ xn; // half != 0: the block maximum beats the row maximum
+						const uint32_t same = Y[k] ^ xn; // half == 0: the block attains the (new) row maximum
+						uint32_t inf = info[k];
+						if (grew & 0x0000FFFFu) inf = (inf & 0xFFFF0000u) | blk | (blk << 8);
+						else if (!(same & 0x0000FFFFu)) inf = (inf & 0xFFFF00FFu) | (blk << 8);
+						if (grew & 0xFFFF0000u) inf = (inf & 0x0000FFFFu) | (blk << 16) | (blk << 24);
+						else if (!(same & 0xFFFF0000u)) inf = (inf & 0x00FFFFFFu) | (blk << 24);
+						info[k] = inf;
+						X[k] = xn;
+						Y[k] = 0;
 					}
 				}
 			}
@@ -460,6 +549,7 @@ __global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ Fa
 			// second sweep (SplitReadAligner.cpp:233-269); the others emit nothing.
 			bool en_any = false;
 			uint32_t ntg[S];
+			int f0 = 255, l0 = 0, f1 = 255, l1 = 0; // checkpoint blocks the second sweep has to visit, per half
 #pragma unroll
 			for (int k = 0; k < S; k++)
 			{
@@ -469,10 +559,30 @@ __global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ Fa
 				{
 					const int a1 = (int)(rows[j] & 0xFFFFu), a2 = (int)(rows[L - j] >> 16);     // this row as matrix-1 row a=j
 					const int b1 = (int)(rows[L - j] & 0xFFFFu), b2 = (int)(rows[j] >> 16);     // this row as matrix-2 row, a=L-j
-					if (a1 > 0 && a2 > 0 && a1 + a2 == best) { tlo = (0u - (X[k] & 0xFFFFu)) & 0xFFFFu; en_any = true; }
-					if (b1 > 0 && b2 > 0 && b1 + b2 == best) { thi = (0u - (X[k] >> 16)) & 0xFFFFu; en_any = true; }
+					if (a1 > 0 && a2 > 0 && a1 + a2 == best)
+					{
+						tlo = (0u - (X[k] & 0xFFFFu)) & 0xFFFFu;
+						en_any = true;
+						f0 = min(f0, (int)(info[k] & 0xFF));
+						l0 = max(l0, (int)((info[k] >> 8) & 0xFF));
+					}
+					if (b1 > 0 && b2 > 0 && b1 + b2 == best)
+					{
+						thi = (0u - (X[k] >> 16)) & 0xFFFFu;
+						en_any = true;
+						f1 = min(f1, (int)((info[k] >> 16) & 0xFF));
+						l1 = max(l1, (int)(info[k] >> 24));
+					}
 				}
 				ntg[k] = tlo | (thi << 16);
+			}
+#pragma unroll
+			for (int o = G / 2; o >= 1; o >>= 1)
+			{
+				f0 = min(f0, __shfl_xor_sync(0xffffffffu, f0, o, G));
+				f1 = min(f1, __shfl_xor_sync(0xffffffffu, f1, o, G));
+				l0 = max(l0, __shfl_xor_sync(0xffffffffu, l0, o, G));
+				l1 = max(l1, __shfl_xor_sync(0xffffffffu, l1, o, G));
 			}
 			const uint32_t ballot = __ballot_sync(0xffffffffu, en_any);
 			const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (q * G));
@@ -486,6 +596,15 @@ __global__ void __launch_bounds__(128) dp_fast_kernel(const __grid_constant__ Fa
 					slot = atomicAdd(p.hit_count, 1);
 					p.hitq[slot] = jid;
 					p.slot_task[slot] = jp.out0;
+					uint32_t rng = 0xFF00FF00u; // no checkpoints: sweep everything
+					if (ck_on)
+					{
+						f0 = min(f0, l0);
+						f1 = min(f1, l1);
+						if (f0 == 0 || f1 == 0) f0 = f1 = 0; // a window that starts at step 0 starts both halves there
+						rng = (uint32_t)f0 | ((uint32_t)l0 << 8) | ((uint32_t)f1 << 16) | ((uint32_t)l1 << 24);
+					}
+					p.slot_rng[slot] = rng;
 				}
 			}
 			slot = __shfl_sync(0xffffffffu, slot, q * G);
