@@ -192,6 +192,22 @@ __device__ __forceinline__ uint32_t decode_base(uint2 w, uint32_t word_index, in
 	return (0x54474341u >> (8 * ((w.x >> (2 * n)) & 3u))) & 0xFFu; // "ACGT"
 }
 
+// Decodes one pool word (16 bases) of a reference into the 16-bit fields of a shared-memory ring.
+// Out of line on purpose: three call sites per kernel x 42 kernels, and the instruction cache is what
+// the short probe jobs wait for.
+__device__ __noinline__ void fill_ring_word(uint16_t* ring16, uint32_t ring_mask, int half, uint2 pw, uint32_t widx,
+                                            uint32_t first_abs_col, uint32_t first_ring_col, uint32_t ref_len,
+                                            const uint8_t* __restrict__ obytes)
+{
+#pragma unroll 4
+	for (int n = 0; n < 16; n++)
+	{
+		uint32_t f = 0xFFFFu; // DFB_REF_PAD
+		if (first_abs_col + n < ref_len) f = decode_base(pw, widx, n, obytes);
+		ring16[2 * ((first_ring_col + n) & ring_mask) + half] = (uint16_t)f;
+	}
+}
+
 #define DFB_READ_PAD 0x7FFEu // read rows beyond L: never equals a reference field
 #define DFB_REF_PAD 0xFFFFu  // reference columns beyond R: never equals a read field; bit 15 doubles as the row-max mask
 
@@ -264,7 +280,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			uint2 pw = make_uint2(0, 0);
 			const uint32_t widx = jp.read_w[h] + wi;
 			if ((uint32_t)wi * 16u < len) pw = __ldg(p.pool + widx);
-#pragma unroll
+#pragma unroll 4
 			for (int n = 0; n < 16; n++)
 			{
 				const int pos = wi * 16 + n;
@@ -272,7 +288,9 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				{
 					uint32_t f = DFB_READ_PAD;
 					if ((uint32_t)pos < len) f = decode_base(pw, widx, n, p.obytes);
-					rows16[2 * pos + h] = (uint16_t)f;
+					// stored negated: (-read + ref) mod 2^16 is 0 exactly on a match, so one
+					// VIADDMNMX.U16x2 (add, min with 1) yields the mismatch indicator
+					rows16[2 * pos + h] = (uint16_t)(0u - f);
 				}
 			}
 		}
@@ -347,23 +365,15 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		};
 		auto fill_block = [&](int blk, uint2 pw) {
 			const uint32_t wrel = (uint32_t)blk * HG + sub;
-			const uint32_t widx = jp.ref_w[h_mine] + offw + wrel;
-#pragma unroll
-			for (int n = 0; n < 16; n++)
-			{
-				const uint32_t t = wrel * 16u + n;            // ring column
-				uint32_t f = DFB_REF_PAD;
-				if ((offw + wrel) * 16u + n < Rh) f = decode_base(pw, widx, n, p.obytes);
-				ring16[2 * (t & (RING - 1)) + h_mine] = (uint16_t)f;
-			}
+			fill_ring_word(ring16, RING - 1, h_mine, pw, jp.ref_w[h_mine] + offw + wrel, (offw + wrel) * 16u, wrel * 16u, Rh,
+			               p.obytes);
 		};
-		fill_block(0, load_block(0));
-		fill_block(1, load_block(1));
+#pragma unroll 1
+		for (int blk = 0; blk < 2; blk++) fill_block(blk, load_block(blk));
 		uint2 pf = load_block(2);
 		int blk_next = 2;
 		// one refill schedule for every group of the warp (valid for pre = 0 and pre = PRE: G-1+PRE <= CH)
 		static_assert(G - 1 + PRE <= CH, "ring refill schedule");
-		int next_refill = CH + G - 1;
 		__syncwarp();
 
 		uint32_t acc = 0x80008000u;
@@ -374,37 +384,14 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 #pragma unroll
 			for (int k = 0; k < S; k++) { Y[k] = 0; info[k] = 0; }
 		}
-		for (int u = 0; u < T; u++)
-		{
-			if (u == next_refill)
-			{
-				__syncwarp();
-				fill_block(blk_next, pf);
-				blk_next++;
-				pf = load_block(blk_next);
-				next_refill += CH;
-				__syncwarp();
-			}
-			if (MODE == MODE_SPLIT)
-			{
-				// checkpoint: the wavefront state in front of every CH-th step (same step for all lanes)
-				if (ck_on && (u & (CH - 1)) == 0 && u > 0)
-				{
-					const size_t cb = ((size_t)jid * p.ckpt_blocks + (size_t)(u / CH - 1)) * (S + 2);
-					if (have)
-					{
-#pragma unroll
-						for (int k = 0; k < S; k++) p.ckpt[(cb + k) * G + g] = F[k];
-						p.ckpt[(cb + S) * G + g] = prev;
-						p.ckpt[(cb + S + 1) * G + g] = Flast;
-					}
-				}
-			}
+		// the sweep, one checkpoint block (CH steps) at a time so that the per-block work (checkpoint,
+		// ring refill, row-maximum bookkeeping) stays out of the per-step instruction stream
+		const int act_off = resumed ? 0 : g; // lane g joins at step g unless the wavefront was restored
+		auto step = [&](const int u) {
 			uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G);
 			if (g == 0) recv = Bp;
 			const int b = u - g; // relative column; absolute column = off + b
-			const bool active = resumed ? (u < Rg) : (b >= 0 && b < Rg);
-			if (active)
+			if ((unsigned)(u - act_off) < (unsigned)Rg)
 			{
 				const uint32_t rf = ring[(b + pre) & (RING - 1)];
 				uint32_t left = recv;
@@ -415,11 +402,11 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 #pragma unroll
 				for (int k = 0; k < S; k++)
 				{
-					const uint32_t d = __vminu2(rd[k] ^ rf, 0x00010001u); // 1 per half on mismatch
-					const uint32_t dg = d * p.xm + dg_in;                  // diagonal: + (match ? 0 : x - m)
+					const uint32_t d = __viaddmin_u16x2(rd[k], rf, 0x00010001u); // min(ref - read, 1): 1 per half on mismatch
+					const uint32_t dg = d * p.xm + dg_in;                         // diagonal: + (match ? 0 : x - m)
 					dg_in = F[k];
-					const uint32_t e = __viaddmax_s16x2(F[k], p.g2, dg);   // max(up + gap, diagonal)
-					left = __viaddmax_s16x2(left, p.gm2, e);               // max(left + gap - m, e)
+					const uint32_t e = __viaddmax_s16x2(F[k], p.g2, dg);          // max(up + gap, diagonal)
+					left = __viaddmax_s16x2(left, p.gm2, e);                      // max(left + gap - m, e)
 					F[k] = left;
 					if (MODE == MODE_SPLIT) Y[k] = __viaddmax_s16x2(left, pen, Y[k]);
 					if (MODE == MODE_SIMPLE) acc = __viaddmax_s16x2(left, p.ck[k], acc);
@@ -470,28 +457,61 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 					}
 				}
 			}
+		};
+		int u = 0;
+		for (int blkno = 0; u < T; blkno++)
+		{
+			if (MODE == MODE_SPLIT)
+			{
+				// checkpoint: the wavefront state in front of every CH-th step (same step for all lanes)
+				if (ck_on && blkno > 0 && have)
+				{
+					const size_t cb = ((size_t)jid * p.ckpt_blocks + (size_t)(blkno - 1)) * (S + 2);
+#pragma unroll
+					for (int k = 0; k < S; k++) p.ckpt[(cb + k) * G + g] = F[k];
+					p.ckpt[(cb + S) * G + g] = prev;
+					p.ckpt[(cb + S + 1) * G + g] = Flast;
+				}
+			}
+			const int u_end = min(T, (blkno + 1) * CH);
+			// ring block blkno+1 replaces block blkno-1 once every lane is past it (G-1 steps into the block)
+			const int u_fill = blkno >= 1 ? blkno * CH + G - 1 : -1;
+#pragma unroll 1
+			for (; u < u_end; u++)
+			{
+				if (u == u_fill)
+				{
+					__syncwarp();
+					fill_block(blk_next, pf);
+					blk_next++;
+					pf = load_block(blk_next);
+					__syncwarp();
+				}
+				step(u);
+			}
 			if (MODE == MODE_SPLIT)
 			{
 				// end of a checkpoint block (or of the sweep), same step for all lanes: fold the block
 				// maxima into the row maxima and remember in which blocks each row maximum occurs
-				if ((u & (CH - 1)) == CH - 1 || u == T - 1)
-				{
-					const uint32_t blk = (uint32_t)(u / CH) & 0xFFu;
+				const uint32_t blk = (uint32_t)blkno & 0xFFu;
 #pragma unroll
-					for (int k = 0; k < S; k++)
+				for (int k = 0; k < S; k++)
+				{
+					const uint32_t xn = __vmaxs2(X[k], Y[k]);
+					const uint32_t same = Y[k] ^ xn; // half == 0: the block attains the (new) row maximum
+					// common case: neither half of the row did anything in this block
+					if (!(same & 0x0000FFFFu) || !(same & 0xFFFF0000u))
 					{
-						const uint32_t xn = __vmaxs2(X[k], Y[k]);
 						const uint32_t grew = X[k] ^ xn; // half != 0: the block maximum beats the row maximum
-						const uint32_t same = Y[k] ^ xn; // half == 0: the block attains the (new) row maximum
 						uint32_t inf = info[k];
 						if (grew & 0x0000FFFFu) inf = (inf & 0xFFFF0000u) | blk | (blk << 8);
 						else if (!(same & 0x0000FFFFu)) inf = (inf & 0xFFFF00FFu) | (blk << 8);
 						if (grew & 0xFFFF0000u) inf = (inf & 0x0000FFFFu) | (blk << 16) | (blk << 24);
 						else if (!(same & 0xFFFF0000u)) inf = (inf & 0x00FFFFFFu) | (blk << 24);
 						info[k] = inf;
-						X[k] = xn;
-						Y[k] = 0;
 					}
+					X[k] = xn;
+					Y[k] = 0;
 				}
 			}
 		}
