@@ -274,13 +274,34 @@ class SimplePlan(_Plan):
 class SplitResult:
     """Winning split rows of a batch, in task order (dfb_split_row + column pool)."""
 
-    def __init__(self, best, rows, cols, read_len, ref2_len):
+    def __init__(self, best, rows, cols, lens):
         self.best = best
         self.rows = rows
         self.cols = cols
-        self._read_len = read_len
-        self._ref2_len = ref2_len
-        self._row_start = np.searchsorted(rows["task"], np.arange(len(best) + 1)) if len(rows) else np.zeros(len(best) + 1, dtype=np.int64)
+        self._lens = lens  # callable -> (read_len[task], ref2_len[task]); evaluated on first use
+        self._lens_cache = None
+        self._row_start_cache = None
+
+    @property
+    def _read_len(self):
+        if self._lens_cache is None:
+            self._lens_cache = self._lens()
+        return self._lens_cache[0]
+
+    @property
+    def _ref2_len(self):
+        if self._lens_cache is None:
+            self._lens_cache = self._lens()
+        return self._lens_cache[1]
+
+    @property
+    def _row_start(self):
+        if self._row_start_cache is None:
+            if len(self.rows):
+                self._row_start_cache = np.searchsorted(np.ascontiguousarray(self.rows["task"]), np.arange(len(self.best) + 1))
+            else:
+                self._row_start_cache = np.zeros(len(self.best) + 1, dtype=np.int64)
+        return self._row_start_cache
 
     def alignments(self, task):
         """What GetAlignments appends for this task (tools/SplitReadAligner.cpp:272-297), as an (n,7) int32
@@ -329,10 +350,9 @@ def _view_arrays(rows_p, n_rows, cols_p, n_cols, copy):
 
 
 class SplitPlan(_Plan):
-    def __init__(self, ctx, handle, n_tasks, read_len, ref2_len):
+    def __init__(self, ctx, handle, n_tasks, lens):
         super().__init__(ctx, handle, n_tasks)
-        self._read_len = read_len
-        self._ref2_len = ref2_len
+        self._lens = lens
 
     def fetch(self, copy=True):
         """Results of the last run.  copy=False returns views into library memory that stay valid until the
@@ -345,7 +365,7 @@ class SplitPlan(_Plan):
         rp, cp = ctypes.c_void_p(), ctypes.c_void_p()
         self.ctx._check(lib.dfb_split_plan_view(self._h, ctypes.byref(rp), ctypes.byref(n_rows), ctypes.byref(cp), ctypes.byref(n_cols)))
         rows, cols = _view_arrays(rp.value, n_rows.value, cp.value, n_cols.value, copy)
-        return SplitResult(best, rows, cols, self._read_len, self._ref2_len)
+        return SplitResult(best, rows, cols, self._lens)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -408,8 +428,7 @@ class SplitReadAligner:
         self.ctx._check(self.ctx._lib.dfb_split_plan_create(self.ctx._h, ctypes.byref(self.params), ctypes.byref(rt),
                                                             ctypes.byref(st), task_cluster.ctypes.data, task_read.ctypes.data,
                                                             task_min_score.ctypes.data, task_cluster.size, ctypes.byref(h)))
-        read_len, ref2_len = self._lens(refs, reads, task_cluster, task_read)
-        return SplitPlan(self.ctx, h, task_cluster.size, read_len, ref2_len)
+        return SplitPlan(self.ctx, h, task_cluster.size, lambda: self._lens(refs, reads, task_cluster, task_read))
 
     def align_batch(self, refs, reads, task_cluster, task_read, task_min_score, copy=True):
         """Batch of Align + GetAlignments(minScore, forceSplits=True, firstOnly=False) through
@@ -427,8 +446,7 @@ class SplitReadAligner:
         self.ctx._check(lib.dfb_split_result_view(self.ctx._h, ctypes.byref(rp), ctypes.byref(n_rows), ctypes.byref(cp),
                                                   ctypes.byref(n_cols)))
         rows, cols = _view_arrays(rp.value, n_rows.value, cp.value, n_cols.value, copy)
-        read_len, ref2_len = self._lens(refs, reads, task_cluster, task_read)
-        return SplitResult(best, rows, cols, read_len, ref2_len)
+        return SplitResult(best, rows, cols, lambda: self._lens(refs, reads, task_cluster, task_read))
 
     # single-task mirror of the reference's two-call protocol
     def Align(self, read, reference1, reference2):

@@ -51,6 +51,51 @@ struct PinnedBuf
 	}
 };
 
+// malloc-backed array without value-initialisation (result arrays of ~10^8 bytes: no memset, and the
+// pages of a recycled buffer are already mapped)
+template <class T>
+struct HostArr
+{
+	T* p = nullptr;
+	size_t n = 0, cap = 0;
+	bool ensure(size_t want)
+	{
+		if (want > cap)
+		{
+			free(p);
+			cap = want + want / 8 + 64;
+			p = (T*)malloc(cap * sizeof(T));
+			if (!p) { cap = 0; n = 0; return false; }
+		}
+		n = want;
+		return true;
+	}
+	void release() { free(p); p = nullptr; n = cap = 0; }
+	void swap(HostArr& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); }
+	size_t size() const { return n; }
+	bool empty() const { return n == 0; }
+	T* data() { return p; }
+	const T* data() const { return p; }
+};
+
+template <class F>
+static void parallel_for(int T, F fn)
+{
+	if (T <= 1) { fn(0); return; }
+	std::vector<std::thread> th;
+	th.reserve((size_t)T - 1);
+	for (int k = 1; k < T; k++) th.emplace_back(fn, k);
+	fn(0);
+	for (auto& x : th) x.join();
+}
+
+struct AsmChunk
+{
+	HostArr<dfb_split_row> rows;
+	HostArr<int32_t> cols;
+	size_t n_rows = 0, n_cols = 0;
+};
+
 struct dfb_ctx
 {
 	int device = 0;
@@ -62,6 +107,11 @@ struct dfb_ctx
 	PinnedBuf h_out; // results on their way back
 	dfb_plan* last_split = nullptr; // result holder of dfb_split_align_batch
 	int host_threads = 1;
+	// recycled host memory of the result assembly (kept mapped between batches)
+	HostArr<dfb_split_row> spare_rows;
+	HostArr<int32_t> spare_cols;
+	std::vector<AsmChunk> asm_chunks;
+	HostArr<int32_t> slot_of;
 };
 
 static thread_local std::string g_create_err;
@@ -181,6 +231,10 @@ extern "C" void dfb_ctx_destroy(dfb_ctx* ctx)
 	cudaStreamSynchronize(ctx->stream);
 	ctx->h_in.release();
 	ctx->h_out.release();
+	ctx->spare_rows.release();
+	ctx->spare_cols.release();
+	ctx->slot_of.release();
+	for (auto& c : ctx->asm_chunks) { c.rows.release(); c.cols.release(); }
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
@@ -322,8 +376,8 @@ struct dfb_plan
 
 	// host
 	std::vector<int32_t> task_L; // read length per task (split)
-	std::vector<dfb_split_row> rows;
-	std::vector<int32_t> cols;
+	HostArr<dfb_split_row> rows;
+	HostArr<int32_t> cols;
 	bool ran = false, fetched = false;
 	bool timing = false;
 	bool pack_timed = false;
@@ -386,7 +440,12 @@ extern "C" void dfb_plan_destroy(dfb_plan* plan)
 		cudaSetDevice(plan->ctx->device);
 		if (plan->ctx->last_split == plan) plan->ctx->last_split = nullptr;
 		release_device(plan);
+		// hand the result arrays back for the next batch
+		if (plan->rows.cap > plan->ctx->spare_rows.cap) plan->rows.swap(plan->ctx->spare_rows);
+		if (plan->cols.cap > plan->ctx->spare_cols.cap) plan->cols.swap(plan->ctx->spare_cols);
 	}
+	plan->rows.release();
+	plan->cols.release();
 	for (int k = 0; k < 3; k++)
 		if (plan->ev[k]) cudaEventDestroy(plan->ev[k]);
 	delete plan;
@@ -798,45 +857,75 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 	classify_params(pl, params->match, params->mismatch, params->gap, params->end_gaps == 0 && params->min_split_score >= 1);
 
 	Trace tr;
+	// pass 1 (host threads): class and reference-length bin of every task, per-thread bin counts
+	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->host_threads, n_tasks / 65536 + 1));
+	const size_t n_bins = (size_t)kNumClasses * kRBins;
 	std::vector<int32_t> bin_of((size_t)n_tasks);
-	std::vector<int64_t> bin_pos((size_t)kNumClasses * kRBins, 0);
+	std::vector<int64_t> bin_pos(n_bins * (size_t)T, 0); // [thread][bin]
 	pl->task_L.resize((size_t)n_tasks);
+	struct Part
+	{
+		int64_t cells = 0, n_gen = 0, bad = -1;
+		uint32_t gen_max_R = 0;
+		uint32_t cls_max_R[kNumClasses] = {0};
+	};
+	std::vector<Part> part((size_t)T);
+	parallel_for(T, [&](int tid) {
+		const int64_t t0 = n_tasks * tid / T, t1 = n_tasks * (tid + 1) / T;
+		Part& pt = part[tid];
+		int64_t* cnt = bin_pos.data() + n_bins * (size_t)tid;
+		for (int64_t t = t0; t < t1; t++)
+		{
+			const int32_t c0 = task_cluster[t], rd = task_read[t];
+			if (c0 < 0 || c0 >= n_clusters || rd < 0 || rd >= reads->n)
+			{
+				if (pt.bad < 0) pt.bad = t;
+				bin_of[t] = -1;
+				continue;
+			}
+			const int64_t c2 = 2 * (int64_t)c0;
+			const int64_t R1 = refs->off[c2 + 1] - refs->off[c2];
+			const int64_t R2 = refs->off[c2 + 2] - refs->off[c2 + 1];
+			const int64_t L = reads->off[rd + 1] - reads->off[rd];
+			pl->task_L[t] = (int32_t)L;
+			pt.cells += (R1 + R2) * L;
+			int32_t bin = -1; // empty read: every row maximum is 0, no split (SplitReadAligner.cpp:224-227)
+			if (L > 0)
+			{
+				int c = (L <= kMaxFastRows && R1 <= 65535 && R2 <= 65535) ? class_for_rows((int)L) : -1;
+				if (c >= 0 && !pl->fast_ok[c]) c = -1;
+				if (c < 0)
+				{
+					bin = -2;
+					pt.n_gen++;
+					pt.gen_max_R = std::max<uint32_t>(pt.gen_max_R, (uint32_t)std::max(R1, R2));
+				}
+				else
+				{
+					bin = c * kRBins + (kRBins - 1 - (int)std::min<int64_t>(std::max(R1, R2) >> 4, kRBins - 1));
+					cnt[bin]++;
+					pt.cls_max_R[c] = std::max<uint32_t>(pt.cls_max_R[c], (uint32_t)std::max(R1, R2));
+				}
+			}
+			bin_of[t] = bin;
+		}
+	});
 	int64_t n_gen_tasks = 0;
 	uint32_t gen_max_R = 0;
-	for (int64_t t = 0; t < n_tasks; t++)
+	for (int k = 0; k < T; k++)
 	{
-		const int32_t c0 = task_cluster[t], rd = task_read[t];
-		if (c0 < 0 || c0 >= n_clusters || rd < 0 || rd >= reads->n)
+		if (part[k].bad >= 0)
 		{
+			const long long bad = (long long)part[k].bad;
 			delete pl;
-			return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)t);
+			return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", bad);
 		}
-		const int64_t c2 = 2 * (int64_t)c0;
-		const int64_t R1 = refs->off[c2 + 1] - refs->off[c2];
-		const int64_t R2 = refs->off[c2 + 2] - refs->off[c2 + 1];
-		const int64_t L = reads->off[rd + 1] - reads->off[rd];
-		pl->task_L[t] = (int32_t)L;
-		pl->stats.cells += (R1 + R2) * L;
-		int32_t bin = -1; // empty read: every row maximum is 0, no split (SplitReadAligner.cpp:224-227)
-		if (L > 0)
-		{
-			int c = (L <= kMaxFastRows && R1 <= 65535 && R2 <= 65535) ? class_for_rows((int)L) : -1;
-			if (c >= 0 && !pl->fast_ok[c]) c = -1;
-			if (c < 0)
-			{
-				bin = -2;
-				n_gen_tasks++;
-				gen_max_R = std::max<uint32_t>(gen_max_R, (uint32_t)std::max(R1, R2));
-			}
-			else
-			{
-				bin = c * kRBins + (kRBins - 1 - (int)std::min<int64_t>(std::max(R1, R2) >> 4, kRBins - 1));
-				bin_pos[bin]++;
-				pl->cls[c].max_R = std::max<uint32_t>(pl->cls[c].max_R, (uint32_t)std::max(R1, R2));
-			}
-		}
-		bin_of[t] = bin;
+		pl->stats.cells += part[k].cells;
+		n_gen_tasks += part[k].n_gen;
+		gen_max_R = std::max(gen_max_R, part[k].gen_max_R);
+		for (int c = 0; c < kNumClasses; c++) pl->cls[c].max_R = std::max(pl->cls[c].max_R, part[k].cls_max_R[c]);
 	}
+	// counts -> write positions: class by class, bin by bin, thread by thread (keeps task order inside a bin)
 	int64_t n_jobs_cls[kNumClasses];
 	int64_t n_fast_jobs = 0;
 	for (int c = 0; c < kNumClasses; c++)
@@ -844,9 +933,13 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 		int64_t in_class = 0;
 		for (int b = 0; b < kRBins; b++)
 		{
-			const int64_t cnt = bin_pos[(size_t)c * kRBins + b];
-			bin_pos[(size_t)c * kRBins + b] = n_fast_jobs + in_class;
-			in_class += cnt;
+			for (int k = 0; k < T; k++)
+			{
+				int64_t& slot = bin_pos[n_bins * (size_t)k + (size_t)c * kRBins + b];
+				const int64_t cnt = slot;
+				slot = n_fast_jobs + in_class;
+				in_class += cnt;
+			}
 		}
 		n_jobs_cls[c] = in_class;
 		n_fast_jobs += in_class;
@@ -871,16 +964,37 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 		return set_err(ctx, DFB_ERR_ARG, "batch too large: more than 2^32 packed words; split it");
 	}
 	tr.lap("split.create: layout");
-	int64_t gi = 0;
-	for (int64_t t = 0; t < n_tasks; t++)
-	{
-		const int32_t bin = bin_of[t];
-		if (bin == -1) continue;
-		const int64_t c2 = 2 * (int64_t)task_cluster[t];
-		const SeqDesc& rdd = st.desc_b[task_read[t]];
-		const uint32_t rev_w = rdd.word + (rdd.len + 15) / 16;
-		if (bin == -2)
+	// pass 2 (host threads): every task into its job slot
+	parallel_for(T, [&](int tid) {
+		const int64_t t0 = n_tasks * tid / T, t1 = n_tasks * (tid + 1) / T;
+		int64_t* pos = bin_pos.data() + n_bins * (size_t)tid;
+		for (int64_t t = t0; t < t1; t++)
 		{
+			const int32_t bin = bin_of[t];
+			if (bin < 0) continue;
+			const int64_t c2 = 2 * (int64_t)task_cluster[t];
+			const SeqDesc& rdd = st.desc_b[task_read[t]];
+			JobPair& jp = st.jobs[pos[bin]++];
+			jp.ref_w[0] = st.desc_a[c2].word;
+			jp.ref_w[1] = st.desc_a[c2 + 1].word;
+			jp.read_w[0] = rdd.word;
+			jp.read_w[1] = rdd.word + (rdd.len + 15) / 16;
+			jp.R[0] = (uint16_t)st.desc_a[c2].len;
+			jp.R[1] = (uint16_t)st.desc_a[c2 + 1].len;
+			jp.L[0] = jp.L[1] = (uint16_t)rdd.len;
+			jp.out0 = (int32_t)t;
+			jp.out1 = task_min_score[t];
+		}
+	});
+	if (n_gen_tasks)
+	{
+		int64_t gi = 0;
+		for (int64_t t = 0; t < n_tasks; t++)
+		{
+			if (bin_of[t] != -2) continue;
+			const int64_t c2 = 2 * (int64_t)task_cluster[t];
+			const SeqDesc& rdd = st.desc_b[task_read[t]];
+			const uint32_t rev_w = rdd.word + (rdd.len + 15) / 16;
 			for (int h = 0; h < 2; h++)
 			{
 				GenJob& j = st.gen[gi++];
@@ -893,18 +1007,7 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 				j.row_off = pl->gen_rows_total;
 				pl->gen_rows_total += (int64_t)j.L + 1;
 			}
-			continue;
 		}
-		JobPair& jp = st.jobs[bin_pos[bin]++];
-		jp.ref_w[0] = st.desc_a[c2].word;
-		jp.ref_w[1] = st.desc_a[c2 + 1].word;
-		jp.read_w[0] = rdd.word;
-		jp.read_w[1] = rev_w;
-		jp.R[0] = (uint16_t)st.desc_a[c2].len;
-		jp.R[1] = (uint16_t)st.desc_a[c2 + 1].len;
-		jp.L[0] = jp.L[1] = (uint16_t)rdd.len;
-		jp.out0 = (int32_t)t;
-		jp.out1 = task_min_score[t];
 	}
 	pl->n_gen_jobs = 2 * n_gen_tasks;
 	tr.lap("split.create: jobs");
@@ -1236,24 +1339,48 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 		return a.col < b.col;
 	});
 
-	// 4. slot of every task; per-thread assembly over contiguous task ranges (rows come out in task order)
-	std::vector<int32_t> slot_of((size_t)pl->n_tasks, -1);
+	// 4. slot of every task (parallel scatter), then per-thread assembly over contiguous task ranges so
+	//    that rows come out in task order
+	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->host_threads, pl->n_tasks / 4096 + 1));
+	if (!ctx->slot_of.ensure((size_t)std::max<int64_t>(pl->n_tasks, 1))) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
+	int32_t* slot_of = ctx->slot_of.data();
+	parallel_for(T, [&](int tid) {
+		const int64_t t0 = pl->n_tasks * tid / T, t1 = pl->n_tasks * (tid + 1) / T;
+		if (t1 > t0) memset(slot_of + t0, 0xff, (size_t)(t1 - t0) * 4);
+	});
+	std::vector<int64_t> ev_part((size_t)T, 0);
+	parallel_for(T, [&](int tid) {
+		const int64_t s0 = n_slots * tid / T, s1 = n_slots * (tid + 1) / T;
+		int64_t ne = 0;
+		for (int64_t s = s0; s < s1; s++)
+		{
+			slot_of[h_task[s]] = (int32_t)s;
+			ne += std::min<int32_t>(h_n[s], DFB_SLOT_EVENTS);
+		}
+		ev_part[tid] = ne;
+	});
 	int64_t n_events = (int64_t)n_ov;
-	for (int64_t s = 0; s < n_slots; s++)
-	{
-		slot_of[h_task[s]] = (int32_t)s;
-		n_events += std::min<int32_t>(h_n[s], DFB_SLOT_EVENTS);
-	}
+	for (int k = 0; k < T; k++) n_events += ev_part[k];
 	pl->stats.events = n_events;
 	tr.lap("split.fetch: slot map");
-	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->host_threads, pl->n_tasks / 4096 + 1));
-	std::vector<Chunk> chunks((size_t)T);
-	auto work = [&](int tid) {
+	if ((int)ctx->asm_chunks.size() < T) ctx->asm_chunks.resize((size_t)T);
+	bool oom = false;
+	parallel_for(T, [&](int tid) {
 		const int64_t t0 = pl->n_tasks * tid / T, t1 = pl->n_tasks * (tid + 1) / T;
-		Chunk& out = chunks[tid];
+		AsmChunk& out = ctx->asm_chunks[tid];
+		// upper bounds for this task range: every event is one column; a row needs two events
+		int64_t ev_here = 0;
 		const Event* ov_begin = h_ov;
 		const Event* ov_end = h_ov + n_ov;
 		const Event* ov = std::lower_bound(ov_begin, ov_end, (int32_t)t0, [](const Event& e, int32_t t) { return e.task < t; });
+		const Event* ov_last = std::lower_bound(ov_begin, ov_end, (int32_t)t1, [](const Event& e, int32_t t) { return e.task < t; });
+		for (int64_t t = t0; t < t1; t++)
+			if (slot_of[t] >= 0) ev_here += std::min<int32_t>(h_n[slot_of[t]], DFB_SLOT_EVENTS);
+		ev_here += ov_last - ov;
+		if (!out.rows.ensure((size_t)ev_here / 2 + 1) || !out.cols.ensure((size_t)ev_here + 1)) { oom = true; return; }
+		dfb_split_row* rows = out.rows.data();
+		int32_t* cols = out.cols.data();
+		size_t nr = 0, nc = 0;
 		std::vector<uint64_t> key, k2;
 		std::vector<int32_t> score, s2;
 		std::vector<int> order;
@@ -1262,6 +1389,52 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 			const int32_t s = slot_of[t];
 			const bool has_ov = ov < ov_end && ov->task == (int32_t)t;
 			if (s < 0 && !has_ov) continue;
+			const int L = pl->task_L[t];
+			if (!has_ov)
+			{
+				// the common case: at most 8 {key,score} entries, all in the slot region.  The 32-bit key
+				// (matrix<<27 | row<<16 | col) orders them the way GetAlignments walks them.
+				const int n = std::min<int32_t>(h_n[s], DFB_SLOT_EVENTS);
+				uint2 e[DFB_SLOT_EVENTS];
+				const uint2* src = h_ev + (size_t)s * DFB_SLOT_EVENTS;
+				for (int k = 0; k < n; k++)
+				{
+					const uint2 v = src[k];
+					int b = k - 1;
+					while (b >= 0 && e[b].x > v.x) { e[b + 1] = e[b]; b--; }
+					e[b + 1] = v;
+				}
+				int n0 = 0;
+				while (n0 < n && !(e[n0].x >> 27)) n0++;
+				int i = 0;
+				while (i < n0)
+				{
+					const uint32_t a = (e[i].x >> 16) & 0x7ff;
+					int i_end = i + 1;
+					while (i_end < n0 && ((e[i_end].x >> 16) & 0x7ff) == a) i_end++;
+					const uint32_t want = (uint32_t)L - a;
+					int j = n0;
+					while (j < n && ((e[j].x >> 16) & 0x7ff) != want) j++;
+					if (j < n)
+					{
+						int j_end = j + 1;
+						while (j_end < n && ((e[j_end].x >> 16) & 0x7ff) == want) j_end++;
+						dfb_split_row& row = rows[nr++];
+						row.task = (int32_t)t;
+						row.read_split = (int32_t)a;
+						row.score1 = (int32_t)e[i].y;
+						row.score2 = (int32_t)e[j].y;
+						row.col_begin = (int64_t)nc;
+						row.n1 = i_end - i;
+						row.n2 = j_end - j;
+						for (int k = i; k < i_end; k++) cols[nc++] = (int32_t)(e[k].x & 0xffff);
+						for (int k = j; k < j_end; k++) cols[nc++] = (int32_t)(e[k].x & 0xffff);
+					}
+					i = i_end;
+				}
+				continue;
+			}
+			// tie-heavy or generic-path task: slot entries + its run of the overflow list
 			key.clear();
 			score.clear();
 			if (s >= 0)
@@ -1283,68 +1456,52 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 			const int n = (int)key.size();
 			order.resize(n);
 			for (int k = 0; k < n; k++) order[k] = k;
-			if (n <= 32)
-			{
-				for (int a = 1; a < n; a++) // few entries: insertion sort
-				{
-					const int v = order[a];
-					int b = a - 1;
-					while (b >= 0 && key[order[b]] > key[v]) { order[b + 1] = order[b]; b--; }
-					order[b + 1] = v;
-				}
-			}
-			else
-			{
-				std::sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
-			}
+			std::sort(order.begin(), order.end(), [&](int x, int y) { return key[x] < key[y]; });
 			k2.resize(n);
 			s2.resize(n);
 			for (int k = 0; k < n; k++) { k2[k] = key[order[k]]; s2[k] = score[order[k]]; }
-			emit_task_rows((int)t, pl->task_L[t], k2.data(), s2.data(), n, out);
+			Chunk tmp;
+			emit_task_rows((int)t, L, k2.data(), s2.data(), n, tmp);
+			for (const dfb_split_row& r0 : tmp.rows)
+			{
+				dfb_split_row r = r0;
+				r.col_begin += (int64_t)nc;
+				rows[nr++] = r;
+			}
+			// tmp.cols are laid out in row order already
+			memcpy(cols + nc, tmp.cols.data(), tmp.cols.size() * 4);
+			nc += tmp.cols.size();
 		}
-	};
-	if (T == 1)
-	{
-		work(0);
-	}
-	else
-	{
-		std::vector<std::thread> th;
-		for (int k = 0; k < T; k++) th.emplace_back(work, k);
-		for (auto& x : th) x.join();
-	}
+		out.n_rows = nr;
+		out.n_cols = nc;
+	});
+	if (oom) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
 	tr.lap("split.fetch: assemble");
-	// 5. concatenate
+	// 5. concatenate into recycled result arrays
 	size_t tot_rows = 0, tot_cols = 0;
 	std::vector<size_t> row_base((size_t)T), col_base((size_t)T);
 	for (int k = 0; k < T; k++)
 	{
 		row_base[k] = tot_rows;
 		col_base[k] = tot_cols;
-		tot_rows += chunks[k].rows.size();
-		tot_cols += chunks[k].cols.size();
+		tot_rows += ctx->asm_chunks[k].n_rows;
+		tot_cols += ctx->asm_chunks[k].n_cols;
 	}
-	pl->rows.resize(tot_rows);
-	pl->cols.resize(tot_cols);
-	auto merge = [&](int k) {
-		for (size_t r = 0; r < chunks[k].rows.size(); r++)
+	if (pl->rows.cap < ctx->spare_rows.cap) pl->rows.swap(ctx->spare_rows);
+	if (pl->cols.cap < ctx->spare_cols.cap) pl->cols.swap(ctx->spare_cols);
+	if (!pl->rows.ensure(tot_rows) || !pl->cols.ensure(tot_cols)) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
+	parallel_for(T, [&](int k) {
+		const AsmChunk& c = ctx->asm_chunks[k];
+		dfb_split_row* dst = pl->rows.data() + row_base[k];
+		const int64_t cb = (int64_t)col_base[k];
+		for (size_t r = 0; r < c.n_rows; r++)
 		{
-			dfb_split_row row = chunks[k].rows[r];
-			row.col_begin += (int64_t)col_base[k];
-			pl->rows[row_base[k] + r] = row;
+			dfb_split_row row = c.rows.p[r];
+			row.col_begin += cb;
+			dst[r] = row;
 		}
-		if (!chunks[k].cols.empty()) memcpy(pl->cols.data() + col_base[k], chunks[k].cols.data(), chunks[k].cols.size() * 4);
-	};
-	if (T == 1)
-	{
-		merge(0);
-	}
-	else
-	{
-		std::vector<std::thread> th;
-		for (int k = 0; k < T; k++) th.emplace_back(merge, k);
-		for (auto& x : th) x.join();
-	}
+		if (c.n_cols) memcpy(pl->cols.data() + col_base[k], c.cols.p, c.n_cols * 4);
+	});
 	tr.lap("split.fetch: concatenate");
 	if (n_rows) *n_rows = (int64_t)pl->rows.size();
 	if (n_cols) *n_cols = (int64_t)pl->cols.size();

@@ -1,6 +1,9 @@
 mkdir -p gpurun_out
-DFB_TRACE=1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/trace.json 2> gpurun_out/trace.err; echo rc=$?
-tail -60 gpurun_out/trace.err
+timeout 150 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_tr.log 2>&1 || { echo SMOKE_FAILED; tail -20 gpurun_out/smoke_tr.log; exit 1; }
+timeout 420 python -m pytest tests -m gpu -x -q --timeout 90 --timeout-method thread > gpurun_out/pytest_tr.log 2>&1; echo pytest_rc=$?
+tail -5 gpurun_out/pytest_tr.log
+DFB_TRACE=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 3 > gpurun_out/trace.json 2> gpurun_out/trace.err; echo rc=$?
+tail -24 gpurun_out/trace.err
 python - <<'PY'
 import json; d=json.load(open('gpurun_out/trace.json')); print(d['value'], d['e2e'])
 PY
