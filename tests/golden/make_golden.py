@@ -97,9 +97,33 @@ def localalign_case():
     return dict(stdin=text, runs=res)
 
 
+def tool_cases():
+    """Whole-tool goldens on synthetic files (synth/files.py): stdout / -a file of the compiled reference tools."""
+    import tempfile
+    from synth import files
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for name, kw in (("split_small", dict(seed=1, n_clusters=30, pairs_per_cluster=25)),
+                         ("split_jitter_lower", dict(seed=7, n_clusters=20, pairs_per_cluster=25, read_len_jitter=20,
+                                                     lower_frac=0.01, n_rate=0.01))):
+            sub = os.path.join(d, name)
+            args = files.make_split_dataset(sub, **kw)
+            res = os.path.join(sub, "ref.alignments")
+            subprocess.run([oracle.ref_tool("ref_dosplitalign")] + args + ["-a", res], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            out[name] = dict(kw=kw, output=open(res).read())
+        sub = os.path.join(d, "mate")
+        args, sam = files.make_matealign_dataset(sub, seed=4, n_pairs=120)
+        p = subprocess.run([oracle.ref_tool("ref_matealign")] + args, input=sam, stdout=subprocess.PIPE,
+                           stderr=subprocess.DEVNULL, check=True)
+        out["mate_small"] = dict(kw=dict(seed=4, n_pairs=120), output=p.stdout.decode())
+    return out
+
+
 if __name__ == "__main__":
     assert oracle.have_ref(), "build the reference first: make -C oracle ref"
     json.dump(split_cases(), open(os.path.join(HERE, "split_aligner.json"), "w"), indent=0)
     json.dump(simple_cases(), open(os.path.join(HERE, "simple_aligner.json"), "w"), indent=0)
     json.dump(localalign_case(), open(os.path.join(HERE, "localalign_tool.json"), "w"), indent=0)
+    json.dump(tool_cases(), open(os.path.join(HERE, "tools.json"), "w"), indent=0)
     print("golden vectors written to", HERE)

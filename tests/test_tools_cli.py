@@ -1,0 +1,51 @@
+"""Command-line grammar and no-GPU behaviour of the drop-in tools (CPU only)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "defuse_b200", "bin")
+
+
+def _tool(name):
+    p = os.path.join(BIN, name)
+    if not os.path.exists(p):
+        pytest.skip("tools not built")
+    return p
+
+
+@pytest.mark.parametrize("tool,args", [("localalign", ["-m", "10"]), ("matealign", ["-m", "1", "-x", "-1", "-g", "-1"]),
+                                       ("dosplitalign", ["-f", "x.fa"])])
+def test_missing_required_arguments(tool, args):
+    p = subprocess.run([_tool(tool)] + args, capture_output=True, input=b"")
+    assert p.returncode == 1
+    assert b"PARSE ERROR" in p.stderr and b"required" in p.stderr.lower()
+    assert p.stdout == b""
+
+
+def test_unknown_flag_and_bad_value():
+    p = subprocess.run([_tool("localalign"), "-m", "10", "-x", "-5", "-g", "-5", "-q", "1"], capture_output=True, input=b"")
+    assert p.returncode == 1 and b"PARSE ERROR" in p.stderr
+    p = subprocess.run([_tool("localalign"), "-m", "ten", "-x", "-5", "-g", "-5"], capture_output=True, input=b"")
+    assert p.returncode == 1 and b"PARSE ERROR" in p.stderr
+
+
+def test_help_lists_the_reference_flags():
+    p = subprocess.run([_tool("dosplitalign"), "--help"], capture_output=True)
+    assert p.returncode == 0
+    for flag in ("--fasta", "--exons", "--ufrag", "--sfrag", "--minread", "--maxread", "--regions", "--improper", "--seq1",
+                 "--seq2", "--align"):
+        assert flag.encode() in p.stdout
+    p = subprocess.run([_tool("matealign"), "-h"], capture_output=True)
+    for flag in ("--match", "--mismatch", "--gap", "--threshold", "--searchlength", "--reference", "--seq1", "--seq2"):
+        assert flag.encode() in p.stdout
+
+
+def test_no_gpu_means_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    p = subprocess.run([_tool("localalign"), "-m", "10", "-x", "-5", "-g", "-5"], capture_output=True, input=b"a\tACGT\tACG\n")
+    assert p.returncode == 1
+    assert p.stdout == b"" and b"Error:" in p.stderr and b"no CPU fallback" in p.stderr
