@@ -173,7 +173,8 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    args.out.write(json.dumps(line) + "\n")
+    args.out.flush()
     return 0
 
 
@@ -339,11 +340,21 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": g, "unit": UNIT, "cores": threads, "kind": kind, "tasks_per_s": tps,
                                     "seconds": dt,
                                     "sample": "first %d tasks of the same workload (%d per host thread)" % (n, args.ref_tasks_per_core)}
-        print(json.dumps(line))
+        args.out.write(json.dumps(line) + "\n")
+        args.out.flush()
     plan.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _claim_stdout():
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; the one JSON line is written
+    to the real stdout through the returned file object."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -359,6 +370,7 @@ def main():
     ap.add_argument("--ref-tasks-per-core", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.out = _claim_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)
