@@ -190,6 +190,41 @@ def pinned(arr):
     return out, t
 
 
+def measure_local(ctx, stream, args):
+    """BASELINE.json configs[1]: localalign, 1 M 100-bp reads against 10 k references of 2001 bp, 10/-5/-5 (reported
+    beside the headline; same timing rules)."""
+    import torch
+    import defuse_b200 as d
+    import synth
+    w = synth.local_workload(2, 10000, args.local_tasks, 2001, 100)
+    refs = d.SeqTable(w["ref_bytes"], w["ref_off"])
+    seqs = d.SeqTable(w["seq_bytes"], w["seq_off"])
+    al = d.SimpleAligner(10, -5, -5, ctx=ctx)
+    plan = al.plan(refs, seqs, w["task_ref"], w["task_seq"])
+    for _ in range(3):
+        plan.run()
+    plan.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 5
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        plan.run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    st = plan.stats()
+    plan.close()
+    t0 = time.perf_counter()
+    al.align_batch(refs, seqs, w["task_ref"], w["task_seq"])
+    t1 = time.perf_counter()
+    al.align_batch(refs, seqs, w["task_ref"], w["task_seq"])
+    e2e_ms = (time.perf_counter() - t1) * 1e3
+    return {"workload": "%d SimpleAligner tasks, R=2001, L=100, 10/-5/-5" % w["n_tasks"], "gcups": w["cells"] / (ms * 1e-3) / 1e9,
+            "ms_per_step": ms, "reads_per_s": w["n_tasks"] / (ms * 1e-3), "e2e_gcups": w["cells"] / (e2e_ms * 1e-3) / 1e9,
+            "e2e_ms": e2e_ms, "first_call_ms": (t1 - t0) * 1e3, "kernel_launches": int(st["kernel_launches"])}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -333,6 +368,8 @@ def run_ours(args):
                         "events": int(st["events"])},
             "device": info["name"],
         }
+        if world == 1 and not args.no_secondary:
+            line["secondary"] = {"localalign_config2": measure_local(ctx, stream, args)}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n = args.ref_tasks_per_core * threads
@@ -369,6 +406,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-tasks-per-core", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--local-tasks", type=int, default=1000000)
     args = ap.parse_args()
     args.out = _claim_stdout()
     if args.impl == "reference":

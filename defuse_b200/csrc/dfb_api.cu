@@ -642,11 +642,11 @@ static int alloc_work(dfb_plan* pl, const Staging& st, const int64_t* n_jobs_cls
 			DALLOC(ctx, cw.d_slot_ev, n * DFB_SLOT_EVENTS * sizeof(uint2));
 			DALLOC(ctx, cw.d_ntg, n * (size_t)kClasses[c].G * kClasses[c].S * sizeof(uint32_t));
 			DALLOC(ctx, cw.d_slot_rng, n * sizeof(uint32_t));
-			// checkpoints every CH = 8G steps of the wavefront (R + G - 1 steps)
-			const int G = kClasses[c].G, CH = 8 * G;
-			cw.ckpt_blocks = (int)(((int64_t)cw.max_R + G - 2) / CH);
+			// checkpoints every CK = 4G steps of the wavefront (R + G - 1 steps)
+			const int G = kClasses[c].G, CK = 4 * G;
+			cw.ckpt_blocks = (int)(((int64_t)cw.max_R + G - 2) / CK);
 			const size_t ck_bytes = n * (size_t)cw.ckpt_blocks * (size_t)(kClasses[c].S + 2) * G * sizeof(uint32_t);
-			if (cw.ckpt_blocks > 0 && cw.max_R + G - 1 <= 255u * CH && ck_bytes <= (size_t)ctx->prop.totalGlobalMem / 4)
+			if (cw.ckpt_blocks > 0 && cw.max_R + G - 1 <= 255u * CK && ck_bytes <= (size_t)ctx->prop.totalGlobalMem / 4)
 				DALLOC(ctx, cw.d_ckpt, ck_bytes);
 			else
 				cw.ckpt_blocks = 0;

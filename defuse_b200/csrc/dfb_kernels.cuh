@@ -208,6 +208,28 @@ __device__ __noinline__ void fill_ring_word(uint16_t* ring16, uint32_t ring_mask
 	}
 }
 
+// One arg-max column found by the probe sweep: the task's fixed region first, the overflow list after.
+__device__ __noinline__ void emit_probe_event(const FastParams& p, int item, int task, int h, int j, int col, int score)
+{
+	const int n = atomicAdd(p.slot_n + item, 1);
+	if (n < DFB_SLOT_EVENTS)
+	{
+		p.slot_ev[(size_t)item * DFB_SLOT_EVENTS + n] =
+		    make_uint2(((uint32_t)h << 27) | ((uint32_t)j << 16) | (uint32_t)(col + 1), (uint32_t)score);
+		return;
+	}
+	const unsigned long long idx = atomicAdd(p.ev_count, 1ull);
+	if (idx < p.ev_cap)
+	{
+		Event ev;
+		ev.task = task;
+		ev.half_row = (h << 30) | j;
+		ev.col = col + 1;
+		ev.score = score;
+		p.events[idx] = ev;
+	}
+}
+
 #define DFB_READ_PAD 0x7FFEu // read rows beyond L: never equals a reference field
 #define DFB_REF_PAD 0xFFFFu  // reference columns beyond R: never equals a read field; bit 15 doubles as the row-max mask
 
@@ -224,7 +246,8 @@ template <int G, int S, int MODE>
 __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_kernel(const __grid_constant__ FastParams p)
 {
 	constexpr int NG = 32 / G;      // job pairs per warp
-	constexpr int CH = 8 * G;       // reference ring: block of CH columns, two blocks resident; also the checkpoint interval
+	constexpr int CH = 8 * G;       // reference ring: block of CH columns, two blocks resident
+	constexpr int CK = 4 * G;       // checkpoint interval (steps): probe windows are whole CK blocks
 	constexpr int RING = 2 * CH;
 	constexpr int ROWS = G * S;
 	constexpr int RDW = (ROWS + 15) / 16;
@@ -320,19 +343,25 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		int Rg = max((int)jp.R[0], (int)jp.R[1]);     // columns (from step 0) or steps (resumed) to run
 		uint32_t Flast = F[S - 1];
 		bool resumed = false;
+		uint32_t en_lo = 0, en_hi = 0; // PROBE: rows of this lane that are being enumerated, per half
 		if (MODE == MODE_PROBE)
 		{
 			const uint32_t rng = have ? p.slot_rng[item] : 0u;
 			const int f0 = rng & 0xFF, l0 = (rng >> 8) & 0xFF, f1 = (rng >> 16) & 0xFF, l1 = rng >> 24;
 #pragma unroll
-			for (int k = 0; k < S; k++) X[k] = have ? p.ntg[((size_t)item * S + k) * G + g] : 0x80018001u;
+			for (int k = 0; k < S; k++)
+			{
+				X[k] = have ? p.ntg[((size_t)item * S + k) * G + g] : 0x80018001u;
+				if ((X[k] & 0xFFFFu) != 0x8001u) en_lo |= 1u << k;
+				if ((X[k] >> 16) != 0x8001u) en_hi |= 1u << k;
+			}
 			if (f0 > 0 && f1 > 0)
 			{
 				resumed = true;
 				pre = PRE;
-				off0 = (uint32_t)f0 * CH;
-				off1 = (uint32_t)f1 * CH;
-				Rg = max(l0 - f0 + 1, l1 - f1 + 1) * CH; // steps
+				off0 = (uint32_t)f0 * CK;
+				off1 = (uint32_t)f1 * CK;
+				Rg = max(l0 - f0 + 1, l1 - f1 + 1) * CK; // steps
 				const size_t cb0 = ((size_t)jid * p.ckpt_blocks + (size_t)(f0 - 1)) * (S + 2);
 				const size_t cb1 = ((size_t)jid * p.ckpt_blocks + (size_t)(f1 - 1)) * (S + 2);
 #pragma unroll
@@ -344,14 +373,14 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			else
 			{
 				// from step 0: columns up to the end of the last needed block (lane g is at column u-g)
-				Rg = have ? max(min((int)jp.R[0], (l0 + 1) * CH), min((int)jp.R[1], (l1 + 1) * CH)) : 0;
+				Rg = have ? max(min((int)jp.R[0], (l0 + 1) * CK), min((int)jp.R[1], (l1 + 1) * CK)) : 0;
 			}
 		}
 		// steps this warp runs: the longest of its groups (every lane takes part in the shuffles)
 		int T = resumed ? Rg : Rg + G - 1;
 #pragma unroll
 		for (int o = 16; o >= 1; o >>= 1) T = max(T, __shfl_xor_sync(0xffffffffu, T, o));
-		const bool ck_on = p.ckpt != nullptr && T <= 255 * CH;
+		const bool ck_on = p.ckpt != nullptr && T <= 255 * CK;
 
 		// ---- reference ring: two blocks of CH columns resident, next block prefetched ----
 		const int h_mine = g / HG;
@@ -384,7 +413,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 #pragma unroll
 			for (int k = 0; k < S; k++) { Y[k] = 0; info[k] = 0; }
 		}
-		// the sweep, one checkpoint block (CH steps) at a time so that the per-block work (checkpoint,
+		// the sweep, one checkpoint block (CK steps) at a time so that the per-block work (checkpoint,
 		// ring refill, row-maximum bookkeeping) stays out of the per-step instruction stream
 		const int act_off = resumed ? 0 : g; // lane g joins at step g unless the wavefront was restored
 		auto step = [&](const int u) {
@@ -422,36 +451,17 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 #pragma unroll
 						for (int k = 0; k < S; k++)
 						{
+							if (!(((en_lo | en_hi) >> k) & 1u)) continue;
 #pragma unroll
 							for (int h = 0; h < 2; h++)
 							{
+								if (!(((h ? en_hi : en_lo) >> k) & 1u)) continue;
 								const int f = (int)((F[k] >> (16 * h)) & 0xFFFFu);
 								const int t = (int)(short)((X[k] >> (16 * h)) & 0xFFFFu);
 								const int j = j0 + k + 1;
 								const int col = (int)(h ? off1 : off0) + b; // 0-based column in the reference
 								if (f + t == 0 && col >= 0 && col < (int)jp.R[h] && j <= (int)jp.L[h])
-								{
-									const int score = f - (int)B + p.m * j;
-									const int n = atomicAdd(p.slot_n + item, 1);
-									if (n < DFB_SLOT_EVENTS)
-									{
-										p.slot_ev[(size_t)item * DFB_SLOT_EVENTS + n] =
-										    make_uint2(((uint32_t)h << 27) | ((uint32_t)j << 16) | (uint32_t)(col + 1), (uint32_t)score);
-									}
-									else
-									{
-										const unsigned long long idx = atomicAdd(p.ev_count, 1ull);
-										if (idx < p.ev_cap)
-										{
-											Event ev;
-											ev.task = jp.out0;
-											ev.half_row = (h << 30) | j;
-											ev.col = col + 1;
-											ev.score = score;
-											p.events[idx] = ev;
-										}
-									}
-								}
+									emit_probe_event(p, item, jp.out0, h, j, col, f - (int)B + p.m * j);
 							}
 						}
 					}
@@ -463,7 +473,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		{
 			if (MODE == MODE_SPLIT)
 			{
-				// checkpoint: the wavefront state in front of every CH-th step (same step for all lanes)
+				// checkpoint: the wavefront state in front of every CK-th step (same step for all lanes)
 				if (ck_on && blkno > 0 && have)
 				{
 					const size_t cb = ((size_t)jid * p.ckpt_blocks + (size_t)(blkno - 1)) * (S + 2);
@@ -473,9 +483,10 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 					p.ckpt[(cb + S + 1) * G + g] = Flast;
 				}
 			}
-			const int u_end = min(T, (blkno + 1) * CH);
-			// ring block blkno+1 replaces block blkno-1 once every lane is past it (G-1 steps into the block)
-			const int u_fill = blkno >= 1 ? blkno * CH + G - 1 : -1;
+			const int u_end = min(T, (blkno + 1) * CK);
+			// ring block n+1 replaces ring block n-1 once every lane is past it (G-1 steps into ring block n >= 1);
+			// a ring block is CH/CK checkpoint blocks long
+			const int u_fill = (blkno >= CH / CK && blkno % (CH / CK) == 0) ? blkno * CK + G - 1 : -1;
 #pragma unroll 1
 			for (; u < u_end; u++)
 			{

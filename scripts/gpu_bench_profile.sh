@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 set -x
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo bench_rc=$?
 cat gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err
-SMALL="python bench.py --steps 2 --warmup 1 --clusters 2000 --no-cpu-baseline --e2e-steps 1"
+SMALL="python bench.py --steps 2 --warmup 1 --clusters 2000 --no-cpu-baseline --no-secondary --e2e-steps 1"
 $SMALL > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $SMALL > gpurun_out/ncu_launch_$TAG.log 2>&1
 echo ncu_launch_rc=$?
