@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <fstream>
 #include <map>
+#include <memory>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 
@@ -642,7 +644,10 @@ int main(int argc, char* argv[])
 		exit(1);
 	}
 
-	Gpu gpu;
+	// one context per GPU (DFB_DEVICES); candidates are dealt out by cluster, no exchange between GPUs
+	std::vector<std::unique_ptr<Gpu>> gpus;
+	for (int dev : DeviceList()) gpus.emplace_back(new Gpu(dev));
+	const int n_gpus = (int)gpus.size();
 
 	// ---- candidates, in the reference's order (SplitAlignment.cpp:266-303): SAM record order x iteration order of
 	//      the overlap set; once per (cluster, read id, revComp) ----
@@ -746,66 +751,147 @@ int main(int argc, char* argv[])
 	// ---- align in batches, write records in candidate order ----
 	const dfb_split_params params{kMatch, kMismatch, kGap, 0, kMinAnchor * kMatch};
 	const dfb_seq_table window_table = windows.View();
-	const size_t kBatch = 1u << 20;
-	TableBuilder batch_reads;
-	std::vector<int32_t> task_cluster, task_read, task_min_score, best, read_len, ref2_len;
+	const size_t kBatch = (size_t)(1u << 20) * (size_t)n_gpus;
+	struct Shard
+	{
+		TableBuilder reads;
+		std::vector<int32_t> task_cluster, task_read, task_min_score, best, read_len, ref2_len;
+		const dfb_split_row* rows = nullptr;
+		const int32_t* cols = nullptr;
+		int64_t n_rows = 0, n_cols = 0, cursor = 0;
+		int rc = DFB_OK;
+	};
+	std::vector<Shard> shards((size_t)n_gpus);
+	std::vector<int> gpu_of;
 	std::string seq;
 	for (size_t first = 0; first < candidates.size(); first += kBatch)
 	{
 		const size_t last = std::min(candidates.size(), first + kBatch);
-		batch_reads.Clear();
-		task_cluster.clear();
-		task_read.clear();
-		task_min_score.clear();
-		read_len.clear();
-		ref2_len.clear();
-		for (size_t k = first; k < last; k++)
+		const size_t n = last - first;
+		// partition by cluster, heaviest first onto the lightest GPU (cost = DP cells); a cluster heavier than a
+		// quarter of the mean load is cut into runs of candidates (every GPU holds every window pair)
+		gpu_of.assign(n, 0);
+		if (n_gpus > 1)
 		{
-			const Candidate& c = candidates[k];
+			struct Unit
+			{
+				double cost;
+				std::vector<int32_t> members;
+			};
+			std::unordered_map<int, std::vector<int32_t>> by_cluster;
+			std::vector<int> cluster_order;
+			std::vector<double> cost(n);
+			double total = 0;
+			for (size_t k = 0; k < n; k++)
+			{
+				const Candidate& c = candidates[first + k];
+				const int slot = cluster_slot[c.cluster_id];
+				auto it = reads.find(c.read_id);
+				const double L = it == reads.end() ? 0.0 : (double)it->second.size();
+				cost[k] = L * (double)(windows.off[2 * slot + 2] - windows.off[2 * slot]);
+				total += cost[k];
+				auto ins = by_cluster.emplace(c.cluster_id, std::vector<int32_t>());
+				if (ins.second) cluster_order.push_back(c.cluster_id);
+				ins.first->second.push_back((int32_t)k);
+			}
+			const double cap = std::max(1.0, total / n_gpus / 4.0);
+			std::vector<Unit> units;
+			for (int cid : cluster_order)
+			{
+				Unit u{0.0, {}};
+				for (int32_t k : by_cluster[cid])
+				{
+					if (u.cost > cap)
+					{
+						units.push_back(std::move(u));
+						u = Unit{0.0, {}};
+					}
+					u.members.push_back(k);
+					u.cost += cost[k];
+				}
+				if (!u.members.empty()) units.push_back(std::move(u));
+			}
+			std::stable_sort(units.begin(), units.end(), [](const Unit& a, const Unit& b) { return a.cost > b.cost; });
+			std::vector<double> load((size_t)n_gpus, 0.0);
+			for (const Unit& u : units)
+			{
+				const int g = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+				load[g] += u.cost;
+				for (int32_t k : u.members) gpu_of[k] = g;
+			}
+		}
+		for (Shard& sh : shards)
+		{
+			sh.reads.Clear();
+			sh.task_cluster.clear();
+			sh.task_read.clear();
+			sh.task_min_score.clear();
+			sh.read_len.clear();
+			sh.ref2_len.clear();
+			sh.cursor = 0;
+		}
+		for (size_t k = 0; k < n; k++)
+		{
+			const Candidate& c = candidates[first + k];
+			Shard& sh = shards[gpu_of[k]];
 			auto it = reads.find(c.read_id);
 			if (it != reads.end()) seq = it->second; else seq.clear();
 			if (c.rev_comp) ReverseComplementInPlace(seq);
 			const int slot = cluster_slot[c.cluster_id];
-			task_cluster.push_back(slot);
-			task_read.push_back((int32_t)batch_reads.Add(seq));
-			task_min_score.push_back((int)((float)seq.length() * (float)kMatch * 0.90)); // SplitAlignment.cpp:379
-			read_len.push_back((int32_t)seq.size());
-			ref2_len.push_back((int32_t)(windows.off[2 * slot + 2] - windows.off[2 * slot + 1]));
+			sh.task_cluster.push_back(slot);
+			sh.task_read.push_back((int32_t)sh.reads.Add(seq));
+			sh.task_min_score.push_back((int)((float)seq.length() * (float)kMatch * 0.90)); // SplitAlignment.cpp:379
+			sh.read_len.push_back((int32_t)seq.size());
+			sh.ref2_len.push_back((int32_t)(windows.off[2 * slot + 2] - windows.off[2 * slot + 1]));
 		}
-		best.resize(last - first);
-		const dfb_seq_table read_table = batch_reads.View();
-		if (dfb_split_align_batch(gpu.ctx(), &params, &window_table, &read_table, task_cluster.data(), task_read.data(),
-		                          task_min_score.data(), (int64_t)(last - first), best.data()) != DFB_OK)
-			gpu.Die("split alignment failed");
-		const dfb_split_row* rows = nullptr;
-		const int32_t* cols = nullptr;
-		int64_t n_rows = 0, n_cols = 0;
-		if (dfb_split_result_view(gpu.ctx(), &rows, &n_rows, &cols, &n_cols) != DFB_OK) gpu.Die("split result");
+		auto run_shard = [&](int g) {
+			Shard& sh = shards[g];
+			sh.best.resize(sh.task_cluster.size());
+			const dfb_seq_table read_table = sh.reads.View();
+			sh.rc = dfb_split_align_batch(gpus[g]->ctx(), &params, &window_table, &read_table, sh.task_cluster.data(),
+			                              sh.task_read.data(), sh.task_min_score.data(), (int64_t)sh.task_cluster.size(),
+			                              sh.best.data());
+			if (sh.rc == DFB_OK) sh.rc = dfb_split_result_view(gpus[g]->ctx(), &sh.rows, &sh.n_rows, &sh.cols, &sh.n_cols);
+		};
+		if (n_gpus == 1)
+		{
+			run_shard(0);
+		}
+		else
+		{
+			std::vector<std::thread> th;
+			for (int g = 0; g < n_gpus; g++) th.emplace_back(run_shard, g);
+			for (auto& t : th) t.join();
+		}
+		for (int g = 0; g < n_gpus; g++)
+			if (shards[g].rc != DFB_OK) gpus[g]->Die("split alignment failed");
 
+		// merge: candidates in their original order; every shard's rows are in its own task order
 		std::ostringstream os;
 		std::unordered_set<std::pair<int, int>, PairHash> ref_splits;
-		int64_t r = 0;
-		for (size_t k = first; k < last; k++)
+		std::vector<int32_t> local_index((size_t)n_gpus, 0);
+		for (size_t k = 0; k < n; k++)
 		{
-			const int32_t t = (int32_t)(k - first);
-			if (r >= n_rows || rows[r].task != t) continue;
-			const Candidate& c = candidates[k];
+			Shard& sh = shards[gpu_of[k]];
+			const int32_t t = local_index[gpu_of[k]]++;
+			if (sh.cursor >= sh.n_rows || sh.rows[sh.cursor].task != t) continue;
+			const Candidate& c = candidates[first + k];
 			ref_splits.clear();
-			for (; r < n_rows && rows[r].task == t; r++)
+			for (; sh.cursor < sh.n_rows && sh.rows[sh.cursor].task == t; sh.cursor++)
 			{
-				const dfb_split_row& row = rows[r];
-				const int32_t* c1 = cols + row.col_begin;
+				const dfb_split_row& row = sh.rows[sh.cursor];
+				const int32_t* c1 = sh.cols + row.col_begin;
 				const int32_t* c2 = c1 + row.n1;
 				const int score = std::min(row.score1, row.score2); // SplitAlignment.cpp:400
 				for (int a = 0; a < row.n1; a++)
 				{
 					for (int b = 0; b < row.n2; b++)
 					{
-						const std::pair<int, int> ref_split(c1[a], ref2_len[t] - c2[b] - 1); // SplitReadAligner.cpp:277-278
-						if (!ref_splits.insert(ref_split).second) continue;                  // first per refSplit (:383-390)
+						const std::pair<int, int> ref_split(c1[a], sh.ref2_len[t] - c2[b] - 1); // SplitReadAligner.cpp:277-278
+						if (!ref_splits.insert(ref_split).second) continue;                     // first per refSplit (:383-390)
 						os << c.cluster_id << "\t" << IdIndex(c.read_id) << "\t" << IdEnd(c.read_id) << "\t" << c.rev_comp << "\t"
 						   << ref_split.first << "\t" << ref_split.second << "\t" << row.read_split << "\t"
-						   << read_len[t] - row.read_split << "\t" << score << "\t" << "\n";
+						   << sh.read_len[t] - row.read_split << "\t" << score << "\t" << "\n";
 					}
 				}
 			}

@@ -334,10 +334,9 @@ private:
 class Gpu
 {
 public:
-	Gpu()
+	Gpu() : Gpu(getenv("DFB_DEVICE") ? atoi(getenv("DFB_DEVICE")) : 0) {}
+	explicit Gpu(int device)
 	{
-		int device = 0;
-		if (const char* e = getenv("DFB_DEVICE")) device = atoi(e);
 		if (dfb_ctx_create(device, &mCtx) != DFB_OK)
 		{
 			std::cerr << "Error: " << dfb_last_error(nullptr) << std::endl;
@@ -352,9 +351,39 @@ public:
 		exit(1);
 	}
 
+	Gpu(const Gpu&) = delete;
+	Gpu& operator=(const Gpu&) = delete;
+
 private:
 	dfb_ctx* mCtx = nullptr;
 };
+
+// Devices a tool may use: DFB_DEVICES="0,1,2" or "all" (every visible GPU); else the single DFB_DEVICE (default 0).
+inline std::vector<int> DeviceList()
+{
+	std::vector<int> out;
+	const char* e = getenv("DFB_DEVICES");
+	if (e && *e)
+	{
+		if (std::string(e) == "all")
+		{
+			const int n = dfb_device_count();
+			for (int k = 0; k < n; k++) out.push_back(k);
+		}
+		else
+		{
+			std::vector<std::string> f;
+			SplitChar(e, ',', f);
+			for (const std::string& t : f)
+			{
+				int v = 0;
+				if (ParseInt(t, v)) out.push_back(v);
+			}
+		}
+	}
+	if (out.empty()) out.push_back(getenv("DFB_DEVICE") ? atoi(getenv("DFB_DEVICE")) : 0);
+	return out;
+}
 
 // CSR table under construction
 struct TableBuilder

@@ -15,8 +15,9 @@ sys.path.insert(0, ROOT)
 pytestmark = pytest.mark.gpu
 
 
-def _run(cmd, stdin=None):
-    p = subprocess.run(cmd, input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+def _run(cmd, stdin=None, env=None):
+    p = subprocess.run(cmd, input=stdin, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300,
+                       env=dict(os.environ, **env) if env else None)
     assert p.returncode == 0, (cmd[0], p.returncode, p.stderr.decode()[-2000:])
     return p.stdout
 
@@ -92,3 +93,24 @@ def test_dosplitalign_vs_reference_tool(oracle_mod, tmp_path, kw):
     assert a == b
     # and after the pipeline's own canonicalisation (scripts/defuse_run.pl:528)
     assert sorted(a.splitlines()) == sorted(b.splitlines())
+
+
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0,0"])
+def test_dosplitalign_sharded_over_contexts(oracle_mod, tmp_path, devices):
+    """Multi-GPU path of the tool (one context per entry of DFB_DEVICES, candidates dealt out by cluster, merged in
+    candidate order), exercised on one GPU by naming it several times: the output must not change."""
+    from synth import files
+    g = json.load(open(os.path.join(HERE, "golden", "tools.json")))
+    sub = str(tmp_path / "s")
+    args = files.make_split_dataset(sub, **g["split_small"]["kw"])
+    res = os.path.join(sub, "ours.alignments")
+    _run([os.path.join(BIN, "dosplitalign")] + args + ["-a", res], env={"DFB_DEVICES": devices})
+    assert open(res).read() == g["split_small"]["output"]
+    ref = oracle_mod.ref_tool("ref_dosplitalign")
+    if ref:
+        d = str(tmp_path / "big")
+        args = files.make_split_dataset(d, seed=41, n_clusters=150, pairs_per_cluster=80)
+        ours, theirs = os.path.join(d, "ours.tmp"), os.path.join(d, "ref.tmp")
+        _run([os.path.join(BIN, "dosplitalign")] + args + ["-a", ours], env={"DFB_DEVICES": devices})
+        _run([ref] + args + ["-a", theirs])
+        assert open(ours).read() == open(theirs).read()
