@@ -190,13 +190,48 @@ def pinned(arr):
     return out, t
 
 
-def measure_local(ctx, stream, args):
-    """BASELINE.json configs[1]: localalign, 1 M 100-bp reads against 10 k references of 2001 bp, 10/-5/-5 (reported
-    beside the headline; same timing rules)."""
+def measure_stress(ctx, stream, args):
+    """BASELINE.json configs[4]: 250-bp reads, 8 % substitutions, 10 % of reads with a deletion, 1 % N, cluster sizes
+    Zipf(1.2) (the heaviest clusters hold most candidates), windows 700-860 bp."""
     import torch
     import defuse_b200 as d
     import synth
-    w = synth.local_workload(2, 10000, args.local_tasks, 2001, 100)
+    w = synth.split_workload(5, 4000, 50, L=250, R_lo=700, R_hi=860, sub=0.08, n_rate=0.01, indel_frac=0.1, zipf=1.2)
+    refs = d.SeqTable(w["ref_bytes"], w["ref_off"])
+    reads = d.SeqTable(w["read_bytes"], w["read_off"])
+    al = d.SplitReadAligner(2, -1, -2, False, 8, ctx=ctx)
+    plan = al.plan(refs, reads, w["task_cluster"], w["task_read"], w["min_score"])
+    plan.set_timing(True)
+    for _ in range(3):
+        plan.run()
+    plan.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 5
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        plan.run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    plan.sync()
+    st = plan.stats()
+    res = plan.fetch(copy=False)
+    n_hit = int((res.best > 0).sum())
+    plan.close()
+    return {"workload": "%d SplitReadAligner tasks, L=250, R 700-860, Zipf(1.2) cluster sizes, 8%% sub" % w["n_tasks"],
+            "gcups": w["cells"] / (ms * 1e-3) / 1e9, "ms_per_step": ms, "sweep_ms": st["ms_sweep"], "probe_ms": st["ms_probe"],
+            "tasks_with_split": n_hit, "tasks_per_s": w["n_tasks"] / (ms * 1e-3)}
+
+
+def measure_local(ctx, stream, args, R=2001, L=100, n_refs=10000, n_tasks=None):
+    """BASELINE.json configs[1]: localalign, 1 M 100-bp reads against 10 k references of 2001 bp, 10/-5/-5; and
+    configs[3]: matealign-shaped, 150-bp reads against searchlength+1 = 1001-bp windows (reported beside the
+    headline; same timing rules)."""
+    import torch
+    import defuse_b200 as d
+    import synth
+    w = synth.local_workload(2, n_refs, n_tasks or args.local_tasks, R, L)
     refs = d.SeqTable(w["ref_bytes"], w["ref_off"])
     seqs = d.SeqTable(w["seq_bytes"], w["seq_off"])
     al = d.SimpleAligner(10, -5, -5, ctx=ctx)
@@ -220,7 +255,7 @@ def measure_local(ctx, stream, args):
     t1 = time.perf_counter()
     al.align_batch(refs, seqs, w["task_ref"], w["task_seq"])
     e2e_ms = (time.perf_counter() - t1) * 1e3
-    return {"workload": "%d SimpleAligner tasks, R=2001, L=100, 10/-5/-5" % w["n_tasks"], "gcups": w["cells"] / (ms * 1e-3) / 1e9,
+    return {"workload": "%d SimpleAligner tasks, R=%d, L=%d, 10/-5/-5" % (w["n_tasks"], R, L), "gcups": w["cells"] / (ms * 1e-3) / 1e9,
             "ms_per_step": ms, "reads_per_s": w["n_tasks"] / (ms * 1e-3), "e2e_gcups": w["cells"] / (e2e_ms * 1e-3) / 1e9,
             "e2e_ms": e2e_ms, "first_call_ms": (t1 - t0) * 1e3, "kernel_launches": int(st["kernel_launches"])}
 
@@ -369,7 +404,10 @@ def run_ours(args):
             "device": info["name"],
         }
         if world == 1 and not args.no_secondary:
-            line["secondary"] = {"localalign_config2": measure_local(ctx, stream, args)}
+            line["secondary"] = {"localalign_config2": measure_local(ctx, stream, args),
+                                 "matealign_config4": measure_local(ctx, stream, args, R=1001, L=150, n_refs=200000,
+                                                                    n_tasks=args.local_tasks // 2),
+                                 "stress_config5": measure_stress(ctx, stream, args)}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n = args.ref_tasks_per_core * threads
