@@ -356,6 +356,8 @@ struct dfb_plan
 	uint2* d_pool = nullptr;
 	uint8_t* d_obytes = nullptr;
 	int32_t* d_out = nullptr; // score / best per task
+	int32_t* d_task_slot = nullptr; // split: result slot of every task (-1: none), written by the first sweep
+	int64_t job_base[kNumClasses] = {0}; // first global slot number of every class
 	int* d_ctrl = nullptr;    // all classes' control words
 	Event* d_events = nullptr;
 	unsigned long long* d_ev_count = nullptr;
@@ -407,6 +409,7 @@ static void release_device(dfb_plan* plan)
 	dfree(ctx, plan->d_pool);
 	dfree(ctx, plan->d_obytes);
 	dfree(ctx, plan->d_out);
+	dfree(ctx, plan->d_task_slot);
 	dfree(ctx, plan->d_ctrl);
 	dfree(ctx, plan->d_events);
 	dfree(ctx, plan->d_ev_count);
@@ -548,15 +551,24 @@ static uint32_t layout_words(const dfb_seq_table* a, int mode_a, const dfb_seq_t
 	return (uint32_t)w;
 }
 
+// Starts the copy of the raw sequence bytes before the host builds descriptors and jobs: with pinned
+// caller buffers the transfer runs underneath that host work.
+static int upload_raw(dfb_plan* pl, const dfb_seq_table* a, const dfb_seq_table* b)
+{
+	dfb_ctx* ctx = pl->ctx;
+	const int64_t na = a->off[a->n], nb = b->off[b->n];
+	// 16 bytes of slack in front, 32 behind (the pack kernel reads whole 16-byte windows)
+	DALLOC(ctx, pl->d_raw, (size_t)(na + nb + 48));
+	if (na) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16, a->bytes, (size_t)na, cudaMemcpyHostToDevice, ctx->stream));
+	if (nb) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16 + na, b->bytes, (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+	return DFB_OK;
+}
+
 static int upload_and_pack(dfb_plan* pl, const dfb_seq_table* a, int mode_a, const dfb_seq_table* b, int mode_b,
                            const Staging& st, uint32_t words_a_end, uint32_t total_words)
 {
 	dfb_ctx* ctx = pl->ctx;
 	const int64_t na = a->off[a->n], nb = b->off[b->n];
-	// raw bytes: 16 bytes of slack in front, 32 behind (the pack kernel reads whole 16-byte windows)
-	DALLOC(ctx, pl->d_raw, (size_t)(na + nb + 48));
-	if (na) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16, a->bytes, (size_t)na, cudaMemcpyHostToDevice, ctx->stream));
-	if (nb) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16 + na, b->bytes, (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
 	DALLOC(ctx, pl->d_stage, st.total);
 	CK(ctx, cudaMemcpyAsync(pl->d_stage, ctx->h_in.p, st.total, cudaMemcpyHostToDevice, ctx->stream));
 	DALLOC(ctx, pl->d_pool, ((size_t)total_words + 2) * sizeof(uint2));
@@ -607,6 +619,8 @@ static void fill_fast_params(dfb_plan* pl, int c, int m, int x, int g, int min_s
 	fp.hit_count = cw.d_ctrl + 1;
 	fp.hitq = cw.d_hitq;
 	fp.slot_task = cw.d_slot_task;
+	fp.task_slot = pl->d_task_slot;
+	fp.slot_base = (int)pl->job_base[c];
 	fp.slot_ev = cw.d_slot_ev;
 	fp.slot_n = cw.d_slot_n;
 	fp.ntg = cw.d_ntg;
@@ -631,6 +645,7 @@ static int alloc_work(dfb_plan* pl, const Staging& st, const int64_t* n_jobs_cls
 		cw.n_jobs = n_jobs_cls[c];
 		cw.d_jobs = (JobPair*)(pl->d_stage + st.off_jobs) + first;
 		cw.d_ctrl = pl->d_ctrl + 4 * c;
+		pl->job_base[c] = first;
 		first += cw.n_jobs;
 		pl->stats.fast_jobs += cw.n_jobs;
 		if (split && cw.n_jobs)
@@ -671,6 +686,7 @@ static int alloc_work(dfb_plan* pl, const Staging& st, const int64_t* n_jobs_cls
 	}
 	DALLOC(ctx, pl->d_out, (size_t)std::max<int64_t>(pl->n_tasks, 1) * sizeof(int32_t));
 	CK(ctx, cudaMemsetAsync(pl->d_out, 0, (size_t)std::max<int64_t>(pl->n_tasks, 1) * sizeof(int32_t), ctx->stream));
+	if (split) DALLOC(ctx, pl->d_task_slot, (size_t)std::max<int64_t>(pl->n_tasks, 1) * sizeof(int32_t));
 	return DFB_OK;
 }
 
@@ -710,6 +726,11 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 	pl->sp.mismatch = params->mismatch;
 	pl->sp.gap = params->gap;
 	classify_params(pl, params->match, params->mismatch, params->gap, true);
+	if ((rc = upload_raw(pl, refs, seqs)))
+	{
+		dfb_plan_destroy(pl);
+		return rc;
+	}
 
 	// pass 1: classify every task, count per (class, reference-length bin)
 	std::vector<int32_t> bin_of((size_t)n_tasks);
@@ -721,7 +742,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 		const int32_t r = task_ref[t], s = task_seq[t];
 		if (r < 0 || r >= refs->n || s < 0 || s >= seqs->n)
 		{
-			delete pl;
+			dfb_plan_destroy(pl);
 			return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)t);
 		}
 		const int64_t R = refs->off[r + 1] - refs->off[r];
@@ -767,7 +788,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 	cudaError_t e = stage_layout(ctx, st, refs->n, seqs->n, n_fast_jobs, n_gen);
 	if (e != cudaSuccess)
 	{
-		delete pl;
+		dfb_plan_destroy(pl);
 		return set_err(ctx, DFB_ERR_NOMEM, "pinned staging buffer: %s", cudaGetErrorString(e));
 	}
 	uint32_t words_a_end = 0;
@@ -775,7 +796,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 	const uint32_t total_words = layout_words(refs, PACK_FWD, seqs, PACK_FWD, st.desc_a, st.desc_b, &words_a_end, &overflow);
 	if (overflow)
 	{
-		delete pl;
+		dfb_plan_destroy(pl);
 		return set_err(ctx, DFB_ERR_ARG, "batch too large: more than 2^32 packed words; split it");
 	}
 	// pass 2: place every task into its job slot
@@ -855,6 +876,11 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 	pl->n_tasks = n_tasks;
 	pl->stats.n_tasks = n_tasks;
 	classify_params(pl, params->match, params->mismatch, params->gap, params->end_gaps == 0 && params->min_split_score >= 1);
+	if ((rc = upload_raw(pl, refs, reads)))
+	{
+		dfb_plan_destroy(pl);
+		return rc;
+	}
 
 	Trace tr;
 	// pass 1 (host threads): class and reference-length bin of every task, per-thread bin counts
@@ -917,7 +943,7 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 		if (part[k].bad >= 0)
 		{
 			const long long bad = (long long)part[k].bad;
-			delete pl;
+			dfb_plan_destroy(pl);
 			return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", bad);
 		}
 		pl->stats.cells += part[k].cells;
@@ -950,7 +976,7 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 	cudaError_t e = stage_layout(ctx, st, refs->n, reads->n, n_fast_jobs, 2 * n_gen_tasks);
 	if (e != cudaSuccess)
 	{
-		delete pl;
+		dfb_plan_destroy(pl);
 		return set_err(ctx, DFB_ERR_NOMEM, "pinned staging buffer: %s", cudaGetErrorString(e));
 	}
 	// reference 1 of every cluster forward, reference 2 reversed (SplitReadAligner.cpp:80-81);
@@ -960,7 +986,7 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 	const uint32_t total_words = layout_words(refs, PACK_REV_ODD, reads, PACK_BOTH, st.desc_a, st.desc_b, &words_a_end, &overflow);
 	if (overflow)
 	{
-		delete pl;
+		dfb_plan_destroy(pl);
 		return set_err(ctx, DFB_ERR_ARG, "batch too large: more than 2^32 packed words; split it");
 	}
 	tr.lap("split.create: layout");
@@ -1120,6 +1146,7 @@ extern "C" int dfb_plan_run(dfb_plan* pl)
 		CK(ctx, cudaEventRecord(pl->ev[0], ctx->stream));
 	}
 	CK(ctx, cudaMemsetAsync(pl->d_ctrl, 0, kNumClasses * 4 * sizeof(int), ctx->stream));
+	if (pl->split) CK(ctx, cudaMemsetAsync(pl->d_task_slot, 0xff, (size_t)std::max<int64_t>(pl->n_tasks, 1) * sizeof(int32_t), ctx->stream));
 	for (int c = 0; c < kNumClasses; c++)
 	{
 		ClassWork& cw = pl->cls[c];
@@ -1288,21 +1315,22 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 		int rc = run_probe(pl);
 		if (rc) return rc;
 	}
-	int64_t hits_cls[kNumClasses], slot_base[kNumClasses], n_slots = 0;
+	// slots are numbered class by class in job space (the first sweep wrote task -> slot with that numbering)
+	int64_t hits_cls[kNumClasses], n_slots = 0, n_slot_space = 0;
 	for (int c = 0; c < kNumClasses; c++)
 	{
 		hits_cls[c] = pl->cls[c].n_jobs ? h_ctrl[4 * c + 1] : 0;
-		slot_base[c] = n_slots;
 		n_slots += hits_cls[c];
+		n_slot_space = std::max<int64_t>(n_slot_space, pl->job_base[c] + pl->cls[c].n_jobs);
 	}
 
 	tr.lap("split.fetch: wait kernels");
-	// 2. bulk copy into pinned staging: best | slot_task | slot_n | slot_ev | overflow events
+	// 2. bulk copy into pinned staging: best | task_slot | slot_n | slot_ev | overflow events
 	const size_t off_best = 0;
 	const size_t off_task = align_up(off_best + (size_t)pl->n_tasks * 4, 256);
-	const size_t off_n = align_up(off_task + (size_t)n_slots * 4, 256);
-	const size_t off_ev = align_up(off_n + (size_t)n_slots * 4, 256);
-	const size_t off_ov = align_up(off_ev + (size_t)n_slots * DFB_SLOT_EVENTS * sizeof(uint2), 256);
+	const size_t off_n = align_up(off_task + (size_t)pl->n_tasks * 4, 256);
+	const size_t off_ev = align_up(off_n + (size_t)n_slot_space * 4, 256);
+	const size_t off_ov = align_up(off_ev + (size_t)n_slot_space * DFB_SLOT_EVENTS * sizeof(uint2), 256);
 	const size_t total = off_ov + (size_t)n_ov * sizeof(Event) + 256;
 	{
 		cudaError_t e = ctx->h_out.ensure(total);
@@ -1310,23 +1338,30 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 	}
 	uint8_t* hb = (uint8_t*)ctx->h_out.p;
 	int32_t* h_best = (int32_t*)(hb + off_best);
-	int32_t* h_task = (int32_t*)(hb + off_task);
+	const int32_t* slot_of = (const int32_t*)(hb + off_task);
 	int32_t* h_n = (int32_t*)(hb + off_n);
 	uint2* h_ev = (uint2*)(hb + off_ev);
 	Event* h_ov = (Event*)(hb + off_ov);
-	if (pl->n_tasks) CK(ctx, cudaMemcpyAsync(h_best, pl->d_out, (size_t)pl->n_tasks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	int64_t d2h = 0;
+	if (pl->n_tasks)
+	{
+		CK(ctx, cudaMemcpyAsync(h_best, pl->d_out, (size_t)pl->n_tasks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaMemcpyAsync((void*)slot_of, pl->d_task_slot, (size_t)pl->n_tasks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		d2h += pl->n_tasks * 8;
+	}
 	for (int c = 0; c < kNumClasses; c++)
 	{
 		if (!hits_cls[c]) continue;
 		const ClassWork& cw = pl->cls[c];
-		CK(ctx, cudaMemcpyAsync(h_task + slot_base[c], cw.d_slot_task, (size_t)hits_cls[c] * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(ctx, cudaMemcpyAsync(h_n + slot_base[c], cw.d_slot_n, (size_t)hits_cls[c] * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(ctx, cudaMemcpyAsync(h_ev + slot_base[c] * DFB_SLOT_EVENTS, cw.d_slot_ev,
+		CK(ctx, cudaMemcpyAsync(h_n + pl->job_base[c], cw.d_slot_n, (size_t)hits_cls[c] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(h_ev + pl->job_base[c] * DFB_SLOT_EVENTS, cw.d_slot_ev,
 		                        (size_t)hits_cls[c] * DFB_SLOT_EVENTS * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+		d2h += hits_cls[c] * (int64_t)(4 + DFB_SLOT_EVENTS * sizeof(uint2));
 	}
 	if (n_ov) CK(ctx, cudaMemcpyAsync(h_ov, pl->d_events, (size_t)n_ov * sizeof(Event), cudaMemcpyDeviceToHost, ctx->stream));
+	d2h += (int64_t)(n_ov * sizeof(Event));
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
-	pl->stats.d2h_bytes = (int64_t)(total - 256);
+	pl->stats.d2h_bytes = d2h;
 	pl->stats.probe_jobs = n_slots;
 	tr.lap("split.fetch: d2h");
 
@@ -1339,31 +1374,10 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 		return a.col < b.col;
 	});
 
-	// 4. slot of every task (parallel scatter), then per-thread assembly over contiguous task ranges so
-	//    that rows come out in task order
+	// 4. per-thread assembly over contiguous task ranges so that rows come out in task order
 	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->host_threads, pl->n_tasks / 4096 + 1));
-	if (!ctx->slot_of.ensure((size_t)std::max<int64_t>(pl->n_tasks, 1))) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
-	int32_t* slot_of = ctx->slot_of.data();
-	parallel_for(T, [&](int tid) {
-		const int64_t t0 = pl->n_tasks * tid / T, t1 = pl->n_tasks * (tid + 1) / T;
-		if (t1 > t0) memset(slot_of + t0, 0xff, (size_t)(t1 - t0) * 4);
-	});
-	std::vector<int64_t> ev_part((size_t)T, 0);
-	parallel_for(T, [&](int tid) {
-		const int64_t s0 = n_slots * tid / T, s1 = n_slots * (tid + 1) / T;
-		int64_t ne = 0;
-		for (int64_t s = s0; s < s1; s++)
-		{
-			slot_of[h_task[s]] = (int32_t)s;
-			ne += std::min<int32_t>(h_n[s], DFB_SLOT_EVENTS);
-		}
-		ev_part[tid] = ne;
-	});
-	int64_t n_events = (int64_t)n_ov;
-	for (int k = 0; k < T; k++) n_events += ev_part[k];
-	pl->stats.events = n_events;
-	tr.lap("split.fetch: slot map");
 	if ((int)ctx->asm_chunks.size() < T) ctx->asm_chunks.resize((size_t)T);
+	std::vector<int64_t> ev_part((size_t)T, 0);
 	bool oom = false;
 	parallel_for(T, [&](int tid) {
 		const int64_t t0 = pl->n_tasks * tid / T, t1 = pl->n_tasks * (tid + 1) / T;
@@ -1374,9 +1388,16 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 		const Event* ov_end = h_ov + n_ov;
 		const Event* ov = std::lower_bound(ov_begin, ov_end, (int32_t)t0, [](const Event& e, int32_t t) { return e.task < t; });
 		const Event* ov_last = std::lower_bound(ov_begin, ov_end, (int32_t)t1, [](const Event& e, int32_t t) { return e.task < t; });
+		// the slot data was just written by DMA: nothing of it is in this core's caches, and the slots of
+		// consecutive tasks are scattered.  Prefetch a few tasks ahead in both passes.
+		const int64_t kAhead = 24;
 		for (int64_t t = t0; t < t1; t++)
+		{
+			if (t + kAhead < t1 && slot_of[t + kAhead] >= 0) __builtin_prefetch(h_n + slot_of[t + kAhead]);
 			if (slot_of[t] >= 0) ev_here += std::min<int32_t>(h_n[slot_of[t]], DFB_SLOT_EVENTS);
+		}
 		ev_here += ov_last - ov;
+		ev_part[tid] = ev_here;
 		if (!out.rows.ensure((size_t)ev_here / 2 + 1) || !out.cols.ensure((size_t)ev_here + 1)) { oom = true; return; }
 		dfb_split_row* rows = out.rows.data();
 		int32_t* cols = out.cols.data();
@@ -1386,6 +1407,11 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 		std::vector<int> order;
 		for (int64_t t = t0; t < t1; t++)
 		{
+			if (t + kAhead < t1 && slot_of[t + kAhead] >= 0)
+			{
+				__builtin_prefetch(h_ev + (size_t)slot_of[t + kAhead] * DFB_SLOT_EVENTS);
+				__builtin_prefetch(h_n + slot_of[t + kAhead]);
+			}
 			const int32_t s = slot_of[t];
 			const bool has_ov = ov < ov_end && ov->task == (int32_t)t;
 			if (s < 0 && !has_ov) continue;
@@ -1476,6 +1502,11 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 		out.n_cols = nc;
 	});
 	if (oom) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
+	{
+		int64_t n_events = 0;
+		for (int k = 0; k < T; k++) n_events += ev_part[k];
+		pl->stats.events = n_events;
+	}
 	tr.lap("split.fetch: assemble");
 	// 5. concatenate into recycled result arrays
 	size_t tot_rows = 0, tot_cols = 0;

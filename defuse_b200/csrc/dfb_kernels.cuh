@@ -171,8 +171,10 @@ struct FastParams
 	uint32_t* ntg;   // [slot][S][G] negated row-max targets (or "row disabled")
 	uint32_t* ckpt;  // [job][ckpt_blocks][S+2][G] wavefront state (F[S], prev, Flast) in front of every CH-th step (null: off)
 	int ckpt_blocks; // checkpoints per job in this launch
+	int slot_base;   // SPLIT: first global slot number of this class (slots are numbered class by class)
 	uint32_t* slot_rng; // per queue slot: checkpoint blocks to re-sweep, first/last per half
 	int32_t* slot_task; // SPLIT (write): task index per queue slot
+	int32_t* task_slot; // SPLIT (write): queue slot per task, -1 when the task needs no second sweep
 	uint2* slot_ev;     // PROBE: [slot][DFB_SLOT_EVENTS] {key = half<<27 | row<<16 | col, score}
 	int* slot_n;        // PROBE: events found per slot (may exceed DFB_SLOT_EVENTS: the rest is in `events`)
 	Event* events;      // PROBE: overflow list
@@ -624,9 +626,10 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				p.out[jp.out0] = hit ? best : 0;
 				if (group_en)
 				{
-					slot = atomicAdd(p.hit_count, 1);
-					p.hitq[slot] = jid;
-					p.slot_task[slot] = jp.out0;
+					slot = atomicAdd(p.hit_count, 1) + p.slot_base;
+					p.hitq[slot - p.slot_base] = jid;
+					p.slot_task[slot - p.slot_base] = jp.out0;
+					p.task_slot[jp.out0] = slot;
 					uint32_t rng = 0xFF00FF00u; // no checkpoints: sweep everything
 					if (ck_on)
 					{
@@ -635,7 +638,8 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 						if (f0 == 0 || f1 == 0) f0 = f1 = 0; // a window that starts at step 0 starts both halves there
 						rng = (uint32_t)f0 | ((uint32_t)l0 << 8) | ((uint32_t)f1 << 16) | ((uint32_t)l1 << 24);
 					}
-					p.slot_rng[slot] = rng;
+					p.slot_rng[slot - p.slot_base] = rng;
+					slot -= p.slot_base;
 				}
 			}
 			slot = __shfl_sync(0xffffffffu, slot, q * G);

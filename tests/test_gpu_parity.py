@@ -178,3 +178,59 @@ def test_event_buffer_overflow_is_recovered(oracle_mod, gpu_ctx):
         assert res.best[t] == best_want
         assert sum(int(r["n1"]) * int(r["n2"]) for r in rows) == n_want
     assert len(res.cols) > (1 << 20)  # more events than the initial buffer held
+
+
+def test_large_batch_properties_and_sampled_parity(oracle_mod, gpu_ctx):
+    """A bench-sized shard (200 k tasks, the shape of BASELINE.json configs[2]): size-independent properties on every
+    task, full oracle parity on a random sample, and identical results from the resident plan and the one-call API."""
+    import defuse_b200 as d
+    import synth
+    w = synth.split_workload(9, 2000, 100)
+    refs, reads = d.SeqTable(w["ref_bytes"], w["ref_off"]), d.SeqTable(w["read_bytes"], w["read_off"])
+    al = d.SplitReadAligner(ctx=gpu_ctx)
+    res = al.align_batch(refs, reads, w["task_cluster"], w["task_read"], w["min_score"])
+    n, L = w["n_tasks"], w["L"]
+    rows = res.rows
+    assert np.all(np.diff(rows["task"]) >= 0)                                    # task order
+    assert np.all(rows["score1"] + rows["score2"] == res.best[rows["task"]])      # every winning row attains the best total
+    assert np.all((res.best == 0) | ((res.best >= w["min_score"]) & (res.best <= 2 * L)))
+    assert np.all((rows["read_split"] >= 1) & (rows["read_split"] <= L - 1))
+    assert np.all((rows["score1"] >= 8) & (rows["score2"] >= 8))                  # minSplitScore floor on both sides
+    assert np.all((rows["n1"] >= 1) & (rows["n2"] >= 1))
+    assert np.all(res.best[np.setdiff1d(np.arange(n), rows["task"])] >= 0)
+    same = rows["task"][1:] == rows["task"][:-1]
+    assert np.all(rows["read_split"][1:][same] > rows["read_split"][:-1][same])   # ascending tie rows inside a task
+    ref_len = w["ref_off"][1:] - w["ref_off"][:-1]
+    r1 = ref_len[2 * w["task_cluster"].astype(np.int64)][rows["task"]]
+    first_col = res.cols[rows["col_begin"]]
+    assert np.all((first_col >= 1) & (first_col <= r1))
+    # the resident plan gives the same answer, run after run
+    plan = al.plan(refs, reads, w["task_cluster"], w["task_read"], w["min_score"])
+    for _ in range(2):
+        plan.run()
+        r2 = plan.fetch()
+        assert np.array_equal(r2.best, res.best) and np.array_equal(r2.rows, rows) and np.array_equal(r2.cols, res.cols)
+    plan.close()
+    # sampled full parity
+    rng = np.random.default_rng(0)
+    sample = np.sort(rng.choice(n, 400, replace=False)).astype(np.int32)
+    cnt, want = oracle_mod.split_align_batch(w["ref_bytes"], w["ref_off"], w["read_bytes"], w["read_off"],
+                                             w["task_cluster"][sample], w["task_read"][sample], w["min_score"][sample])
+    pos = np.concatenate([[0], np.cumsum(cnt)])
+    for k, t in enumerate(sample):
+        a = res.alignments(int(t))
+        b = want[pos[k]:pos[k + 1]]
+        assert a.shape == b.shape and (a == b).all(), t
+
+
+def test_large_simple_batch_sampled_parity(oracle_mod, gpu_ctx):
+    import defuse_b200 as d
+    import synth
+    w = synth.local_workload(12, 500, 60000, 2001, 100)
+    refs, seqs = d.SeqTable(w["ref_bytes"], w["ref_off"]), d.SeqTable(w["seq_bytes"], w["seq_off"])
+    got = d.SimpleAligner(10, -5, -5, ctx=gpu_ctx).align_batch(refs, seqs, w["task_ref"], w["task_seq"])
+    assert np.all((got >= 0) & (got <= 1000))
+    sample = np.sort(np.random.default_rng(1).choice(w["n_tasks"], 300, replace=False)).astype(np.int32)
+    want = oracle_mod.simple_align_batch(10, -5, -5, w["ref_bytes"], w["ref_off"], w["seq_bytes"], w["seq_off"],
+                                         w["task_ref"][sample], w["task_seq"][sample])
+    assert np.array_equal(got[sample], want)
