@@ -103,8 +103,10 @@ struct dfb_ctx
 	cudaStream_t stream = nullptr;
 	cudaDeviceProp prop;
 	mutable std::string err;
-	PinnedBuf h_in;  // host-built descriptors and job lists, on their way to the device
-	PinnedBuf h_out; // results on their way back
+	static const int kStageSlots = 8;
+	PinnedBuf h_in[kStageSlots]; // host-built descriptors and job lists, on their way to the device (one per batch chunk in flight)
+	PinnedBuf h_out;             // results on their way back
+	cudaStream_t copy_stream = nullptr; // device->host result copies, ordered after a plan's kernels by an event
 	dfb_plan* last_split = nullptr; // result holder of dfb_split_align_batch
 	int host_threads = 1;
 	// recycled host memory of the result assembly (kept mapped between batches)
@@ -112,6 +114,8 @@ struct dfb_ctx
 	HostArr<int32_t> spare_cols;
 	std::vector<AsmChunk> asm_chunks;
 	HostArr<int32_t> slot_of;
+	HostArr<dfb_split_row> chunk_rows[kStageSlots]; // per-chunk results of a pipelined batch, before the merge
+	HostArr<int32_t> chunk_cols[kStageSlots];
 };
 
 static thread_local std::string g_create_err;
@@ -210,6 +214,12 @@ extern "C" int dfb_ctx_create(int device_ordinal, dfb_ctx** out)
 		return set_err(nullptr, DFB_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(e));
 	}
 	ctx->stream = ctx->own_stream;
+	if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+	{
+		cudaStreamDestroy(ctx->own_stream);
+		delete ctx;
+		return set_err(nullptr, DFB_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(e));
+	}
 	// keep freed blocks in the stream-ordered pool: a batch re-uses the previous batch's memory
 	cudaMemPool_t pool;
 	if (cudaDeviceGetDefaultMemPool(&pool, device_ordinal) == cudaSuccess)
@@ -229,12 +239,15 @@ extern "C" void dfb_ctx_destroy(dfb_ctx* ctx)
 	cudaSetDevice(ctx->device);
 	if (ctx->last_split) dfb_plan_destroy(ctx->last_split);
 	cudaStreamSynchronize(ctx->stream);
-	ctx->h_in.release();
+	for (auto& b : ctx->h_in) b.release();
 	ctx->h_out.release();
+	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	ctx->spare_rows.release();
 	ctx->spare_cols.release();
 	ctx->slot_of.release();
 	for (auto& c : ctx->asm_chunks) { c.rows.release(); c.cols.release(); }
+	for (auto& c : ctx->chunk_rows) c.release();
+	for (auto& c : ctx->chunk_cols) c.release();
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
@@ -385,6 +398,8 @@ struct dfb_plan
 	bool pack_timed = false;
 	bool run_timed = false;
 	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+	cudaEvent_t done_ev = nullptr; // recorded behind the last kernel of dfb_plan_run
+	int result_slot = -1;          // chunk of a pipelined batch: which recycled result arrays of the ctx to use
 	dfb_plan_stats stats{};
 };
 
@@ -444,9 +459,18 @@ extern "C" void dfb_plan_destroy(dfb_plan* plan)
 		if (plan->ctx->last_split == plan) plan->ctx->last_split = nullptr;
 		release_device(plan);
 		// hand the result arrays back for the next batch
-		if (plan->rows.cap > plan->ctx->spare_rows.cap) plan->rows.swap(plan->ctx->spare_rows);
-		if (plan->cols.cap > plan->ctx->spare_cols.cap) plan->cols.swap(plan->ctx->spare_cols);
+		if (plan->result_slot >= 0)
+		{
+			plan->rows.swap(plan->ctx->chunk_rows[plan->result_slot]);
+			plan->cols.swap(plan->ctx->chunk_cols[plan->result_slot]);
+		}
+		else
+		{
+			if (plan->rows.cap > plan->ctx->spare_rows.cap) plan->rows.swap(plan->ctx->spare_rows);
+			if (plan->cols.cap > plan->ctx->spare_cols.cap) plan->cols.swap(plan->ctx->spare_cols);
+		}
 	}
+	if (plan->done_ev) cudaEventDestroy(plan->done_ev);
 	plan->rows.release();
 	plan->cols.release();
 	for (int k = 0; k < 3; k++)
@@ -459,6 +483,7 @@ static int check_table(const dfb_ctx* ctx, const dfb_seq_table* t, const char* w
 	if (!t || !t->off || t->n < 0 || (t->n > 0 && !t->bytes && t->off[t->n] > 0))
 		return set_err(ctx, DFB_ERR_ARG, "%s: null table", what);
 	if (t->off[0] != 0) return set_err(ctx, DFB_ERR_ARG, "%s: off[0] must be 0", what);
+	// (internally, views with off[0] != 0 are used for chunks of a table; every size below is off[k] - off[0])
 	for (int64_t k = 0; k < t->n; k++)
 	{
 		const int64_t len = t->off[k + 1] - t->off[k];
@@ -501,22 +526,25 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 struct Staging
 {
 	size_t off_desc_a = 0, off_desc_b = 0, off_jobs = 0, off_gen = 0, total = 0;
+	void* host = nullptr;
 	SeqDesc* desc_a = nullptr;
 	SeqDesc* desc_b = nullptr;
 	JobPair* jobs = nullptr;
 	GenJob* gen = nullptr;
 };
 
-static cudaError_t stage_layout(dfb_ctx* ctx, Staging& st, int64_t na, int64_t nb, int64_t n_fast, int64_t n_gen)
+static cudaError_t stage_layout(dfb_ctx* ctx, int stage_slot, Staging& st, int64_t na, int64_t nb, int64_t n_fast, int64_t n_gen)
 {
+	PinnedBuf& hin = ctx->h_in[stage_slot];
 	st.off_desc_a = 0;
 	st.off_desc_b = align_up(st.off_desc_a + (size_t)na * sizeof(SeqDesc), 256);
 	st.off_jobs = align_up(st.off_desc_b + (size_t)nb * sizeof(SeqDesc), 256);
 	st.off_gen = align_up(st.off_jobs + (size_t)n_fast * sizeof(JobPair), 256);
 	st.total = align_up(st.off_gen + (size_t)n_gen * sizeof(GenJob), 256) + 256;
-	cudaError_t e = ctx->h_in.ensure(st.total);
+	cudaError_t e = hin.ensure(st.total);
 	if (e != cudaSuccess) return e;
-	uint8_t* base = (uint8_t*)ctx->h_in.p;
+	uint8_t* base = (uint8_t*)hin.p;
+	st.host = hin.p;
 	st.desc_a = (SeqDesc*)(base + st.off_desc_a);
 	st.desc_b = (SeqDesc*)(base + st.off_desc_b);
 	st.jobs = (JobPair*)(base + st.off_jobs);
@@ -529,11 +557,12 @@ static uint32_t layout_words(const dfb_seq_table* a, int mode_a, const dfb_seq_t
                              SeqDesc* db, uint32_t* words_a_end, bool* overflow)
 {
 	uint64_t w = 0;
-	const int64_t b_src_base = a->off[a->n];
+	const int64_t a0 = a->off[0], b0 = b->off[0];
+	const int64_t b_src_base = a->off[a->n] - a0;
 	for (int64_t k = 0; k < a->n; k++)
 	{
 		const uint32_t len = (uint32_t)(a->off[k + 1] - a->off[k]);
-		da[k].src = 16 + a->off[k];
+		da[k].src = 16 + (a->off[k] - a0);
 		da[k].len = len;
 		da[k].word = (uint32_t)w;
 		w += (uint64_t)((len + 15) / 16) * (mode_a == PACK_BOTH ? 2 : 1);
@@ -542,7 +571,7 @@ static uint32_t layout_words(const dfb_seq_table* a, int mode_a, const dfb_seq_t
 	for (int64_t k = 0; k < b->n; k++)
 	{
 		const uint32_t len = (uint32_t)(b->off[k + 1] - b->off[k]);
-		db[k].src = 16 + b_src_base + b->off[k];
+		db[k].src = 16 + b_src_base + (b->off[k] - b0);
 		db[k].len = len;
 		db[k].word = (uint32_t)w;
 		w += (uint64_t)((len + 15) / 16) * (mode_b == PACK_BOTH ? 2 : 1);
@@ -556,11 +585,11 @@ static uint32_t layout_words(const dfb_seq_table* a, int mode_a, const dfb_seq_t
 static int upload_raw(dfb_plan* pl, const dfb_seq_table* a, const dfb_seq_table* b)
 {
 	dfb_ctx* ctx = pl->ctx;
-	const int64_t na = a->off[a->n], nb = b->off[b->n];
+	const int64_t na = a->off[a->n] - a->off[0], nb = b->off[b->n] - b->off[0];
 	// 16 bytes of slack in front, 32 behind (the pack kernel reads whole 16-byte windows)
 	DALLOC(ctx, pl->d_raw, (size_t)(na + nb + 48));
-	if (na) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16, a->bytes, (size_t)na, cudaMemcpyHostToDevice, ctx->stream));
-	if (nb) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16 + na, b->bytes, (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+	if (na) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16, a->bytes + a->off[0], (size_t)na, cudaMemcpyHostToDevice, ctx->stream));
+	if (nb) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16 + na, b->bytes + b->off[0], (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
 	return DFB_OK;
 }
 
@@ -568,9 +597,9 @@ static int upload_and_pack(dfb_plan* pl, const dfb_seq_table* a, int mode_a, con
                            const Staging& st, uint32_t words_a_end, uint32_t total_words)
 {
 	dfb_ctx* ctx = pl->ctx;
-	const int64_t na = a->off[a->n], nb = b->off[b->n];
+	const int64_t na = a->off[a->n] - a->off[0], nb = b->off[b->n] - b->off[0];
 	DALLOC(ctx, pl->d_stage, st.total);
-	CK(ctx, cudaMemcpyAsync(pl->d_stage, ctx->h_in.p, st.total, cudaMemcpyHostToDevice, ctx->stream));
+	CK(ctx, cudaMemcpyAsync(pl->d_stage, st.host, st.total, cudaMemcpyHostToDevice, ctx->stream));
 	DALLOC(ctx, pl->d_pool, ((size_t)total_words + 2) * sizeof(uint2));
 	DALLOC(ctx, pl->d_obytes, ((size_t)total_words + 2) * 16);
 	for (int k = 0; k < 3; k++)
@@ -785,7 +814,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 	}
 
 	Staging st;
-	cudaError_t e = stage_layout(ctx, st, refs->n, seqs->n, n_fast_jobs, n_gen);
+	cudaError_t e = stage_layout(ctx, 0, st, refs->n, seqs->n, n_fast_jobs, n_gen);
 	if (e != cudaSuccess)
 	{
 		dfb_plan_destroy(pl);
@@ -854,18 +883,15 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 
 // ---- SplitReadAligner plan ------------------------------------------------------------------
 
-extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
-                                     const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
-                                     const int32_t* task_min_score, int64_t n_tasks, dfb_plan** out)
+// `reads` may be a view into a larger table (off[0] != 0) whose first entry is read `read_base` of the caller's
+// numbering; `async` skips the final stream synchronisation (chunks of a pipelined batch).
+static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
+                                  const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
+                                  const int32_t* task_min_score, int64_t n_tasks, int32_t read_base, int stage_slot,
+                                  bool async, dfb_plan** out)
 {
-	if (!ctx) return DFB_ERR_ARG;
-	if (!params || !out || n_tasks < 0 || (n_tasks > 0 && (!task_cluster || !task_read || !task_min_score)))
-		return set_err(ctx, DFB_ERR_ARG, "dfb_split_plan_create: null argument");
 	*out = nullptr;
 	int rc;
-	if ((rc = check_table(ctx, refs, "refs")) || (rc = check_table(ctx, reads, "reads"))) return rc;
-	if (refs->n & 1) return set_err(ctx, DFB_ERR_ARG, "refs must hold two windows per cluster (n is odd)");
-	if (n_tasks > 0x7fffff00LL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
 	const int64_t n_clusters = refs->n / 2;
 	CK(ctx, cudaSetDevice(ctx->device));
 	dfb_plan* pl = new (std::nothrow) dfb_plan();
@@ -902,7 +928,7 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 		int64_t* cnt = bin_pos.data() + n_bins * (size_t)tid;
 		for (int64_t t = t0; t < t1; t++)
 		{
-			const int32_t c0 = task_cluster[t], rd = task_read[t];
+			const int32_t c0 = task_cluster[t], rd = task_read[t] - read_base;
 			if (c0 < 0 || c0 >= n_clusters || rd < 0 || rd >= reads->n)
 			{
 				if (pt.bad < 0) pt.bad = t;
@@ -973,7 +999,7 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 
 	tr.lap("split.create: classify");
 	Staging st;
-	cudaError_t e = stage_layout(ctx, st, refs->n, reads->n, n_fast_jobs, 2 * n_gen_tasks);
+	cudaError_t e = stage_layout(ctx, stage_slot, st, refs->n, reads->n, n_fast_jobs, 2 * n_gen_tasks);
 	if (e != cudaSuccess)
 	{
 		dfb_plan_destroy(pl);
@@ -999,7 +1025,7 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 			const int32_t bin = bin_of[t];
 			if (bin < 0) continue;
 			const int64_t c2 = 2 * (int64_t)task_cluster[t];
-			const SeqDesc& rdd = st.desc_b[task_read[t]];
+			const SeqDesc& rdd = st.desc_b[task_read[t] - read_base];
 			JobPair& jp = st.jobs[pos[bin]++];
 			jp.ref_w[0] = st.desc_a[c2].word;
 			jp.ref_w[1] = st.desc_a[c2 + 1].word;
@@ -1019,7 +1045,7 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 		{
 			if (bin_of[t] != -2) continue;
 			const int64_t c2 = 2 * (int64_t)task_cluster[t];
-			const SeqDesc& rdd = st.desc_b[task_read[t]];
+			const SeqDesc& rdd = st.desc_b[task_read[t] - read_base];
 			const uint32_t rev_w = rdd.word + (rdd.len + 15) / 16;
 			for (int h = 0; h < 2; h++)
 			{
@@ -1061,7 +1087,7 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 			if (pl->cls[c].n_jobs)
 				fill_fast_params(pl, c, params->match, params->mismatch, params->gap, params->min_split_score);
 		tr.lap("split.create: alloc");
-		rc = finish_create(pl);
+		if (!async) rc = finish_create(pl);
 		tr.lap("split.create: sync");
 	}
 	if (rc)
@@ -1071,6 +1097,21 @@ extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* param
 	}
 	*out = pl;
 	return DFB_OK;
+}
+
+extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
+                                     const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
+                                     const int32_t* task_min_score, int64_t n_tasks, dfb_plan** out)
+{
+	if (!ctx) return DFB_ERR_ARG;
+	if (!params || !out || n_tasks < 0 || (n_tasks > 0 && (!task_cluster || !task_read || !task_min_score)))
+		return set_err(ctx, DFB_ERR_ARG, "dfb_split_plan_create: null argument");
+	*out = nullptr;
+	int rc;
+	if ((rc = check_table(ctx, refs, "refs")) || (rc = check_table(ctx, reads, "reads"))) return rc;
+	if (refs->n & 1) return set_err(ctx, DFB_ERR_ARG, "refs must hold two windows per cluster (n is odd)");
+	if (n_tasks > 0x7fffff00LL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
+	return split_plan_create_impl(ctx, params, refs, reads, task_cluster, task_read, task_min_score, n_tasks, 0, 0, false, out);
 }
 
 // ---- run / fetch -------------------------------------------------------------------------------
@@ -1195,6 +1236,8 @@ extern "C" int dfb_plan_run(dfb_plan* pl)
 		CK(ctx, cudaEventRecord(pl->ev[2], ctx->stream));
 		pl->run_timed = true;
 	}
+	if (!pl->done_ev) CK(ctx, cudaEventCreateWithFlags(&pl->done_ev, cudaEventDisableTiming));
+	CK(ctx, cudaEventRecord(pl->done_ev, ctx->stream));
 	pl->ran = true;
 	return DFB_OK;
 }
@@ -1296,15 +1339,19 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 	if (!pl->ran) return set_err(ctx, DFB_ERR_STATE, "dfb_split_plan_fetch before dfb_plan_run");
 	CK(ctx, cudaSetDevice(ctx->device));
 	Trace tr;
+	// result copies run on the copy stream, ordered behind this plan's kernels only (later batches may
+	// already be queued on the compute stream)
+	cudaStream_t cs = ctx->copy_stream;
+	CK(ctx, cudaStreamWaitEvent(cs, pl->done_ev, 0));
 
 	// 1. counters: overflow-list length and winning tasks per class
 	int h_ctrl[kNumClasses * 4];
 	unsigned long long n_ov = 0;
 	for (int attempt = 0;; attempt++)
 	{
-		CK(ctx, cudaMemcpyAsync(&n_ov, pl->d_ev_count, sizeof(n_ov), cudaMemcpyDeviceToHost, ctx->stream));
-		CK(ctx, cudaMemcpyAsync(h_ctrl, pl->d_ctrl, sizeof(h_ctrl), cudaMemcpyDeviceToHost, ctx->stream));
-		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		CK(ctx, cudaMemcpyAsync(&n_ov, pl->d_ev_count, sizeof(n_ov), cudaMemcpyDeviceToHost, cs));
+		CK(ctx, cudaMemcpyAsync(h_ctrl, pl->d_ctrl, sizeof(h_ctrl), cudaMemcpyDeviceToHost, cs));
+		CK(ctx, cudaStreamSynchronize(cs));
 		if (n_ov <= pl->ev_cap) break;
 		if (attempt >= 2) return set_err(ctx, DFB_ERR_STATE, "event buffer overflow persists");
 		// the probe sweep found more arg-max columns than the overflow list holds: size it exactly, redo the sweep
@@ -1314,6 +1361,8 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 		if (e != cudaSuccess) return set_err(ctx, DFB_ERR_NOMEM, "event buffer of %llu entries: %s", pl->ev_cap, cudaGetErrorString(e));
 		int rc = run_probe(pl);
 		if (rc) return rc;
+		CK(ctx, cudaEventRecord(pl->done_ev, ctx->stream));
+		CK(ctx, cudaStreamWaitEvent(cs, pl->done_ev, 0));
 	}
 	// slots are numbered class by class in job space (the first sweep wrote task -> slot with that numbering)
 	int64_t hits_cls[kNumClasses], n_slots = 0, n_slot_space = 0;
@@ -1345,22 +1394,22 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 	int64_t d2h = 0;
 	if (pl->n_tasks)
 	{
-		CK(ctx, cudaMemcpyAsync(h_best, pl->d_out, (size_t)pl->n_tasks * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(ctx, cudaMemcpyAsync((void*)slot_of, pl->d_task_slot, (size_t)pl->n_tasks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(h_best, pl->d_out, (size_t)pl->n_tasks * 4, cudaMemcpyDeviceToHost, cs));
+		CK(ctx, cudaMemcpyAsync((void*)slot_of, pl->d_task_slot, (size_t)pl->n_tasks * 4, cudaMemcpyDeviceToHost, cs));
 		d2h += pl->n_tasks * 8;
 	}
 	for (int c = 0; c < kNumClasses; c++)
 	{
 		if (!hits_cls[c]) continue;
 		const ClassWork& cw = pl->cls[c];
-		CK(ctx, cudaMemcpyAsync(h_n + pl->job_base[c], cw.d_slot_n, (size_t)hits_cls[c] * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(h_n + pl->job_base[c], cw.d_slot_n, (size_t)hits_cls[c] * 4, cudaMemcpyDeviceToHost, cs));
 		CK(ctx, cudaMemcpyAsync(h_ev + pl->job_base[c] * DFB_SLOT_EVENTS, cw.d_slot_ev,
-		                        (size_t)hits_cls[c] * DFB_SLOT_EVENTS * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+		                        (size_t)hits_cls[c] * DFB_SLOT_EVENTS * sizeof(uint2), cudaMemcpyDeviceToHost, cs));
 		d2h += hits_cls[c] * (int64_t)(4 + DFB_SLOT_EVENTS * sizeof(uint2));
 	}
-	if (n_ov) CK(ctx, cudaMemcpyAsync(h_ov, pl->d_events, (size_t)n_ov * sizeof(Event), cudaMemcpyDeviceToHost, ctx->stream));
+	if (n_ov) CK(ctx, cudaMemcpyAsync(h_ov, pl->d_events, (size_t)n_ov * sizeof(Event), cudaMemcpyDeviceToHost, cs));
 	d2h += (int64_t)(n_ov * sizeof(Event));
-	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	CK(ctx, cudaStreamSynchronize(cs));
 	pl->stats.d2h_bytes = d2h;
 	pl->stats.probe_jobs = n_slots;
 	tr.lap("split.fetch: d2h");
@@ -1518,8 +1567,16 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 		tot_rows += ctx->asm_chunks[k].n_rows;
 		tot_cols += ctx->asm_chunks[k].n_cols;
 	}
-	if (pl->rows.cap < ctx->spare_rows.cap) pl->rows.swap(ctx->spare_rows);
-	if (pl->cols.cap < ctx->spare_cols.cap) pl->cols.swap(ctx->spare_cols);
+	if (pl->result_slot >= 0)
+	{
+		if (pl->rows.cap < ctx->chunk_rows[pl->result_slot].cap) pl->rows.swap(ctx->chunk_rows[pl->result_slot]);
+		if (pl->cols.cap < ctx->chunk_cols[pl->result_slot].cap) pl->cols.swap(ctx->chunk_cols[pl->result_slot]);
+	}
+	else
+	{
+		if (pl->rows.cap < ctx->spare_rows.cap) pl->rows.swap(ctx->spare_rows);
+		if (pl->cols.cap < ctx->spare_cols.cap) pl->cols.swap(ctx->spare_cols);
+	}
 	if (!pl->rows.ensure(tot_rows) || !pl->cols.ensure(tot_cols)) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
 	parallel_for(T, [&](int k) {
 		const AsmChunk& c = ctx->asm_chunks[k];
@@ -1583,6 +1640,103 @@ extern "C" int dfb_simple_align_batch(dfb_ctx* ctx, const dfb_simple_params* par
 	return rc;
 }
 
+// Large batches whose task_read is non-decreasing (the usual case: reads are listed in task order) are cut
+// into chunks that flow through the GPU back to back while the host builds the next chunk and assembles the
+// previous one.  Results are merged into one task-ordered row list.
+static const int64_t kPipelineMinTasks = 1 << 18;
+
+static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
+                                 const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
+                                 const int32_t* task_min_score, int64_t n_tasks, int32_t* out_best)
+{
+	const int K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), n_tasks / 400000));
+	std::vector<dfb_plan*> plans((size_t)K, nullptr);
+	std::vector<int64_t> t0((size_t)K + 1);
+	for (int k = 0; k <= K; k++) t0[k] = n_tasks * k / K;
+	int rc = DFB_OK;
+	auto fetch = [&](int k) -> int {
+		return dfb_split_plan_fetch(plans[k], out_best ? out_best + t0[k] : nullptr, nullptr, nullptr);
+	};
+	for (int k = 0; k < K && !rc; k++)
+	{
+		const int64_t a = t0[k], b = t0[k + 1];
+		const int32_t r_lo = task_read[a], r_hi = task_read[b - 1] + 1;
+		if (r_lo < 0 || r_hi > reads->n)
+		{
+			rc = set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)a);
+			break;
+		}
+		dfb_seq_table view{reads->bytes, reads->off + r_lo, (int64_t)(r_hi - r_lo)};
+		rc = split_plan_create_impl(ctx, params, refs, &view, task_cluster + a, task_read + a, task_min_score + a, b - a, r_lo, k,
+		                            true, &plans[k]);
+		if (rc) break;
+		plans[k]->result_slot = k;
+		rc = dfb_plan_run(plans[k]);
+		if (!rc && k >= 1) rc = fetch(k - 1);
+	}
+	if (!rc) rc = fetch(K - 1);
+	dfb_plan* holder = nullptr;
+	if (!rc)
+	{
+		holder = new (std::nothrow) dfb_plan();
+		if (!holder) rc = set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
+	}
+	if (!rc)
+	{
+		holder->ctx = ctx;
+		holder->split = true;
+		holder->n_tasks = n_tasks;
+		std::vector<size_t> row_base((size_t)K), col_base((size_t)K);
+		size_t n_rows = 0, n_cols = 0;
+		for (int k = 0; k < K; k++)
+		{
+			row_base[k] = n_rows;
+			col_base[k] = n_cols;
+			n_rows += plans[k]->rows.size();
+			n_cols += plans[k]->cols.size();
+		}
+		if (holder->rows.cap < ctx->spare_rows.cap) holder->rows.swap(ctx->spare_rows);
+		if (holder->cols.cap < ctx->spare_cols.cap) holder->cols.swap(ctx->spare_cols);
+		if (!holder->rows.ensure(n_rows) || !holder->cols.ensure(n_cols))
+		{
+			rc = set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
+		}
+		else
+		{
+			// every chunk is split over a few threads: rows need their task and column offsets shifted
+			const int per = std::max(1, ctx->host_threads / K);
+			parallel_for(K * per, [&](int id) {
+				const int k = id / per, part = id % per;
+				const dfb_plan* p = plans[k];
+				const size_t nr = p->rows.size(), r0 = nr * part / per, r1 = nr * (part + 1) / per;
+				dfb_split_row* dst = holder->rows.data() + row_base[k];
+				const int32_t task_shift = (int32_t)t0[k];
+				const int64_t col_shift = (int64_t)col_base[k];
+				for (size_t r = r0; r < r1; r++)
+				{
+					dfb_split_row row = p->rows.p[r];
+					row.task += task_shift;
+					row.col_begin += col_shift;
+					dst[r] = row;
+				}
+				const size_t nc = p->cols.size(), c0 = nc * part / per, c1 = nc * (part + 1) / per;
+				if (c1 > c0) memcpy(holder->cols.data() + col_base[k] + c0, p->cols.p + c0, (c1 - c0) * 4);
+			});
+			holder->fetched = true;
+			holder->ran = true;
+		}
+	}
+	for (int k = 0; k < K; k++)
+		if (plans[k]) dfb_plan_destroy(plans[k]);
+	if (rc)
+	{
+		if (holder) dfb_plan_destroy(holder);
+		return rc;
+	}
+	ctx->last_split = holder;
+	return DFB_OK;
+}
+
 extern "C" int dfb_split_align_batch(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
                                      const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
                                      const int32_t* task_min_score, int64_t n_tasks, int32_t* out_best)
@@ -1592,6 +1746,19 @@ extern "C" int dfb_split_align_batch(dfb_ctx* ctx, const dfb_split_params* param
 	{
 		dfb_plan_destroy(ctx->last_split);
 		ctx->last_split = nullptr;
+	}
+	int64_t pipeline_min = kPipelineMinTasks;
+	if (const char* e = getenv("DFB_PIPELINE_MIN_TASKS")) pipeline_min = std::max<long long>(2, atoll(e)); // tests
+	if (n_tasks >= pipeline_min && params && refs && reads && task_cluster && task_read && task_min_score)
+	{
+		int rc;
+		if ((rc = check_table(ctx, refs, "refs")) || (rc = check_table(ctx, reads, "reads"))) return rc;
+		if (refs->n & 1) return set_err(ctx, DFB_ERR_ARG, "refs must hold two windows per cluster (n is odd)");
+		if (n_tasks > 0x7fffff00LL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
+		bool monotone = true;
+		for (int64_t t = 1; t < n_tasks && monotone; t++) monotone = task_read[t] >= task_read[t - 1];
+		if (monotone)
+			return split_align_pipelined(ctx, params, refs, reads, task_cluster, task_read, task_min_score, n_tasks, out_best);
 	}
 	dfb_plan* pl = nullptr;
 	int rc = dfb_split_plan_create(ctx, params, refs, reads, task_cluster, task_read, task_min_score, n_tasks, &pl);

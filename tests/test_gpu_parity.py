@@ -234,3 +234,30 @@ def test_large_simple_batch_sampled_parity(oracle_mod, gpu_ctx):
     want = oracle_mod.simple_align_batch(10, -5, -5, w["ref_bytes"], w["ref_off"], w["seq_bytes"], w["seq_off"],
                                          w["task_ref"][sample], w["task_seq"][sample])
     assert np.array_equal(got[sample], want)
+
+
+def test_pipelined_one_call_path(oracle_mod, gpu_ctx, monkeypatch):
+    """dfb_split_align_batch cuts large batches (non-decreasing task_read) into chunks that overlap host and GPU work;
+    forced here on a small batch.  Results must equal the single-plan path and the oracle, including shared reads
+    across a chunk boundary, empty reads and the generic (s32) path."""
+    import defuse_b200 as d
+    rng = np.random.default_rng(31)
+    refs, reads, tc, trd = util.split_batch(rng, 40, 25, (0, 120), 60, 400, sub=0.02, indel=0.005, n_rate=0.01)
+    # several tasks per read (same read against neighbouring clusters), still non-decreasing
+    tc = np.concatenate([tc, (tc + 1) % 40]).astype(np.int32)
+    trd = np.concatenate([trd, trd]).astype(np.int32)
+    order = np.argsort(trd, kind="stable")
+    tc, trd = tc[order], trd[order]
+    ms = np.array([d.split_min_score(len(reads[r])) for r in trd], np.int32)
+    rt, st = _tables(refs, reads)
+    al = d.SplitReadAligner(ctx=gpu_ctx)
+    single = al.align_batch(rt, st, tc, trd, ms)
+    monkeypatch.setenv("DFB_PIPELINE_MIN_TASKS", "16")
+    piped = al.align_batch(rt, st, tc, trd, ms)
+    assert np.array_equal(piped.best, single.best)
+    assert np.array_equal(piped.rows, single.rows) and np.array_equal(piped.cols, single.cols)
+    _check_split(oracle_mod, gpu_ctx, refs, reads, tc, trd, ms)                       # pipelined vs oracle
+    _check_split(oracle_mod, gpu_ctx, refs, reads, tc, trd, ms, (2, -1, -2, True, 0))   # generic kernels, pipelined
+    # a batch whose task_read decreases somewhere falls back to the single plan
+    back = al.align_batch(rt, st, tc[::-1].copy(), trd[::-1].copy(), ms[::-1].copy())
+    assert np.array_equal(back.best, single.best[::-1])
