@@ -16,7 +16,10 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -78,10 +81,86 @@ struct HostArr
 	const T* data() const { return p; }
 };
 
+// Persistent host workers of a context: the batch path runs a dozen short parallel loops per call, and
+// spawning threads for each of them costs more than the loops.
+class HostPool
+{
+public:
+	explicit HostPool(int n_threads)
+	{
+		for (int k = 1; k < n_threads; k++) mWorkers.emplace_back([this, k] { Work(k); });
+	}
+	~HostPool()
+	{
+		{
+			std::lock_guard<std::mutex> lk(mMutex);
+			mStop = true;
+			mGeneration++;
+		}
+		mStart.notify_all();
+		for (auto& t : mWorkers) t.join();
+	}
+	int Size() const { return (int)mWorkers.size() + 1; }
+	// runs fn(0..T-1) on T threads (the caller is thread 0) and waits for all of them
+	void Run(int T, const std::function<void(int)>& fn)
+	{
+		T = std::max(1, std::min(T, Size()));
+		if (T == 1) { fn(0); return; }
+		{
+			std::lock_guard<std::mutex> lk(mMutex);
+			mFn = &fn;
+			mActive = T;
+			mPending = T - 1;
+			mGeneration++;
+		}
+		mStart.notify_all();
+		fn(0);
+		std::unique_lock<std::mutex> lk(mMutex);
+		mDone.wait(lk, [this] { return mPending == 0; });
+		mFn = nullptr;
+	}
+
+private:
+	void Work(int k)
+	{
+		long long seen = 0;
+		for (;;)
+		{
+			const std::function<void(int)>* fn = nullptr;
+			{
+				std::unique_lock<std::mutex> lk(mMutex);
+				mStart.wait(lk, [&] { return mGeneration != seen; });
+				seen = mGeneration;
+				if (mStop) return;
+				if (k < mActive) fn = mFn;
+			}
+			if (fn)
+			{
+				(*fn)(k);
+				std::lock_guard<std::mutex> lk(mMutex);
+				if (--mPending == 0) mDone.notify_one();
+			}
+		}
+	}
+	std::vector<std::thread> mWorkers;
+	std::mutex mMutex;
+	std::condition_variable mStart, mDone;
+	const std::function<void(int)>* mFn = nullptr;
+	long long mGeneration = 0;
+	int mActive = 0, mPending = 0;
+	bool mStop = false;
+};
+
 template <class F>
-static void parallel_for(int T, F fn)
+static void parallel_for(HostPool* pool, int T, F fn)
 {
 	if (T <= 1) { fn(0); return; }
+	if (pool && T <= pool->Size())
+	{
+		const std::function<void(int)> f = fn;
+		pool->Run(T, f);
+		return;
+	}
 	std::vector<std::thread> th;
 	th.reserve((size_t)T - 1);
 	for (int k = 1; k < T; k++) th.emplace_back(fn, k);
@@ -107,6 +186,8 @@ struct dfb_ctx
 	PinnedBuf h_in[kStageSlots]; // host-built descriptors and job lists, on their way to the device (one per batch chunk in flight)
 	PinnedBuf h_out;             // results on their way back
 	cudaStream_t copy_stream = nullptr; // device->host result copies, ordered after a plan's kernels by an event
+	cudaStream_t upload_stream = nullptr; // uploads + packing of the next chunk of a pipelined batch
+	HostPool* pool = nullptr;
 	dfb_plan* last_split = nullptr; // result holder of dfb_split_align_batch
 	int host_threads = 1;
 	// recycled host memory of the result assembly (kept mapped between batches)
@@ -214,7 +295,8 @@ extern "C" int dfb_ctx_create(int device_ordinal, dfb_ctx** out)
 		return set_err(nullptr, DFB_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(e));
 	}
 	ctx->stream = ctx->own_stream;
-	if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+	if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking)) != cudaSuccess)
 	{
 		cudaStreamDestroy(ctx->own_stream);
 		delete ctx;
@@ -229,6 +311,7 @@ extern "C" int dfb_ctx_create(int device_ordinal, dfb_ctx** out)
 	}
 	unsigned hc = std::thread::hardware_concurrency();
 	ctx->host_threads = (int)std::max(1u, std::min(hc ? hc : 1u, 16u));
+	ctx->pool = new (std::nothrow) HostPool(ctx->host_threads);
 	*out = ctx;
 	return DFB_OK;
 }
@@ -242,6 +325,8 @@ extern "C" void dfb_ctx_destroy(dfb_ctx* ctx)
 	for (auto& b : ctx->h_in) b.release();
 	ctx->h_out.release();
 	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+	if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+	delete ctx->pool;
 	ctx->spare_rows.release();
 	ctx->spare_cols.release();
 	ctx->slot_of.release();
@@ -399,6 +484,8 @@ struct dfb_plan
 	bool run_timed = false;
 	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 	cudaEvent_t done_ev = nullptr; // recorded behind the last kernel of dfb_plan_run
+	cudaStream_t up = nullptr;     // stream of the upload + pack work (the compute stream unless pipelined)
+	cudaEvent_t packed_ev = nullptr; // recorded behind the pack kernels when `up` is not the compute stream
 	int result_slot = -1;          // chunk of a pipelined batch: which recycled result arrays of the ctx to use
 	dfb_plan_stats stats{};
 };
@@ -471,6 +558,7 @@ extern "C" void dfb_plan_destroy(dfb_plan* plan)
 		}
 	}
 	if (plan->done_ev) cudaEventDestroy(plan->done_ev);
+	if (plan->packed_ev) cudaEventDestroy(plan->packed_ev);
 	plan->rows.release();
 	plan->cols.release();
 	for (int k = 0; k < 3; k++)
@@ -585,11 +673,12 @@ static uint32_t layout_words(const dfb_seq_table* a, int mode_a, const dfb_seq_t
 static int upload_raw(dfb_plan* pl, const dfb_seq_table* a, const dfb_seq_table* b)
 {
 	dfb_ctx* ctx = pl->ctx;
+	cudaStream_t up = pl->up ? pl->up : ctx->stream;
 	const int64_t na = a->off[a->n] - a->off[0], nb = b->off[b->n] - b->off[0];
 	// 16 bytes of slack in front, 32 behind (the pack kernel reads whole 16-byte windows)
-	DALLOC(ctx, pl->d_raw, (size_t)(na + nb + 48));
-	if (na) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16, a->bytes + a->off[0], (size_t)na, cudaMemcpyHostToDevice, ctx->stream));
-	if (nb) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16 + na, b->bytes + b->off[0], (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+	CK(ctx, cudaMallocAsync((void**)&pl->d_raw, std::max<size_t>(256, (size_t)(na + nb + 48)), up));
+	if (na) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16, a->bytes + a->off[0], (size_t)na, cudaMemcpyHostToDevice, up));
+	if (nb) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16 + na, b->bytes + b->off[0], (size_t)nb, cudaMemcpyHostToDevice, up));
 	return DFB_OK;
 }
 
@@ -597,14 +686,15 @@ static int upload_and_pack(dfb_plan* pl, const dfb_seq_table* a, int mode_a, con
                            const Staging& st, uint32_t words_a_end, uint32_t total_words)
 {
 	dfb_ctx* ctx = pl->ctx;
+	cudaStream_t up = pl->up ? pl->up : ctx->stream;
 	const int64_t na = a->off[a->n] - a->off[0], nb = b->off[b->n] - b->off[0];
-	DALLOC(ctx, pl->d_stage, st.total);
-	CK(ctx, cudaMemcpyAsync(pl->d_stage, st.host, st.total, cudaMemcpyHostToDevice, ctx->stream));
-	DALLOC(ctx, pl->d_pool, ((size_t)total_words + 2) * sizeof(uint2));
-	DALLOC(ctx, pl->d_obytes, ((size_t)total_words + 2) * 16);
+	CK(ctx, cudaMallocAsync((void**)&pl->d_stage, std::max<size_t>(256, st.total), up));
+	CK(ctx, cudaMemcpyAsync(pl->d_stage, st.host, st.total, cudaMemcpyHostToDevice, up));
+	CK(ctx, cudaMallocAsync((void**)&pl->d_pool, ((size_t)total_words + 2) * sizeof(uint2), up));
+	CK(ctx, cudaMallocAsync((void**)&pl->d_obytes, ((size_t)total_words + 2) * 16, up));
 	for (int k = 0; k < 3; k++)
 		if (!pl->ev[k]) CK(ctx, cudaEventCreate(&pl->ev[k]));
-	CK(ctx, cudaEventRecord(pl->ev[0], ctx->stream));
+	CK(ctx, cudaEventRecord(pl->ev[0], up));
 	const SeqDesc* d_da = (const SeqDesc*)(pl->d_stage + st.off_desc_a);
 	const SeqDesc* d_db = (const SeqDesc*)(pl->d_stage + st.off_desc_b);
 	const int max_grid = ctx->prop.multiProcessorCount * 16;
@@ -612,17 +702,22 @@ static int upload_and_pack(dfb_plan* pl, const dfb_seq_table* a, int mode_a, con
 		if (n == 0 || w1 <= w0) return cudaSuccess;
 		const int grid = (int)std::min<uint32_t>((w1 - w0 + 255) / 256, (uint32_t)max_grid);
 		if (mode == PACK_FWD)
-			pack_kernel<PACK_FWD><<<grid, 256, 0, ctx->stream>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
+			pack_kernel<PACK_FWD><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
 		else if (mode == PACK_REV_ODD)
-			pack_kernel<PACK_REV_ODD><<<grid, 256, 0, ctx->stream>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
+			pack_kernel<PACK_REV_ODD><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
 		else
-			pack_kernel<PACK_BOTH><<<grid, 256, 0, ctx->stream>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
+			pack_kernel<PACK_BOTH><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
 		return cudaGetLastError();
 	};
 	CK(ctx, launch(mode_a, d_da, a->n, 0, words_a_end));
 	CK(ctx, launch(mode_b, d_db, b->n, words_a_end, total_words));
-	CK(ctx, cudaEventRecord(pl->ev[1], ctx->stream));
+	CK(ctx, cudaEventRecord(pl->ev[1], up));
 	pl->pack_timed = true;
+	if (up != ctx->stream)
+	{
+		if (!pl->packed_ev) CK(ctx, cudaEventCreateWithFlags(&pl->packed_ev, cudaEventDisableTiming));
+		CK(ctx, cudaEventRecord(pl->packed_ev, up));
+	}
 	pl->stats.h2d_bytes += na + nb + (int64_t)st.total;
 	pl->stats.raw_bytes = na * (mode_a == PACK_BOTH ? 2 : 1) + nb * (mode_b == PACK_BOTH ? 2 : 1);
 	pl->stats.packed_bytes = (int64_t)total_words * 8;
@@ -902,6 +997,7 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 	pl->n_tasks = n_tasks;
 	pl->stats.n_tasks = n_tasks;
 	classify_params(pl, params->match, params->mismatch, params->gap, params->end_gaps == 0 && params->min_split_score >= 1);
+	pl->up = async ? ctx->upload_stream : nullptr;
 	if ((rc = upload_raw(pl, refs, reads)))
 	{
 		dfb_plan_destroy(pl);
@@ -922,7 +1018,7 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 		uint32_t cls_max_R[kNumClasses] = {0};
 	};
 	std::vector<Part> part((size_t)T);
-	parallel_for(T, [&](int tid) {
+	parallel_for(ctx->pool, T, [&](int tid) {
 		const int64_t t0 = n_tasks * tid / T, t1 = n_tasks * (tid + 1) / T;
 		Part& pt = part[tid];
 		int64_t* cnt = bin_pos.data() + n_bins * (size_t)tid;
@@ -1017,7 +1113,7 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 	}
 	tr.lap("split.create: layout");
 	// pass 2 (host threads): every task into its job slot
-	parallel_for(T, [&](int tid) {
+	parallel_for(ctx->pool, T, [&](int tid) {
 		const int64_t t0 = n_tasks * tid / T, t1 = n_tasks * (tid + 1) / T;
 		int64_t* pos = bin_pos.data() + n_bins * (size_t)tid;
 		for (int64_t t = t0; t < t1; t++)
@@ -1180,6 +1276,7 @@ extern "C" int dfb_plan_run(dfb_plan* pl)
 	pl->stats.kernel_launches = 0;
 	pl->fetched = false;
 	pl->run_timed = false;
+	if (pl->packed_ev) CK(ctx, cudaStreamWaitEvent(ctx->stream, pl->packed_ev, 0));
 	if (pl->timing)
 	{
 		for (int k = 0; k < 3; k++)
@@ -1428,7 +1525,7 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 	if ((int)ctx->asm_chunks.size() < T) ctx->asm_chunks.resize((size_t)T);
 	std::vector<int64_t> ev_part((size_t)T, 0);
 	bool oom = false;
-	parallel_for(T, [&](int tid) {
+	parallel_for(ctx->pool, T, [&](int tid) {
 		const int64_t t0 = pl->n_tasks * tid / T, t1 = pl->n_tasks * (tid + 1) / T;
 		AsmChunk& out = ctx->asm_chunks[tid];
 		// upper bounds for this task range: every event is one column; a row needs two events
@@ -1578,7 +1675,7 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 		if (pl->cols.cap < ctx->spare_cols.cap) pl->cols.swap(ctx->spare_cols);
 	}
 	if (!pl->rows.ensure(tot_rows) || !pl->cols.ensure(tot_cols)) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
-	parallel_for(T, [&](int k) {
+	parallel_for(ctx->pool, T, [&](int k) {
 		const AsmChunk& c = ctx->asm_chunks[k];
 		dfb_split_row* dst = pl->rows.data() + row_base[k];
 		const int64_t cb = (int64_t)col_base[k];
@@ -1705,7 +1802,7 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 		{
 			// every chunk is split over a few threads: rows need their task and column offsets shifted
 			const int per = std::max(1, ctx->host_threads / K);
-			parallel_for(K * per, [&](int id) {
+			parallel_for(ctx->pool, K * per, [&](int id) {
 				const int k = id / per, part = id % per;
 				const dfb_plan* p = plans[k];
 				const size_t nr = p->rows.size(), r0 = nr * part / per, r1 = nr * (part + 1) / per;
