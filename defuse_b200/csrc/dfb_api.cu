@@ -426,12 +426,13 @@ struct ClassWork
 {
 	int64_t n_jobs = 0;
 	JobPair* d_jobs = nullptr; // inside the plan's staged upload
-	int* d_ctrl = nullptr;     // [0] cursor, [1] hit_count, [2] probe cursor (inside plan->d_ctrl)
+	int* d_ctrl = nullptr;     // [0] cursor, [1] short-window hits, [2] probe cursor, [3] long-window hits (inside plan->d_ctrl)
 	int* d_hitq = nullptr;
 	int32_t* d_slot_task = nullptr;
 	int* d_slot_n = nullptr;
 	uint2* d_slot_ev = nullptr;
 	uint32_t* d_ntg = nullptr;
+	uint32_t* d_rdq = nullptr;
 	uint32_t* d_ckpt = nullptr;    // wavefront checkpoints of the first sweep (probe windows resume from them)
 	uint32_t* d_slot_rng = nullptr;
 	int ckpt_blocks = 0;
@@ -525,6 +526,7 @@ static void release_device(dfb_plan* plan)
 		dfree(ctx, cw.d_slot_n);
 		dfree(ctx, cw.d_slot_ev);
 		dfree(ctx, cw.d_ntg);
+		dfree(ctx, cw.d_rdq);
 		dfree(ctx, cw.d_ckpt);
 		dfree(ctx, cw.d_slot_rng);
 	}
@@ -741,6 +743,7 @@ static void fill_fast_params(dfb_plan* pl, int c, int m, int x, int g, int min_s
 	fp.min_split = min_split;
 	fp.out = pl->d_out;
 	fp.hit_count = cw.d_ctrl + 1;
+	fp.hit_count_long = cw.d_ctrl + 3;
 	fp.hitq = cw.d_hitq;
 	fp.slot_task = cw.d_slot_task;
 	fp.task_slot = pl->d_task_slot;
@@ -748,6 +751,7 @@ static void fill_fast_params(dfb_plan* pl, int c, int m, int x, int g, int min_s
 	fp.slot_ev = cw.d_slot_ev;
 	fp.slot_n = cw.d_slot_n;
 	fp.ntg = cw.d_ntg;
+	fp.rdq = cw.d_rdq;
 	fp.ckpt = cw.d_ckpt;
 	fp.ckpt_blocks = cw.ckpt_blocks;
 	fp.slot_rng = cw.d_slot_rng;
@@ -780,6 +784,7 @@ static int alloc_work(dfb_plan* pl, const Staging& st, const int64_t* n_jobs_cls
 			DALLOC(ctx, cw.d_slot_n, n * sizeof(int));
 			DALLOC(ctx, cw.d_slot_ev, n * DFB_SLOT_EVENTS * sizeof(uint2));
 			DALLOC(ctx, cw.d_ntg, n * (size_t)kClasses[c].G * kClasses[c].S * sizeof(uint32_t));
+			DALLOC(ctx, cw.d_rdq, n * (size_t)kClasses[c].G * kClasses[c].S * sizeof(uint32_t));
 			DALLOC(ctx, cw.d_slot_rng, n * sizeof(uint32_t));
 			// checkpoints every CK = 4G steps of the wavefront (R + G - 1 steps)
 			const int G = kClasses[c].G, CK = 4 * G;
@@ -1462,11 +1467,12 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 		CK(ctx, cudaStreamWaitEvent(cs, pl->done_ev, 0));
 	}
 	// slots are numbered class by class in job space (the first sweep wrote task -> slot with that numbering)
-	int64_t hits_cls[kNumClasses], n_slots = 0, n_slot_space = 0;
+	int64_t hits_cls[kNumClasses], hits_long[kNumClasses], n_slots = 0, n_slot_space = 0;
 	for (int c = 0; c < kNumClasses; c++)
 	{
-		hits_cls[c] = pl->cls[c].n_jobs ? h_ctrl[4 * c + 1] : 0;
-		n_slots += hits_cls[c];
+		hits_cls[c] = pl->cls[c].n_jobs ? h_ctrl[4 * c + 1] : 0;  // slots 0 .. hits-1 of the class
+		hits_long[c] = pl->cls[c].n_jobs ? h_ctrl[4 * c + 3] : 0; // slots n_jobs-hits_long .. n_jobs-1
+		n_slots += hits_cls[c] + hits_long[c];
 		n_slot_space = std::max<int64_t>(n_slot_space, pl->job_base[c] + pl->cls[c].n_jobs);
 	}
 
@@ -1497,12 +1503,17 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 	}
 	for (int c = 0; c < kNumClasses; c++)
 	{
-		if (!hits_cls[c]) continue;
 		const ClassWork& cw = pl->cls[c];
-		CK(ctx, cudaMemcpyAsync(h_n + pl->job_base[c], cw.d_slot_n, (size_t)hits_cls[c] * 4, cudaMemcpyDeviceToHost, cs));
-		CK(ctx, cudaMemcpyAsync(h_ev + pl->job_base[c] * DFB_SLOT_EVENTS, cw.d_slot_ev,
-		                        (size_t)hits_cls[c] * DFB_SLOT_EVENTS * sizeof(uint2), cudaMemcpyDeviceToHost, cs));
-		d2h += hits_cls[c] * (int64_t)(4 + DFB_SLOT_EVENTS * sizeof(uint2));
+		const int64_t first[2] = {0, cw.n_jobs - hits_long[c]}, count[2] = {hits_cls[c], hits_long[c]};
+		for (int part = 0; part < 2; part++)
+		{
+			if (!count[part]) continue;
+			const int64_t lo = first[part], n = count[part];
+			CK(ctx, cudaMemcpyAsync(h_n + pl->job_base[c] + lo, cw.d_slot_n + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
+			CK(ctx, cudaMemcpyAsync(h_ev + (pl->job_base[c] + lo) * DFB_SLOT_EVENTS, cw.d_slot_ev + lo * DFB_SLOT_EVENTS,
+			                        (size_t)n * DFB_SLOT_EVENTS * sizeof(uint2), cudaMemcpyDeviceToHost, cs));
+			d2h += n * (int64_t)(4 + DFB_SLOT_EVENTS * sizeof(uint2));
+		}
 	}
 	if (n_ov) CK(ctx, cudaMemcpyAsync(h_ov, pl->d_events, (size_t)n_ov * sizeof(Event), cudaMemcpyDeviceToHost, cs));
 	d2h += (int64_t)(n_ov * sizeof(Event));

@@ -166,9 +166,11 @@ struct FastParams
 	int min_split;   // SPLIT: minSplitScore
 	// outputs
 	int32_t* out;    // SIMPLE: score per task.  SPLIT: best per task
-	int* hit_count;  // SPLIT (write) / PROBE (read): number of queued tasks
+	int* hit_count;  // SPLIT (write) / PROBE (read): queued tasks with a one-block window (slots from the front)
+	int* hit_count_long; // ... with a longer window (slots from the back), so that a warp's job pairs run equally long
 	int* hitq;       // job index per queue slot
 	uint32_t* ntg;   // [slot][S][G] negated row-max targets (or "row disabled")
+	uint32_t* rdq;   // [slot][S][G] the lanes' (negated) read symbols, so that the probe does not decode them again
 	uint32_t* ckpt;  // [job][ckpt_blocks][S+2][G] wavefront state (F[S], prev, Flast) in front of every CH-th step (null: off)
 	int ckpt_blocks; // checkpoints per job in this launch
 	int slot_base;   // SPLIT: first global slot number of this class (slots are numbered class by class)
@@ -241,7 +243,8 @@ struct FastOcc
 {
 	static constexpr int kArrays = (MODE == MODE_SPLIT) ? 5 : (MODE == MODE_PROBE ? 3 : 2);
 	static constexpr int kEst = kArrays * S + 48;
-	static constexpr int kMinBlocks = kEst <= 128 ? 4 : (kEst <= 168 ? 3 : (kEst <= 255 ? 2 : 1));
+	static constexpr int kMinBlocks =
+	    (MODE == MODE_PROBE && kEst <= 96) ? 5 : (kEst <= 128 ? 4 : (kEst <= 168 ? 3 : (kEst <= 255 ? 2 : 1)));
 };
 
 template <int G, int S, int MODE>
@@ -274,7 +277,12 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 	const uint32_t gm16 = p.gm2 & 0xFFFFu;
 
 	int n_items = p.n_jobs;
-	if (MODE == MODE_PROBE) n_items = *p.hit_count;
+	int n_short = 0;
+	if (MODE == MODE_PROBE)
+	{
+		n_short = *p.hit_count;
+		n_items = n_short + *p.hit_count_long;
+	}
 
 	for (;;)
 	{
@@ -282,8 +290,9 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		if (lane == 0) base = atomicAdd(p.cursor, NG);
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= n_items) break;
-		const int item = base + q;
-		const bool have = item < n_items;
+		const bool have = base + q < n_items;
+		// PROBE: queue position -> slot (short windows were queued from the front, long ones from the back)
+		const int item = (MODE == MODE_PROBE && base + q >= n_short) ? p.n_jobs - 1 - (base + q - n_short) : base + q;
 		int jid = 0;
 		JobPair jp;
 		jp.ref_w[0] = jp.ref_w[1] = jp.read_w[0] = jp.read_w[1] = 0;
@@ -295,37 +304,41 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			jp = p.jobs[jid];
 		}
 
-		// ---- stage the reads: pool words -> 16-bit fields -> S registers per lane ----
+		// ---- stage the reads: pool words -> 16-bit fields -> S registers per lane (the probe sweep gets them
+		//      from the first sweep instead) ----
 		__syncwarp();
-		for (int w = g; w < 2 * RDW; w += G)
+		if (MODE != MODE_PROBE)
 		{
-			const int h = w / RDW;
-			const int wi = w % RDW;
-			const uint32_t len = jp.L[h];
-			uint2 pw = make_uint2(0, 0);
-			const uint32_t widx = jp.read_w[h] + wi;
-			if ((uint32_t)wi * 16u < len) pw = __ldg(p.pool + widx);
-#pragma unroll 4
-			for (int n = 0; n < 16; n++)
+			for (int w = g; w < 2 * RDW; w += G)
 			{
-				const int pos = wi * 16 + n;
-				if (pos < ROWS)
+				const int h = w / RDW;
+				const int wi = w % RDW;
+				const uint32_t len = jp.L[h];
+				uint2 pw = make_uint2(0, 0);
+				const uint32_t widx = jp.read_w[h] + wi;
+				if ((uint32_t)wi * 16u < len) pw = __ldg(p.pool + widx);
+#pragma unroll 4
+				for (int n = 0; n < 16; n++)
 				{
-					uint32_t f = DFB_READ_PAD;
-					if ((uint32_t)pos < len) f = decode_base(pw, widx, n, p.obytes);
-					// stored negated: (-read + ref) mod 2^16 is 0 exactly on a match, so one
-					// VIADDMNMX.U16x2 (add, min with 1) yields the mismatch indicator
-					rows16[2 * pos + h] = (uint16_t)(0u - f);
+					const int pos = wi * 16 + n;
+					if (pos < ROWS)
+					{
+						uint32_t f = DFB_READ_PAD;
+						if ((uint32_t)pos < len) f = decode_base(pw, widx, n, p.obytes);
+						// stored negated: (-read + ref) mod 2^16 is 0 exactly on a match, so one
+						// VIADDMNMX.U16x2 (add, min with 1) yields the mismatch indicator
+						rows16[2 * pos + h] = (uint16_t)(0u - f);
+					}
 				}
 			}
+			__syncwarp();
 		}
-		__syncwarp();
 		uint32_t rd[S], F[S], X[S];
 		const int j0 = g * S; // rows owned: j0+1 .. j0+S
 #pragma unroll
 		for (int k = 0; k < S; k++)
 		{
-			rd[k] = rows[j0 + k];
+			rd[k] = (MODE == MODE_PROBE) ? (have ? p.rdq[((size_t)item * S + k) * G + g] : 0u) : rows[j0 + k];
 			// column i = 0: H(0,j) = j*gap  ->  stored value B + j*(gap - match)
 			const uint32_t v = (B + (uint32_t)(j0 + k + 1) * gm16) & 0xFFFFu;
 			F[k] = v | (v << 16);
@@ -399,9 +412,12 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			fill_ring_word(ring16, RING - 1, h_mine, pw, jp.ref_w[h_mine] + offw + wrel, (offw + wrel) * 16u, wrel * 16u, Rh,
 			               p.obytes);
 		};
+		// ring columns this warp will read: T steps, PRE columns in front of a resumed window
+		const int ring_blocks = min(2, (T + PRE + CH - 1) / CH);
 #pragma unroll 1
-		for (int blk = 0; blk < 2; blk++) fill_block(blk, load_block(blk));
-		uint2 pf = load_block(2);
+		for (int blk = 0; blk < ring_blocks; blk++) fill_block(blk, load_block(blk));
+		uint2 pf = make_uint2(0, 0);
+		if (T + PRE > 2 * CH) pf = load_block(2);
 		int blk_next = 2;
 		// one refill schedule for every group of the warp (valid for pre = 0 and pre = PRE: G-1+PRE <= CH)
 		static_assert(G - 1 + PRE <= CH, "ring refill schedule");
@@ -626,15 +642,18 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				p.out[jp.out0] = hit ? best : 0;
 				if (group_en)
 				{
-					slot = atomicAdd(p.hit_count, 1) + p.slot_base;
+					// one checkpoint block per half is the common case; longer windows go to the other end of the
+					// queue so that the job pairs of a probe warp sweep windows of similar length
+					f0 = min(f0, l0);
+					f1 = min(f1, l1);
+					const bool short_window = ck_on && f0 > 0 && f1 > 0 && l0 == f0 && l1 == f1;
+					slot = (short_window ? atomicAdd(p.hit_count, 1) : p.n_jobs - 1 - atomicAdd(p.hit_count_long, 1)) + p.slot_base;
 					p.hitq[slot - p.slot_base] = jid;
 					p.slot_task[slot - p.slot_base] = jp.out0;
 					p.task_slot[jp.out0] = slot;
 					uint32_t rng = 0xFF00FF00u; // no checkpoints: sweep everything
 					if (ck_on)
 					{
-						f0 = min(f0, l0);
-						f1 = min(f1, l1);
 						if (f0 == 0 || f1 == 0) f0 = f1 = 0; // a window that starts at step 0 starts both halves there
 						rng = (uint32_t)f0 | ((uint32_t)l0 << 8) | ((uint32_t)f1 << 16) | ((uint32_t)l1 << 24);
 					}
@@ -646,7 +665,11 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			if (group_en && have)
 			{
 #pragma unroll
-				for (int k = 0; k < S; k++) p.ntg[((size_t)slot * S + k) * G + g] = ntg[k];
+				for (int k = 0; k < S; k++)
+				{
+					p.ntg[((size_t)slot * S + k) * G + g] = ntg[k];
+					p.rdq[((size_t)slot * S + k) * G + g] = rd[k];
+				}
 			}
 		}
 	}
