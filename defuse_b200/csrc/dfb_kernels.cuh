@@ -17,6 +17,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace dfb
 {
@@ -434,7 +435,21 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		// the sweep, one checkpoint block (CK steps) at a time so that the per-block work (checkpoint,
 		// ring refill, row-maximum bookkeeping) stays out of the per-step instruction stream
 		const int act_off = resumed ? 0 : g; // lane g joins at step g unless the wavefront was restored
-		auto step = [&](const int u) {
+		constexpr int kEach = 0, kEven = 1, kOdd = 2;
+		// SPLIT: steps below the shorter reference of every job pair of the warp touch real columns only (lane g is at
+		// column u-g <= u), rounded down to a whole pair.  SIMPLE tolerates the padding columns: all steps.
+		int u_paired = T;
+		if (MODE == MODE_SPLIT)
+		{
+			u_paired = have ? min((int)jp.R[0], (int)jp.R[1]) : 0x7fffffff;
+#pragma unroll
+			for (int o = 16; o >= 1; o >>= 1) u_paired = min(u_paired, __shfl_xor_sync(0xffffffffu, u_paired, o));
+			u_paired &= ~1;
+		}
+		// sink kinds: kEach = fold the new column into the row state at every step; kEven/kOdd = the two steps of a
+		// pair, where the odd step folds both columns with one three-input max (half the sink issues)
+		auto step = [&](const int u, auto sink_kind) {
+			constexpr int SINK = decltype(sink_kind)::value;
 			uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G);
 			if (g == 0) recv = Bp;
 			const int b = u - g; // relative column; absolute column = off + b
@@ -444,19 +459,28 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				uint32_t left = recv;
 				uint32_t dg_in = prev;
 				uint32_t pen = 0;
-				if (MODE == MODE_SPLIT) pen = rf & 0x80008000u;
+				if (MODE == MODE_SPLIT && SINK == kEach) pen = rf & 0x80008000u;
 				if (MODE == MODE_PROBE) acc = 0x80008000u;
 #pragma unroll
 				for (int k = 0; k < S; k++)
 				{
 					const uint32_t d = __viaddmin_u16x2(rd[k], rf, 0x00010001u); // min(ref - read, 1): 1 per half on mismatch
 					const uint32_t dg = d * p.xm + dg_in;                         // diagonal: + (match ? 0 : x - m)
-					dg_in = F[k];
-					const uint32_t e = __viaddmax_s16x2(F[k], p.g2, dg);          // max(up + gap, diagonal)
+					const uint32_t fold = F[k];                                   // this row in the previous column
+					dg_in = fold;
+					const uint32_t e = __viaddmax_s16x2(fold, p.g2, dg);          // max(up + gap, diagonal)
 					left = __viaddmax_s16x2(left, p.gm2, e);                      // max(left + gap - m, e)
 					F[k] = left;
-					if (MODE == MODE_SPLIT) Y[k] = __viaddmax_s16x2(left, pen, Y[k]);
-					if (MODE == MODE_SIMPLE) acc = __viaddmax_s16x2(left, p.ck[k], acc);
+					if (MODE == MODE_SPLIT)
+					{
+						if (SINK == kEach) Y[k] = __viaddmax_s16x2(left, pen, Y[k]);
+						if (SINK == kOdd) Y[k] = __vimax3_s16x2(Y[k], fold, left);
+					}
+					if (MODE == MODE_SIMPLE)
+					{
+						if (SINK == kEach) acc = __viaddmax_s16x2(left, p.ck[k], acc);
+						if (SINK == kOdd) X[k] = __vimax3_s16x2(X[k], fold, left);
+					}
 					if (MODE == MODE_PROBE) acc = __viaddmax_s16x2(left, X[k], acc);
 				}
 				prev = recv;
@@ -505,18 +529,28 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			// ring block n+1 replaces ring block n-1 once every lane is past it (G-1 steps into ring block n >= 1);
 			// a ring block is CH/CK checkpoint blocks long
 			const int u_fill = (blkno >= CH / CK && blkno % (CH / CK) == 0) ? blkno * CK + G - 1 : -1;
+			auto refill = [&]() {
+				__syncwarp();
+				fill_block(blk_next, pf);
+				blk_next++;
+				pf = load_block(blk_next);
+				__syncwarp();
+			};
+			// paired steps while every lane's column is inside both references (no row-max masking needed)
+			const int u_pair_end = (MODE == MODE_PROBE) ? u : min(u_end, u_paired);
+#pragma unroll 1
+			for (; u + 1 < u_pair_end; u += 2)
+			{
+				if (u == u_fill) refill();
+				step(u, std::integral_constant<int, kEven>());
+				if (u + 1 == u_fill) refill();
+				step(u + 1, std::integral_constant<int, kOdd>());
+			}
 #pragma unroll 1
 			for (; u < u_end; u++)
 			{
-				if (u == u_fill)
-				{
-					__syncwarp();
-					fill_block(blk_next, pf);
-					blk_next++;
-					pf = load_block(blk_next);
-					__syncwarp();
-				}
-				step(u);
+				if (u == u_fill) refill();
+				step(u, std::integral_constant<int, kEach>());
 			}
 			if (MODE == MODE_SPLIT)
 			{
@@ -548,6 +582,10 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		// ---- epilogues ----
 		if (MODE == MODE_SIMPLE)
 		{
+			// row maxima gathered by the paired steps, plus the last column of every lane (a lane whose last
+			// step was the even one of a pair has not folded it yet)
+#pragma unroll
+			for (int k = 0; k < S; k++) acc = __viaddmax_s16x2(__vmaxs2(X[k], F[k]), p.ck[k], acc);
 			int lo = (int)(short)(acc & 0xFFFFu);
 			int hi = (int)(short)(acc >> 16);
 			lo = lo - (int)B + p.m * j0;
