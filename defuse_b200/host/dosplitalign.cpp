@@ -601,6 +601,11 @@ int main(int argc, char* argv[])
 	    {'a', "align", "Split Alignments Filename", true, "string", "", false},
 	});
 	cmd.Parse(argc, argv);
+	PhaseTimer timer;
+	// one context per GPU (DFB_DEVICES), created in the background while the inputs are parsed; candidates are
+	// dealt out by cluster, no exchange between GPUs
+	std::vector<std::unique_ptr<Gpu>> gpus;
+	for (int dev : DeviceList()) gpus.emplace_back(new Gpu(dev));
 	const double frag_mean = cmd.Double('u', 0.0), frag_sd = cmd.Double('s', 0.0);
 	const int min_read = cmd.Int('n'), max_read = cmd.Int('x');
 
@@ -622,6 +627,7 @@ int main(int argc, char* argv[])
 	for (const auto& kv : regions)
 		InitializeTask(tasks[kv.first], kv.first, kv.second, reference, exons, frag_mean, frag_sd, min_read, max_read);
 
+	timer.Lap("regions, fasta, exons, tasks");
 	BinnedRegions binned(2000);
 	std::unordered_map<int, int> cluster_slot; // fusion id -> dense index (window pair 2k, 2k+1)
 	TableBuilder windows;
@@ -644,11 +650,10 @@ int main(int argc, char* argv[])
 		exit(1);
 	}
 
-	// one context per GPU (DFB_DEVICES); candidates are dealt out by cluster, no exchange between GPUs
-	std::vector<std::unique_ptr<Gpu>> gpus;
-	for (int dev : DeviceList()) gpus.emplace_back(new Gpu(dev));
+	timer.Lap("bins");
 	const int n_gpus = (int)gpus.size();
 
+	timer.Lap("gpu contexts");
 	// ---- candidates, in the reference's order (SplitAlignment.cpp:266-303): SAM record order x iteration order of
 	//      the overlap set; once per (cluster, read id, revComp) ----
 	std::vector<Candidate> candidates;
@@ -728,6 +733,7 @@ int main(int argc, char* argv[])
 		}
 	}
 
+	timer.Lap("sam -> candidates");
 	// ---- the reads the candidates need (the reference keeps every read of both files, SplitAlignment.cpp:253-264;
 	//      a read id that is absent aligns as the empty string, :286) ----
 	std::unordered_map<int, std::string> reads;
@@ -741,6 +747,7 @@ int main(int argc, char* argv[])
 		}
 	}
 
+	timer.Lap("fastq");
 	std::ofstream out(cmd.Str('a').c_str());
 	if (!out.good())
 	{
@@ -904,5 +911,7 @@ int main(int argc, char* argv[])
 		out << os.str();
 	}
 	out.flush();
-	return 0;
+	out.close();
+	timer.Lap("align + write");
+	FinishProcess(0);
 }

@@ -12,9 +12,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <iostream>
 #include <sstream>
 #include <string>
+#include <thread>
+#include <unistd.h>
 #include <vector>
 
 namespace dfbhost
@@ -331,32 +334,59 @@ private:
 // ---------------------------------------------------------------------------------------------
 // GPU context shared by a tool
 // ---------------------------------------------------------------------------------------------
+// A context on one GPU.  CUDA start-up costs 2-3 s on a B200 box, so the context is created on a helper thread
+// the moment the tool starts and only joined at the first use: parsing the inputs runs underneath it.
 class Gpu
 {
 public:
 	Gpu() : Gpu(getenv("DFB_DEVICE") ? atoi(getenv("DFB_DEVICE")) : 0) {}
-	explicit Gpu(int device)
+	explicit Gpu(int device) : mDevice(device)
 	{
-		if (dfb_ctx_create(device, &mCtx) != DFB_OK)
+		mThread = std::thread([this] {
+			mStatus = dfb_ctx_create(mDevice, &mCtx);
+			if (mStatus != DFB_OK) mError = dfb_last_error(nullptr);
+		});
+	}
+	~Gpu()
+	{
+		if (mThread.joinable()) mThread.join();
+		dfb_ctx_destroy(mCtx);
+	}
+	dfb_ctx* ctx()
+	{
+		if (mThread.joinable()) mThread.join();
+		if (mStatus != DFB_OK)
 		{
-			std::cerr << "Error: " << dfb_last_error(nullptr) << std::endl;
+			std::cerr << "Error: " << mError << std::endl;
 			exit(1);
 		}
+		return mCtx;
 	}
-	~Gpu() { dfb_ctx_destroy(mCtx); }
-	dfb_ctx* ctx() { return mCtx; }
 	[[noreturn]] void Die(const char* what)
 	{
 		std::cerr << "Error: " << what << ": " << dfb_last_error(mCtx) << std::endl;
 		exit(1);
 	}
-
 	Gpu(const Gpu&) = delete;
 	Gpu& operator=(const Gpu&) = delete;
 
 private:
+	int mDevice;
 	dfb_ctx* mCtx = nullptr;
+	int mStatus = DFB_OK;
+	std::string mError;
+	std::thread mThread;
 };
+
+// The tools end like the reference's do (return from main), minus the seconds CUDA spends tearing its context
+// down: outputs are flushed, then the process leaves without running the teardown.
+[[noreturn]] inline void FinishProcess(int code)
+{
+	std::cout.flush();
+	std::cerr.flush();
+	fflush(nullptr);
+	_exit(code);
+}
 
 // Devices a tool may use: DFB_DEVICES="0,1,2" or "all" (every visible GPU); else the single DFB_DEVICE (default 0).
 inline std::vector<int> DeviceList()
@@ -384,6 +414,25 @@ inline std::vector<int> DeviceList()
 	if (out.empty()) out.push_back(getenv("DFB_DEVICE") ? atoi(getenv("DFB_DEVICE")) : 0);
 	return out;
 }
+
+// DFB_TRACE=1: phase timings of a tool on stderr (stdout / the -a file stay byte-exact)
+class PhaseTimer
+{
+public:
+	PhaseTimer() : mOn(getenv("DFB_TRACE") && *getenv("DFB_TRACE") && *getenv("DFB_TRACE") != '0') { clock_gettime(CLOCK_MONOTONIC, &mT); }
+	void Lap(const char* what)
+	{
+		if (!mOn) return;
+		timespec t;
+		clock_gettime(CLOCK_MONOTONIC, &t);
+		fprintf(stderr, "[tool] %-28s %9.3f ms\n", what, (t.tv_sec - mT.tv_sec) * 1e3 + (t.tv_nsec - mT.tv_nsec) * 1e-6);
+		mT = t;
+	}
+
+private:
+	bool mOn;
+	timespec mT;
+};
 
 // CSR table under construction
 struct TableBuilder

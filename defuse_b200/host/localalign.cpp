@@ -108,5 +108,5 @@ int main(int argc, char* argv[])
 		if (pending.size() >= kBatchTasks || refs.bytes.size() + seqs.bytes.size() >= kBatchBytes) flush();
 	}
 	flush();
-	return 0;
+	FinishProcess(0);
 }

@@ -224,5 +224,5 @@ int main(int argc, char* argv[])
 		}
 	}
 	flush();
-	return 0;
+	FinishProcess(0);
 }
