@@ -1763,7 +1763,10 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	for (int k = 0; k <= K; k++) t0[k] = n_tasks * k / K;
 	int rc = DFB_OK;
 	auto fetch = [&](int k) -> int {
-		return dfb_split_plan_fetch(plans[k], out_best ? out_best + t0[k] : nullptr, nullptr, nullptr);
+		int frc = dfb_split_plan_fetch(plans[k], out_best ? out_best + t0[k] : nullptr, nullptr, nullptr);
+		// the chunk's device buffers go back to the pool right away: only its host-side rows are still needed
+		if (!frc) release_device(plans[k]);
+		return frc;
 	};
 	for (int k = 0; k < K && !rc; k++)
 	{

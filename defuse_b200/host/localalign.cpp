@@ -40,7 +40,8 @@ int main(int argc, char* argv[])
 	std::vector<int32_t> task_ref, task_seq;
 	std::vector<Pending> pending;
 	std::vector<int32_t> score;
-	const size_t kBatchTasks = 1u << 20;
+	size_t kBatchTasks = 1u << 20;
+	if (const char* e = getenv("DFB_TOOL_BATCH")) kBatchTasks = (size_t)std::max(1, atoi(e)); // tests: force several batches
 	const size_t kBatchBytes = 1u << 28;
 
 	std::ios::sync_with_stdio(false);

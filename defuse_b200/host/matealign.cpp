@@ -165,7 +165,8 @@ int main(int argc, char* argv[])
 	// ---- tasks: (window, read) in fastq order x SAM order; flushed in batches ----
 	TableBuilder windows, reads;
 	std::vector<int32_t> task_ref, task_seq, task_fragment, task_len, score;
-	const size_t kBatchTasks = 1u << 19;
+	size_t kBatchTasks = 1u << 19;
+	if (const char* e = getenv("DFB_TOOL_BATCH")) kBatchTasks = (size_t)std::max(1, atoi(e)); // tests: force several batches
 	const size_t kBatchBytes = 1u << 28;
 	auto flush = [&]() {
 		if (task_ref.empty()) return;

@@ -114,3 +114,22 @@ def test_dosplitalign_sharded_over_contexts(oracle_mod, tmp_path, devices):
         _run([os.path.join(BIN, "dosplitalign")] + args + ["-a", ours], env={"DFB_DEVICES": devices})
         _run([ref] + args + ["-a", theirs])
         assert open(ours).read() == open(theirs).read()
+
+
+def test_tools_with_many_small_batches(oracle_mod, tmp_path):
+    """The tools flush work to the GPU in batches (1 M tasks by default); DFB_TOOL_BATCH forces many small batches on
+    small inputs.  Output bytes must not depend on the batch size."""
+    from synth import files
+    g = json.load(open(os.path.join(HERE, "golden", "tools.json")))
+    sub = str(tmp_path / "s")
+    args = files.make_split_dataset(sub, **g["split_small"]["kw"])
+    res = os.path.join(sub, "ours.alignments")
+    for batch, devices in (("37", "0"), ("64", "0,0")):
+        _run([os.path.join(BIN, "dosplitalign")] + args + ["-a", res], env={"DFB_TOOL_BATCH": batch, "DFB_DEVICES": devices})
+        assert open(res).read() == g["split_small"]["output"]
+    margs, sam = files.make_matealign_dataset(str(tmp_path / "mate"), **g["mate_small"]["kw"])
+    assert _run([os.path.join(BIN, "matealign")] + margs, sam, env={"DFB_TOOL_BATCH": "29"}).decode() == g["mate_small"]["output"]
+    gl = json.load(open(os.path.join(HERE, "golden", "localalign_tool.json")))
+    for run in gl["runs"].values():
+        out = _run([os.path.join(BIN, "localalign")] + run["args"], gl["stdin"].encode(), env={"DFB_TOOL_BATCH": "7"})
+        assert out.decode() == run["stdout"]
