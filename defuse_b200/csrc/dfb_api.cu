@@ -187,7 +187,8 @@ struct dfb_ctx
 	PinnedBuf h_out;             // results on their way back
 	cudaStream_t copy_stream = nullptr; // device->host result copies, ordered after a plan's kernels by an event
 	cudaStream_t upload_stream = nullptr; // uploads + packing of the next chunk of a pipelined batch
-	HostPool* pool = nullptr;
+	HostPool* pool = nullptr;       // plan building (and everything else on the caller's thread)
+	HostPool* pool_fetch = nullptr; // result assembly when it runs on the pipelining helper thread
 	dfb_plan* last_split = nullptr; // result holder of dfb_split_align_batch
 	int host_threads = 1;
 	// recycled host memory of the result assembly (kept mapped between batches)
@@ -312,6 +313,7 @@ extern "C" int dfb_ctx_create(int device_ordinal, dfb_ctx** out)
 	unsigned hc = std::thread::hardware_concurrency();
 	ctx->host_threads = (int)std::max(1u, std::min(hc ? hc : 1u, 16u));
 	ctx->pool = new (std::nothrow) HostPool(ctx->host_threads);
+	ctx->pool_fetch = new (std::nothrow) HostPool(std::max(2, ctx->host_threads / 2));
 	*out = ctx;
 	return DFB_OK;
 }
@@ -327,6 +329,7 @@ extern "C" void dfb_ctx_destroy(dfb_ctx* ctx)
 	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
 	delete ctx->pool;
+	delete ctx->pool_fetch;
 	ctx->spare_rows.release();
 	ctx->spare_cols.release();
 	ctx->slot_of.release();
@@ -1433,9 +1436,16 @@ void emit_task_rows(int task, int L, const uint64_t* key, const int32_t* score, 
 }
 }  // namespace
 
+static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols, HostPool* pool);
+
 extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols)
 {
 	if (!pl) return DFB_ERR_ARG;
+	return split_fetch_impl(pl, out_best, n_rows, n_cols, pl->ctx->pool);
+}
+
+static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols, HostPool* pool)
+{
 	dfb_ctx* ctx = pl->ctx;
 	if (!pl->split) return set_err(ctx, DFB_ERR_STATE, "dfb_split_plan_fetch on a simple plan");
 	if (!pl->ran) return set_err(ctx, DFB_ERR_STATE, "dfb_split_plan_fetch before dfb_plan_run");
@@ -1532,11 +1542,11 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 	});
 
 	// 4. per-thread assembly over contiguous task ranges so that rows come out in task order
-	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->host_threads, pl->n_tasks / 4096 + 1));
+	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(pool ? pool->Size() : ctx->host_threads, pl->n_tasks / 4096 + 1));
 	if ((int)ctx->asm_chunks.size() < T) ctx->asm_chunks.resize((size_t)T);
 	std::vector<int64_t> ev_part((size_t)T, 0);
 	bool oom = false;
-	parallel_for(ctx->pool, T, [&](int tid) {
+	parallel_for(pool, T, [&](int tid) {
 		const int64_t t0 = pl->n_tasks * tid / T, t1 = pl->n_tasks * (tid + 1) / T;
 		AsmChunk& out = ctx->asm_chunks[tid];
 		// upper bounds for this task range: every event is one column; a row needs two events
@@ -1686,7 +1696,7 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 		if (pl->cols.cap < ctx->spare_cols.cap) pl->cols.swap(ctx->spare_cols);
 	}
 	if (!pl->rows.ensure(tot_rows) || !pl->cols.ensure(tot_cols)) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
-	parallel_for(ctx->pool, T, [&](int k) {
+	parallel_for(pool, T, [&](int k) {
 		const AsmChunk& c = ctx->asm_chunks[k];
 		dfb_split_row* dst = pl->rows.data() + row_base[k];
 		const int64_t cb = (int64_t)col_base[k];
@@ -1762,12 +1772,32 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	std::vector<int64_t> t0((size_t)K + 1);
 	for (int k = 0; k <= K; k++) t0[k] = n_tasks * k / K;
 	int rc = DFB_OK;
-	auto fetch = [&](int k) -> int {
-		int frc = dfb_split_plan_fetch(plans[k], out_best ? out_best + t0[k] : nullptr, nullptr, nullptr);
-		// the chunk's device buffers go back to the pool right away: only its host-side rows are still needed
-		if (!frc) release_device(plans[k]);
-		return frc;
-	};
+	Trace trp;
+	// lane 2 (helper thread): waits for chunk k to be queued on the GPU, copies its results back and assembles its
+	// rows -- while lane 1 (this thread) builds and queues the following chunks
+	std::mutex mu;
+	std::condition_variable cv;
+	int queued = 0;      // chunks handed to the GPU so far
+	bool abort = false;  // lane 1 failed: lane 2 stops after the chunks already queued
+	int fetch_rc = DFB_OK;
+	std::thread lane2([&] {
+		for (int k = 0; k < K; k++)
+		{
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				cv.wait(lk, [&] { return queued > k || abort; });
+				if (queued <= k) return;
+			}
+			// (the chunk's device buffers are released with the others at the end: a stream-ordered free in the middle
+			// of the pipeline cannot be reused by the chunks still being built and only makes the pool grow)
+			int frc = split_fetch_impl(plans[k], out_best ? out_best + t0[k] : nullptr, nullptr, nullptr, ctx->pool_fetch);
+			if (frc)
+			{
+				fetch_rc = frc;
+				return;
+			}
+		}
+	});
 	for (int k = 0; k < K && !rc; k++)
 	{
 		const int64_t a = t0[k], b = t0[k + 1];
@@ -1778,14 +1808,28 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 			break;
 		}
 		dfb_seq_table view{reads->bytes, reads->off + r_lo, (int64_t)(r_hi - r_lo)};
+		dfb_plan* pk = nullptr;
 		rc = split_plan_create_impl(ctx, params, refs, &view, task_cluster + a, task_read + a, task_min_score + a, b - a, r_lo, k,
-		                            true, &plans[k]);
+		                            true, &pk);
 		if (rc) break;
-		plans[k]->result_slot = k;
-		rc = dfb_plan_run(plans[k]);
-		if (!rc && k >= 1) rc = fetch(k - 1);
+		pk->result_slot = k;
+		rc = dfb_plan_run(pk);
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			plans[k] = pk;
+			if (!rc) queued = k + 1;
+		}
+		cv.notify_all();
 	}
-	if (!rc) rc = fetch(K - 1);
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		if (rc) abort = true;
+	}
+	cv.notify_all();
+	trp.lap("pipelined: lane 1 done");
+	lane2.join();
+	trp.lap("pipelined: lane 2 joined");
+	if (!rc) rc = fetch_rc;
 	dfb_plan* holder = nullptr;
 	if (!rc)
 	{
@@ -1837,8 +1881,10 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 			holder->ran = true;
 		}
 	}
+	trp.lap("pipelined: merged");
 	for (int k = 0; k < K; k++)
 		if (plans[k]) dfb_plan_destroy(plans[k]);
+	trp.lap("pipelined: chunks destroyed");
 	if (rc)
 	{
 		if (holder) dfb_plan_destroy(holder);
