@@ -114,6 +114,8 @@ def load_library():
         "dfb_plan_get_stats": ([vp, P(_PlanStats)], ctypes.c_int),
         "dfb_plan_destroy": ([vp], None),
         "dfb_microbench_issue_rate": ([vp, ctypes.c_int, ctypes.c_int, P(ctypes.c_double), P(ctypes.c_double)], ctypes.c_int),
+        "dfb_split_backtrace_batch": ([vp, P(_SplitParams), P(_SeqTable), P(_SeqTable), vp, vp, vp, vp, vp, i64, vp, vp, i64,
+                                       P(i64)], ctypes.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)
@@ -129,7 +131,7 @@ ABI_SYMBOLS = (
     "dfb_split_result_copy", "dfb_split_result_view", "dfb_split_plan_view", "dfb_simple_plan_create", "dfb_split_plan_create", "dfb_plan_run", "dfb_plan_sync",
     "dfb_plan_set_timing",
     "dfb_simple_plan_fetch", "dfb_split_plan_fetch", "dfb_split_plan_copy", "dfb_plan_get_stats", "dfb_plan_destroy",
-    "dfb_microbench_issue_rate",
+    "dfb_microbench_issue_rate", "dfb_split_backtrace_batch",
 )
 
 
@@ -448,17 +450,44 @@ class SplitReadAligner:
         rows, cols = _view_arrays(rp.value, n_rows.value, cp.value, n_cols.value, copy)
         return SplitResult(best, rows, cols, lambda: self._lens(refs, reads, task_cluster, task_read))
 
+    def backtrace_batch(self, refs, reads, task_cluster, task_read, ref_split1, ref_split2, read_split):
+        """matches1 / matches2 of chosen alignments (GetAlignments(..., backtrace=True), tools/SplitReadAligner.cpp:
+        124-154,287-292) through dfb_split_backtrace_batch.  Task t names the alignment of reads[task_read[t]] against
+        cluster task_cluster[t] with refSplit (ref_split1[t], ref_split2[t]) and readSplit.first read_split[t].
+        Returns (match_off[2n+1], pairs[(total,2)]): pairs[match_off[2t]:match_off[2t+1]] = matches1 of task t,
+        pairs[match_off[2t+1]:match_off[2t+2]] = matches2, each row (refPos, readPos)."""
+        task_cluster, task_read = _i32(task_cluster), _i32(task_read)
+        a1, a2, a3 = _i32(ref_split1), _i32(ref_split2), _i32(read_split)
+        n = task_cluster.size
+        cap = int((reads.off[1:] - reads.off[:-1])[task_read].sum()) if n else 0
+        off = np.zeros(2 * n + 1, dtype=np.int64)
+        pairs = np.zeros((max(cap, 1), 2), dtype=np.int32)
+        total = ctypes.c_int64()
+        rt, st = refs.c_struct(), reads.c_struct()
+        self.ctx._check(self.ctx._lib.dfb_split_backtrace_batch(
+            self.ctx._h, ctypes.byref(self.params), ctypes.byref(rt), ctypes.byref(st), task_cluster.ctypes.data,
+            task_read.ctypes.data, a1.ctypes.data, a2.ctypes.data, a3.ctypes.data, n, off.ctypes.data, pairs.ctypes.data,
+            cap, ctypes.byref(total)))
+        return off, pairs[:total.value].copy()
+
     # single-task mirror of the reference's two-call protocol
     def Align(self, read, reference1, reference2):
         self._last = (bytes(read), bytes(reference1), bytes(reference2))
 
     def GetAlignments(self, min_score, force_splits=True, first_only=False, backtrace=False):
-        if not force_splits or first_only or backtrace:
-            raise NotImplementedError("only forceSplits=true, firstOnly=false, backtrace=false is on the hot path "
+        """(n,7) array as the reference emits it; with backtrace=True a list of (row, matches1, matches2)."""
+        if not force_splits or first_only:
+            raise NotImplementedError("only forceSplits=true, firstOnly=false is on the hot path "
                                       "(tools/SplitAlignment.cpp:379)")
         read, r1, r2 = self._last
-        res = self.align_batch(SeqTable.from_list([r1, r2]), SeqTable.from_list([read]), [0], [0], [min_score])
-        return res.alignments(0)
+        refs, reads = SeqTable.from_list([r1, r2]), SeqTable.from_list([read])
+        res = self.align_batch(refs, reads, [0], [0], [min_score])
+        al = res.alignments(0)
+        if not backtrace:
+            return al
+        n = len(al)
+        off, pairs = self.backtrace_batch(refs, reads, np.zeros(n, np.int32), np.zeros(n, np.int32), al[:, 0], al[:, 1], al[:, 2])
+        return [(al[k], pairs[off[2 * k]:off[2 * k + 1]], pairs[off[2 * k + 1]:off[2 * k + 2]]) for k in range(n)]
 
 
 def split_min_score(read_len, match=2):

@@ -1956,3 +1956,5 @@ extern "C" int dfb_split_result_view(const dfb_ctx* ctx, const dfb_split_row** r
 	if (!ctx->last_split) return set_err(ctx, DFB_ERR_STATE, "no split result on this context");
 	return dfb_split_plan_view(ctx->last_split, rows, n_rows, cols, n_cols);
 }
+
+#include "dfb_trace.cuh"

@@ -184,6 +184,29 @@ DFB_API int dfb_split_result_copy(const dfb_ctx* ctx, dfb_split_row* rows, int32
 DFB_API int dfb_split_result_view(const dfb_ctx* ctx, const dfb_split_row** rows, int64_t* n_rows,
                                   const int32_t** cols, int64_t* n_cols);
 
+/* ---- backtrace of chosen split alignments (GetAlignments(..., backtrace=true)) ------------- */
+
+/* The matches1 / matches2 lists of SplitReadAlignment (tools/SplitReadAligner.h:21-30) for alignments the caller
+ * picked from a dfb_split_align_batch result -- what SplitAlignmentTask::ReAlign needs (tools/SplitAlignment.cpp:
+ * 443-464, caller tools/splitseq.cpp:122).  Task t names one alignment of reads[task_read[t]] against cluster
+ * task_cluster[t] by its refSplit = (task_ref_split1[t], task_ref_split2[t]) and readSplit.first =
+ * task_read_split[t]; the start cells are (refSplit.first, readSplit.first) in matrix 1 and
+ * (len(reference2) - refSplit.second - 1, len(read) - readSplit.first) in matrix 2 (SplitReadAligner.cpp:271-292).
+ * Pointers follow the reference's rule -- (i,j-1) over (i-1,j) over the diagonal when scores tie (:56-69) -- and
+ * every diagonal step on the way to read position 0 is a match pair (refPos, readPos) (:124-143); matrix 2's pairs
+ * are mapped back to the unreversed sequences (:145-154).  Both lists come out ascending.
+ *   match_off : 2*n_tasks + 1 entries; pairs [match_off[2t], match_off[2t+1]) are matches1 of task t,
+ *               [match_off[2t+1], match_off[2t+2]) its matches2
+ *   matches   : interleaved (refPos, readPos); at most sum(len(read)) pairs are produced, so a buffer of
+ *               2 * sum(len(read)) int32 always suffices (matches_cap counts pairs); NULL only sizes
+ *   n_pairs   : total number of pairs */
+DFB_API int dfb_split_backtrace_batch(dfb_ctx* ctx, const dfb_split_params* params,
+                          const dfb_seq_table* refs, const dfb_seq_table* reads,
+                          const int32_t* task_cluster, const int32_t* task_read,
+                          const int32_t* task_ref_split1, const int32_t* task_ref_split2,
+                          const int32_t* task_read_split, int64_t n_tasks,
+                          int64_t* match_off, int32_t* matches, int64_t matches_cap, int64_t* n_pairs);
+
 /* ---- staged form: the same work with the batch resident in HBM -------------------------- */
 
 /* Copies the tables to the device, packs them (2-bit codes + exception plane) and builds

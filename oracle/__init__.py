@@ -69,6 +69,8 @@ def _lib(impl):
         lib.dpo_split_align_batch.argtypes = ([ctypes.c_int] * 5 + [_c_u8p, _c_i64p, _c_u8p, _c_i64p, _c_i32p, _c_i32p,
                                                                    _c_i32p, ctypes.c_int64, _c_i32p, _c_i32p, ctypes.c_int64])
         lib.dpo_split_align_batch.restype = ctypes.c_int64
+        lib.dpo_split_backtrace.argtypes = ([_c_u8p, ctypes.c_int] * 3 + [ctypes.c_int] * 7 + [_c_i32p] * 4)
+        lib.dpo_split_backtrace.restype = None
     elif impl == "ref":
         if not os.path.exists(REF_LIB):
             raise FileNotFoundError("oracle/_ref/libref_aligners.so not built (run `make -C oracle ref` where /root/reference exists)")
@@ -84,6 +86,9 @@ def _lib(impl):
         lib.ref_split_align_batch.argtypes = ([ctypes.c_int] * 5 + [_c_u8p, _c_i64p, _c_u8p, _c_i64p, _c_i32p, _c_i32p,
                                                                    _c_i32p, ctypes.c_int64, _c_i32p, _c_i32p, ctypes.c_int64])
         lib.ref_split_align_batch.restype = ctypes.c_int64
+        lib.ref_split_backtrace.argtypes = ([ctypes.c_int] * 5 + [ctypes.c_char_p, ctypes.c_int] * 3 +
+                                            [ctypes.c_int, ctypes.c_int64] + [_c_i32p] * 5)
+        lib.ref_split_backtrace.restype = ctypes.c_int64
         lib.ref_reverse_complement.argtypes = [ctypes.c_char_p, ctypes.c_int]
         lib.ref_reverse_complement.restype = None
     else:
@@ -182,6 +187,41 @@ def fill_matrix(ref, read, match, mismatch, gap, end_gaps=False):
     _lib("port").dpo_fill_matrix(_p(a, _c_u8p), len(ref), _p(b, _c_u8p), len(read), match, mismatch, gap,
                                  int(end_gaps), _p(H, _c_i32p))
     return H
+
+
+def split_backtrace(read, ref1, ref2, ref_split, read_split, match=2, mismatch=-1, gap=-2, end_gaps=False):
+    """matches1, matches2 of the alignment with this refSplit / readSplit.first -- GetAlignments(backtrace=True),
+    tools/SplitReadAligner.cpp:124-154,287-292 (port).  Two (n,2) int32 arrays of (refPos, readPos)."""
+    read, ref1, ref2 = bytes(read), bytes(ref1), bytes(ref2)
+    L = len(read)
+    m1 = np.zeros((L + 1, 2), dtype=np.int32)
+    m2 = np.zeros((L + 1, 2), dtype=np.int32)
+    n1 = np.zeros(1, dtype=np.int32)
+    n2 = np.zeros(1, dtype=np.int32)
+    a, b, c = _u8(read), _u8(ref1), _u8(ref2)
+    _lib("port").dpo_split_backtrace(_p(a, _c_u8p), L, _p(b, _c_u8p), len(ref1), _p(c, _c_u8p), len(ref2),
+                                     match, mismatch, gap, int(end_gaps), int(ref_split[0]), int(ref_split[1]),
+                                     int(read_split), _p(m1, _c_i32p), _p(n1, _c_i32p), _p(m2, _c_i32p), _p(n2, _c_i32p))
+    return m1[:n1[0]].copy(), m2[:n2[0]].copy()
+
+
+def ref_split_backtrace(read, ref1, ref2, min_score, which, match=2, mismatch=-1, gap=-2, end_gaps=False,
+                        min_split_score=8):
+    """The compiled reference's GetAlignments(backtrace=True): alignment number `which` in emission order.
+    Returns (n_alignments, header[7], matches1, matches2) or (n_alignments, None, None, None)."""
+    read, ref1, ref2 = bytes(read), bytes(ref1), bytes(ref2)
+    L = len(read)
+    hdr = np.zeros(7, dtype=np.int32)
+    m1 = np.zeros((L + 1, 2), dtype=np.int32)
+    m2 = np.zeros((L + 1, 2), dtype=np.int32)
+    n1 = np.zeros(1, dtype=np.int32)
+    n2 = np.zeros(1, dtype=np.int32)
+    n = _lib("ref").ref_split_backtrace(match, mismatch, gap, int(end_gaps), min_split_score, read, L, ref1, len(ref1),
+                                        ref2, len(ref2), min_score, which, _p(hdr, _c_i32p), _p(m1, _c_i32p),
+                                        _p(n1, _c_i32p), _p(m2, _c_i32p), _p(n2, _c_i32p))
+    if n < 0:
+        return 0, None, None, None
+    return int(n), hdr, m1[:n1[0]].copy(), m2[:n2[0]].copy()
 
 
 def split_min_score(read_len, match=2):

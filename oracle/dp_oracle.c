@@ -307,3 +307,100 @@ DPO_API int64_t dpo_split_align_batch(int match, int mismatch, int gap, int end_
 	}
 	return total;
 }
+
+/* tools/SplitReadAligner.cpp:124-143 (BackTracePath) over the pointers FillMatrix leaves (:56-69):
+ * at (i,j) the pointer is (i-1,j-1) when the diagonal attains the cell's score, overwritten by
+ * (i-1,j) when that one does, overwritten by (i,j-1) when that one does; row i == 0 points to
+ * (0,j-1) (:46-47).  The walk starts at (start_i,start_j), stops at j == 0 and collects
+ * (refPos,readPos) = (i-1,j-1) of every diagonal step; the list is reversed at the end (:142).
+ * The pointers are recomputed from H here instead of being stored.  Returns the number of pairs. */
+static int backtrace_path(const int32_t* H, const uint8_t* ref, int R, const uint8_t* read,
+                          int match, int mismatch, int gap, int start_i, int start_j, int32_t* pairs)
+{
+	const size_t W = (size_t)R + 1;
+	int i = start_i, j = start_j, n = 0;
+	while (j > 0)
+	{
+		int dir;
+		if (i == 0)
+		{
+			dir = 2;
+		}
+		else
+		{
+			int v = H[j * W + i];
+			int diag = H[(j - 1) * W + (i - 1)] + (ref[i - 1] == read[j - 1] ? match : mismatch);
+			int gap_ref = H[j * W + (i - 1)] + gap;
+			int gap_read = H[(j - 1) * W + i] + gap;
+			dir = -1;
+			if (diag == v) dir = 0;     /* :56-59 */
+			if (gap_ref == v) dir = 1;  /* :61-64 */
+			if (gap_read == v) dir = 2; /* :66-69 */
+		}
+		if (dir == 0)
+		{
+			pairs[2 * n] = i - 1;
+			pairs[2 * n + 1] = j - 1;
+			n++;
+			i--;
+			j--;
+		}
+		else if (dir == 1)
+		{
+			i--;
+		}
+		else
+		{
+			j--;
+		}
+	}
+	for (int a = 0, b = n - 1; a < b; a++, b--)
+	{
+		int32_t t0 = pairs[2 * a], t1 = pairs[2 * a + 1];
+		pairs[2 * a] = pairs[2 * b];
+		pairs[2 * a + 1] = pairs[2 * b + 1];
+		pairs[2 * b] = t0;
+		pairs[2 * b + 1] = t1;
+	}
+	return n;
+}
+
+/* GetAlignments(..., backTrace=true) for ONE alignment named by its refSplit and readSplit.first
+ * (tools/SplitReadAligner.cpp:271-292): start cells (ref_split1, read_split) in matrix 1 and
+ * (R2 - ref_split2 - 1, L - read_split) in matrix 2; matches2 goes through ReverseMatches
+ * (:145-154: coordinates mapped back to the unreversed sequences, list reversed again).
+ * matches1/matches2 hold up to L pairs each; n1/n2 receive the counts. */
+DPO_API void dpo_split_backtrace(const uint8_t* read, int L, const uint8_t* ref1, int R1,
+                                 const uint8_t* ref2, int R2, int match, int mismatch, int gap,
+                                 int end_gaps, int ref_split1, int ref_split2, int read_split,
+                                 int32_t* matches1, int32_t* n1, int32_t* matches2, int32_t* n2)
+{
+	uint8_t* ref2r = (uint8_t*)malloc((size_t)R2 + 1);
+	uint8_t* readr = (uint8_t*)malloc((size_t)L + 1);
+	reverse_copy(ref2r, ref2, R2);
+	reverse_copy(readr, read, L);
+	int32_t* H1 = (int32_t*)malloc(sizeof(int32_t) * (size_t)(R1 + 1) * (size_t)(L + 1));
+	int32_t* H2 = (int32_t*)malloc(sizeof(int32_t) * (size_t)(R2 + 1) * (size_t)(L + 1));
+	dpo_fill_matrix(ref1, R1, read, L, match, mismatch, gap, end_gaps, H1);
+	dpo_fill_matrix(ref2r, R2, readr, L, match, mismatch, gap, end_gaps, H2);
+	*n1 = backtrace_path(H1, ref1, R1, read, match, mismatch, gap, ref_split1, read_split, matches1);
+	int m = backtrace_path(H2, ref2r, R2, readr, match, mismatch, gap, R2 - ref_split2 - 1, L - read_split, matches2);
+	for (int k = 0; k < m; k++) /* :147-151 */
+	{
+		matches2[2 * k] = R2 - matches2[2 * k] - 1;
+		matches2[2 * k + 1] = L - matches2[2 * k + 1] - 1;
+	}
+	for (int a = 0, b = m - 1; a < b; a++, b--) /* :153 */
+	{
+		int32_t t0 = matches2[2 * a], t1 = matches2[2 * a + 1];
+		matches2[2 * a] = matches2[2 * b];
+		matches2[2 * a + 1] = matches2[2 * b + 1];
+		matches2[2 * b] = t0;
+		matches2[2 * b + 1] = t1;
+	}
+	*n2 = m;
+	free(H1);
+	free(H2);
+	free(ref2r);
+	free(readr);
+}

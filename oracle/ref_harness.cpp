@@ -122,6 +122,43 @@ int64_t ref_split_align_batch(int match, int mismatch, int gap, int end_gaps, in
 	return total;
 }
 
+// GetAlignments(minScore, forceSplits=true, firstOnly=false, backtrace=TRUE): the match lists of alignment
+// number `which` in emission order (tools/SplitReadAligner.cpp:287-292), as interleaved (refPos, readPos).
+// Returns the number of alignments the reference produced, or -1 when `which` is out of range.
+int64_t ref_split_backtrace(int match, int mismatch, int gap, int end_gaps, int min_split_score,
+                            const char* read, int read_len, const char* ref1, int ref1_len,
+                            const char* ref2, int ref2_len, int min_score, int64_t which,
+                            int32_t* header /* 7 ints as in ref_split_align */,
+                            int32_t* matches1, int32_t* n1, int32_t* matches2, int32_t* n2)
+{
+	SplitReadAligner aligner(match, mismatch, gap, end_gaps != 0, min_split_score);
+	aligner.Align(std::string(read, read_len), std::string(ref1, ref1_len), std::string(ref2, ref2_len));
+	SplitReadAlignVec alignments;
+	aligner.GetAlignments(alignments, min_score, true, false, true);
+	if (which < 0 || which >= (int64_t)alignments.size()) return -1;
+	const SplitReadAlignment& a = alignments[which];
+	header[0] = a.refSplit.first;
+	header[1] = a.refSplit.second;
+	header[2] = a.readSplit.first;
+	header[3] = a.readSplit.second;
+	header[4] = a.score;
+	header[5] = a.score1;
+	header[6] = a.score2;
+	*n1 = (int32_t)a.matches1.size();
+	for (size_t k = 0; k < a.matches1.size(); k++)
+	{
+		matches1[2 * k] = a.matches1[k].first;
+		matches1[2 * k + 1] = a.matches1[k].second;
+	}
+	*n2 = (int32_t)a.matches2.size();
+	for (size_t k = 0; k < a.matches2.size(); k++)
+	{
+		matches2[2 * k] = a.matches2[k].first;
+		matches2[2 * k + 1] = a.matches2[k].second;
+	}
+	return (int64_t)alignments.size();
+}
+
 // ReverseComplement of tools/Common.cpp:32-54 (ACGTacgt only), for fixture generation.
 void ref_reverse_complement(char* seq, int len)
 {

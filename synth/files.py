@@ -151,6 +151,46 @@ def make_split_dataset(outdir, seed=1, n_clusters=40, pairs_per_cluster=30, L=10
             "-2", os.path.join(outdir, "reads.2.fastq")]
 
 
+def write_read_index(outdir):
+    """<outdir>/reads.fqi for reads.{1,2}.fastq: little-endian int64 offsets of the '@' lines, entry 2*fragment+end
+    (tools/ReadIndex.cpp:67-77; writer scripts/index_paired_fastq.pl:56-60).  Returns the reads prefix."""
+    offs = {}
+    n = 0
+    for end in (0, 1):
+        pos = 0
+        with open(os.path.join(outdir, "reads.%d.fastq" % (end + 1)), "rb") as f:
+            for k, line in enumerate(f):
+                if k % 4 == 0:
+                    frag = int(line[1:line.index(b"/")])
+                    offs[(frag, end)] = pos
+                    n = max(n, frag + 1)
+                pos += len(line)
+    idx = np.zeros(2 * n, dtype="<i8")
+    for (frag, end), pos in offs.items():
+        idx[2 * frag + end] = pos
+    idx.tofile(os.path.join(outdir, "reads.fqi"))
+    return os.path.join(outdir, "reads")
+
+
+def sort_alignments(src, dst):
+    """What the pipeline does between dosplitalign and evalsplitalign (scripts/defuse_run.pl:528, `sort -n -k 1`):
+    records grouped by fusion id; ties ordered bytewise so that the result does not depend on the locale."""
+    lines = open(src, "rb").read().splitlines(keepends=True)
+    lines.sort(key=lambda l: (int(l.split(b"\t", 1)[0]), l))
+    open(dst, "wb").write(b"".join(lines))
+
+
+def downstream_args(split_args, outdir):
+    """Argument lists of evalsplitalign / splitseq from a make_split_dataset argument list."""
+    common, k = [], 0
+    while k < len(split_args):
+        if split_args[k] not in ("-i", "-1", "-2"):
+            common += split_args[k:k + 2]
+        k += 2
+    ev = common + ["-a", os.path.join(outdir, "sorted.alignments")]
+    return common, ev
+
+
 def make_localalign_input(seed=2, n_refs=20, n_lines=400, R=2001, L=(60, 140)):
     """stdin of localalign: id \\t reference \\t sequence."""
     rng = np.random.default_rng(seed)

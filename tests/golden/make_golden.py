@@ -120,10 +120,38 @@ def tool_cases():
     return out
 
 
+def downstream_cases():
+    """evalsplitalign and splitseq of the compiled reference on the sorted output of ref_dosplitalign."""
+    import tempfile
+    from synth import files
+    kw = dict(seed=5, n_clusters=24, pairs_per_cluster=40)
+    with tempfile.TemporaryDirectory() as d:
+        args = files.make_split_dataset(d, **kw)
+        raw = os.path.join(d, "ref.alignments")
+        subprocess.run([oracle.ref_tool("ref_dosplitalign")] + args + ["-a", raw], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        files.sort_alignments(raw, os.path.join(d, "sorted.alignments"))
+        common, ev = files.downstream_args(args, d)
+        names = {k: os.path.join(d, "ref." + k) for k in ("seq", "break", "predalign")}
+        subprocess.run([oracle.ref_tool("ref_evalsplitalign")] + ev + ["-q", names["seq"], "-b", names["break"],
+                                                                       "-p", names["predalign"]], check=True)
+        out = dict(kw=kw, sorted=open(os.path.join(d, "sorted.alignments")).read())
+        for k, v in names.items():
+            out[k] = open(v).read()
+        prefix = files.write_read_index(d)
+        base = common + ["-p", prefix, "-a", names["predalign"]]
+        out["splitseq"] = subprocess.run([oracle.ref_tool("ref_splitseq")] + base, stdout=subprocess.PIPE, check=True).stdout.decode()
+        ids = sorted({int(l.split("\t")[0]) for l in out["predalign"].splitlines()})
+        out["splitseq_id"] = {str(i): subprocess.run([oracle.ref_tool("ref_splitseq")] + base + ["-i", str(i)],
+                                                     stdout=subprocess.PIPE, check=True).stdout.decode() for i in ids[:2]}
+    return out
+
+
 if __name__ == "__main__":
     assert oracle.have_ref(), "build the reference first: make -C oracle ref"
     json.dump(split_cases(), open(os.path.join(HERE, "split_aligner.json"), "w"), indent=0)
     json.dump(simple_cases(), open(os.path.join(HERE, "simple_aligner.json"), "w"), indent=0)
     json.dump(localalign_case(), open(os.path.join(HERE, "localalign_tool.json"), "w"), indent=0)
     json.dump(tool_cases(), open(os.path.join(HERE, "tools.json"), "w"), indent=0)
+    json.dump(downstream_cases(), open(os.path.join(HERE, "tools_downstream.json"), "w"), indent=0)
     print("golden vectors written to", HERE)

@@ -261,3 +261,72 @@ def test_pipelined_one_call_path(oracle_mod, gpu_ctx, monkeypatch):
     # a batch whose task_read decreases somewhere falls back to the single plan
     back = al.align_batch(rt, st, tc[::-1].copy(), trd[::-1].copy(), ms[::-1].copy())
     assert np.array_equal(back.best, single.best[::-1])
+
+
+# ---------------------------------------------------------------------------------------------
+# backtrace: GetAlignments(..., backtrace=true) -- dfb_split_backtrace_batch against the oracle
+# ---------------------------------------------------------------------------------------------
+
+def _check_backtrace(oracle, ctx, refs, reads, task_cluster, task_read, min_score, params=(2, -1, -2, False, 8), per_task=4):
+    import defuse_b200 as d
+    rt, st = _tables(refs, reads)
+    m, x, g, eg, ms = params
+    al = d.SplitReadAligner(m, x, g, eg, ms, ctx=ctx)
+    res = al.align_batch(rt, st, task_cluster, task_read, min_score)
+    tc, trd, s1, s2, a = [], [], [], [], []
+    for t in range(len(task_cluster)):
+        for row in res.alignments(t)[:per_task]:
+            tc.append(task_cluster[t]); trd.append(task_read[t]); s1.append(row[0]); s2.append(row[1]); a.append(row[2])
+    off, pairs = al.backtrace_batch(rt, st, tc, trd, s1, s2, a)
+    assert off[0] == 0 and off[-1] == len(pairs) and (np.diff(off) >= 0).all()
+    for k in range(len(tc)):
+        w1, w2 = oracle.split_backtrace(reads[trd[k]], refs[2 * tc[k]], refs[2 * tc[k] + 1], (s1[k], s2[k]), a[k], m, x, g, eg)
+        g1, g2 = pairs[off[2 * k]:off[2 * k + 1]], pairs[off[2 * k + 1]:off[2 * k + 2]]
+        assert g1.shape == w1.shape and (g1 == w1).all(), "alignment %d matches1: got\n%s\nwant\n%s" % (k, g1[:6], w1[:6])
+        assert g2.shape == w2.shape and (g2 == w2).all(), "alignment %d matches2: got\n%s\nwant\n%s" % (k, g2[:6], w2[:6])
+    return len(tc)
+
+
+def test_backtrace_dosplitalign_shape(oracle_mod, gpu_ctx):
+    import defuse_b200 as d
+    rng = np.random.default_rng(41)
+    refs, reads, tc, trd = util.split_batch(rng, 12, 10, 100, 300, 380, sub=0.02, indel=0.01)
+    ms = np.array([d.split_min_score(len(reads[r])) for r in trd], np.int32)
+    assert _check_backtrace(oracle_mod, gpu_ctx, refs, reads, tc, trd, ms) > 40
+
+
+@pytest.mark.parametrize("params", [(2, -1, -2, True, 8), (1, -1, 1, False, 3), (5, -4, -3, False, -2), (3, -2, 0, False, 1)])
+def test_backtrace_generic_scoring(oracle_mod, gpu_ctx, params):
+    rng = np.random.default_rng(42)
+    refs, reads, tc, trd = util.split_batch(rng, 8, 6, (1, 90), 1, 200, sub=0.04, indel=0.02, n_rate=0.01)
+    ms = np.array([int(0.5 * params[0] * len(reads[r])) for r in trd], np.int32)
+    assert _check_backtrace(oracle_mod, gpu_ctx, refs, reads, tc, trd, ms, params) > 5
+
+
+def test_backtrace_long_reads_and_ties(oracle_mod, gpu_ctx):
+    """Reads longer than one 32-row tile, repeats (many equal-score paths), non-ACGT bytes."""
+    rng = np.random.default_rng(43)
+    refs, reads, tc, trd = [], [], [], []
+    for c in range(6):
+        unit = util.rand_seq(rng, int(rng.integers(2, 7)))
+        r1 = (unit * 80)[:int(rng.integers(150, 420))]
+        r2 = util.rand_seq(rng, 30) + (unit * 80)[:int(rng.integers(150, 400))]
+        refs += [r1, r2]
+        for _ in range(4):
+            L = int(rng.integers(33, 300))
+            read = util.mutate(rng, (r1[-L // 2:] + r2[:L - L // 2]), 0.03, 0.01, 0.02)
+            tc.append(c); trd.append(len(reads)); reads.append(read)
+    ms = np.array([int(1.2 * len(reads[r])) for r in trd], np.int32)
+    assert _check_backtrace(oracle_mod, gpu_ctx, refs, reads, np.array(tc, np.int32), np.array(trd, np.int32), ms, per_task=6) > 10
+
+
+def test_backtrace_argument_errors(gpu_ctx):
+    import defuse_b200 as d
+    rt, st = _tables([b"ACGTACGT", b"TTTTACGT"], [b"ACGTTTTT"])
+    al = d.SplitReadAligner(ctx=gpu_ctx)
+    with pytest.raises(d.DefuseB200Error):
+        al.backtrace_batch(rt, st, [0], [0], [9], [0], [4])   # i1 beyond reference 1
+    with pytest.raises(d.DefuseB200Error):
+        al.backtrace_batch(rt, st, [0], [0], [4], [0], [9])   # read split beyond the read
+    off, pairs = al.backtrace_batch(rt, st, [], [], [], [], [])
+    assert len(off) == 1 and len(pairs) == 0

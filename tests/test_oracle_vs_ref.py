@@ -43,3 +43,25 @@ def test_reverse_complement_vs_ref(ref):
     for _ in range(50):
         s = bytes(rng.integers(32, 127, int(rng.integers(0, 60))).astype(np.uint8))
         assert ref.reverse_complement(s, impl="port") == ref.reverse_complement(s, impl="ref")
+
+
+@pytest.mark.parametrize("params", [(2, -1, -2, False, 8), (2, -1, -2, True, 8), (1, -1, 1, False, 3), (5, -4, -3, False, -2),
+                                    (3, -2, 0, False, 1)])
+def test_backtrace_vs_ref(ref, params):
+    """GetAlignments(backtrace=True): match lists of every alignment (up to a cap per task), port vs reference."""
+    rng = np.random.default_rng(8)
+    refs, reads, tc, trd = util.split_batch(rng, 6, 5, (0, 70), 0, 150, sub=0.04, indel=0.02, n_rate=0.01)
+    m, x, g, eg, ms = params
+    checked = 0
+    for c, r in zip(tc, trd):
+        read, ref1, ref2 = reads[r], refs[2 * c], refs[2 * c + 1]
+        thr = int(0.6 * m * len(read))
+        for which in range(6):
+            n, hdr, m1, m2 = ref.ref_split_backtrace(read, ref1, ref2, thr, which, m, x, g, eg, ms)
+            if which >= n:
+                break
+            p1, p2 = ref.split_backtrace(read, ref1, ref2, (hdr[0], hdr[1]), hdr[2], m, x, g, eg)
+            assert p1.shape == m1.shape and (p1 == m1).all()
+            assert p2.shape == m2.shape and (p2 == m2).all()
+            checked += 1
+    assert checked > 10

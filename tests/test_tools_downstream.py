@@ -1,0 +1,119 @@
+"""evalsplitalign (host-only, runs without a GPU) and splitseq (GPU: alignment + backtrace) against the committed
+golden outputs of the compiled reference tools and, where oracle/_ref exists, against those tools on fresh files."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BIN = os.path.join(ROOT, "defuse_b200", "bin")
+sys.path.insert(0, ROOT)
+
+
+def _tool(name):
+    p = os.path.join(BIN, name)
+    if not os.path.exists(p):
+        pytest.skip("tools not built")
+    return p
+
+
+def _run(cmd, **kw):
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300, **kw)
+    assert p.returncode == 0, (cmd[0], p.returncode, p.stderr.decode()[-2000:])
+    return p.stdout
+
+
+def _golden_dataset(tmp_path):
+    from synth import files
+    g = json.load(open(os.path.join(HERE, "golden", "tools_downstream.json")))
+    d = str(tmp_path / "g")
+    args = files.make_split_dataset(d, **g["kw"])
+    open(os.path.join(d, "sorted.alignments"), "w").write(g["sorted"])
+    common, ev = files.downstream_args(args, d)
+    return g, d, common, ev
+
+
+def _eval(tool, ev, d, tag):
+    names = {k: os.path.join(d, "%s.%s" % (tag, k)) for k in ("seq", "break", "predalign")}
+    _run([tool] + ev + ["-q", names["seq"], "-b", names["break"], "-p", names["predalign"]])
+    return {k: open(v).read() for k, v in names.items()}
+
+
+def test_evalsplitalign_golden(tmp_path):
+    g, d, common, ev = _golden_dataset(tmp_path)
+    got = _eval(_tool("evalsplitalign"), ev, d, "ours")
+    for k in ("seq", "break", "predalign"):
+        assert got[k] == g[k], k
+
+
+@pytest.mark.parametrize("kw", [dict(seed=51, n_clusters=80, pairs_per_cluster=50),
+                                dict(seed=52, n_clusters=40, pairs_per_cluster=40, read_len_jitter=20, lower_frac=0.02, n_rate=0.01)])
+def test_evalsplitalign_vs_reference_tool(oracle_mod, tmp_path, kw):
+    from synth import files
+    ref_split, ref_eval = oracle_mod.ref_tool("ref_dosplitalign"), oracle_mod.ref_tool("ref_evalsplitalign")
+    if not ref_split or not ref_eval:
+        pytest.skip("oracle/_ref tools not built")
+    d = str(tmp_path / "d")
+    args = files.make_split_dataset(d, **kw)
+    _run([ref_split] + args + ["-a", os.path.join(d, "raw.alignments")])
+    files.sort_alignments(os.path.join(d, "raw.alignments"), os.path.join(d, "sorted.alignments"))
+    common, ev = files.downstream_args(args, d)
+    ours, theirs = _eval(_tool("evalsplitalign"), ev, d, "ours"), _eval(ref_eval, ev, d, "ref")
+    assert len(theirs["seq"].splitlines()) > 10
+    assert ours == theirs
+
+
+def test_evalsplitalign_errors(tmp_path):
+    g, d, common, ev = _golden_dataset(tmp_path)
+    tool = _tool("evalsplitalign")
+    outs = ["-q", os.path.join(d, "q"), "-b", os.path.join(d, "b"), "-p", os.path.join(d, "p")]
+    open(os.path.join(d, "bad.alignments"), "w").write("0\t1\t0\t1\t5\n")
+    p = subprocess.run([tool] + common + ["-a", os.path.join(d, "bad.alignments")] + outs, capture_output=True)
+    assert p.returncode == 1 and b"Error: Format error for candidate reads line:" in p.stderr
+    p = subprocess.run([tool] + common + ["-a", os.path.join(d, "missing.alignments")] + outs, capture_output=True)
+    assert p.returncode == 1 and b"Error: Unable to open" in p.stderr
+    p = subprocess.run([tool] + common + outs, capture_output=True)
+    assert p.returncode == 1 and b"PARSE ERROR" in p.stderr
+
+
+@pytest.mark.gpu
+def test_splitseq_golden(tmp_path):
+    from synth import files
+    g, d, common, ev = _golden_dataset(tmp_path)
+    open(os.path.join(d, "ref.predalign"), "w").write(g["predalign"])
+    prefix = files.write_read_index(d)
+    base = [_tool("splitseq")] + common + ["-p", prefix, "-a", os.path.join(d, "ref.predalign")]
+    assert _run(base).decode() == g["splitseq"]
+    for fid, want in g["splitseq_id"].items():
+        assert _run(base + ["-i", fid]).decode() == want
+    p = subprocess.run(base + ["-i", "99999"], capture_output=True)
+    assert p.returncode == 1 and b"Error: Unable to find fusion 99999" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(seed=61, n_clusters=60, pairs_per_cluster=50),
+                                dict(seed=62, n_clusters=30, pairs_per_cluster=40, read_len_jitter=20, lower_frac=0.02, n_rate=0.01)])
+def test_splitseq_vs_reference_tool(oracle_mod, tmp_path, kw):
+    """Whole chain on fresh files: our dosplitalign -> sort -> our evalsplitalign -> our splitseq, against the compiled
+    reference tools fed the same files.  splitseq is run on the full sorted alignments too (every record re-aligned and
+    back-traced), not only on the predicted ones."""
+    from synth import files
+    refs = {n: oracle_mod.ref_tool("ref_" + n) for n in ("dosplitalign", "evalsplitalign", "splitseq")}
+    if not all(refs.values()):
+        pytest.skip("oracle/_ref tools not built")
+    d = str(tmp_path / "d")
+    args = files.make_split_dataset(d, **kw)
+    _run([_tool("dosplitalign")] + args + ["-a", os.path.join(d, "raw.alignments")])
+    files.sort_alignments(os.path.join(d, "raw.alignments"), os.path.join(d, "sorted.alignments"))
+    common, ev = files.downstream_args(args, d)
+    ours, theirs = _eval(_tool("evalsplitalign"), ev, d, "ours"), _eval(refs["evalsplitalign"], ev, d, "ref")
+    assert ours == theirs
+    prefix = files.write_read_index(d)
+    for name in ("ref.predalign", "sorted.alignments"):
+        tail = common + ["-p", prefix, "-a", os.path.join(d, name)]
+        a, b = _run([_tool("splitseq")] + tail), _run([refs["splitseq"]] + tail)
+        assert len(b) > 1000
+        assert a == b, name
