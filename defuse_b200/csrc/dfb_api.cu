@@ -218,7 +218,9 @@ struct Trace
 	{
 		if (!trace_on()) return;
 		auto t1 = std::chrono::steady_clock::now();
-		fprintf(stderr, "[dfb] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		static const auto origin = t1;
+		fprintf(stderr, "[dfb] %-28s %8.3f ms   (at %9.3f)\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+		        std::chrono::duration<double, std::milli>(t1 - origin).count());
 		t0 = t1;
 	}
 };

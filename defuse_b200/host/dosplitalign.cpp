@@ -8,6 +8,7 @@
 // SplitReadAligner::Align + GetAlignments (tools/SplitAlignment.cpp:376-379) run on the GPU through
 // dfb_split_align_batch; de-duplication and min(score1,score2) (:381-400) stay on the host.
 #include "split_tasks.h"
+#include "fast_io.h"
 
 #include <algorithm>
 #include <fstream>
@@ -86,113 +87,194 @@ int main(int argc, char* argv[])
 			for (const Location& loc : t.mate_regions[end]) binned.Add(PackId(t.fusion_id, end), loc);
 	}
 
-	FastqReader streams[2];
-	const bool ok0 = streams[0].Open(cmd.Str('1'));
-	const bool ok1 = streams[1].Open(cmd.Str('2'));
+	// ---- reads: both fastq files indexed in place on a helper thread while the SAM file is parsed ----
+	FastqIndex fastq[2];
+	const bool ok0 = fastq[0].Open(cmd.Str('1'));
+	const bool ok1 = fastq[1].Open(cmd.Str('2'));
+	std::cerr << fastq[0].Message() << fastq[1].Message();
 	if (!ok0 || !ok1)
 	{
 		std::cout << "Error: unable to read sequences" << std::endl;
 		exit(1);
 	}
+	const int T = ToolThreads();
+	std::thread fastq_thread([&] {
+		fastq[0].Scan(std::max(1, T / 2));
+		fastq[1].Scan(std::max(1, T / 2));
+	});
 
 	timer.Lap("bins");
 	const int n_gpus = (int)gpus.size();
 
-	timer.Lap("gpu contexts");
 	// ---- candidates, in the reference's order (SplitAlignment.cpp:266-303): SAM record order x iteration order of
-	//      the overlap set; once per (cluster, read id, revComp) ----
+	//      the overlap set; once per (cluster, read id, revComp).  Chunks of lines are parsed in parallel (every chunk
+	//      keeps, per record, the overlap set in its iteration order), then merged in file order. ----
 	std::vector<Candidate> candidates;
-	std::unordered_set<int> needed_reads;
 	{
-		std::istream* in = &std::cin;
-		std::ifstream file;
-		if (cmd.Str('i') != "-")
+		MappedInput sam;
+		const bool opened = cmd.Str('i') == "-" ? sam.OpenStdin() : sam.OpenFile(cmd.Str('i'));
+		if (!opened)
 		{
-			file.open(cmd.Str('i').c_str());
-			if (!file.good())
-			{
-				std::cerr << "Error: Unable to open sam file " << cmd.Str('i') << std::endl;
-				exit(1);
-			}
-			in = &file;
+			fastq_thread.join();
+			std::cerr << "Error: Unable to open sam file " << cmd.Str('i') << std::endl;
+			exit(1);
 		}
-		std::unordered_map<int, std::unordered_set<std::pair<int, int>, PairHash>> seen;
-		std::string line;
-		std::vector<std::string> f, q;
-		int line_number = 0;
-		while (std::getline(*in, line))
+		const char* const base = sam.data();
+		std::vector<LineChunk> chunks = SplitLines(base, sam.size(), T);
+		struct Part
 		{
-			line_number++;
-			if (line.empty())
+			std::vector<int32_t> stream; // per record with overlaps: fragment index, read end of the record, k, k ids
+			int64_t error_line = -1;     // first fatal line of the chunk (1-based, global)
+			std::string error;
+		};
+		std::vector<Part> parts(chunks.size());
+		ParallelRun((int)chunks.size(), [&](int c) {
+			Part& part = parts[(size_t)c];
+			const char* a = base + chunks[(size_t)c].begin;
+			const char* const end = base + chunks[(size_t)c].end;
+			int64_t line_number = chunks[(size_t)c].first_line;
+			std::string ref_name;
+			auto fail = [&](const std::string& msg) {
+				part.error_line = line_number;
+				part.error = msg;
+			};
+			while (a < end)
 			{
-				std::cerr << "Error: Empty alignment line " << line_number << std::endl;
+				const char* nl = (const char*)memchr(a, '\n', (size_t)(end - a));
+				const char* const b = a;
+				const char* const e = nl ? nl : end;
+				a = nl ? nl + 1 : end;
+				line_number++;
+				if (b == e) return fail("Error: Empty alignment line " + std::to_string(line_number));
+				if (*b == '@') continue;
+				const char* f[11]; // starts of fields 0..9, f[10] = one past field 9
+				int nf = 0;
+				f[0] = b;
+				for (const char* q = b; nf < 10;)
+				{
+					const char* t = (const char*)memchr(q, '\t', (size_t)(e - q));
+					if (!t)
+					{
+						if (nf == 9) f[++nf] = e + 1;
+						break;
+					}
+					f[++nf] = t + 1;
+					q = t + 1;
+				}
+				if (nf < 10) return fail("Error: Format error for alignment line " + std::to_string(line_number));
+				int flag = 0, pos = 0;
+				if (!ParseIntRange(f[1], f[2] - 1, flag)) return fail("Error: bad lexical cast: flag '" + std::string(f[1], f[2] - 1) + "'");
+				if (!ParseIntRange(f[3], f[4] - 1, pos)) return fail("Error: bad lexical cast: pos '" + std::string(f[3], f[4] - 1) + "'");
+				if (f[3] - 1 - f[2] == 1 && *f[2] == '*') continue;
+				const int strand = (flag & 0x0010) == 0 ? kPlus : kMinus;
+				const char* const qb = f[0];
+				const char* const qe = f[1] - 1;
+				const char* slash = (const char*)memchr(qb, '/', (size_t)(qe - qb));
+				const bool one_slash = slash && !memchr(slash + 1, '/', (size_t)(qe - slash - 1));
+				const char* fragment_end = qe;
+				int read_end = 0;
+				if (one_slash)
+				{
+					if (qe - slash != 2 || (slash[1] != '1' && slash[1] != '2'))
+						return fail("Error: Unable to interpret qname for alignment line " + std::to_string(line_number));
+					fragment_end = slash;
+					read_end = slash[1] == '1' ? 0 : 1;
+				}
+				else
+				{
+					if (flag & 0x0040) read_end = 0;
+					else if (flag & 0x0080) read_end = 1;
+					// (neither flag: the reference leaves readEnd uninitialised, AlignmentStream.cpp:108-116; end 0 here)
+				}
+				const Region r{pos, pos + (int)(f[10] - 1 - f[9]) - 1};
+				ref_name.assign(f[2], f[3] - 1);
+				std::unordered_set<int> overlapping;
+				binned.Overlapping(ref_name, strand, r, overlapping);
+				if (overlapping.empty()) continue;
+				int fragment_index = 0;
+				if (!ParseIntRange(qb, fragment_end, fragment_index))
+					return fail("Error: bad lexical cast: fragment index '" + std::string(qb, fragment_end) + "'");
+				part.stream.push_back(fragment_index);
+				part.stream.push_back(read_end);
+				part.stream.push_back((int32_t)overlapping.size());
+				for (int cluster_end_id : overlapping) part.stream.push_back(cluster_end_id);
+			}
+		});
+		for (const Part& part : parts)
+			if (part.error_line >= 0)
+			{
+				// (chunks are in file order: this is the first line a sequential reader would have died on)
+				fastq_thread.join();
+				std::cerr << part.error << std::endl;
 				exit(1);
 			}
-			if (line[0] == '@') continue;
-			SplitChar(line, '\t', f);
-			if (f.size() < 10)
-			{
-				std::cerr << "Error: Format error for alignment line " << line_number << std::endl;
-				exit(1);
-			}
-			const int flag = IntOrDie(f[1], "flag");
-			const int pos = IntOrDie(f[3], "pos");
-			if (f[2] == "*") continue;
-			const int strand = (flag & 0x0010) == 0 ? kPlus : kMinus;
-			std::string fragment;
-			int read_end = 0;
-			SplitChar(f[0], '/', q);
-			if (q.size() == 2)
-			{
-				if (q[1] != "1" && q[1] != "2")
-				{
-					std::cerr << "Error: Unable to interpret qname for alignment line " << line_number << std::endl;
-					exit(1);
-				}
-				fragment = q[0];
-				read_end = q[1] == "1" ? 0 : 1;
-			}
-			else
-			{
-				fragment = f[0];
-				if (flag & 0x0040) read_end = 0;
-				else if (flag & 0x0080) read_end = 1;
-				// (neither flag: the reference leaves readEnd uninitialised, AlignmentStream.cpp:108-116; we use end 1)
-			}
-			const Region r{pos, pos + (int)f[9].length() - 1};
-			std::unordered_set<int> overlapping;
-			binned.Overlapping(f[2], strand, r, overlapping);
-			if (overlapping.empty()) continue;
-			const int fragment_index = IntOrDie(fragment, "fragment index");
-			for (int cluster_end_id : overlapping)
-			{
-				const int cluster_id = IdIndex(cluster_end_id), cluster_end = IdEnd(cluster_end_id);
-				const int read_id = PackId(fragment_index, read_end == 0 ? 1 : 0);
-				const int rev_comp = cluster_end == 0 ? 1 : 0;
-				if (seen[cluster_id].insert(std::make_pair(read_id, rev_comp)).second)
-				{
-					candidates.push_back(Candidate{cluster_id, read_id, rev_comp});
-					needed_reads.insert(read_id);
-				}
-			}
+		timer.Lap("sam parse + overlaps");
+		// expand the per-chunk streams into one candidate list (file order), then keep the first occurrence of every
+		// (cluster, read id, revComp): the keys are dealt out to threads by hash, every thread walks the list in order
+		// and decides the keys it owns
+		std::vector<size_t> part_base(parts.size() + 1, 0);
+		for (size_t c = 0; c < parts.size(); c++)
+		{
+			size_t m = 0;
+			const std::vector<int32_t>& st = parts[c].stream;
+			for (size_t q = 0; q < st.size(); q += 3 + (size_t)st[q + 2]) m += (size_t)st[q + 2];
+			part_base[c + 1] = part_base[c] + m;
 		}
+		const size_t total = part_base.back();
+		std::vector<Candidate> all(total);
+		std::vector<uint64_t> keys(total);
+		ParallelRun((int)parts.size(), [&](int c) {
+			const std::vector<int32_t>& st = parts[(size_t)c].stream;
+			size_t at = part_base[(size_t)c];
+			for (size_t q = 0; q < st.size();)
+			{
+				const int fragment_index = st[q], read_end = st[q + 1], k = st[q + 2];
+				q += 3;
+				for (int j = 0; j < k; j++, q++, at++)
+				{
+					const int cluster_id = IdIndex(st[q]), cluster_end = IdEnd(st[q]);
+					const int read_id = PackId(fragment_index, read_end == 0 ? 1 : 0);
+					const int rev_comp = cluster_end == 0 ? 1 : 0;
+					all[at] = Candidate{cluster_id, read_id, rev_comp};
+					keys[at] = ((uint64_t)(uint32_t)cluster_id << 33) | ((uint64_t)(uint32_t)read_id << 1) | (uint64_t)rev_comp;
+				}
+			}
+		});
+		parts.clear();
+		std::vector<uint8_t> keep(total, 0);
+		const int P = total < 100000 ? 1 : T;
+		ParallelRun(P, [&](int tid) {
+			KeySet seen(total / (size_t)P + 16);
+			for (size_t k = 0; k < total; k++)
+			{
+				const uint64_t key = keys[k];
+				if ((int)(((key * 0xD6E8FEB86659FD93ull) >> 40) % (uint64_t)P) != tid) continue;
+				if (seen.Insert(key)) keep[k] = 1;
+			}
+		});
+		size_t kept = 0;
+		for (size_t k = 0; k < total; k++) kept += keep[k];
+		candidates.reserve(kept);
+		for (size_t k = 0; k < total; k++)
+			if (keep[k]) candidates.push_back(all[k]);
 	}
 
-	timer.Lap("sam -> candidates");
-	// ---- the reads the candidates need (the reference keeps every read of both files, SplitAlignment.cpp:253-264;
-	//      a read id that is absent aligns as the empty string, :286) ----
-	std::unordered_map<int, std::string> reads;
+	timer.Lap("candidates (dedupe)");
+	// ---- the reads the candidates need (the reference keeps every read of both files, SplitAlignment.cpp:253-264, the
+	//      second file overwriting the first; a read id that is absent aligns as the empty string, :286) ----
+	fastq_thread.join();
 	for (int file = 0; file <= 1; file++)
 	{
-		FastqRead rd;
-		while (streams[file].Next(rd))
-		{
-			const int id = PackId(IntOrDie(rd.fragment, "fragment index"), rd.read_end);
-			if (needed_reads.find(id) != needed_reads.end()) reads[id] = rd.sequence;
-		}
+		std::cerr << fastq[file].Message();
+		if (fastq[file].Fatal()) exit(1);
 	}
+	auto find_read = [&](int id, const char*& seq, uint32_t& len) {
+		if (fastq[1].Find(id, seq, len) || fastq[0].Find(id, seq, len)) return;
+		seq = nullptr;
+		len = 0;
+	};
 
-	timer.Lap("fastq");
+	timer.Lap("fastq (wait)");
 	std::ofstream out(cmd.Str('a').c_str());
 	if (!out.good())
 	{
@@ -203,24 +285,45 @@ int main(int argc, char* argv[])
 	// ---- align in batches, write records in candidate order ----
 	const dfb_split_params params{kMatch, kMismatch, kGap, 0, kMinAnchor * kMatch};
 	const dfb_seq_table window_table = windows.View();
-	size_t kBatch = (size_t)(1u << 20) * (size_t)n_gpus;
+	size_t kBatch = (size_t)(1u << 21) * (size_t)n_gpus;
 	if (const char* e = getenv("DFB_TOOL_BATCH")) kBatch = (size_t)std::max(1, atoi(e)); // tests: force several batches
 	struct Shard
 	{
 		TableBuilder reads;
 		std::vector<int32_t> task_cluster, task_read, task_min_score, best, read_len, ref2_len;
+		std::vector<int64_t> row_begin; // first result row of each task (n_rows when it has none)
 		const dfb_split_row* rows = nullptr;
 		const int32_t* cols = nullptr;
-		int64_t n_rows = 0, n_cols = 0, cursor = 0;
+		int64_t n_rows = 0, n_cols = 0;
 		int rc = DFB_OK;
 	};
 	std::vector<Shard> shards((size_t)n_gpus);
 	std::vector<int> gpu_of;
-	std::string seq;
+	std::vector<int32_t> local_of;        // index of a candidate inside its shard
+	std::vector<const char*> cand_seq;    // the candidate's read in the mapped fastq (forward orientation)
+	std::vector<uint32_t> cand_len;
+	std::vector<int32_t> cand_slot;
+	std::vector<std::string> out_parts((size_t)T);
+	timer.Lap("open output");
+	static unsigned char complement[256];
+	for (int k = 0; k < 256; k++) complement[k] = (unsigned char)k;
+	for (int k = 0; k < 8; k++) complement[(unsigned char)"ACGTacgt"[k]] = (unsigned char)"TGCAtgca"[k]; // tools/Common.cpp:32-54
 	for (size_t first = 0; first < candidates.size(); first += kBatch)
 	{
 		const size_t last = std::min(candidates.size(), first + kBatch);
 		const size_t n = last - first;
+		cand_seq.resize(n);
+		cand_len.resize(n);
+		cand_slot.resize(n);
+		ParallelRun(T, [&](int tid) {
+			for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
+			{
+				const Candidate& c = candidates[first + k];
+				find_read(c.read_id, cand_seq[k], cand_len[k]);
+				cand_slot[k] = cluster_slot.find(c.cluster_id)->second;
+			}
+		});
+		timer.Add("batch: read lookup");
 		// partition by cluster, heaviest first onto the lightest GPU (cost = DP cells); a cluster heavier than a
 		// quarter of the mean load is cut into runs of candidates (every GPU holds every window pair)
 		gpu_of.assign(n, 0);
@@ -237,14 +340,11 @@ int main(int argc, char* argv[])
 			double total = 0;
 			for (size_t k = 0; k < n; k++)
 			{
-				const Candidate& c = candidates[first + k];
-				const int slot = cluster_slot[c.cluster_id];
-				auto it = reads.find(c.read_id);
-				const double L = it == reads.end() ? 0.0 : (double)it->second.size();
-				cost[k] = L * (double)(windows.off[2 * slot + 2] - windows.off[2 * slot]);
+				const int slot = cand_slot[k];
+				cost[k] = (double)cand_len[k] * (double)(windows.off[2 * slot + 2] - windows.off[2 * slot]);
 				total += cost[k];
-				auto ins = by_cluster.emplace(c.cluster_id, std::vector<int32_t>());
-				if (ins.second) cluster_order.push_back(c.cluster_id);
+				auto ins = by_cluster.emplace(candidates[first + k].cluster_id, std::vector<int32_t>());
+				if (ins.second) cluster_order.push_back(candidates[first + k].cluster_id);
 				ins.first->second.push_back((int32_t)k);
 			}
 			const double cap = std::max(1.0, total / n_gpus / 4.0);
@@ -273,38 +373,66 @@ int main(int argc, char* argv[])
 				for (int32_t k : u.members) gpu_of[k] = g;
 			}
 		}
+		// shard tables: offsets by one sequential pass, bytes (reverse-complemented where the candidate says so) in parallel
+		local_of.resize(n);
 		for (Shard& sh : shards)
 		{
 			sh.reads.Clear();
 			sh.task_cluster.clear();
-			sh.task_read.clear();
-			sh.task_min_score.clear();
-			sh.read_len.clear();
-			sh.ref2_len.clear();
-			sh.cursor = 0;
 		}
 		for (size_t k = 0; k < n; k++)
 		{
-			const Candidate& c = candidates[first + k];
 			Shard& sh = shards[gpu_of[k]];
-			auto it = reads.find(c.read_id);
-			if (it != reads.end()) seq = it->second; else seq.clear();
-			if (c.rev_comp) ReverseComplementInPlace(seq);
-			const int slot = cluster_slot[c.cluster_id];
-			sh.task_cluster.push_back(slot);
-			sh.task_read.push_back((int32_t)sh.reads.Add(seq));
-			sh.task_min_score.push_back((int)((float)seq.length() * (float)kMatch * 0.90)); // SplitAlignment.cpp:379
-			sh.read_len.push_back((int32_t)seq.size());
-			sh.ref2_len.push_back((int32_t)(windows.off[2 * slot + 2] - windows.off[2 * slot + 1]));
+			local_of[k] = (int32_t)sh.task_cluster.size();
+			sh.task_cluster.push_back(cand_slot[k]);
+			sh.reads.off.push_back(sh.reads.off.back() + (int64_t)cand_len[k]);
 		}
+		for (Shard& sh : shards)
+		{
+			const size_t m = sh.task_cluster.size();
+			sh.reads.bytes.resize((size_t)sh.reads.off.back());
+			sh.task_read.resize(m);
+			sh.task_min_score.resize(m);
+			sh.read_len.resize(m);
+			sh.ref2_len.resize(m);
+			sh.best.resize(m);
+		}
+		ParallelRun(T, [&](int tid) {
+			for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
+			{
+				Shard& sh = shards[gpu_of[k]];
+				const int32_t t = local_of[k];
+				const uint32_t len = cand_len[k];
+				char* dst = &sh.reads.bytes[0] + sh.reads.off[(size_t)t];
+				const char* src = cand_seq[k];
+				if (candidates[first + k].rev_comp)
+					for (uint32_t q = 0; q < len; q++) dst[q] = (char)complement[(unsigned char)src[len - 1 - q]];
+				else if (len)
+					memcpy(dst, src, len);
+				const int slot = cand_slot[k];
+				sh.task_read[(size_t)t] = t;
+				sh.task_min_score[(size_t)t] = (int)((float)len * (float)kMatch * 0.90); // SplitAlignment.cpp:379
+				sh.read_len[(size_t)t] = (int32_t)len;
+				sh.ref2_len[(size_t)t] = (int32_t)(windows.off[2 * slot + 2] - windows.off[2 * slot + 1]);
+			}
+		});
+		timer.Add("batch: tables");
+		for (auto& g : gpus) g->ctx();
+		timer.Add("batch: wait for gpu context");
 		auto run_shard = [&](int g) {
 			Shard& sh = shards[g];
-			sh.best.resize(sh.task_cluster.size());
 			const dfb_seq_table read_table = sh.reads.View();
 			sh.rc = dfb_split_align_batch(gpus[g]->ctx(), &params, &window_table, &read_table, sh.task_cluster.data(),
 			                              sh.task_read.data(), sh.task_min_score.data(), (int64_t)sh.task_cluster.size(),
 			                              sh.best.data());
 			if (sh.rc == DFB_OK) sh.rc = dfb_split_result_view(gpus[g]->ctx(), &sh.rows, &sh.n_rows, &sh.cols, &sh.n_cols);
+			if (sh.rc != DFB_OK) return;
+			if (n_gpus == 1) timer.Add("batch: gpu call");
+			// rows come in task order: where each task's rows start
+			sh.row_begin.assign(sh.task_cluster.size() + 1, sh.n_rows);
+			for (int64_t r = sh.n_rows - 1; r >= 0; r--) sh.row_begin[(size_t)sh.rows[r].task] = r;
+			for (int64_t t = (int64_t)sh.task_cluster.size() - 1; t >= 0; t--)
+				if (sh.row_begin[(size_t)t] == sh.n_rows) sh.row_begin[(size_t)t] = sh.row_begin[(size_t)t + 1];
 		};
 		if (n_gpus == 1)
 		{
@@ -319,45 +447,76 @@ int main(int argc, char* argv[])
 		for (int g = 0; g < n_gpus; g++)
 			if (shards[g].rc != DFB_OK) gpus[g]->Die("split alignment failed");
 
-		// merge: candidates in their original order; every shard's rows are in its own task order
-		std::ostringstream os;
-		std::unordered_set<std::pair<int, int>, PairHash> ref_splits;
-		std::vector<int32_t> local_index((size_t)n_gpus, 0);
-		for (size_t k = 0; k < n; k++)
-		{
-			Shard& sh = shards[gpu_of[k]];
-			const int32_t t = local_index[gpu_of[k]]++;
-			if (sh.cursor >= sh.n_rows || sh.rows[sh.cursor].task != t) continue;
-			const Candidate& c = candidates[first + k];
-			ref_splits.clear();
-			for (; sh.cursor < sh.n_rows && sh.rows[sh.cursor].task == t; sh.cursor++)
+		timer.Add("batch: row index");
+		// records of the candidates in their original order, formatted by ranges of candidates
+		ParallelRun(T, [&](int tid) {
+			std::string& os = out_parts[(size_t)tid];
+			os.clear();
+			std::vector<std::pair<int, int>> small; // refSplits of the task seen so far
+			std::unordered_set<std::pair<int, int>, PairHash> large;
+			for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
 			{
-				const dfb_split_row& row = sh.rows[sh.cursor];
-				const int32_t* c1 = sh.cols + row.col_begin;
-				const int32_t* c2 = c1 + row.n1;
-				const int score = std::min(row.score1, row.score2); // SplitAlignment.cpp:400
-				for (int a = 0; a < row.n1; a++)
+				const Shard& sh = shards[gpu_of[k]];
+				const int32_t t = local_of[k];
+				const int64_t r0 = sh.row_begin[(size_t)t], r1 = sh.row_begin[(size_t)t + 1];
+				if (r0 == r1) continue;
+				const Candidate& c = candidates[first + k];
+				small.clear();
+				large.clear();
+				for (int64_t r = r0; r < r1; r++)
 				{
-					for (int b = 0; b < row.n2; b++)
+					const dfb_split_row& row = sh.rows[r];
+					const int32_t* c1 = sh.cols + row.col_begin;
+					const int32_t* c2 = c1 + row.n1;
+					const int score = std::min(row.score1, row.score2); // SplitAlignment.cpp:400
+					for (int a = 0; a < row.n1; a++)
 					{
-						const std::pair<int, int> ref_split(c1[a], sh.ref2_len[t] - c2[b] - 1); // SplitReadAligner.cpp:277-278
-						if (!ref_splits.insert(ref_split).second) continue;                     // first per refSplit (:383-390)
-						os << c.cluster_id << "\t" << IdIndex(c.read_id) << "\t" << IdEnd(c.read_id) << "\t" << c.rev_comp << "\t"
-						   << ref_split.first << "\t" << ref_split.second << "\t" << row.read_split << "\t"
-						   << sh.read_len[t] - row.read_split << "\t" << score << "\t" << "\n";
+						for (int b = 0; b < row.n2; b++)
+						{
+							const std::pair<int, int> ref_split(c1[a], sh.ref2_len[(size_t)t] - c2[b] - 1); // SplitReadAligner.cpp:277-278
+							// first per refSplit (SplitAlignment.cpp:383-390)
+							bool fresh;
+							if (large.empty() && small.size() < 32)
+							{
+								fresh = std::find(small.begin(), small.end(), ref_split) == small.end();
+								if (fresh) small.push_back(ref_split);
+							}
+							else
+							{
+								if (large.empty()) large.insert(small.begin(), small.end());
+								fresh = large.insert(ref_split).second;
+							}
+							if (!fresh) continue;
+							AppendInt(os, c.cluster_id);
+							os += '\t';
+							AppendInt(os, IdIndex(c.read_id));
+							os += '\t';
+							AppendInt(os, IdEnd(c.read_id));
+							os += '\t';
+							AppendInt(os, c.rev_comp);
+							os += '\t';
+							AppendInt(os, ref_split.first);
+							os += '\t';
+							AppendInt(os, ref_split.second);
+							os += '\t';
+							AppendInt(os, row.read_split);
+							os += '\t';
+							AppendInt(os, sh.read_len[(size_t)t] - row.read_split);
+							os += '\t';
+							AppendInt(os, score);
+							os += "\t\n";
+						}
 					}
 				}
 			}
-			if (os.tellp() > (1 << 22))
-			{
-				out << os.str();
-				os.str(std::string());
-			}
-		}
-		out << os.str();
+		});
+		timer.Add("batch: format");
+		for (const std::string& part : out_parts) out.write(part.data(), (std::streamsize)part.size());
+		timer.Add("batch: write");
 	}
 	out.flush();
 	out.close();
-	timer.Lap("align + write");
+	timer.Report();
+	timer.Lap("close");
 	FinishProcess(0);
 }

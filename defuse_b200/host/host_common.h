@@ -429,9 +429,33 @@ public:
 		mT = t;
 	}
 
+	// accumulating form for phases that repeat per batch: Add("name") charges the time since the last call to a
+	// named bucket, Report() prints the buckets
+	void Add(const char* what)
+	{
+		if (!mOn) return;
+		timespec t;
+		clock_gettime(CLOCK_MONOTONIC, &t);
+		const double ms = (t.tv_sec - mT.tv_sec) * 1e3 + (t.tv_nsec - mT.tv_nsec) * 1e-6;
+		mT = t;
+		for (auto& b : mBuckets)
+			if (b.first == what)
+			{
+				b.second += ms;
+				return;
+			}
+		mBuckets.emplace_back(what, ms);
+	}
+	void Report()
+	{
+		for (auto& b : mBuckets) fprintf(stderr, "[tool] %-28s %9.3f ms\n", b.first.c_str(), b.second);
+		mBuckets.clear();
+	}
+
 private:
 	bool mOn;
 	timespec mT;
+	std::vector<std::pair<std::string, double>> mBuckets;
 };
 
 // CSR table under construction
