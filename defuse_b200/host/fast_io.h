@@ -5,6 +5,7 @@
 #define DFB_FAST_IO_H
 
 #include <algorithm>
+#include <cerrno>
 #include <charconv>
 #include <cstdint>
 #include <cstdio>
@@ -298,7 +299,8 @@ public:
 
 	// Parses the whole file on T threads.  Afterwards: Message() = what to print on stderr ("" if nothing),
 	// Fatal() = whether the reference would have died at that point.
-	void Scan(int T)
+	// keep_order: also keep the reads as a list in file order (Count / Record), for tools that walk the file
+	void Scan(int T, bool keep_order = false)
 	{
 		const char* p = mInput.data();
 		const size_t n = mInput.size();
@@ -410,6 +412,16 @@ public:
 		unsigned max_index = 0;
 		for (size_t k = 0; k < last_part && k < parts.size(); k++)
 			for (int id : parts[k].id) max_index = std::max(max_index, (unsigned)id & 0x7fffffffu);
+		if (keep_order)
+		{
+			for (size_t k = 0; k < last_part && k < parts.size(); k++)
+			{
+				mOrderId.insert(mOrderId.end(), parts[k].id.begin(), parts[k].id.end());
+				mOrderOff.insert(mOrderOff.end(), parts[k].off.begin(), parts[k].off.end());
+				mOrderLen.insert(mOrderLen.end(), parts[k].len.begin(), parts[k].len.end());
+			}
+			return;
+		}
 		mDense = (size_t)max_index < 8 * total + 4096;
 		if (mDense)
 		{
@@ -438,6 +450,15 @@ public:
 	const std::string& Message() const { return mMessage; }
 	bool Fatal() const { return mFatal; }
 
+	// file-order view (Scan(T, true)): read k is PackId(fragment, end) = id, sequence [seq, seq + len)
+	size_t Count() const { return mOrderId.size(); }
+	void Record(size_t k, int& id, const char*& seq, uint32_t& len) const
+	{
+		id = mOrderId[k];
+		seq = mInput.data() + mOrderOff[k];
+		len = mOrderLen[k];
+	}
+
 	// the sequence of read `id` (PackId(fragment, end)), or false when this file does not hold it
 	bool Find(int id, const char*& seq, uint32_t& len) const
 	{
@@ -463,8 +484,147 @@ private:
 	std::vector<uint64_t> mOff;
 	std::vector<uint32_t> mLen;
 	std::unordered_map<int, std::pair<uint64_t, uint32_t>> mSparse;
+	std::vector<int> mOrderId;
+	std::vector<uint64_t> mOrderOff;
+	std::vector<uint32_t> mOrderLen;
 	std::string mMessage;
 	bool mFatal = false;
+};
+
+// Whole-line blocks of an input that may be too large to hold at once (localalign reads gigabytes from stdin): a
+// mapped file is handed out in windows, a pipe is read block by block on a helper thread while the previous block
+// is being processed.  Every block ends behind a '\n' except possibly the last.
+class LineBlocks
+{
+public:
+	LineBlocks() = default;
+	LineBlocks(const LineBlocks&) = delete;
+	LineBlocks& operator=(const LineBlocks&) = delete;
+	~LineBlocks()
+	{
+		if (mPrefetch.joinable()) mPrefetch.join();
+		if (mMap) munmap((void*)mMap, mMapSize);
+		free(mBuf[0].p);
+		free(mBuf[1].p);
+	}
+	void Open(int fd, size_t block_bytes)
+	{
+		mFd = fd;
+		mBlock = std::max<size_t>(block_bytes, 16);
+		struct stat st;
+		if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0)
+		{
+			const off_t at = lseek(fd, 0, SEEK_CUR);
+			void* p = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+			if (p != MAP_FAILED)
+			{
+				mMap = (const char*)p;
+				mMapSize = (size_t)st.st_size;
+				mMapPos = at > 0 ? (size_t)at : 0;
+				madvise(p, mMapSize, MADV_SEQUENTIAL);
+				return;
+			}
+		}
+		StartRead(0, 0);
+	}
+	// next block of whole lines; false at the end of the input.  The memory stays valid until the next call.
+	bool Next(const char*& p, size_t& n)
+	{
+		if (mMap)
+		{
+			if (mMapPos >= mMapSize) return false;
+			size_t end = std::min(mMapSize, mMapPos + mBlock);
+			if (end < mMapSize)
+			{
+				const char* nl = (const char*)memchr(mMap + end - 1, '\n', mMapSize - end + 1);
+				end = nl ? (size_t)(nl - mMap) + 1 : mMapSize;
+			}
+			p = mMap + mMapPos;
+			n = end - mMapPos;
+			mMapPos = end;
+			return true;
+		}
+		for (;;)
+		{
+			if (mPrefetch.joinable()) mPrefetch.join();
+			if (mFinished) return false;
+			Buf& cur = mBuf[mFill];
+			const size_t have = mHave;
+			if (mEof)
+			{
+				mFinished = true;
+				p = cur.p;
+				n = have;
+				return have > 0;
+			}
+			size_t cut = have;
+			while (cut > 0 && cur.p[cut - 1] != '\n') cut--;
+			if (cut == 0)
+			{
+				// one line longer than the block: keep reading into the same buffer
+				StartRead(mFill, have);
+				continue;
+			}
+			const int other = 1 - mFill;
+			mBuf[other].Ensure(have - cut + mBlock);
+			if (have > cut) memcpy(mBuf[other].p, cur.p + cut, have - cut);
+			p = cur.p;
+			n = cut;
+			StartRead(other, have - cut);
+			return true;
+		}
+	}
+
+private:
+	struct Buf
+	{
+		char* p = nullptr;
+		size_t cap = 0;
+		void Ensure(size_t n)
+		{
+			if (n <= cap) return;
+			char* q = (char*)realloc(p, n);
+			if (!q)
+			{
+				fprintf(stderr, "Error: out of memory reading the input\n");
+				exit(1);
+			}
+			p = q;
+			cap = n;
+		}
+	};
+	// reads up to one more block into mBuf[which] behind `carry` bytes, on a helper thread
+	void StartRead(int which, size_t carry)
+	{
+		mFill = which;
+		mBuf[which].Ensure(carry + mBlock);
+		mPrefetch = std::thread([this, carry, which] {
+			size_t have = carry;
+			const size_t want = carry + mBlock;
+			char* const buf = mBuf[which].p;
+			while (have < want)
+			{
+				const ssize_t got = read(mFd, buf + have, want - have);
+				if (got < 0 && errno == EINTR) continue;
+				if (got <= 0)
+				{
+					mEof = true;
+					break;
+				}
+				have += (size_t)got;
+			}
+			mHave = have;
+		});
+	}
+	int mFd = 0;
+	size_t mBlock = 1 << 28;
+	const char* mMap = nullptr;
+	size_t mMapSize = 0, mMapPos = 0;
+	Buf mBuf[2];
+	int mFill = 0;
+	size_t mHave = 0;
+	bool mEof = false, mFinished = false;
+	std::thread mPrefetch;
 };
 
 }  // namespace dfbhost

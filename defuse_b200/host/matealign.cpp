@@ -3,10 +3,14 @@
 // For every read whose OTHER end has alignments in the SAM, the read is aligned against the
 // searchlength+1 window downstream of each of those alignments (N-padded at the sequence ends),
 // in fastq order x SAM order (tools/matealign.cpp:179-223).  SimpleAligner::Align (:209) runs on
-// the GPU in batches; everything else is the same host logic, written for batching.
+// the GPU in batches; everything else is the same host logic, written for batching: the SAM is parsed by
+// line-aligned chunks on all host threads, both fastq files are indexed in place meanwhile, windows are cut and
+// reverse-complemented in parallel straight into the upload table, records are formatted in parallel.
 #include "host_common.h"
+#include "fast_io.h"
 
 #include <fstream>
+#include <string_view>
 #include <unordered_map>
 
 using namespace dfbhost;
@@ -26,57 +30,78 @@ struct FastaSequences
 	std::unordered_map<std::string, std::string> seqs;
 	void Read(const std::string& filename)
 	{
-		std::ifstream in(filename.c_str());
-		if (!in.good())
+		MappedInput in;
+		if (!in.OpenFile(filename))
 		{
 			std::cerr << "Error: unable to open file " << filename << std::endl;
 			exit(1);
 		}
-		std::string id, sequence, line;
-		while (std::getline(in, line))
+		const char* a = in.data();
+		const char* const end = a + in.size();
+		std::string id, sequence;
+		while (a < end)
 		{
-			if (line.empty()) continue;
-			if (line[0] == '>')
+			const char* nl = (const char*)memchr(a, '\n', (size_t)(end - a));
+			const char* const e = nl ? nl : end;
+			if (e > a)
 			{
-				if (!id.empty()) seqs[id] = sequence;
-				id = line.substr(1);
-				sequence.clear();
+				if (*a == '>')
+				{
+					if (!id.empty()) seqs[id].swap(sequence);
+					id.assign(a + 1, e);
+					sequence.clear();
+				}
+				else
+				{
+					sequence.append(a, e);
+				}
 			}
-			else
-			{
-				sequence.append(line);
-			}
+			a = nl ? nl + 1 : end;
 		}
-		if (!id.empty()) seqs[id] = sequence;
+		if (!id.empty()) seqs[id].swap(sequence);
 	}
-	// [start, end] 1-based inclusive, 'N' where the window leaves the sequence (tools/Sequences.cpp:60-79)
-	void Window(const std::string& id, int start, int end, std::string& out) const
+	const std::string* Find(const std::string& id) const
 	{
 		auto it = seqs.find(id);
-		if (it == seqs.end())
-		{
-			std::cerr << "Error: Unable to find sequence " << id << std::endl;
-			exit(1);
-		}
-		const std::string& full = it->second;
-		const long long len = (long long)full.size();
-		const long long seq_start = std::max<long long>(1, start);
-		const long long prepend = seq_start - start;
-		const long long seq_end = std::min<long long>(len, end);
-		const long long append = (long long)end - seq_end;
-		out.assign((size_t)prepend, 'N');
-		if (seq_start - 1 > len || append < 0)
-		{
-			// std::string::substr / string(n,'N') would throw here in the reference (window starts beyond the
-			// sequence, or ends before position 1): it aborts; we report and fail the same way (non-zero exit)
-			std::cerr << "Error: window " << start << "-" << end << " outside sequence " << id << std::endl;
-			exit(1);
-		}
-		const long long take = seq_end - seq_start + 1;
-		if (take > 0) out.append(full, (size_t)(seq_start - 1), (size_t)take);
-		else if (take < 0) out.append(full, (size_t)(seq_start - 1), std::string::npos); // substr(pos, huge) semantics
-		out.append((size_t)append, 'N');
+		return it == seqs.end() ? nullptr : &it->second;
 	}
+};
+
+// [start, end] 1-based inclusive of `full`, 'N' where the window leaves the sequence (tools/Sequences.cpp:60-79):
+// string(prepend,'N') + full.substr(seq_start-1, seq_length) + string(append,'N'), with substr's own clipping.
+struct WindowPlan
+{
+	long long prepend, from, take, append; // take < 0: substr(pos, huge) = the rest of the sequence
+	bool bad;                              // the reference would throw (and abort) building this string
+	long long Length(long long full_len) const { return prepend + (take < 0 ? full_len - from : take) + append; }
+};
+
+inline WindowPlan PlanWindow(long long full_len, int start, int end)
+{
+	WindowPlan w;
+	const long long seq_start = std::max<long long>(1, start);
+	w.prepend = seq_start - start;
+	const long long seq_end = std::min<long long>(full_len, end);
+	w.append = (long long)end - seq_end;
+	w.from = seq_start - 1;
+	w.bad = w.from > full_len || w.append < 0;
+	w.take = seq_end - seq_start + 1;
+	if (!w.bad && w.take > full_len - w.from) w.take = full_len - w.from;
+	return w;
+}
+
+struct SamEntry
+{
+	int read_id;
+	int strand;
+	int position;
+	std::string_view ref_name;
+};
+
+struct Task
+{
+	uint32_t record;  // index into the fastq order of the file being walked
+	uint32_t mate;    // index into the sorted SAM entries
 };
 }  // namespace
 
@@ -100,130 +125,260 @@ int main(int argc, char* argv[])
 	const std::string reads_filename[2] = {cmd.Str('1'), cmd.Str('2')};
 
 	Gpu gpu;
+	PhaseTimer timer;
 	const dfb_simple_params params{match, mismatch, gap};
+	const int T = ToolThreads();
 
 	// ---- SAM on stdin -> alignments per read id, in input order (tools/matealign.cpp:80-158) ----
-	std::unordered_map<int, std::vector<MatePosition>> read_alignments;
-	std::unordered_map<std::string, int> ref_lookup;
-	std::vector<std::string> ref_names;
-	std::ios::sync_with_stdio(false);
-	std::string line;
-	int line_number = 0;
-	std::vector<std::string> f, q;
-	while (std::getline(std::cin, line))
+	MappedInput sam;
+	sam.OpenStdin();
+	std::vector<SamEntry> entries;
 	{
-		line_number++;
-		if (line.length() == 0)
+		const char* const base = sam.data();
+		std::vector<LineChunk> chunks = SplitLines(base, sam.size(), T);
+		struct Part
 		{
-			std::cerr << "Error: Empty alignment line " << line_number << std::endl;
-			exit(1);
-		}
-		if (line[0] == '@') continue;
-		SplitChar(line, '\t', f);
-		if (f.size() < 10)
-		{
-			std::cerr << "Error: Format error for alignment line " << line_number << std::endl;
-			exit(1);
-		}
-		const int flag = IntOrDie(f[1], "flag");
-		const int pos = IntOrDie(f[3], "pos");
-		if (f[2] == "*") continue;
-		const int strand = (flag & 0x0010) == 0 ? 0 : 1;
-		SplitChar(f[0], '/', q);
-		if (q.size() != 2 || (q[1] != "1" && q[1] != "2"))
-		{
-			std::cerr << "Error: Unable to interpret qname for alignment line " << line_number << std::endl;
-			exit(1);
-		}
-		const int read_end = q[1] == "1" ? 0 : 1;
-		const int start = pos;
-		const int end = start + (int)f[9].length() - 1;
-		const int fragment_index = IntOrDie(q[0], "fragment index");
-		auto ins = ref_lookup.emplace(f[2], (int)ref_names.size());
-		if (ins.second) ref_names.push_back(f[2]);
-		MatePosition mp;
-		mp.ref_index = ins.first->second;
-		mp.strand = strand;
-		mp.position = strand == 0 ? start : end;
-		read_alignments[PackId(fragment_index, read_end)].push_back(mp);
+			std::vector<SamEntry> entries;
+			int64_t error_line = -1;
+			std::string error;
+		};
+		std::vector<Part> parts(chunks.size());
+		ParallelRun((int)chunks.size(), [&](int c) {
+			Part& part = parts[(size_t)c];
+			const char* a = base + chunks[(size_t)c].begin;
+			const char* const end = base + chunks[(size_t)c].end;
+			int64_t line_number = chunks[(size_t)c].first_line;
+			auto fail = [&](const std::string& msg) {
+				part.error_line = line_number;
+				part.error = msg;
+			};
+			while (a < end)
+			{
+				const char* nl = (const char*)memchr(a, '\n', (size_t)(end - a));
+				const char* const b = a;
+				const char* const e = nl ? nl : end;
+				a = nl ? nl + 1 : end;
+				line_number++;
+				if (b == e) return fail("Error: Empty alignment line " + std::to_string(line_number));
+				if (*b == '@') continue;
+				const char* f[11];
+				int nf = 0;
+				f[0] = b;
+				for (const char* q = b; nf < 10;)
+				{
+					const char* t = (const char*)memchr(q, '\t', (size_t)(e - q));
+					if (!t)
+					{
+						if (nf == 9) f[++nf] = e + 1;
+						break;
+					}
+					f[++nf] = t + 1;
+					q = t + 1;
+				}
+				if (nf < 10) return fail("Error: Format error for alignment line " + std::to_string(line_number));
+				int flag = 0, pos = 0;
+				if (!ParseIntRange(f[1], f[2] - 1, flag)) return fail("Error: bad lexical cast: flag '" + std::string(f[1], f[2] - 1) + "'");
+				if (!ParseIntRange(f[3], f[4] - 1, pos)) return fail("Error: bad lexical cast: pos '" + std::string(f[3], f[4] - 1) + "'");
+				if (f[3] - 1 - f[2] == 1 && *f[2] == '*') continue;
+				const char* const qb = f[0];
+				const char* const qe = f[1] - 1;
+				const char* slash = (const char*)memchr(qb, '/', (size_t)(qe - qb));
+				if (!slash || memchr(slash + 1, '/', (size_t)(qe - slash - 1)) || qe - slash != 2 || (slash[1] != '1' && slash[1] != '2'))
+					return fail("Error: Unable to interpret qname for alignment line " + std::to_string(line_number));
+				int fragment_index = 0;
+				if (!ParseIntRange(qb, slash, fragment_index))
+					return fail("Error: bad lexical cast: fragment index '" + std::string(qb, slash) + "'");
+				SamEntry en;
+				en.strand = (flag & 0x0010) == 0 ? 0 : 1;
+				const int start = pos, stop = start + (int)(f[10] - 1 - f[9]) - 1;
+				en.position = en.strand == 0 ? start : stop;
+				en.read_id = PackId(fragment_index, slash[1] == '1' ? 0 : 1);
+				en.ref_name = std::string_view(f[2], (size_t)(f[3] - 1 - f[2]));
+				part.entries.push_back(en);
+			}
+		});
+		for (const Part& part : parts)
+			if (part.error_line >= 0)
+			{
+				std::cerr << part.error << std::endl;
+				exit(1);
+			}
+		size_t total = 0;
+		for (const Part& part : parts) total += part.entries.size();
+		entries.reserve(total);
+		for (const Part& part : parts) entries.insert(entries.end(), part.entries.begin(), part.entries.end());
 	}
+	// alignments of one read stay in input order: stable sort by read id, then ranges by binary search
+	std::stable_sort(entries.begin(), entries.end(), [](const SamEntry& a, const SamEntry& b) { return (unsigned)a.read_id < (unsigned)b.read_id; });
 	std::cerr << "Read alignments" << std::endl;
+	timer.Lap("sam");
 
 	FastaSequences reference;
 	reference.Read(reference_fasta);
 	std::cerr << "Read reference fasta" << std::endl;
+	timer.Lap("fasta");
+	// reference name -> sequence, resolved once per distinct name
+	std::unordered_map<std::string_view, const std::string*> ref_of;
+	for (const SamEntry& en : entries)
+		if (ref_of.find(en.ref_name) == ref_of.end()) ref_of.emplace(en.ref_name, reference.Find(std::string(en.ref_name)));
 
-	FastqReader streams[2];
-	const bool ok0 = streams[0].Open(reads_filename[0]);
-	const bool ok1 = streams[1].Open(reads_filename[1]);
+	FastqIndex fastq[2];
+	const bool ok0 = fastq[0].Open(reads_filename[0]);
+	const bool ok1 = fastq[1].Open(reads_filename[1]);
+	std::cerr << fastq[0].Message() << fastq[1].Message();
 	if (!ok0 || !ok1)
 	{
 		std::cout << "Error: unable to read sequences" << std::endl;
 		exit(1);
 	}
 
-	// ---- tasks: (window, read) in fastq order x SAM order; flushed in batches ----
-	TableBuilder windows, reads;
-	std::vector<int32_t> task_ref, task_seq, task_fragment, task_len, score;
 	size_t kBatchTasks = 1u << 19;
 	if (const char* e = getenv("DFB_TOOL_BATCH")) kBatchTasks = (size_t)std::max(1, atoi(e)); // tests: force several batches
-	const size_t kBatchBytes = 1u << 28;
-	auto flush = [&]() {
-		if (task_ref.empty()) return;
-		score.resize(task_ref.size());
-		dfb_seq_table wt = windows.View(), rt = reads.View();
-		if (dfb_simple_align_batch(gpu.ctx(), &params, &wt, &rt, task_ref.data(), task_seq.data(), (int64_t)task_ref.size(),
-		                           score.data()) != DFB_OK)
-			gpu.Die("alignment failed");
-		std::ostringstream os;
-		for (size_t k = 0; k < task_ref.size(); k++)
-		{
-			const int max_score = task_len[k] * match;                   // tools/matealign.cpp:211
-			const double percent = (double)score[k] / (double)max_score; // :212
-			if (percent < threshold) continue;
-			os << task_fragment[k] << "\t" << score[k] << "\t" << percent << "\n";
-		}
-		std::cout << os.str();
-		std::cout.flush();
-		windows.Clear();
-		reads.Clear();
-		task_ref.clear();
-		task_seq.clear();
-		task_fragment.clear();
-		task_len.clear();
-	};
+	const size_t kBatchBytes = (size_t)1 << 29;
+	TableBuilder windows, reads;
+	std::vector<int32_t> task_ref, task_seq, score;
+	std::vector<Task> tasks;
+	std::vector<std::string> out_parts((size_t)T);
+	static unsigned char complement[256];
+	for (int k = 0; k < 256; k++) complement[k] = (unsigned char)k;
+	for (int k = 0; k < 8; k++) complement[(unsigned char)"ACGTacgt"[k]] = (unsigned char)"TGCAtgca"[k]; // tools/Common.cpp:32-54
 
-	std::string window;
+	// ---- tasks: (window, read) in fastq order x SAM order; flushed in batches ----
 	for (int file = 0; file <= 1; file++)
 	{
-		FastqRead read;
-		while (streams[file].Next(read))
-		{
-			const int fragment_index = IntOrDie(read.fragment, "fragment index");
-			const int other_id = PackId(fragment_index, 1 - read.read_end);
-			auto it = read_alignments.find(other_id);
-			if (it == read_alignments.end()) continue;
-			int32_t read_slot = -1;
-			for (const MatePosition& mp : it->second)
+		fastq[file].Scan(T, true);
+		timer.Add("fastq index");
+		const FastqIndex& fq = fastq[file];
+		// one batch: tasks [tasks of records r0..r1)
+		auto flush = [&]() {
+			const size_t n = tasks.size();
+			if (n == 0) return;
+			// window lengths and read slots (a read is uploaded once, its tasks are consecutive)
+			windows.Clear();
+			reads.Clear();
+			task_ref.resize(n);
+			task_seq.resize(n);
+			score.resize(n);
+			std::vector<const std::string*> full(n);
+			std::vector<WindowPlan> plan(n);
+			int64_t bad = -1;
+			for (size_t k = 0; k < n; k++)
 			{
-				if (mp.strand == 0)
+				const SamEntry& en = entries[tasks[k].mate];
+				const std::string* seq = ref_of.find(en.ref_name)->second;
+				if (!seq)
 				{
-					reference.Window(ref_names[mp.ref_index], mp.position, mp.position + search_length, window);
-					ReverseComplementInPlace(window);
+					std::cerr << "Error: Unable to find sequence " << en.ref_name << std::endl;
+					exit(1);
 				}
-				else
+				full[k] = seq;
+				plan[k] = en.strand == 0 ? PlanWindow((long long)seq->size(), en.position, en.position + search_length)
+				                         : PlanWindow((long long)seq->size(), en.position - search_length, en.position);
+				if (plan[k].bad && bad < 0) bad = (int64_t)k;
+				windows.off.push_back(windows.off.back() + (plan[k].bad ? 0 : plan[k].Length((long long)seq->size())));
+				if (k == 0 || tasks[k].record != tasks[k - 1].record)
 				{
-					reference.Window(ref_names[mp.ref_index], mp.position - search_length, mp.position, window);
+					int id;
+					const char* s;
+					uint32_t len;
+					fq.Record(tasks[k].record, id, s, len);
+					reads.Add(s, len);
 				}
-				if (read_slot < 0) read_slot = (int32_t)reads.Add(read.sequence);
-				task_ref.push_back((int32_t)windows.Add(window));
-				task_seq.push_back(read_slot);
-				task_fragment.push_back((int32_t)((unsigned)fragment_index & 0x7fffffffu)); // readID.fragmentIndex is a 31-bit field
-				task_len.push_back((int)read.sequence.size());
+				task_ref[k] = (int32_t)k;
+				task_seq[k] = (int32_t)reads.Count() - 1;
 			}
-			if (task_ref.size() >= kBatchTasks || windows.bytes.size() + reads.bytes.size() >= kBatchBytes) flush();
+			if (bad >= 0)
+			{
+				// std::string(n,'N') / substr would throw here in the reference (window starts beyond the sequence, or ends
+				// before position 1): it aborts; we report and fail the same way (non-zero exit)
+				const SamEntry& en = entries[tasks[(size_t)bad].mate];
+				std::cerr << "Error: window around " << en.position << " outside sequence " << en.ref_name << std::endl;
+				exit(1);
+			}
+			windows.bytes.resize((size_t)windows.off.back());
+			ParallelRun(T, [&](int tid) {
+				for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
+				{
+					const WindowPlan& w = plan[k];
+					const std::string& seq = *full[k];
+					char* dst = &windows.bytes[0] + windows.off[k];
+					const long long take = w.take < 0 ? (long long)seq.size() - w.from : w.take;
+					const long long len = w.prepend + take + w.append;
+					if (entries[tasks[k].mate].strand == 0)
+					{
+						// plus-strand mate: the window is reverse-complemented (tools/matealign.cpp:197-201)
+						char* q = dst + len;
+						for (long long j = 0; j < w.prepend; j++) *--q = 'N';
+						const char* src = seq.data() + w.from;
+						for (long long j = 0; j < take; j++) *--q = (char)complement[(unsigned char)src[j]];
+						for (long long j = 0; j < w.append; j++) *--q = 'N';
+					}
+					else
+					{
+						memset(dst, 'N', (size_t)w.prepend);
+						if (take) memcpy(dst + w.prepend, seq.data() + w.from, (size_t)take);
+						memset(dst + w.prepend + take, 'N', (size_t)w.append);
+					}
+				}
+			});
+			timer.Add("tables");
+			dfb_seq_table wt = windows.View(), rt = reads.View();
+			if (dfb_simple_align_batch(gpu.ctx(), &params, &wt, &rt, task_ref.data(), task_seq.data(), (int64_t)n, score.data()) != DFB_OK)
+				gpu.Die("alignment failed");
+			timer.Add("gpu");
+			ParallelRun(T, [&](int tid) {
+				std::string& os = out_parts[(size_t)tid];
+				os.clear();
+				char num[64];
+				for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
+				{
+					int id;
+					const char* s;
+					uint32_t len;
+					fq.Record(tasks[k].record, id, s, len);
+					const int max_score = (int)len * match;                       // tools/matealign.cpp:211
+					const double percent = (double)score[k] / (double)max_score; // :212
+					if (percent < threshold) continue;
+					AppendInt(os, IdIndex(id)); // readID.fragmentIndex is a 31-bit field
+					os += '\t';
+					AppendInt(os, score[k]);
+					os += '\t';
+					os.append(num, (size_t)snprintf(num, sizeof(num), "%.6g", percent)); // ostream's default float format
+					os += '\n';
+				}
+			});
+			for (const std::string& part : out_parts) fwrite(part.data(), 1, part.size(), stdout);
+			fflush(stdout);
+			timer.Add("format + write");
+			tasks.clear();
+		};
+		size_t batch_bytes = 0;
+		for (size_t r = 0; r < fq.Count(); r++)
+		{
+			int id;
+			const char* s;
+			uint32_t len;
+			fq.Record(r, id, s, len);
+			const unsigned other = (unsigned)PackId(IdIndex(id), 1 - IdEnd(id));
+			auto lo = std::lower_bound(entries.begin(), entries.end(), other,
+			                           [](const SamEntry& a, unsigned key) { return (unsigned)a.read_id < key; });
+			for (; lo != entries.end() && (unsigned)lo->read_id == other; ++lo)
+			{
+				tasks.push_back(Task{(uint32_t)r, (uint32_t)(lo - entries.begin())});
+				batch_bytes += (size_t)search_length + 1 + len;
+			}
+			if (tasks.size() >= kBatchTasks || batch_bytes >= kBatchBytes)
+			{
+				flush();
+				batch_bytes = 0;
+			}
 		}
+		flush();
+		// a malformed record ends this file's stream with the reference's message; a fragment name that is not an
+		// integer is where the reference dies
+		std::cerr << fastq[file].Message();
+		if (fastq[file].Fatal()) exit(1);
 	}
-	flush();
+	timer.Report();
 	FinishProcess(0);
 }

@@ -133,3 +133,39 @@ def test_tools_with_many_small_batches(oracle_mod, tmp_path):
     for run in gl["runs"].values():
         out = _run([os.path.join(BIN, "localalign")] + run["args"], gl["stdin"].encode(), env={"DFB_TOOL_BATCH": "7"})
         assert out.decode() == run["stdout"]
+
+
+def test_localalign_blocks_pipe_and_mapped_file(oracle_mod, tmp_path):
+    """stdin is consumed in blocks of whole lines: read ahead from a pipe, or mapped when it is a file.  Block and
+    chunk boundaries anywhere, output bytes unchanged; a bad line still ends the run where the reference ends it."""
+    from synth import files
+    ref = _ref(oracle_mod, "ref_localalign")
+    sc = ["-m", "10", "-x", "-5", "-g", "-5", "-t", "0.3"]
+    text = files.make_localalign_input(seed=17, n_refs=12, n_lines=900)
+    want = _run([ref] + sc, text)
+    path = str(tmp_path / "in.txt")
+    open(path, "wb").write(text)
+    for block, chunk in (("5000", "1"), ("70000", "3000"), ("1", "1"), ("300000000", "65536")):
+        env = {"DFB_TOOL_BLOCK": block, "DFB_TOOL_CHUNK_MIN": chunk}
+        assert _run([os.path.join(BIN, "localalign")] + sc, text, env=env) == want, ("pipe", block, chunk)
+        with open(path, "rb") as f:
+            p = subprocess.run([os.path.join(BIN, "localalign")] + sc, stdin=f, capture_output=True, env=dict(os.environ, **env))
+        assert p.returncode == 0 and p.stdout == want, ("file", block, chunk)
+    bad = text + b"oops no tabs\n" + text[:5000]
+    theirs = subprocess.run([ref] + sc, input=bad, capture_output=True)
+    for block in ("4000", "300000000"):
+        ours = subprocess.run([os.path.join(BIN, "localalign")] + sc, input=bad, capture_output=True,
+                              env=dict(os.environ, DFB_TOOL_BLOCK=block, DFB_TOOL_CHUNK_MIN="500"))
+        assert ours.returncode == theirs.returncode == 1
+        assert ours.stdout == theirs.stdout and ours.stderr == theirs.stderr
+
+
+def test_matealign_chunked_ingest(oracle_mod, tmp_path):
+    from synth import files
+    ref = _ref(oracle_mod, "ref_matealign")
+    args, sam = files.make_matealign_dataset(str(tmp_path / "m"), seed=23, n_pairs=700)
+    want = _run([ref] + args, sam)
+    for chunk, threads, batch in (("1", "16", "50"), ("900", "3", "100000")):
+        got = _run([os.path.join(BIN, "matealign")] + args, sam,
+                   env={"DFB_TOOL_CHUNK_MIN": chunk, "DFB_TOOL_THREADS": threads, "DFB_TOOL_BATCH": batch})
+        assert got == want
