@@ -263,8 +263,10 @@ extern "C" int dfb_ctx_create(int device_ordinal, dfb_ctx** out)
 {
 	if (!out) return set_err(nullptr, DFB_ERR_ARG, "dfb_ctx_create: null output pointer");
 	*out = nullptr;
+	Trace tr;
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
+	tr.lap("ctx: cudaGetDeviceCount");
 	if (e != cudaSuccess || n <= 0)
 	{
 		return set_err(nullptr, DFB_ERR_NODEVICE, "no CUDA device available (%s); this library has no CPU fallback",
@@ -316,6 +318,7 @@ extern "C" int dfb_ctx_create(int device_ordinal, dfb_ctx** out)
 	ctx->host_threads = (int)std::max(1u, std::min(hc ? hc : 1u, 16u));
 	ctx->pool = new (std::nothrow) HostPool(ctx->host_threads);
 	ctx->pool_fetch = new (std::nothrow) HostPool(std::max(2, ctx->host_threads / 2));
+	tr.lap("ctx: context, streams, pools");
 	*out = ctx;
 	return DFB_OK;
 }
@@ -860,11 +863,13 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 	pl->sp.mismatch = params->mismatch;
 	pl->sp.gap = params->gap;
 	classify_params(pl, params->match, params->mismatch, params->gap, true);
+	Trace tr;
 	if ((rc = upload_raw(pl, refs, seqs)))
 	{
 		dfb_plan_destroy(pl);
 		return rc;
 	}
+	tr.lap("simple.create: raw upload");
 
 	// pass 1: classify every task, count per (class, reference-length bin)
 	std::vector<int32_t> bin_of((size_t)n_tasks);
@@ -918,6 +923,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 		n_fast_jobs += n_jobs_cls[c];
 	}
 
+	tr.lap("simple.create: classify");
 	Staging st;
 	cudaError_t e = stage_layout(ctx, 0, st, refs->n, seqs->n, n_fast_jobs, n_gen);
 	if (e != cudaSuccess)
@@ -925,6 +931,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 		dfb_plan_destroy(pl);
 		return set_err(ctx, DFB_ERR_NOMEM, "pinned staging buffer: %s", cudaGetErrorString(e));
 	}
+	tr.lap("simple.create: staging");
 	uint32_t words_a_end = 0;
 	bool overflow = false;
 	const uint32_t total_words = layout_words(refs, PACK_FWD, seqs, PACK_FWD, st.desc_a, st.desc_b, &words_a_end, &overflow);
@@ -968,15 +975,19 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 		if (h == 0) jp.out0 = (int32_t)t; else jp.out1 = (int32_t)t;
 	}
 	pl->n_gen_jobs = n_gen;
+	tr.lap("simple.create: jobs");
 
 	rc = upload_and_pack(pl, refs, PACK_FWD, seqs, PACK_FWD, st, words_a_end, total_words);
+	tr.lap("simple.create: enqueue pack");
 	if (!rc) rc = alloc_work(pl, st, n_jobs_cls, false, gen_max_R);
+	tr.lap("simple.create: alloc");
 	if (!rc)
 	{
 		for (int c = 0; c < kNumClasses; c++)
 			if (pl->cls[c].n_jobs) fill_fast_params(pl, c, params->match, params->mismatch, params->gap, 0);
 		rc = finish_create(pl);
 	}
+	tr.lap("simple.create: sync");
 	if (rc)
 	{
 		dfb_plan_destroy(pl);
@@ -1752,11 +1763,15 @@ extern "C" int dfb_simple_align_batch(dfb_ctx* ctx, const dfb_simple_params* par
                                       int64_t n_tasks, int32_t* out_score)
 {
 	dfb_plan* pl = nullptr;
+	Trace tr;
 	int rc = dfb_simple_plan_create(ctx, params, refs, seqs, task_ref, task_seq, n_tasks, &pl);
 	if (rc) return rc;
+	tr.lap("simple: create");
 	rc = dfb_plan_run(pl);
 	if (!rc) rc = dfb_simple_plan_fetch(pl, out_score);
+	tr.lap("simple: run + fetch");
 	dfb_plan_destroy(pl);
+	tr.lap("simple: destroy");
 	return rc;
 }
 

@@ -59,5 +59,100 @@ def main():
     print(json.dumps(out))
 
 
+def localalign_scale(n_lines, n_refs):
+    """BASELINE.json configs[1]: localalign, 100-bp reads against 2001-bp references, input redirected from a file."""
+    import numpy as np
+    out = {"lines": n_lines, "refs": n_refs}
+    sc = ["-m", "10", "-x", "-5", "-g", "-5", "-t", "0.8"]
+    with tempfile.TemporaryDirectory() as d:
+        rng = np.random.default_rng(2)
+        refs = [files.rand_seq(rng, 2001) for _ in range(n_refs)]
+        path = os.path.join(d, "in.txt")
+        t0 = time.perf_counter()
+        sample_lines = max(2000, n_lines // 100)
+        with open(path, "wb") as f, open(path + ".sample", "wb") as fs:
+            per_ref = max(1, n_lines // n_refs)
+            k = 0
+            for r in refs:                         # the pipeline repeats a reference on consecutive lines
+                offs = rng.integers(0, 2001 - 100, per_ref)
+                unrelated = rng.random(per_ref) < 0.2
+                buf = []
+                for o, u in zip(offs, unrelated):
+                    seq = files.rand_seq(rng, 100) if u else files.mutate(rng, r[o:o + 100], 0.02, 0.0)
+                    buf.append(b"c%d\t%s\t%s\n" % (k, r, seq))
+                    k += 1
+                blob = b"".join(buf)
+                f.write(blob)
+                if k <= sample_lines:
+                    fs.write(blob)
+        out["generate_s"] = time.perf_counter() - t0
+        out["stdin_MB"] = os.path.getsize(path) / 1e6
+        runs = []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            with open(path, "rb") as f:
+                p = subprocess.run([os.path.join(BIN, "localalign")] + sc, stdin=f, capture_output=True, env=dict(os.environ, DFB_TRACE="1"))
+            runs.append(time.perf_counter() - t0)
+            assert p.returncode == 0, p.stderr.decode()[-2000:]
+        out["ours_s"], out["ours_runs_s"] = min(runs), runs
+        out["lines_per_s"] = k / out["ours_s"]
+        out["gcups_wall"] = k * 2001 * 100 / out["ours_s"] / 1e9
+        out["trace_last_run"] = [l for l in p.stderr.decode().splitlines() if l.startswith("[tool]")]
+        ours_full = p.stdout
+        # through a pipe as the pipeline does it (cat | localalign)
+        t0 = time.perf_counter()
+        p2 = subprocess.run("cat %s | %s %s" % (path, os.path.join(BIN, "localalign"), " ".join(sc)), shell=True, capture_output=True)
+        out["ours_pipe_s"] = time.perf_counter() - t0
+        out["pipe_identical"] = p2.stdout == ours_full
+        ref = oracle.ref_tool("ref_localalign")
+        if ref:
+            n_sample = sum(1 for _ in open(path + ".sample", "rb"))
+            t0 = time.perf_counter()
+            with open(path + ".sample", "rb") as f:
+                q = subprocess.run([ref] + sc, stdin=f, capture_output=True)
+            ref_s = time.perf_counter() - t0
+            with open(path + ".sample", "rb") as f:
+                o = subprocess.run([os.path.join(BIN, "localalign")] + sc, stdin=f, capture_output=True)
+            out["reference_sample"] = {"lines": n_sample, "seconds": ref_s, "lines_per_s": n_sample / ref_s,
+                                       "identical": q.stdout == o.stdout}
+            out["speedup_in_lines_per_s"] = out["lines_per_s"] / out["reference_sample"]["lines_per_s"]
+    return out
+
+
+def matealign_scale(n_pairs):
+    """BASELINE.json configs[3]: matealign, 150-bp pairs, search length 1000."""
+    out = {"pairs": n_pairs}
+    with tempfile.TemporaryDirectory() as d:
+        t0 = time.perf_counter()
+        margs, sam = files.make_matealign_dataset(os.path.join(d, "m"), seed=4, n_pairs=n_pairs)
+        out["generate_s"] = time.perf_counter() - t0
+        runs = []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            p = subprocess.run([os.path.join(BIN, "matealign")] + margs, input=sam, capture_output=True, env=dict(os.environ, DFB_TRACE="1"))
+            runs.append(time.perf_counter() - t0)
+            assert p.returncode == 0, p.stderr.decode()[-2000:]
+        out["ours_s"], out["ours_runs_s"] = min(runs), runs
+        out["records"] = p.stdout.count(b"\n")
+        out["pairs_per_s"] = n_pairs / out["ours_s"]
+        out["trace_last_run"] = [l for l in p.stderr.decode().splitlines() if l.startswith("[tool]")]
+        ref = oracle.ref_tool("ref_matealign")
+        if ref:
+            n_sample = max(2000, n_pairs // 50)
+            sargs, ssam = files.make_matealign_dataset(os.path.join(d, "s"), seed=4, n_pairs=n_sample)
+            t0 = time.perf_counter()
+            q = subprocess.run([ref] + sargs, input=ssam, capture_output=True)
+            ref_s = time.perf_counter() - t0
+            o = subprocess.run([os.path.join(BIN, "matealign")] + sargs, input=ssam, capture_output=True)
+            out["reference_sample"] = {"pairs": n_sample, "seconds": ref_s, "pairs_per_s": n_sample / ref_s, "identical": q.stdout == o.stdout}
+            out["speedup_in_pairs_per_s"] = out["pairs_per_s"] / out["reference_sample"]["pairs_per_s"]
+    return out
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "localalign":
+        print(json.dumps(localalign_scale(int(sys.argv[2]) if len(sys.argv) > 2 else 1000000, int(sys.argv[3]) if len(sys.argv) > 3 else 10000)))
+    elif len(sys.argv) > 1 and sys.argv[1] == "matealign":
+        print(json.dumps(matealign_scale(int(sys.argv[2]) if len(sys.argv) > 2 else 300000)))
+    else:
+        main()
