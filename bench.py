@@ -276,6 +276,10 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if world > 1:
+        # one process per GPU on one host: the ranks share its cores (the context's worker pool defaults to 16 threads)
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        os.environ.setdefault("DFB_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 16) // max(1, local_world)))))
     ctx = d.Context(local_rank)
     # a side stream: the legacy default stream has handle 0, which the C ABI reads as "use your own"
     stream = torch.cuda.Stream()

@@ -12,6 +12,7 @@
 //    spread over host threads.
 #include "../../include/defuse_b200.h"
 #include "dfb_kernels.cuh"
+#include "dfb_assemble.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -316,6 +317,9 @@ extern "C" int dfb_ctx_create(int device_ordinal, dfb_ctx** out)
 	}
 	unsigned hc = std::thread::hardware_concurrency();
 	ctx->host_threads = (int)std::max(1u, std::min(hc ? hc : 1u, 16u));
+	// several contexts share one host (one process per GPU): DFB_HOST_THREADS caps the workers of each
+	if (const char* e = getenv("DFB_HOST_THREADS"))
+		if (atoi(e) > 0) ctx->host_threads = std::min(atoi(e), 64);
 	ctx->pool = new (std::nothrow) HostPool(ctx->host_threads);
 	ctx->pool_fetch = new (std::nothrow) HostPool(std::max(2, ctx->host_threads / 2));
 	tr.lap("ctx: context, streams, pools");
@@ -482,6 +486,12 @@ struct dfb_plan
 	int* d_gen_probe_flag = nullptr;
 	int32_t* d_task_min_score = nullptr;
 	int64_t gen_rows_total = 0;
+	// result assembly on the device (split): rows / columns of the tasks whose arg-max columns fit their region
+	dfb_split_row* d_asm_rows = nullptr;
+	int32_t* d_asm_cols = nullptr;
+	unsigned long long* d_asm_sums = nullptr; // [blocks][2] + totals[2] behind them
+	int64_t asm_blocks = 0;
+	int64_t n_fast_tasks = 0;
 
 	// host
 	std::vector<int32_t> task_L; // read length per task (split)
@@ -545,6 +555,9 @@ static void release_device(dfb_plan* plan)
 	dfree(ctx, plan->d_gen_bnd);
 	dfree(ctx, plan->d_gen_probe_flag);
 	dfree(ctx, plan->d_task_min_score);
+	dfree(ctx, plan->d_asm_rows);
+	dfree(ctx, plan->d_asm_cols);
+	dfree(ctx, plan->d_asm_sums);
 }
 
 extern "C" void dfb_plan_destroy(dfb_plan* plan)
@@ -824,6 +837,15 @@ static int alloc_work(dfb_plan* pl, const Staging& st, const int64_t* n_jobs_cls
 	DALLOC(ctx, pl->d_out, (size_t)std::max<int64_t>(pl->n_tasks, 1) * sizeof(int32_t));
 	CK(ctx, cudaMemsetAsync(pl->d_out, 0, (size_t)std::max<int64_t>(pl->n_tasks, 1) * sizeof(int32_t), ctx->stream));
 	if (split) DALLOC(ctx, pl->d_task_slot, (size_t)std::max<int64_t>(pl->n_tasks, 1) * sizeof(int32_t));
+	if (split && first > 0)
+	{
+		// a task assembled on the device has at most DFB_SLOT_EVENTS columns, hence at most half as many rows
+		pl->n_fast_tasks = first;
+		pl->asm_blocks = (pl->n_tasks + DFB_ASM_BLOCK - 1) / DFB_ASM_BLOCK;
+		DALLOC(ctx, pl->d_asm_rows, (size_t)first * (DFB_SLOT_EVENTS / 2) * sizeof(dfb_split_row));
+		DALLOC(ctx, pl->d_asm_cols, (size_t)first * DFB_SLOT_EVENTS * sizeof(int32_t));
+		DALLOC(ctx, pl->d_asm_sums, ((size_t)pl->asm_blocks + 1) * 2 * sizeof(unsigned long long));
+	}
 	return DFB_OK;
 }
 
@@ -1287,6 +1309,42 @@ static int run_probe(dfb_plan* pl)
 	return DFB_OK;
 }
 
+// rows and column lists of the tasks whose arg-max columns all sit in their region, in task order (dfb_assemble.cuh)
+static int run_assemble(dfb_plan* pl)
+{
+	dfb_ctx* ctx = pl->ctx;
+	if (!pl->d_asm_rows) return DFB_OK;
+	static_assert(kNumClasses <= DFB_ASM_MAX_CLASSES, "AsmParams class tables too small");
+	AsmParams ap;
+	memset(&ap, 0, sizeof(ap));
+	ap.n_tasks = pl->n_tasks;
+	ap.task_slot = pl->d_task_slot;
+	ap.n_classes = kNumClasses;
+	for (int c = 0; c < kNumClasses; c++)
+	{
+		const ClassWork& cw = pl->cls[c];
+		ap.job_base[c] = pl->job_base[c];
+		ap.slot_n[c] = cw.d_slot_n;
+		ap.slot_ev[c] = cw.d_slot_ev;
+		ap.hitq[c] = cw.d_hitq;
+		ap.jobs[c] = cw.d_jobs;
+	}
+	ap.job_base[kNumClasses] = pl->n_fast_tasks;
+	ap.block_sums = pl->d_asm_sums;
+	ap.totals = pl->d_asm_sums + 2 * (size_t)pl->asm_blocks;
+	ap.rows = pl->d_asm_rows;
+	ap.cols = pl->d_asm_cols;
+	ap.events = pl->d_events;
+	ap.ev_count = pl->d_ev_count;
+	ap.ev_cap = pl->ev_cap;
+	asm_count_kernel<<<(unsigned)pl->asm_blocks, DFB_ASM_BLOCK, 0, ctx->stream>>>(ap);
+	asm_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ap.block_sums, pl->asm_blocks, ap.totals);
+	asm_write_kernel<<<(unsigned)pl->asm_blocks, DFB_ASM_BLOCK, 0, ctx->stream>>>(ap);
+	CK(ctx, cudaGetLastError());
+	pl->stats.kernel_launches += 3;
+	return DFB_OK;
+}
+
 extern "C" int dfb_plan_run(dfb_plan* pl)
 {
 	if (!pl) return DFB_ERR_ARG;
@@ -1347,6 +1405,7 @@ extern "C" int dfb_plan_run(dfb_plan* pl)
 	if (pl->split)
 	{
 		int rc = run_probe(pl);
+		if (!rc) rc = run_assemble(pl);
 		if (rc) return rc;
 	}
 	if (pl->timing)
@@ -1472,10 +1531,13 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 	// 1. counters: overflow-list length and winning tasks per class
 	int h_ctrl[kNumClasses * 4];
 	unsigned long long n_ov = 0;
+	unsigned long long asm_totals[2] = {0, 0}; // rows, columns assembled on the device
 	for (int attempt = 0;; attempt++)
 	{
 		CK(ctx, cudaMemcpyAsync(&n_ov, pl->d_ev_count, sizeof(n_ov), cudaMemcpyDeviceToHost, cs));
 		CK(ctx, cudaMemcpyAsync(h_ctrl, pl->d_ctrl, sizeof(h_ctrl), cudaMemcpyDeviceToHost, cs));
+		if (pl->d_asm_sums)
+			CK(ctx, cudaMemcpyAsync(asm_totals, pl->d_asm_sums + 2 * (size_t)pl->asm_blocks, sizeof(asm_totals), cudaMemcpyDeviceToHost, cs));
 		CK(ctx, cudaStreamSynchronize(cs));
 		if (n_ov <= pl->ev_cap) break;
 		if (attempt >= 2) return set_err(ctx, DFB_ERR_STATE, "event buffer overflow persists");
@@ -1485,27 +1547,22 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 		cudaError_t e = dalloc(ctx, (void**)&pl->d_events, (size_t)pl->ev_cap * sizeof(Event));
 		if (e != cudaSuccess) return set_err(ctx, DFB_ERR_NOMEM, "event buffer of %llu entries: %s", pl->ev_cap, cudaGetErrorString(e));
 		int rc = run_probe(pl);
+		if (!rc) rc = run_assemble(pl);
 		if (rc) return rc;
 		CK(ctx, cudaEventRecord(pl->done_ev, ctx->stream));
 		CK(ctx, cudaStreamWaitEvent(cs, pl->done_ev, 0));
 	}
-	// slots are numbered class by class in job space (the first sweep wrote task -> slot with that numbering)
-	int64_t hits_cls[kNumClasses], hits_long[kNumClasses], n_slots = 0, n_slot_space = 0;
+	int64_t n_slots = 0;
 	for (int c = 0; c < kNumClasses; c++)
-	{
-		hits_cls[c] = pl->cls[c].n_jobs ? h_ctrl[4 * c + 1] : 0;  // slots 0 .. hits-1 of the class
-		hits_long[c] = pl->cls[c].n_jobs ? h_ctrl[4 * c + 3] : 0; // slots n_jobs-hits_long .. n_jobs-1
-		n_slots += hits_cls[c] + hits_long[c];
-		n_slot_space = std::max<int64_t>(n_slot_space, pl->job_base[c] + pl->cls[c].n_jobs);
-	}
+		if (pl->cls[c].n_jobs) n_slots += (int64_t)h_ctrl[4 * c + 1] + h_ctrl[4 * c + 3]; // short- and long-window queue slots
 
 	tr.lap("split.fetch: wait kernels");
-	// 2. bulk copy into pinned staging: best | task_slot | slot_n | slot_ev | overflow events
+	// 2. bulk copy into pinned staging: best | device-assembled rows | their columns | overflow events
+	const size_t g_rows = (size_t)asm_totals[0], g_cols = (size_t)asm_totals[1];
 	const size_t off_best = 0;
-	const size_t off_task = align_up(off_best + (size_t)pl->n_tasks * 4, 256);
-	const size_t off_n = align_up(off_task + (size_t)pl->n_tasks * 4, 256);
-	const size_t off_ev = align_up(off_n + (size_t)n_slot_space * 4, 256);
-	const size_t off_ov = align_up(off_ev + (size_t)n_slot_space * DFB_SLOT_EVENTS * sizeof(uint2), 256);
+	const size_t off_rows = align_up(off_best + (size_t)pl->n_tasks * 4, 256);
+	const size_t off_cols = align_up(off_rows + g_rows * sizeof(dfb_split_row), 256);
+	const size_t off_ov = align_up(off_cols + g_cols * sizeof(int32_t), 256);
 	const size_t total = off_ov + (size_t)n_ov * sizeof(Event) + 256;
 	{
 		cudaError_t e = ctx->h_out.ensure(total);
@@ -1513,31 +1570,18 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 	}
 	uint8_t* hb = (uint8_t*)ctx->h_out.p;
 	int32_t* h_best = (int32_t*)(hb + off_best);
-	const int32_t* slot_of = (const int32_t*)(hb + off_task);
-	int32_t* h_n = (int32_t*)(hb + off_n);
-	uint2* h_ev = (uint2*)(hb + off_ev);
+	const dfb_split_row* h_rows = (const dfb_split_row*)(hb + off_rows);
+	const int32_t* h_cols = (const int32_t*)(hb + off_cols);
 	Event* h_ov = (Event*)(hb + off_ov);
 	int64_t d2h = 0;
 	if (pl->n_tasks)
 	{
 		CK(ctx, cudaMemcpyAsync(h_best, pl->d_out, (size_t)pl->n_tasks * 4, cudaMemcpyDeviceToHost, cs));
-		CK(ctx, cudaMemcpyAsync((void*)slot_of, pl->d_task_slot, (size_t)pl->n_tasks * 4, cudaMemcpyDeviceToHost, cs));
-		d2h += pl->n_tasks * 8;
+		d2h += pl->n_tasks * 4;
 	}
-	for (int c = 0; c < kNumClasses; c++)
-	{
-		const ClassWork& cw = pl->cls[c];
-		const int64_t first[2] = {0, cw.n_jobs - hits_long[c]}, count[2] = {hits_cls[c], hits_long[c]};
-		for (int part = 0; part < 2; part++)
-		{
-			if (!count[part]) continue;
-			const int64_t lo = first[part], n = count[part];
-			CK(ctx, cudaMemcpyAsync(h_n + pl->job_base[c] + lo, cw.d_slot_n + lo, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
-			CK(ctx, cudaMemcpyAsync(h_ev + (pl->job_base[c] + lo) * DFB_SLOT_EVENTS, cw.d_slot_ev + lo * DFB_SLOT_EVENTS,
-			                        (size_t)n * DFB_SLOT_EVENTS * sizeof(uint2), cudaMemcpyDeviceToHost, cs));
-			d2h += n * (int64_t)(4 + DFB_SLOT_EVENTS * sizeof(uint2));
-		}
-	}
+	if (g_rows) CK(ctx, cudaMemcpyAsync((void*)h_rows, pl->d_asm_rows, g_rows * sizeof(dfb_split_row), cudaMemcpyDeviceToHost, cs));
+	if (g_cols) CK(ctx, cudaMemcpyAsync((void*)h_cols, pl->d_asm_cols, g_cols * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+	d2h += (int64_t)(g_rows * sizeof(dfb_split_row) + g_cols * sizeof(int32_t));
 	if (n_ov) CK(ctx, cudaMemcpyAsync(h_ov, pl->d_events, (size_t)n_ov * sizeof(Event), cudaMemcpyDeviceToHost, cs));
 	d2h += (int64_t)(n_ov * sizeof(Event));
 	CK(ctx, cudaStreamSynchronize(cs));
@@ -1547,157 +1591,81 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 
 	if (out_best && pl->n_tasks) memcpy(out_best, h_best, (size_t)pl->n_tasks * 4);
 
-	// 3. overflow list (tie-heavy tasks, generic-path tasks): order by task, then (matrix,row,col)
-	std::sort(h_ov, h_ov + n_ov, [](const Event& a, const Event& b) {
-		if (a.task != b.task) return a.task < b.task;
-		if (a.half_row != b.half_row) return a.half_row < b.half_row;
-		return a.col < b.col;
-	});
-
-	// 4. per-thread assembly over contiguous task ranges so that rows come out in task order
-	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(pool ? pool->Size() : ctx->host_threads, pl->n_tasks / 4096 + 1));
-	if ((int)ctx->asm_chunks.size() < T) ctx->asm_chunks.resize((size_t)T);
-	std::vector<int64_t> ev_part((size_t)T, 0);
-	bool oom = false;
-	parallel_for(pool, T, [&](int tid) {
-		const int64_t t0 = pl->n_tasks * tid / T, t1 = pl->n_tasks * (tid + 1) / T;
-		AsmChunk& out = ctx->asm_chunks[tid];
-		// upper bounds for this task range: every event is one column; a row needs two events
-		int64_t ev_here = 0;
-		const Event* ov_begin = h_ov;
-		const Event* ov_end = h_ov + n_ov;
-		const Event* ov = std::lower_bound(ov_begin, ov_end, (int32_t)t0, [](const Event& e, int32_t t) { return e.task < t; });
-		const Event* ov_last = std::lower_bound(ov_begin, ov_end, (int32_t)t1, [](const Event& e, int32_t t) { return e.task < t; });
-		// the slot data was just written by DMA: nothing of it is in this core's caches, and the slots of
-		// consecutive tasks are scattered.  Prefetch a few tasks ahead in both passes.
-		const int64_t kAhead = 24;
-		for (int64_t t = t0; t < t1; t++)
-		{
-			if (t + kAhead < t1 && slot_of[t + kAhead] >= 0) __builtin_prefetch(h_n + slot_of[t + kAhead]);
-			if (slot_of[t] >= 0) ev_here += std::min<int32_t>(h_n[slot_of[t]], DFB_SLOT_EVENTS);
-		}
-		ev_here += ov_last - ov;
-		ev_part[tid] = ev_here;
-		if (!out.rows.ensure((size_t)ev_here / 2 + 1) || !out.cols.ensure((size_t)ev_here + 1)) { oom = true; return; }
-		dfb_split_row* rows = out.rows.data();
-		int32_t* cols = out.cols.data();
-		size_t nr = 0, nc = 0;
-		std::vector<uint64_t> key, k2;
-		std::vector<int32_t> score, s2;
-		std::vector<int> order;
-		for (int64_t t = t0; t < t1; t++)
-		{
-			if (t + kAhead < t1 && slot_of[t + kAhead] >= 0)
-			{
-				__builtin_prefetch(h_ev + (size_t)slot_of[t + kAhead] * DFB_SLOT_EVENTS);
-				__builtin_prefetch(h_n + slot_of[t + kAhead]);
-			}
-			const int32_t s = slot_of[t];
-			const bool has_ov = ov < ov_end && ov->task == (int32_t)t;
-			if (s < 0 && !has_ov) continue;
-			const int L = pl->task_L[t];
-			if (!has_ov)
-			{
-				// the common case: at most 8 {key,score} entries, all in the slot region.  The 32-bit key
-				// (matrix<<27 | row<<16 | col) orders them the way GetAlignments walks them.
-				const int n = std::min<int32_t>(h_n[s], DFB_SLOT_EVENTS);
-				uint2 e[DFB_SLOT_EVENTS];
-				const uint2* src = h_ev + (size_t)s * DFB_SLOT_EVENTS;
-				for (int k = 0; k < n; k++)
-				{
-					const uint2 v = src[k];
-					int b = k - 1;
-					while (b >= 0 && e[b].x > v.x) { e[b + 1] = e[b]; b--; }
-					e[b + 1] = v;
-				}
-				int n0 = 0;
-				while (n0 < n && !(e[n0].x >> 27)) n0++;
-				int i = 0;
-				while (i < n0)
-				{
-					const uint32_t a = (e[i].x >> 16) & 0x7ff;
-					int i_end = i + 1;
-					while (i_end < n0 && ((e[i_end].x >> 16) & 0x7ff) == a) i_end++;
-					const uint32_t want = (uint32_t)L - a;
-					int j = n0;
-					while (j < n && ((e[j].x >> 16) & 0x7ff) != want) j++;
-					if (j < n)
-					{
-						int j_end = j + 1;
-						while (j_end < n && ((e[j_end].x >> 16) & 0x7ff) == want) j_end++;
-						dfb_split_row& row = rows[nr++];
-						row.task = (int32_t)t;
-						row.read_split = (int32_t)a;
-						row.score1 = (int32_t)e[i].y;
-						row.score2 = (int32_t)e[j].y;
-						row.col_begin = (int64_t)nc;
-						row.n1 = i_end - i;
-						row.n2 = j_end - j;
-						for (int k = i; k < i_end; k++) cols[nc++] = (int32_t)(e[k].x & 0xffff);
-						for (int k = j; k < j_end; k++) cols[nc++] = (int32_t)(e[k].x & 0xffff);
-					}
-					i = i_end;
-				}
-				continue;
-			}
-			// tie-heavy or generic-path task: slot entries + its run of the overflow list
-			key.clear();
-			score.clear();
-			if (s >= 0)
-			{
-				const int n = std::min<int32_t>(h_n[s], DFB_SLOT_EVENTS);
-				const uint2* e = h_ev + (size_t)s * DFB_SLOT_EVENTS;
-				for (int k = 0; k < n; k++)
-				{
-					key.push_back(wide_key((int)(e[k].x >> 27), (int)((e[k].x >> 16) & 0x7ff), (int)(e[k].x & 0xffff)));
-					score.push_back((int32_t)e[k].y);
-				}
-			}
-			while (ov < ov_end && ov->task == (int32_t)t)
-			{
-				key.push_back(wide_key(ov->half_row >> 30, ov->half_row & 0x3fffffff, ov->col));
-				score.push_back(ov->score);
-				ov++;
-			}
-			const int n = (int)key.size();
-			order.resize(n);
-			for (int k = 0; k < n; k++) order[k] = k;
-			std::sort(order.begin(), order.end(), [&](int x, int y) { return key[x] < key[y]; });
-			k2.resize(n);
-			s2.resize(n);
-			for (int k = 0; k < n; k++) { k2[k] = key[order[k]]; s2[k] = score[order[k]]; }
-			Chunk tmp;
-			emit_task_rows((int)t, L, k2.data(), s2.data(), n, tmp);
-			for (const dfb_split_row& r0 : tmp.rows)
-			{
-				dfb_split_row r = r0;
-				r.col_begin += (int64_t)nc;
-				rows[nr++] = r;
-			}
-			// tmp.cols are laid out in row order already
-			memcpy(cols + nc, tmp.cols.data(), tmp.cols.size() * 4);
-			nc += tmp.cols.size();
-		}
-		out.n_rows = nr;
-		out.n_cols = nc;
-	});
-	if (oom) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
+	// 3. overflow list = every arg-max column of the tie-heavy and generic-path tasks.  Its tasks are assembled here:
+	//    events are dealt into buckets of consecutive tasks, every bucket is ordered by (task, matrix, row, column)
+	//    and walked by one thread
+	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(pool ? pool->Size() : ctx->host_threads, (int64_t)(g_rows + n_ov) / 32768 + 1));
+	std::vector<Chunk> host_part((size_t)T);
+	if (n_ov)
 	{
-		int64_t n_events = 0;
-		for (int k = 0; k < T; k++) n_events += ev_part[k];
-		pl->stats.events = n_events;
+		std::vector<Event> bucketed((size_t)n_ov);
+		std::vector<size_t> hist((size_t)T * (size_t)T, 0); // [thread][bucket]
+		const int64_t n_tasks = std::max<int64_t>(pl->n_tasks, 1);
+		auto bucket_of = [&](int32_t task) { return (int)((int64_t)task * T / n_tasks); };
+		parallel_for(pool, T, [&](int tid) {
+			size_t* h = hist.data() + (size_t)tid * (size_t)T;
+			for (size_t k = n_ov * (size_t)tid / (size_t)T; k < n_ov * ((size_t)tid + 1) / (size_t)T; k++) h[bucket_of(h_ov[k].task)]++;
+		});
+		std::vector<size_t> bucket_begin((size_t)T + 1, 0);
+		{
+			size_t at = 0;
+			for (int b = 0; b < T; b++)
+			{
+				bucket_begin[(size_t)b] = at;
+				for (int tid = 0; tid < T; tid++)
+				{
+					size_t& h = hist[(size_t)tid * (size_t)T + (size_t)b];
+					const size_t cnt = h;
+					h = at;
+					at += cnt;
+				}
+			}
+			bucket_begin[(size_t)T] = at;
+		}
+		parallel_for(pool, T, [&](int tid) {
+			size_t* h = hist.data() + (size_t)tid * (size_t)T;
+			for (size_t k = n_ov * (size_t)tid / (size_t)T; k < n_ov * ((size_t)tid + 1) / (size_t)T; k++)
+				bucketed[h[bucket_of(h_ov[k].task)]++] = h_ov[k];
+		});
+		parallel_for(pool, T, [&](int b) {
+			Event* ov = bucketed.data() + bucket_begin[(size_t)b];
+			Event* const last = bucketed.data() + bucket_begin[(size_t)b + 1];
+			std::sort(ov, last, [](const Event& x, const Event& y) {
+				if (x.task != y.task) return x.task < y.task;
+				if (x.half_row != y.half_row) return x.half_row < y.half_row;
+				return x.col < y.col;
+			});
+			Chunk& out = host_part[(size_t)b];
+			std::vector<uint64_t> key;
+			std::vector<int32_t> score;
+			while (ov < last)
+			{
+				const int32_t t = ov->task;
+				key.clear();
+				score.clear();
+				for (; ov < last && ov->task == t; ov++)
+				{
+					key.push_back(wide_key(ov->half_row >> 30, ov->half_row & 0x3fffffff, ov->col));
+					score.push_back(ov->score);
+				}
+				emit_task_rows((int)t, pl->task_L[(size_t)t], key.data(), score.data(), (int)key.size(), out);
+			}
+		});
 	}
-	tr.lap("split.fetch: assemble");
-	// 5. concatenate into recycled result arrays
-	size_t tot_rows = 0, tot_cols = 0;
-	std::vector<size_t> row_base((size_t)T), col_base((size_t)T);
+	size_t x_rows = 0, x_cols = 0; // assembled on the host
+	std::vector<size_t> part_row((size_t)T + 1, 0), part_col((size_t)T + 1, 0);
 	for (int k = 0; k < T; k++)
 	{
-		row_base[k] = tot_rows;
-		col_base[k] = tot_cols;
-		tot_rows += ctx->asm_chunks[k].n_rows;
-		tot_cols += ctx->asm_chunks[k].n_cols;
+		part_row[(size_t)k + 1] = (x_rows += host_part[(size_t)k].rows.size());
+		part_col[(size_t)k + 1] = (x_cols += host_part[(size_t)k].cols.size());
 	}
+	pl->stats.events = (int64_t)(g_cols + x_cols);
+	if (trace_on()) fprintf(stderr, "[dfb] fetch: %zu device rows, %llu overflow events -> %zu host rows\n", g_rows, n_ov, x_rows);
+	tr.lap("split.fetch: assemble");
+
+	// 4. result arrays (recycled): rows merged by task -- the two sources never share a task --, columns of the
+	//    device part first, of the host part behind them
+	const size_t tot_rows = g_rows + x_rows, tot_cols = g_cols + x_cols;
 	if (pl->result_slot >= 0)
 	{
 		if (pl->rows.cap < ctx->chunk_rows[pl->result_slot].cap) pl->rows.swap(ctx->chunk_rows[pl->result_slot]);
@@ -1709,17 +1677,51 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 		if (pl->cols.cap < ctx->spare_cols.cap) pl->cols.swap(ctx->spare_cols);
 	}
 	if (!pl->rows.ensure(tot_rows) || !pl->cols.ensure(tot_cols)) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
-	parallel_for(pool, T, [&](int k) {
-		const AsmChunk& c = ctx->asm_chunks[k];
-		dfb_split_row* dst = pl->rows.data() + row_base[k];
-		const int64_t cb = (int64_t)col_base[k];
-		for (size_t r = 0; r < c.n_rows; r++)
+	// host rows in one list (col_begin moved behind the device columns)
+	std::vector<dfb_split_row> x((size_t)x_rows);
+	for (int k = 0; k < T; k++)
+	{
+		const Chunk& c = host_part[(size_t)k];
+		for (size_t r = 0; r < c.rows.size(); r++)
 		{
-			dfb_split_row row = c.rows.p[r];
-			row.col_begin += cb;
-			dst[r] = row;
+			dfb_split_row row = c.rows[r];
+			row.col_begin += (int64_t)(g_cols + part_col[(size_t)k]);
+			x[part_row[(size_t)k] + r] = row;
 		}
-		if (c.n_cols) memcpy(pl->cols.data() + col_base[k], c.cols.p, c.n_cols * 4);
+		if (!c.cols.empty()) memcpy(pl->cols.data() + g_cols + part_col[(size_t)k], c.cols.data(), c.cols.size() * 4);
+	}
+	parallel_for(pool, T, [&](int tid) {
+		// device rows [g0, g1) and the host rows that sort between them
+		const size_t g0 = g_rows * (size_t)tid / (size_t)T, g1 = g_rows * ((size_t)tid + 1) / (size_t)T;
+		auto before = [&](size_t g) -> size_t { // host rows with a task below device row g's
+			if (g >= g_rows) return x_rows;
+			const int32_t task = h_rows[g].task;
+			return (size_t)(std::lower_bound(x.begin(), x.end(), task, [](const dfb_split_row& r, int32_t t) { return r.task < t; }) - x.begin());
+		};
+		size_t h = tid == 0 ? 0 : before(g0);
+		const size_t h1 = tid == T - 1 ? x_rows : before(g1);
+		dfb_split_row* dst = pl->rows.data() + g0 + h;
+		size_t g = g0;
+		while (g < g1 || h < h1)
+		{
+			if (h < h1 && (g >= g1 || x[h].task < h_rows[g].task))
+				*dst++ = x[h++];
+			else
+			{
+				// a run of device rows up to the next host task
+				size_t run_end = g1;
+				if (h < h1)
+				{
+					const int32_t stop = x[h].task;
+					run_end = (size_t)(std::lower_bound(h_rows + g, h_rows + g1, stop, [](const dfb_split_row& r, int32_t t) { return r.task < t; }) - h_rows);
+				}
+				memcpy(dst, h_rows + g, (run_end - g) * sizeof(dfb_split_row));
+				dst += run_end - g;
+				g = run_end;
+			}
+		}
+		const size_t c0 = g_cols * (size_t)tid / (size_t)T, c1 = g_cols * ((size_t)tid + 1) / (size_t)T;
+		if (c1 > c0) memcpy(pl->cols.data() + c0, h_cols + c0, (c1 - c0) * 4);
 	});
 	tr.lap("split.fetch: concatenate");
 	if (n_rows) *n_rows = (int64_t)pl->rows.size();
