@@ -304,6 +304,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- resident: inputs already packed in HBM ----
+    # (a small plan first: the first launch of a kernel pays for loading it, which would be charged to the pack timing)
+    warm = aligner.plan(refs, reads, host["task_cluster"][:1024], host["task_read"][:1024], host["min_score"][:1024])
+    warm.run()
+    warm.sync()
+    del warm
     plan = aligner.plan(refs, reads, host["task_cluster"], host["task_read"], host["min_score"])
     plan.set_timing(True)
     for _ in range(max(args.warmup, 3)):

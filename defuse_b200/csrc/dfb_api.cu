@@ -74,6 +74,22 @@ struct HostArr
 		n = want;
 		return true;
 	}
+	// grows without losing the first `keep` elements
+	bool ensure_keep(size_t want, size_t keep)
+	{
+		if (want > cap)
+		{
+			const size_t ncap = want + want / 4 + 64;
+			T* q = (T*)malloc(ncap * sizeof(T));
+			if (!q) return false;
+			if (keep) memcpy(q, p, keep * sizeof(T));
+			free(p);
+			p = q;
+			cap = ncap;
+		}
+		n = want;
+		return true;
+	}
 	void release() { free(p); p = nullptr; n = cap = 0; }
 	void swap(HostArr& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); }
 	size_t size() const { return n; }
@@ -723,7 +739,7 @@ static int upload_and_pack(dfb_plan* pl, const dfb_seq_table* a, int mode_a, con
 	const int max_grid = ctx->prop.multiProcessorCount * 16;
 	auto launch = [&](int mode, const SeqDesc* d, int64_t n, uint32_t w0, uint32_t w1) -> cudaError_t {
 		if (n == 0 || w1 <= w0) return cudaSuccess;
-		const int grid = (int)std::min<uint32_t>((w1 - w0 + 255) / 256, (uint32_t)max_grid);
+		const int grid = (int)std::min<uint64_t>(((uint64_t)n * 16 + 255) / 256, (uint64_t)max_grid); // sixteen lanes per sequence
 		if (mode == PACK_FWD)
 			pack_kernel<PACK_FWD><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
 		else if (mode == PACK_REV_ODD)
@@ -1508,7 +1524,16 @@ void emit_task_rows(int task, int L, const uint64_t* key, const int32_t* score, 
 }
 }  // namespace
 
-static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols, HostPool* pool);
+// where a chunk of a pipelined batch leaves its rows: straight behind the previous chunks' in the batch's result arrays
+struct ResultSink
+{
+	HostArr<dfb_split_row>* rows;
+	HostArr<int32_t>* cols;
+	size_t row_base, col_base; // filled so far
+	int32_t task_shift;        // first task of the chunk in the batch's numbering
+};
+
+static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols, HostPool* pool, ResultSink* sink = nullptr);
 
 extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols)
 {
@@ -1516,7 +1541,7 @@ extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_
 	return split_fetch_impl(pl, out_best, n_rows, n_cols, pl->ctx->pool);
 }
 
-static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols, HostPool* pool)
+static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols, HostPool* pool, ResultSink* sink)
 {
 	dfb_ctx* ctx = pl->ctx;
 	if (!pl->split) return set_err(ctx, DFB_ERR_STATE, "dfb_split_plan_fetch on a simple plan");
@@ -1666,17 +1691,29 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 	// 4. result arrays (recycled): rows merged by task -- the two sources never share a task --, columns of the
 	//    device part first, of the host part behind them
 	const size_t tot_rows = g_rows + x_rows, tot_cols = g_cols + x_cols;
-	if (pl->result_slot >= 0)
+	dfb_split_row* out_rows = nullptr;
+	int32_t* out_cols = nullptr;
+	int32_t task_shift = 0;
+	int64_t col_shift = 0;
+	if (sink)
 	{
-		if (pl->rows.cap < ctx->chunk_rows[pl->result_slot].cap) pl->rows.swap(ctx->chunk_rows[pl->result_slot]);
-		if (pl->cols.cap < ctx->chunk_cols[pl->result_slot].cap) pl->cols.swap(ctx->chunk_cols[pl->result_slot]);
+		if (!sink->rows->ensure_keep(sink->row_base + tot_rows, sink->row_base) || !sink->cols->ensure_keep(sink->col_base + tot_cols, sink->col_base))
+			return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
+		out_rows = sink->rows->data() + sink->row_base;
+		out_cols = sink->cols->data() + sink->col_base;
+		task_shift = sink->task_shift;
+		col_shift = (int64_t)sink->col_base;
+		sink->row_base += tot_rows;
+		sink->col_base += tot_cols;
 	}
 	else
 	{
 		if (pl->rows.cap < ctx->spare_rows.cap) pl->rows.swap(ctx->spare_rows);
 		if (pl->cols.cap < ctx->spare_cols.cap) pl->cols.swap(ctx->spare_cols);
+		if (!pl->rows.ensure(tot_rows) || !pl->cols.ensure(tot_cols)) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
+		out_rows = pl->rows.data();
+		out_cols = pl->cols.data();
 	}
-	if (!pl->rows.ensure(tot_rows) || !pl->cols.ensure(tot_cols)) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
 	// host rows in one list (col_begin moved behind the device columns)
 	std::vector<dfb_split_row> x((size_t)x_rows);
 	for (int k = 0; k < T; k++)
@@ -1685,26 +1722,27 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 		for (size_t r = 0; r < c.rows.size(); r++)
 		{
 			dfb_split_row row = c.rows[r];
-			row.col_begin += (int64_t)(g_cols + part_col[(size_t)k]);
+			row.col_begin += (int64_t)(g_cols + part_col[(size_t)k]) + col_shift;
+			row.task += task_shift;
 			x[part_row[(size_t)k] + r] = row;
 		}
-		if (!c.cols.empty()) memcpy(pl->cols.data() + g_cols + part_col[(size_t)k], c.cols.data(), c.cols.size() * 4);
+		if (!c.cols.empty()) memcpy(out_cols + g_cols + part_col[(size_t)k], c.cols.data(), c.cols.size() * 4);
 	}
 	parallel_for(pool, T, [&](int tid) {
 		// device rows [g0, g1) and the host rows that sort between them
 		const size_t g0 = g_rows * (size_t)tid / (size_t)T, g1 = g_rows * ((size_t)tid + 1) / (size_t)T;
 		auto before = [&](size_t g) -> size_t { // host rows with a task below device row g's
 			if (g >= g_rows) return x_rows;
-			const int32_t task = h_rows[g].task;
+			const int32_t task = h_rows[g].task + task_shift;
 			return (size_t)(std::lower_bound(x.begin(), x.end(), task, [](const dfb_split_row& r, int32_t t) { return r.task < t; }) - x.begin());
 		};
 		size_t h = tid == 0 ? 0 : before(g0);
 		const size_t h1 = tid == T - 1 ? x_rows : before(g1);
-		dfb_split_row* dst = pl->rows.data() + g0 + h;
+		dfb_split_row* dst = out_rows + g0 + h;
 		size_t g = g0;
 		while (g < g1 || h < h1)
 		{
-			if (h < h1 && (g >= g1 || x[h].task < h_rows[g].task))
+			if (h < h1 && (g >= g1 || x[h].task < h_rows[g].task + task_shift))
 				*dst++ = x[h++];
 			else
 			{
@@ -1712,20 +1750,24 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 				size_t run_end = g1;
 				if (h < h1)
 				{
-					const int32_t stop = x[h].task;
+					const int32_t stop = x[h].task - task_shift;
 					run_end = (size_t)(std::lower_bound(h_rows + g, h_rows + g1, stop, [](const dfb_split_row& r, int32_t t) { return r.task < t; }) - h_rows);
 				}
-				memcpy(dst, h_rows + g, (run_end - g) * sizeof(dfb_split_row));
-				dst += run_end - g;
-				g = run_end;
+				for (; g < run_end; g++)
+				{
+					dfb_split_row row = h_rows[g];
+					row.task += task_shift;
+					row.col_begin += col_shift;
+					*dst++ = row;
+				}
 			}
 		}
 		const size_t c0 = g_cols * (size_t)tid / (size_t)T, c1 = g_cols * ((size_t)tid + 1) / (size_t)T;
-		if (c1 > c0) memcpy(pl->cols.data() + c0, h_cols + c0, (c1 - c0) * 4);
+		if (c1 > c0) memcpy(out_cols + c0, h_cols + c0, (c1 - c0) * 4);
 	});
 	tr.lap("split.fetch: concatenate");
-	if (n_rows) *n_rows = (int64_t)pl->rows.size();
-	if (n_cols) *n_cols = (int64_t)pl->cols.size();
+	if (n_rows) *n_rows = (int64_t)tot_rows;
+	if (n_cols) *n_cols = (int64_t)tot_cols;
 	pl->fetched = true;
 	return DFB_OK;
 }
@@ -1786,12 +1828,39 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
                                  const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
                                  const int32_t* task_min_score, int64_t n_tasks, int32_t* out_best)
 {
-	const int K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), n_tasks / 400000));
+	const int K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), n_tasks / 330000));
 	std::vector<dfb_plan*> plans((size_t)K, nullptr);
+	// chunk boundaries: a short first chunk puts the GPU to work early, a short last one keeps the part of the result
+	// assembly that nothing overlaps small; the chunks in between share the rest
 	std::vector<int64_t> t0((size_t)K + 1);
-	for (int k = 0; k <= K; k++) t0[k] = n_tasks * k / K;
+	{
+		std::vector<double> weight((size_t)K, 1.0);
+		if (K >= 4)
+		{
+			weight[0] = 0.4;
+			weight[(size_t)K - 1] = 0.45;
+		}
+		double total = 0, run = 0;
+		for (double w : weight) total += w;
+		t0[0] = 0;
+		for (int k = 0; k < K; k++)
+		{
+			run += weight[(size_t)k];
+			t0[(size_t)k + 1] = k + 1 == K ? n_tasks : (int64_t)((double)n_tasks * run / total);
+		}
+	}
 	int rc = DFB_OK;
 	Trace trp;
+	// the batch's result holder: every chunk's rows go straight behind the previous chunk's
+	dfb_plan* holder = new (std::nothrow) dfb_plan();
+	if (!holder) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
+	holder->ctx = ctx;
+	holder->split = true;
+	holder->n_tasks = n_tasks;
+	if (holder->rows.cap < ctx->spare_rows.cap) holder->rows.swap(ctx->spare_rows);
+	if (holder->cols.cap < ctx->spare_cols.cap) holder->cols.swap(ctx->spare_cols);
+	holder->rows.n = holder->cols.n = 0;
+	ResultSink sink{&holder->rows, &holder->cols, 0, 0, 0};
 	// lane 2 (helper thread): waits for chunk k to be queued on the GPU, copies its results back and assembles its
 	// rows -- while lane 1 (this thread) builds and queues the following chunks
 	std::mutex mu;
@@ -1809,7 +1878,8 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 			}
 			// (the chunk's device buffers are released with the others at the end: a stream-ordered free in the middle
 			// of the pipeline cannot be reused by the chunks still being built and only makes the pool grow)
-			int frc = split_fetch_impl(plans[k], out_best ? out_best + t0[k] : nullptr, nullptr, nullptr, ctx->pool_fetch);
+			sink.task_shift = (int32_t)t0[(size_t)k];
+			int frc = split_fetch_impl(plans[k], out_best ? out_best + t0[k] : nullptr, nullptr, nullptr, ctx->pool_fetch, &sink);
 			if (frc)
 			{
 				fetch_rc = frc;
@@ -1820,6 +1890,11 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	for (int k = 0; k < K && !rc; k++)
 	{
 		const int64_t a = t0[k], b = t0[k + 1];
+		if (b <= a)
+		{
+			rc = set_err(ctx, DFB_ERR_STATE, "empty chunk in a pipelined batch");
+			break;
+		}
 		const int32_t r_lo = task_read[a], r_hi = task_read[b - 1] + 1;
 		if (r_lo < 0 || r_hi > reads->n)
 		{
@@ -1849,58 +1924,17 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	lane2.join();
 	trp.lap("pipelined: lane 2 joined");
 	if (!rc) rc = fetch_rc;
-	dfb_plan* holder = nullptr;
 	if (!rc)
 	{
-		holder = new (std::nothrow) dfb_plan();
-		if (!holder) rc = set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
-	}
-	if (!rc)
-	{
-		holder->ctx = ctx;
-		holder->split = true;
-		holder->n_tasks = n_tasks;
-		std::vector<size_t> row_base((size_t)K), col_base((size_t)K);
-		size_t n_rows = 0, n_cols = 0;
+		holder->fetched = true;
+		holder->ran = true;
 		for (int k = 0; k < K; k++)
 		{
-			row_base[k] = n_rows;
-			col_base[k] = n_cols;
-			n_rows += plans[k]->rows.size();
-			n_cols += plans[k]->cols.size();
-		}
-		if (holder->rows.cap < ctx->spare_rows.cap) holder->rows.swap(ctx->spare_rows);
-		if (holder->cols.cap < ctx->spare_cols.cap) holder->cols.swap(ctx->spare_cols);
-		if (!holder->rows.ensure(n_rows) || !holder->cols.ensure(n_cols))
-		{
-			rc = set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
-		}
-		else
-		{
-			// every chunk is split over a few threads: rows need their task and column offsets shifted
-			const int per = std::max(1, ctx->host_threads / K);
-			parallel_for(ctx->pool, K * per, [&](int id) {
-				const int k = id / per, part = id % per;
-				const dfb_plan* p = plans[k];
-				const size_t nr = p->rows.size(), r0 = nr * part / per, r1 = nr * (part + 1) / per;
-				dfb_split_row* dst = holder->rows.data() + row_base[k];
-				const int32_t task_shift = (int32_t)t0[k];
-				const int64_t col_shift = (int64_t)col_base[k];
-				for (size_t r = r0; r < r1; r++)
-				{
-					dfb_split_row row = p->rows.p[r];
-					row.task += task_shift;
-					row.col_begin += col_shift;
-					dst[r] = row;
-				}
-				const size_t nc = p->cols.size(), c0 = nc * part / per, c1 = nc * (part + 1) / per;
-				if (c1 > c0) memcpy(holder->cols.data() + col_base[k] + c0, p->cols.p + c0, (c1 - c0) * 4);
-			});
-			holder->fetched = true;
-			holder->ran = true;
+			holder->stats.events += plans[k]->stats.events;
+			holder->stats.probe_jobs += plans[k]->stats.probe_jobs;
+			holder->stats.d2h_bytes += plans[k]->stats.d2h_bytes;
 		}
 	}
-	trp.lap("pipelined: merged");
 	for (int k = 0; k < K; k++)
 		if (plans[k]) dfb_plan_destroy(plans[k]);
 	trp.lap("pipelined: chunks destroyed");

@@ -55,18 +55,20 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ r
                                                     int n_seqs, uint32_t word_begin, uint32_t word_end,
                                                     uint2* __restrict__ pool, uint8_t* __restrict__ obytes)
 {
-	for (uint32_t w = word_begin + blockIdx.x * blockDim.x + threadIdx.x; w < word_end; w += gridDim.x * blockDim.x)
+	// sixteen lanes per sequence (a 100-bp read in both orientations is 14 words, a 340-bp window 22): the owner of a
+	// word is known without a search, a sequence's words are written side by side
+	(void)word_begin;
+	(void)word_end;
+	const uint32_t lane16 = threadIdx.x & 15u;
+	const uint32_t n_groups = (gridDim.x * blockDim.x) >> 4;
+	for (uint32_t lo = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; lo < (uint32_t)n_seqs; lo += n_groups)
+	for (uint32_t local_all = lane16, seq_words = ((descs[lo].len + 15u) >> 4) * (MODE == PACK_BOTH ? 2u : 1u); local_all < seq_words; local_all += 16u)
 	{
-		int lo = 0, hi = n_seqs; // last sequence whose first word <= w
-		while (hi - lo > 1)
-		{
-			const int mid = (lo + hi) >> 1;
-			if (__ldg(&descs[mid].word) <= w) lo = mid; else hi = mid;
-		}
 		const SeqDesc sd = descs[lo];
-		uint32_t local = w - sd.word;
+		const uint32_t w = sd.word + local_all;
+		uint32_t local = local_all;
 		bool rev = false;
-		if (MODE == PACK_REV_ODD) rev = (lo & 1) != 0;
+		if (MODE == PACK_REV_ODD) rev = (lo & 1u) != 0;
 		if (MODE == PACK_BOTH)
 		{
 			const uint32_t nw = (sd.len + 15u) >> 4;
