@@ -4,6 +4,7 @@
 // so that nothing folds), on every SM at full occupancy, and reports warp-instructions / s.
 #include "../../include/defuse_b200.h"
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -12,6 +13,9 @@ namespace
 
 constexpr int kChains = 8;
 constexpr int kUnroll = 16; // rotations per loop iteration; 3 instructions per rotation per chain
+
+__device__ __forceinline__ __half2 h2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+__device__ __forceinline__ uint32_t u32(__half2 v) { return *reinterpret_cast<uint32_t*>(&v); }
 
 template <int KIND>
 __device__ __forceinline__ void rot(uint32_t& a, uint32_t& b, uint32_t& c)
@@ -64,6 +68,30 @@ __device__ __forceinline__ void rot(uint32_t& a, uint32_t& b, uint32_t& c)
 		b = __shfl_up_sync(0xffffffffu, b, 1);
 		c = __shfl_up_sync(0xffffffffu, c, 1);
 	}
+	else if (KIND == 10) // HMNMX2
+	{
+		a = u32(__hmax2(h2(b), h2(c)));
+		b = u32(__hmin2(h2(c), h2(a)));
+		c = u32(__hmax2(h2(a), h2(b)));
+	}
+	else if (KIND == 11) // HADD2
+	{
+		a = u32(__hadd2(h2(b), h2(c)));
+		b = u32(__hadd2(h2(c), h2(a)));
+		c = u32(__hadd2(h2(a), h2(b)));
+	}
+	else if (KIND == 12) // HFMA2
+	{
+		a = u32(__hfma2(h2(a), h2(b), h2(c)));
+		b = u32(__hfma2(h2(b), h2(c), h2(a)));
+		c = u32(__hfma2(h2(c), h2(a), h2(b)));
+	}
+	else if (KIND == 13) // HSET2 (compare -> 1.0 / 0.0 per half)
+	{
+		a = u32(__hne2(h2(b), h2(c)));
+		b = u32(__hne2(h2(c), h2(a)));
+		c = u32(__hne2(h2(a), h2(b)));
+	}
 	else if (KIND == 9)
 	{
 		a = (uint32_t)__viaddmax_s32((int)b, (int)c, (int)a);
@@ -91,6 +119,39 @@ __global__ void __launch_bounds__(256) issue_kernel(const uint32_t* __restrict__
 		{
 #pragma unroll
 			for (int k = 0; k < kChains; k++) rot<KIND>(a[k], b[k], c[k]);
+		}
+	}
+	uint32_t r = 0;
+#pragma unroll
+	for (int k = 0; k < kChains; k++) r ^= a[k] ^ b[k] ^ c[k];
+	out[tid] = r;
+}
+
+// KINDs 14..16: four chains of VIADDMNMX.S16x2 interleaved with four chains of HMNMX2 / HFMA2 / HADD2 -- do the
+// two kinds issue side by side (alu + fma pipe) or queue for one pipe?
+template <int HALF_KIND>
+__global__ void __launch_bounds__(256) mixed_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int iters)
+{
+	uint32_t a[kChains], b[kChains], c[kChains];
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+	for (int k = 0; k < kChains; k++)
+	{
+		a[k] = in[(tid + k) & 1023];
+		b[k] = in[(tid + 3 * k + 1) & 1023];
+		c[k] = in[(tid + 5 * k + 2) & 1023];
+	}
+	for (int it = 0; it < iters; it++)
+	{
+#pragma unroll
+		for (int u = 0; u < kUnroll; u++)
+		{
+#pragma unroll
+			for (int k = 0; k < kChains; k += 2)
+			{
+				rot<0>(a[k], b[k], c[k]);
+				rot<HALF_KIND>(a[k + 1], b[k + 1], c[k + 1]);
+			}
 		}
 	}
 	uint32_t r = 0;
@@ -145,7 +206,7 @@ __global__ void __launch_bounds__(256) cell_body_kernel(const uint32_t* __restri
 
 extern "C" int dfb_microbench_issue_rate(dfb_ctx* ctx, int kind, int iters, double* warp_instr_per_s, double* elapsed_ms)
 {
-	if (!ctx || !warp_instr_per_s || kind < 0 || kind > 9 || iters <= 0) return DFB_ERR_ARG;
+	if (!ctx || !warp_instr_per_s || kind < 0 || kind > 16 || iters <= 0) return DFB_ERR_ARG;
 	dfb_device_info info;
 	int rc = dfb_ctx_device_info(ctx, &info);
 	if (rc) return rc;
@@ -186,7 +247,14 @@ extern "C" int dfb_microbench_issue_rate(dfb_ctx* ctx, int kind, int iters, doub
 			case 6: issue_kernel<6><<<blocks, threads>>>(d_in, d_out, iters); break;
 			case 7: cell_body_kernel<<<blocks, threads>>>(d_in, d_out, iters, 0xFFFFFFFDu, 0xFFFEFFFEu, 0xFFFCFFFCu); break;
 			case 8: issue_kernel<8><<<blocks, threads>>>(d_in, d_out, iters); break;
-			default: issue_kernel<9><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 9: issue_kernel<9><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 10: issue_kernel<10><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 11: issue_kernel<11><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 12: issue_kernel<12><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 13: issue_kernel<13><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 14: mixed_kernel<10><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 15: mixed_kernel<12><<<blocks, threads>>>(d_in, d_out, iters); break;
+			default: mixed_kernel<11><<<blocks, threads>>>(d_in, d_out, iters); break;
 		}
 		cudaEventRecord(e1, 0);
 		if (cudaEventSynchronize(e1) != cudaSuccess) break;

@@ -246,6 +246,8 @@ DFB_API void dfb_plan_destroy(dfb_plan* plan);
  *   0 VIADDMNMX.S16x2   1 VIMNMX.U16x2   2 VIMNMX3.S16x2   3 LOP3   4 IMAD   5 IADD3
  *   6 PRMT              7 the 6-instruction s16x2 DP cell body (per body, not per instruction)
  *   8 SHFL.UP           9 VIADDMNMX (s32)
+ *   10 HMNMX2   11 HADD2   12 HFMA2   13 HSET2 (fp16x2: candidates for the fma pipe)
+ *   14 / 15 / 16  VIADDMNMX.S16x2 interleaved 1:1 with HMNMX2 / HFMA2 / HADD2 (do the two pipes issue side by side?)
  * *elapsed_ms receives the kernel time. */
 DFB_API int dfb_microbench_issue_rate(dfb_ctx* ctx, int kind, int iters, double* warp_instr_per_s,
                               double* elapsed_ms);

@@ -17,3 +17,6 @@ echo ncu_full_rc=$?
 tail -3 gpurun_out/ncu_full_$TAG.log
 timeout 600 python scripts/gpu_tools_bench.py > gpurun_out/tools_bench_$TAG.json 2> gpurun_out/tools_bench_$TAG.err; echo tools_rc=$?
 cat gpurun_out/tools_bench_$TAG.json; tail -3 gpurun_out/tools_bench_$TAG.err
+timeout 300 python scripts/gpu_tool_scale.py > gpurun_out/tool_scale_split_$TAG.json 2> gpurun_out/tool_scale_split_$TAG.err; echo scale_split_rc=$?
+timeout 300 python scripts/gpu_tool_scale.py localalign 1000000 10000 > gpurun_out/tool_scale_local_$TAG.json 2> gpurun_out/tool_scale_local_$TAG.err; echo scale_local_rc=$?
+timeout 300 python scripts/gpu_tool_scale.py matealign 300000 > gpurun_out/tool_scale_mate_$TAG.json 2> gpurun_out/tool_scale_mate_$TAG.err; echo scale_mate_rc=$?
