@@ -620,6 +620,30 @@ static int check_table(const dfb_ctx* ctx, const dfb_seq_table* t, const char* w
 	return DFB_OK;
 }
 
+// the same checks over a table of millions of sequences, spread over the context's workers
+static int check_table_parallel(const dfb_ctx* ctx, const dfb_seq_table* t, const char* what)
+{
+	if (!t || !t->off || t->n < (1 << 18)) return check_table(ctx, t, what);
+	if (t->n > 0 && !t->bytes && t->off[t->n] > 0) return set_err(ctx, DFB_ERR_ARG, "%s: null table", what);
+	if (t->off[0] != 0) return set_err(ctx, DFB_ERR_ARG, "%s: off[0] must be 0", what);
+	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->host_threads, t->n / 262144 + 1));
+	std::vector<int64_t> bad((size_t)T, -1);
+	parallel_for(ctx->pool, T, [&](int tid) {
+		for (int64_t k = t->n * tid / T; k < t->n * (tid + 1) / T; k++)
+		{
+			const int64_t len = t->off[k + 1] - t->off[k];
+			if (len < 0 || len > 0x7fffff00LL)
+			{
+				bad[(size_t)tid] = k;
+				return;
+			}
+		}
+	});
+	for (int64_t k : bad)
+		if (k >= 0) return check_table(ctx, t, what); // (the sequential pass words the message)
+	return DFB_OK;
+}
+
 // Scoring triples the s16x2 kernels are exact for (DESIGN.md "number range"):
 //   match >= 1, mismatch <= 0, gap <= 0  =>  j*gap <= H(i,j) <= j*match  for every cell,
 // so H - match*j fits 16 bits for the class' row capacity.  Everything else goes to s32.
@@ -909,53 +933,81 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 	}
 	tr.lap("simple.create: raw upload");
 
-	// pass 1: classify every task, count per (class, reference-length bin)
+	// pass 1 (host threads): classify every task, count per (thread, class, reference-length bin)
+	const int T = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->host_threads, n_tasks / 65536 + 1));
+	const size_t n_bins = (size_t)kNumClasses * kRBins;
 	std::vector<int32_t> bin_of((size_t)n_tasks);
-	std::vector<int64_t> bin_pos((size_t)kNumClasses * kRBins, 0);
+	std::vector<int64_t> bin_pos(n_bins * (size_t)T, 0);
+	struct Part
+	{
+		int64_t cells = 0, n_gen = 0, bad = -1;
+		uint32_t gen_max_R = 0;
+	};
+	std::vector<Part> part((size_t)T);
+	parallel_for(ctx->pool, T, [&](int tid) {
+		Part& pt = part[(size_t)tid];
+		int64_t* cnt = bin_pos.data() + n_bins * (size_t)tid;
+		for (int64_t t = n_tasks * tid / T; t < n_tasks * (tid + 1) / T; t++)
+		{
+			const int32_t r = task_ref[t], sq = task_seq[t];
+			if (r < 0 || r >= refs->n || sq < 0 || sq >= seqs->n)
+			{
+				if (pt.bad < 0) pt.bad = t;
+				bin_of[t] = -1;
+				continue;
+			}
+			const int64_t R = refs->off[r + 1] - refs->off[r];
+			const int64_t L = seqs->off[sq + 1] - seqs->off[sq];
+			pt.cells += R * L;
+			int32_t bin = -1; // no interior cell: score 0 (d_out is zero-initialised)
+			if (R > 0 && L > 0)
+			{
+				int c = (L <= kMaxFastRows && R <= 65535) ? class_for_rows((int)L) : -1;
+				if (c >= 0 && !pl->fast_ok[c]) c = -1;
+				if (c < 0)
+				{
+					bin = -2;
+					pt.n_gen++;
+					pt.gen_max_R = std::max<uint32_t>(pt.gen_max_R, (uint32_t)R);
+				}
+				else
+				{
+					bin = c * kRBins + (kRBins - 1 - (int)std::min<int64_t>(R >> 4, kRBins - 1));
+					cnt[bin]++;
+				}
+			}
+			bin_of[t] = bin;
+		}
+	});
 	int64_t n_gen = 0;
 	uint32_t gen_max_R = 0;
-	for (int64_t t = 0; t < n_tasks; t++)
+	for (int k = 0; k < T; k++)
 	{
-		const int32_t r = task_ref[t], s = task_seq[t];
-		if (r < 0 || r >= refs->n || s < 0 || s >= seqs->n)
+		if (part[(size_t)k].bad >= 0)
 		{
+			const long long bad = (long long)part[(size_t)k].bad;
 			dfb_plan_destroy(pl);
-			return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)t);
+			return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", bad);
 		}
-		const int64_t R = refs->off[r + 1] - refs->off[r];
-		const int64_t L = seqs->off[s + 1] - seqs->off[s];
-		pl->stats.cells += R * L;
-		int32_t bin = -1; // no interior cell: score 0 (d_out is zero-initialised)
-		if (R > 0 && L > 0)
-		{
-			int c = (L <= kMaxFastRows && R <= 65535) ? class_for_rows((int)L) : -1;
-			if (c >= 0 && !pl->fast_ok[c]) c = -1;
-			if (c < 0)
-			{
-				bin = -2;
-				n_gen++;
-				gen_max_R = std::max<uint32_t>(gen_max_R, (uint32_t)R);
-			}
-			else
-			{
-				bin = c * kRBins + (kRBins - 1 - (int)std::min<int64_t>(R >> 4, kRBins - 1));
-				bin_pos[bin]++;
-			}
-		}
-		bin_of[t] = bin;
+		pl->stats.cells += part[(size_t)k].cells;
+		n_gen += part[(size_t)k].n_gen;
+		gen_max_R = std::max(gen_max_R, part[(size_t)k].gen_max_R);
 	}
-	// two tasks share a job (low / high half): task position p inside its class -> job p/2, half p%2
+	// two tasks share a job (low / high half): task position p inside its class -> job p/2, half p%2.
+	// counts -> positions: class by class, bin by bin, thread by thread (keeps task order inside a bin)
 	int64_t n_jobs_cls[kNumClasses], job_base[kNumClasses];
 	int64_t n_fast_jobs = 0;
 	for (int c = 0; c < kNumClasses; c++)
 	{
 		int64_t tasks_c = 0;
-		for (int b = 0; b < kRBins; b++)
-		{
-			const int64_t cnt = bin_pos[(size_t)c * kRBins + b];
-			bin_pos[(size_t)c * kRBins + b] = tasks_c;
-			tasks_c += cnt;
-		}
+		for (int bb = 0; bb < kRBins; bb++)
+			for (int k = 0; k < T; k++)
+			{
+				int64_t& slot = bin_pos[n_bins * (size_t)k + (size_t)c * kRBins + bb];
+				const int64_t cnt = slot;
+				slot = tasks_c;
+				tasks_c += cnt;
+			}
 		job_base[c] = n_fast_jobs;
 		n_jobs_cls[c] = (tasks_c + 1) / 2;
 		n_fast_jobs += n_jobs_cls[c];
@@ -978,39 +1030,48 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 		dfb_plan_destroy(pl);
 		return set_err(ctx, DFB_ERR_ARG, "batch too large: more than 2^32 packed words; split it");
 	}
-	// pass 2: place every task into its job slot
-	for (int64_t j = 0; j < n_fast_jobs; j++)
-	{
-		JobPair& jp = st.jobs[j];
-		memset(&jp, 0, sizeof(jp));
-		jp.out0 = jp.out1 = -1;
-	}
-	int64_t gi = 0;
-	for (int64_t t = 0; t < n_tasks; t++)
-	{
-		const int32_t bin = bin_of[t];
-		if (bin == -1) continue;
-		const int32_t r = task_ref[t], s = task_seq[t];
-		if (bin == -2)
+	// pass 2 (host threads): place every task into its job slot
+	parallel_for(ctx->pool, T, [&](int tid) {
+		for (int64_t j = n_fast_jobs * tid / T; j < n_fast_jobs * (tid + 1) / T; j++)
 		{
+			JobPair& jp = st.jobs[j];
+			memset(&jp, 0, sizeof(jp));
+			jp.out0 = jp.out1 = -1;
+		}
+	});
+	parallel_for(ctx->pool, T, [&](int tid) {
+		int64_t* pos = bin_pos.data() + n_bins * (size_t)tid;
+		for (int64_t t = n_tasks * tid / T; t < n_tasks * (tid + 1) / T; t++)
+		{
+			const int32_t bin = bin_of[t];
+			if (bin < 0) continue;
+			const int32_t r = task_ref[t], sq = task_seq[t];
+			const int64_t p = pos[bin]++;
+			JobPair& jp = st.jobs[job_base[bin / kRBins] + (p >> 1)];
+			const int h = (int)(p & 1);
+			jp.ref_w[h] = st.desc_a[r].word;
+			jp.read_w[h] = st.desc_b[sq].word;
+			jp.R[h] = (uint16_t)st.desc_a[r].len;
+			jp.L[h] = (uint16_t)st.desc_b[sq].len;
+			if (h == 0) jp.out0 = (int32_t)t; else jp.out1 = (int32_t)t;
+		}
+	});
+	if (n_gen)
+	{
+		int64_t gi = 0;
+		for (int64_t t = 0; t < n_tasks; t++)
+		{
+			if (bin_of[t] != -2) continue;
+			const int32_t r = task_ref[t], sq = task_seq[t];
 			GenJob& j = st.gen[gi++];
 			j.ref_w = st.desc_a[r].word;
-			j.read_w = st.desc_b[s].word;
+			j.read_w = st.desc_b[sq].word;
 			j.R = st.desc_a[r].len;
-			j.L = st.desc_b[s].len;
+			j.L = st.desc_b[sq].len;
 			j.task = (int32_t)t;
 			j.half = 0;
 			j.row_off = 0;
-			continue;
 		}
-		const int64_t p = bin_pos[bin]++;
-		JobPair& jp = st.jobs[job_base[bin / kRBins] + (p >> 1)];
-		const int h = (int)(p & 1);
-		jp.ref_w[h] = st.desc_a[r].word;
-		jp.read_w[h] = st.desc_b[s].word;
-		jp.R[h] = (uint16_t)st.desc_a[r].len;
-		jp.L[h] = (uint16_t)st.desc_b[s].len;
-		if (h == 0) jp.out0 = (int32_t)t; else jp.out1 = (int32_t)t;
 	}
 	pl->n_gen_jobs = n_gen;
 	tr.lap("simple.create: jobs");
@@ -1828,14 +1889,22 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
                                  const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
                                  const int32_t* task_min_score, int64_t n_tasks, int32_t* out_best)
 {
-	const int K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), n_tasks / 330000));
+	const int K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), n_tasks / 280000));
 	std::vector<dfb_plan*> plans((size_t)K, nullptr);
-	// chunk boundaries: a short first chunk puts the GPU to work early, a short last one keeps the part of the result
-	// assembly that nothing overlaps small; the chunks in between share the rest
+	// chunk boundaries: short chunks in front put the GPU to work early, chunks that taper off at the end keep the part
+	// of the result assembly that nothing overlaps small (lane 2 finishes chunk k while the GPU runs chunk k+1); the
+	// chunks in between share the rest
 	std::vector<int64_t> t0((size_t)K + 1);
 	{
 		std::vector<double> weight((size_t)K, 1.0);
-		if (K >= 4)
+		if (K >= 6)
+		{
+			weight[0] = 0.25;
+			weight[1] = 0.6;
+			weight[(size_t)K - 2] = 0.6;
+			weight[(size_t)K - 1] = 0.3;
+		}
+		else if (K >= 4)
 		{
 			weight[0] = 0.4;
 			weight[(size_t)K - 1] = 0.45;
@@ -1962,11 +2031,21 @@ extern "C" int dfb_split_align_batch(dfb_ctx* ctx, const dfb_split_params* param
 	if (n_tasks >= pipeline_min && params && refs && reads && task_cluster && task_read && task_min_score)
 	{
 		int rc;
-		if ((rc = check_table(ctx, refs, "refs")) || (rc = check_table(ctx, reads, "reads"))) return rc;
+		if ((rc = check_table(ctx, refs, "refs")) || (rc = check_table_parallel(ctx, reads, "reads"))) return rc;
 		if (refs->n & 1) return set_err(ctx, DFB_ERR_ARG, "refs must hold two windows per cluster (n is odd)");
 		if (n_tasks > 0x7fffff00LL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
 		bool monotone = true;
-		for (int64_t t = 1; t < n_tasks && monotone; t++) monotone = task_read[t] >= task_read[t - 1];
+		{
+			const int T = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->host_threads, n_tasks / 262144 + 1));
+			std::vector<char> ok((size_t)T, 1);
+			parallel_for(ctx->pool, T, [&](int tid) {
+				const int64_t a = std::max<int64_t>(1, n_tasks * tid / T), b = n_tasks * (tid + 1) / T;
+				bool m = true;
+				for (int64_t t = a; t < b && m; t++) m = task_read[t] >= task_read[t - 1];
+				ok[(size_t)tid] = m;
+			});
+			for (char c : ok) monotone = monotone && c;
+		}
 		if (monotone)
 			return split_align_pipelined(ctx, params, refs, reads, task_cluster, task_read, task_min_score, n_tasks, out_best);
 	}
