@@ -223,6 +223,52 @@ def test_large_batch_properties_and_sampled_parity(oracle_mod, gpu_ctx):
         assert a.shape == b.shape and (a == b).all(), t
 
 
+def _expand_cols(res):
+    """Per row, its column list as a fixed-width array (padded with -1): layout-independent comparison of results."""
+    rows, cols = res.rows, res.cols
+    width = int((rows["n1"] + rows["n2"]).max()) if len(rows) else 0
+    out = np.full((len(rows), width), -1, dtype=np.int64)
+    for k in range(width):
+        m = (rows["n1"] + rows["n2"]) > k
+        out[m, k] = cols[rows["col_begin"][m] + k]
+    return out
+
+
+def test_full_size_batch_pipelined_equals_resident(oracle_mod, gpu_ctx):
+    """BASELINE.json configs[2] at the size bench.py runs (2 M tasks): the one-call path cuts it into seven tapered chunks
+    whose rows go straight into the batch's result arrays; the resident plan assembles the same batch in one piece.
+    Same rows, same column lists, task by task; size-independent properties on every row; sampled oracle parity."""
+    import defuse_b200 as d
+    import synth
+    w = synth.split_workload(21, 20000, 100)
+    refs, reads = d.SeqTable(w["ref_bytes"], w["ref_off"]), d.SeqTable(w["read_bytes"], w["read_off"])
+    al = d.SplitReadAligner(ctx=gpu_ctx)
+    piped = al.align_batch(refs, reads, w["task_cluster"], w["task_read"], w["min_score"])
+    plan = al.plan(refs, reads, w["task_cluster"], w["task_read"], w["min_score"])
+    plan.run()
+    whole = plan.fetch()
+    plan.close()
+    assert np.array_equal(piped.best, whole.best)
+    assert len(piped.rows) == len(whole.rows) > 10 ** 6
+    for f in ("task", "read_split", "score1", "score2", "n1", "n2"):
+        assert np.array_equal(piped.rows[f], whole.rows[f]), f
+    assert np.array_equal(_expand_cols(piped), _expand_cols(whole))
+    rows, L = piped.rows, w["L"]
+    assert np.all(np.diff(rows["task"]) >= 0)
+    assert np.all(rows["score1"] + rows["score2"] == piped.best[rows["task"]])
+    assert np.all((piped.best == 0) | ((piped.best >= w["min_score"]) & (piped.best <= 2 * L)))
+    assert np.all((rows["n1"] >= 1) & (rows["n2"] >= 1) & (rows["col_begin"] >= 0))
+    assert int((rows["col_begin"] + rows["n1"] + rows["n2"]).max()) <= len(piped.cols)
+    sample = np.sort(np.random.default_rng(2).choice(w["n_tasks"], 300, replace=False)).astype(np.int32)
+    cnt, want = oracle_mod.split_align_batch(w["ref_bytes"], w["ref_off"], w["read_bytes"], w["read_off"],
+                                             w["task_cluster"][sample], w["task_read"][sample], w["min_score"][sample])
+    pos = np.concatenate([[0], np.cumsum(cnt)])
+    for k, t in enumerate(sample):
+        a = piped.alignments(int(t))
+        b = want[pos[k]:pos[k + 1]]
+        assert a.shape == b.shape and (a == b).all(), t
+
+
 def test_large_simple_batch_sampled_parity(oracle_mod, gpu_ctx):
     import defuse_b200 as d
     import synth
