@@ -340,14 +340,19 @@ def run_ours(args):
     # ---- end to end through the C ABI with host buffers ----
     e2e_ms = []
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    import resource
+    cpu_ms = []
     for s in range(1 + e2e_steps):  # first one is the warm-up
         barrier()
+        ru0 = resource.getrusage(resource.RUSAGE_SELF)
         t0 = time.perf_counter()
         r2 = aligner.align_batch(refs, reads, host["task_cluster"], host["task_read"], host["min_score"], copy=False)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) * 1e3
+        ru1 = resource.getrusage(resource.RUSAGE_SELF)
         if s > 0:
             e2e_ms.append(dt)
+            cpu_ms.append(((ru1.ru_utime - ru0.ru_utime) + (ru1.ru_stime - ru0.ru_stime)) * 1e3)  # all threads of this rank
     assert (r2.best == best_resident).all() and len(r2.rows) == n_rows
     clocks = sampler.stop() if rank == 0 else None
 
@@ -394,7 +399,9 @@ def run_ours(args):
             "e2e": {"value": cells_all / (e2e_mean * 1e-3) / 1e9, "unit": UNIT,
                     "tasks_per_s": tasks_all / (e2e_mean * 1e-3), "ms_per_step": e2e_mean,
                     "h2d_bytes_per_step": st["h2d_bytes"] + 3 * 4 * st["n_tasks"],
-                    "d2h_bytes_per_step": st["d2h_bytes"], "steps": e2e_steps},
+                    "d2h_bytes_per_step": st["d2h_bytes"], "steps": e2e_steps,
+                    "host_cpu_ms_per_step": float(np.mean(cpu_ms)),   # user+sys of all threads of rank 0 during the call
+                    "host_cpus": os.cpu_count(), "host_threads_cap": os.environ.get("DFB_HOST_THREADS")},
             "gpu_launches": int(st["kernel_launches"]) * args.steps,
             "roofline": {"bound": "int_issue", "kernel": "dp_fast_kernel<8,13,SPLIT> (first sweep)",
                          "achieved": achieved, "peak": peak_gcups, "unit": UNIT, "frac": achieved / peak_gcups,

@@ -204,6 +204,7 @@ struct dfb_ctx
 	PinnedBuf h_out;             // results on their way back
 	cudaStream_t copy_stream = nullptr; // device->host result copies, ordered after a plan's kernels by an event
 	cudaStream_t upload_stream = nullptr; // uploads + packing of the next chunk of a pipelined batch
+	cudaEvent_t copied_ev = nullptr;      // blocking-sync event behind the result copies of a fetch
 	HostPool* pool = nullptr;       // plan building (and everything else on the caller's thread)
 	HostPool* pool_fetch = nullptr; // result assembly when it runs on the pipelining helper thread
 	dfb_plan* last_split = nullptr; // result holder of dfb_split_align_batch
@@ -324,6 +325,7 @@ extern "C" int dfb_ctx_create(int device_ordinal, dfb_ctx** out)
 		delete ctx;
 		return set_err(nullptr, DFB_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(e));
 	}
+	cudaEventCreateWithFlags(&ctx->copied_ev, cudaEventDisableTiming | cudaEventBlockingSync);
 	// keep freed blocks in the stream-ordered pool: a batch re-uses the previous batch's memory
 	cudaMemPool_t pool;
 	if (cudaDeviceGetDefaultMemPool(&pool, device_ordinal) == cudaSuccess)
@@ -353,6 +355,7 @@ extern "C" void dfb_ctx_destroy(dfb_ctx* ctx)
 	ctx->h_out.release();
 	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+	if (ctx->copied_ev) cudaEventDestroy(ctx->copied_ev);
 	delete ctx->pool;
 	delete ctx->pool_fetch;
 	ctx->spare_rows.release();
@@ -1490,7 +1493,9 @@ extern "C" int dfb_plan_run(dfb_plan* pl)
 		CK(ctx, cudaEventRecord(pl->ev[2], ctx->stream));
 		pl->run_timed = true;
 	}
-	if (!pl->done_ev) CK(ctx, cudaEventCreateWithFlags(&pl->done_ev, cudaEventDisableTiming));
+	// (blocking-sync event: the thread that waits for a chunk's kernels sleeps instead of spinning on a core the other
+	// lanes -- or the other ranks of the host -- could use)
+	if (!pl->done_ev) CK(ctx, cudaEventCreateWithFlags(&pl->done_ev, cudaEventDisableTiming | cudaEventBlockingSync));
 	CK(ctx, cudaEventRecord(pl->done_ev, ctx->stream));
 	pl->ran = true;
 	return DFB_OK;
@@ -1612,6 +1617,7 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 	// result copies run on the copy stream, ordered behind this plan's kernels only (later batches may
 	// already be queued on the compute stream)
 	cudaStream_t cs = ctx->copy_stream;
+	CK(ctx, cudaEventSynchronize(pl->done_ev));
 	CK(ctx, cudaStreamWaitEvent(cs, pl->done_ev, 0));
 
 	// 1. counters: overflow-list length and winning tasks per class
@@ -1670,6 +1676,11 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 	d2h += (int64_t)(g_rows * sizeof(dfb_split_row) + g_cols * sizeof(int32_t));
 	if (n_ov) CK(ctx, cudaMemcpyAsync(h_ov, pl->d_events, (size_t)n_ov * sizeof(Event), cudaMemcpyDeviceToHost, cs));
 	d2h += (int64_t)(n_ov * sizeof(Event));
+	if (ctx->copied_ev)
+	{
+		CK(ctx, cudaEventRecord(ctx->copied_ev, cs));
+		CK(ctx, cudaEventSynchronize(ctx->copied_ev)); // sleeps through the transfer
+	}
 	CK(ctx, cudaStreamSynchronize(cs));
 	pl->stats.d2h_bytes = d2h;
 	pl->stats.probe_jobs = n_slots;
