@@ -279,7 +279,8 @@ def run_ours(args):
     if world > 1:
         # one process per GPU on one host: the ranks share its cores (the context's worker pool defaults to 16 threads)
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-        os.environ.setdefault("DFB_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 16) // max(1, local_world)))))
+        # (measured on 8 GPUs / 32 host threads: 4 workers per rank 79.9 ms per e2e step, 8 -> 67.3, 12 -> 63.6)
+        os.environ.setdefault("DFB_HOST_THREADS", str(max(4, min(16, 3 * (os.cpu_count() or 16) // max(1, local_world)))))
     ctx = d.Context(local_rank)
     # a side stream: the legacy default stream has handle 0, which the C ABI reads as "use your own"
     stream = torch.cuda.Stream()
