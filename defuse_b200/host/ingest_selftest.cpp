@@ -8,8 +8,31 @@
 
 using namespace dfbhost;
 
+// --blocks <bytes>: stdin through LineBlocks back to stdout; exit 1 when a block that is not the last one does not
+// end behind a newline
+static int BlocksMode(size_t block_bytes)
+{
+	LineBlocks in;
+	in.Open(0, block_bytes);
+	const char* p = nullptr;
+	size_t n = 0;
+	bool open_tail = false; // a block without a final newline must be the last
+	size_t blocks = 0;
+	while (in.Next(p, n))
+	{
+		if (open_tail) return 1;
+		if (n == 0) return 1;
+		open_tail = p[n - 1] != '\n';
+		fwrite(p, 1, n, stdout);
+		blocks++;
+	}
+	fprintf(stderr, "blocks %zu\n", blocks);
+	return 0;
+}
+
 int main(int argc, char* argv[])
 {
+	if (argc >= 3 && std::string(argv[1]) == "--blocks") return BlocksMode((size_t)atoll(argv[2]));
 	if (argc < 3) return 2;
 	const std::string path = argv[1];
 	const int threads = atoi(argv[2]);

@@ -80,3 +80,25 @@ def test_dosplitalign_sam_errors_are_the_first_in_file_order(tmp_path):
         if ref:
             q = subprocess.run([ref] + a, capture_output=True)
             assert q.returncode == 1 and message in q.stderr.decode(), q.stderr.decode()[-300:]
+
+
+@pytest.mark.parametrize("mode", ["pipe", "file"])
+def test_line_blocks_reproduce_the_input(tmp_path, mode):
+    """LineBlocks (what localalign reads stdin through): whole-line blocks, read ahead from a pipe or windows of a
+    mapped file; concatenated they are the input, whatever the block size -- including lines longer than a block and
+    an input without a final newline."""
+    if not os.path.exists(TOOL):
+        pytest.skip("tools not built")
+    rng = np.random.default_rng(5)
+    lines = [bytes(rng.integers(65, 91, int(n)).astype(np.uint8)) for n in rng.integers(0, 400, 300)]
+    lines[17] = b"x" * 9000                      # longer than most block sizes below
+    for text in (b"\n".join(lines) + b"\n", b"\n".join(lines), b"", b"\n", b"no newline at all"):
+        path = str(tmp_path / "in.txt")
+        open(path, "wb").write(text)
+        for block in (1, 16, 333, 4096, 1 << 20):
+            if mode == "pipe":
+                p = subprocess.run([TOOL, "--blocks", str(block)], input=text, capture_output=True)
+            else:
+                with open(path, "rb") as f:
+                    p = subprocess.run([TOOL, "--blocks", str(block)], stdin=f, capture_output=True)
+            assert p.returncode == 0 and p.stdout == text, (mode, block, len(text), p.stderr[-200:])
