@@ -117,3 +117,40 @@ def test_splitseq_vs_reference_tool(oracle_mod, tmp_path, kw):
         a, b = _run([_tool("splitseq")] + tail), _run([refs["splitseq"]] + tail)
         assert len(b) > 1000
         assert a == b, name
+
+
+def test_evalsplitalign_score_ties_follow_the_reference_container_order(oracle_mod, tmp_path):
+    """Evaluate picks the first split with the highest summed score in the ITERATION order of an
+    unordered_map<pair<int,int>,int> (tools/SplitAlignment.cpp:505-528).  Engineered records: many distinct refSplits
+    per fusion, summed scores tied on purpose, enough keys to force rehashes.  Host-only, so it runs without a GPU."""
+    import numpy as np
+    from synth import files
+    ref_eval = oracle_mod.ref_tool("ref_evalsplitalign")
+    if not ref_eval:
+        pytest.skip("oracle/_ref tools not built")
+    d = str(tmp_path / "d")
+    args = files.make_split_dataset(d, seed=71, n_clusters=40, pairs_per_cluster=2)
+    common, ev = files.downstream_args(args, d)
+    rng = np.random.default_rng(72)
+    lines = []
+    for fusion in range(40):
+        n_splits = int(rng.choice([1, 2, 3, 8, 20, 60, 200]))
+        splits = {(int(rng.integers(0, 120)), int(rng.integers(-1, 100))) for _ in range(n_splits)}
+        tie_score = int(rng.integers(20, 60))
+        for (s1, s2) in splits:
+            # every split reaches the same total through a different number of records (some fall short, some tie)
+            parts = int(rng.integers(1, 4))
+            total = tie_score if rng.random() < 0.7 else int(rng.integers(1, tie_score))
+            cuts = sorted(rng.integers(0, total + 1, parts - 1).tolist())
+            scores = [b - a for a, b in zip([0] + cuts, cuts + [total])]
+            for sc in scores:
+                a = int(rng.integers(4, 97))
+                lines.append((fusion, "%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t\n" % (
+                    fusion, int(rng.integers(0, 10 ** 6)), int(rng.integers(0, 2)), int(rng.integers(0, 2)), s1, s2, a, 100 - a, sc)))
+    # records of a fusion stay together, their order inside the fusion is shuffled (insertion order matters too)
+    order = rng.permutation(len(lines))
+    text = "".join(l for _, l in sorted((lines[k] for k in order), key=lambda x: x[0]))
+    open(os.path.join(d, "sorted.alignments"), "w").write(text)
+    ours, theirs = _eval(_tool("evalsplitalign"), ev, d, "ours"), _eval(ref_eval, ev, d, "ref")
+    assert len(theirs["seq"].splitlines()) == 40
+    assert ours == theirs
