@@ -49,3 +49,34 @@ def test_no_gpu_means_failure_not_fallback():
     p = subprocess.run([_tool("localalign"), "-m", "10", "-x", "-5", "-g", "-5"], capture_output=True, input=b"a\tACGT\tACG\n")
     assert p.returncode == 1
     assert p.stdout == b"" and b"Error:" in p.stderr and b"no CPU fallback" in p.stderr
+
+
+def test_dosplitalign_input_errors_like_the_reference(tmp_path):
+    """Errors that come before any alignment (so no GPU is needed): same exit code, stdout and stderr as the compiled
+    reference tool for unreadable inputs and malformed region tables."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from synth import files
+    from oracle import ref_tool
+    ref = ref_tool("ref_dosplitalign")
+    if not ref:
+        pytest.skip("oracle/_ref tools not built")
+    d = str(tmp_path / "s")
+    args = files.make_split_dataset(d, seed=3, n_clusters=6, pairs_per_cluster=10)
+
+    def swap(flag, val):
+        a = list(args)
+        a[a.index(flag) + 1] = val
+        return a + ["-a", os.path.join(d, "o.tmp")]
+
+    open(os.path.join(d, "bad2.regions"), "w").write("0\t0\tchr1\t?\t100\t200\n0\t1\tchr1\t+\t100\t200\n")
+    open(os.path.join(d, "bad3.regions"), "w").write("0\t0\tnochrom\t+\t100\t200\n0\t1\tchr1\t+\t100\t200\n")
+    open(os.path.join(d, "reads.1.txt"), "w").write(open(os.path.join(d, "reads.1.fastq")).read())
+    cases = [swap("-e", d + "/nope"), swap("-r", d + "/nope"), swap("-r", d + "/bad2.regions"), swap("-r", d + "/bad3.regions"),
+             swap("-1", d + "/reads.1.txt"), swap("-2", d + "/nope.fastq"), swap("-i", d + "/nope.sam")]
+    strip = lambda b: b.replace(b"[fai_load] build FASTA index.\n", b"")   # printed when the .fai does not exist yet
+    for a in cases:
+        ours = subprocess.run([_tool("dosplitalign")] + a, capture_output=True)
+        theirs = subprocess.run([ref] + a, capture_output=True)
+        assert ours.returncode == theirs.returncode == 1, a
+        assert ours.stdout == theirs.stdout and strip(ours.stderr) == strip(theirs.stderr), a
