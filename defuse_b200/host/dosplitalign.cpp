@@ -66,7 +66,7 @@ int main(int argc, char* argv[])
 		if (!in.good() || !exons.Read(in))
 		{
 			std::cerr << "Error: Unable to read exon regions file " << cmd.Str('e') << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 	}
 	std::unordered_map<int, ClusterTask> tasks; // its iteration order is the order mate regions are registered in
@@ -95,7 +95,7 @@ int main(int argc, char* argv[])
 	if (!ok0 || !ok1)
 	{
 		std::cout << "Error: unable to read sequences" << std::endl;
-		exit(1);
+		ExitNow(1);
 	}
 	const int T = ToolThreads();
 	std::thread fastq_thread([&] {
@@ -117,7 +117,7 @@ int main(int argc, char* argv[])
 		{
 			fastq_thread.join();
 			std::cerr << "Error: Unable to open sam file " << cmd.Str('i') << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		const char* const base = sam.data();
 		std::vector<LineChunk> chunks = SplitLines(base, sam.size(), T);
@@ -206,7 +206,7 @@ int main(int argc, char* argv[])
 				// (chunks are in file order: this is the first line a sequential reader would have died on)
 				fastq_thread.join();
 				std::cerr << part.error << std::endl;
-				exit(1);
+				ExitNow(1);
 			}
 		timer.Lap("sam parse + overlaps");
 		// expand the per-chunk streams into one candidate list (file order), then keep the first occurrence of every
@@ -266,7 +266,7 @@ int main(int argc, char* argv[])
 	for (int file = 0; file <= 1; file++)
 	{
 		std::cerr << fastq[file].Message();
-		if (fastq[file].Fatal()) exit(1);
+		if (fastq[file].Fatal()) ExitNow(1);
 	}
 	auto find_read = [&](int id, const char*& seq, uint32_t& len) {
 		if (fastq[1].Find(id, seq, len) || fastq[0].Find(id, seq, len)) return;
@@ -279,7 +279,7 @@ int main(int argc, char* argv[])
 	if (!out.good())
 	{
 		std::cerr << "Error: Unable to open " << cmd.Str('a') << std::endl;
-		exit(1);
+		ExitNow(1);
 	}
 
 	// ---- align in batches, write records in candidate order ----

@@ -56,7 +56,7 @@ bool ReadRun(std::istream& in, std::string& pending, bool& have_pending, std::ve
 		if (f.size() < 9)
 		{
 			std::cerr << "Error: Format error for candidate reads line:" << std::endl << line << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		Record r;
 		r.fusion_id = IntOrDie(f[0], "fusion id");
@@ -73,7 +73,7 @@ bool ReadRun(std::istream& in, std::string& pending, bool& have_pending, std::ve
 		if (!ParseBool(f[3], r.rev_comp))
 		{
 			std::cerr << "Error: bad lexical cast: revComp '" << f[3] << "'" << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		r.ref_split = std::make_pair(IntOrDie(f[4], "ref split"), IntOrDie(f[5], "ref split"));
 		r.read_split = std::make_pair(IntOrDie(f[6], "read split"), IntOrDie(f[7], "read split"));
@@ -114,7 +114,7 @@ int main(int argc, char* argv[])
 		if (!in.good() || !exons.Read(in))
 		{
 			std::cerr << "Error: Unable to read exon regions file " << cmd.Str('e') << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 	}
 	std::unordered_map<int, ClusterTask> tasks;
@@ -135,7 +135,7 @@ int main(int argc, char* argv[])
 		if (!f.ok)
 		{
 			std::cerr << "Error: Unable to open " << f.name << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 
 	std::vector<Record> run, support;
@@ -149,7 +149,7 @@ int main(int argc, char* argv[])
 		{
 			// the reference default-constructs a task here (operator[]) and trips a DebugCheck on its empty windows
 			std::cerr << "Error: no fusion regions for fusion " << fusion_id << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		const ClusterTask& task = it->second;
 
@@ -183,7 +183,7 @@ int main(int argc, char* argv[])
 			    !(best.second + 1 >= 0 && (size_t)(best.second + 1) < task.window[1].length()))
 			{
 				std::cerr << "Error: split outside the breakpoint windows of fusion " << fusion_id << std::endl;
-				exit(1);
+				ExitNow(1);
 			}
 			sequence = task.remainder[0] + task.window[0].substr(0, (size_t)best.first) + "|" +
 			           task.window[1].substr((size_t)(best.second + 1)) + task.remainder[1];

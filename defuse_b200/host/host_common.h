@@ -22,6 +22,17 @@
 
 namespace dfbhost
 {
+// Error exits of the tools: the reference calls exit(1) (tools/DebugCheck.cpp:15-19 and the I/O checks).  Here a GPU
+// context may still be coming up on a helper thread, and exit() would run the CUDA runtime's teardown against it:
+// flush what was written and leave at once.
+[[noreturn]] inline void ExitNow(int code)
+{
+	std::cout.flush();
+	std::cerr.flush();
+	fflush(nullptr);
+	_exit(code);
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // command line: the grammar the reference gets from TCLAP (include/tclap/CmdLine.h):
@@ -57,12 +68,12 @@ public:
 			if (a == "-h" || a == "--help")
 			{
 				Usage(std::cout, true);
-				exit(0);
+				ExitNow(0);
 			}
 			if (a == "--version")
 			{
 				std::cout << std::endl << mProg << "  version: none" << std::endl << std::endl;
-				exit(0);
+				ExitNow(0);
 			}
 			ArgSpec* spec = nullptr;
 			if (a.size() == 2 && a[0] == '-' && a[1] != '-')
@@ -117,7 +128,7 @@ private:
 		for (auto& s : mSpecs)
 			if (s.flag == flag) return s;
 		std::cerr << "internal error: unknown flag " << flag << std::endl;
-		exit(1);
+		ExitNow(1);
 	}
 	static std::string ArgId(const ArgSpec& s) { return std::string("Argument: -") + s.flag + " (--" + s.name + ")"; }
 
@@ -147,7 +158,7 @@ private:
 		std::cerr << "PARSE ERROR: " << arg_id << std::endl << "             " << what << std::endl << std::endl;
 		Usage(std::cerr, false);
 		std::cerr << std::endl << "For complete USAGE and HELP type: " << std::endl << "   " << mProg << " --help" << std::endl << std::endl;
-		exit(1);
+		ExitNow(1);
 	}
 
 	std::string mProg;
@@ -209,7 +220,7 @@ inline int IntOrDie(const std::string& s, const char* what)
 	if (!ParseInt(s, v))
 	{
 		std::cerr << "Error: bad lexical cast: " << what << " '" << s << "'" << std::endl;
-		exit(1);
+		ExitNow(1);
 	}
 	return v;
 }
@@ -358,14 +369,14 @@ public:
 		if (mStatus != DFB_OK)
 		{
 			std::cerr << "Error: " << mError << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		return mCtx;
 	}
 	[[noreturn]] void Die(const char* what)
 	{
 		std::cerr << "Error: " << what << ": " << dfb_last_error(mCtx) << std::endl;
-		exit(1);
+		ExitNow(1);
 	}
 	Gpu(const Gpu&) = delete;
 	Gpu& operator=(const Gpu&) = delete;

@@ -227,7 +227,7 @@ int main(int argc, char* argv[])
 		if (error)
 		{
 			std::cerr << error << lines_before + error_line + 1 << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		if (!chunks.empty()) lines_before += chunks.back().first_line + (int64_t)parsed.back().lines.size();
 	}

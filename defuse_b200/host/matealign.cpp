@@ -34,7 +34,7 @@ struct FastaSequences
 		if (!in.OpenFile(filename))
 		{
 			std::cerr << "Error: unable to open file " << filename << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		const char* a = in.data();
 		const char* const end = a + in.size();
@@ -201,7 +201,7 @@ int main(int argc, char* argv[])
 			if (part.error_line >= 0)
 			{
 				std::cerr << part.error << std::endl;
-				exit(1);
+				ExitNow(1);
 			}
 		size_t total = 0;
 		for (const Part& part : parts) total += part.entries.size();
@@ -229,7 +229,7 @@ int main(int argc, char* argv[])
 	if (!ok0 || !ok1)
 	{
 		std::cout << "Error: unable to read sequences" << std::endl;
-		exit(1);
+		ExitNow(1);
 	}
 
 	size_t kBatchTasks = 1u << 19;
@@ -269,7 +269,7 @@ int main(int argc, char* argv[])
 				if (!seq)
 				{
 					std::cerr << "Error: Unable to find sequence " << en.ref_name << std::endl;
-					exit(1);
+					ExitNow(1);
 				}
 				full[k] = seq;
 				plan[k] = en.strand == 0 ? PlanWindow((long long)seq->size(), en.position, en.position + search_length)
@@ -293,7 +293,7 @@ int main(int argc, char* argv[])
 				// before position 1): it aborts; we report and fail the same way (non-zero exit)
 				const SamEntry& en = entries[tasks[(size_t)bad].mate];
 				std::cerr << "Error: window around " << en.position << " outside sequence " << en.ref_name << std::endl;
-				exit(1);
+				ExitNow(1);
 			}
 			windows.bytes.resize((size_t)windows.off.back());
 			ParallelRun(T, [&](int tid) {
@@ -377,7 +377,7 @@ int main(int argc, char* argv[])
 		// a malformed record ends this file's stream with the reference's message; a fragment name that is not an
 		// integer is where the reference dies
 		std::cerr << fastq[file].Message();
-		if (fastq[file].Fatal()) exit(1);
+		if (fastq[file].Fatal()) ExitNow(1);
 	}
 	timer.Report();
 	FinishProcess(0);

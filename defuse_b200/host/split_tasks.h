@@ -40,7 +40,7 @@ inline int StrandOrDie(const std::string& s)
 	if (s == "+") return kPlus;
 	if (s == "-") return kMinus;
 	std::cerr << "Error: Unable to intepret strand " << s << std::endl;
-	exit(1);
+	ExitNow(1);
 }
 
 // clusterID \t clusterEnd \t refName \t +|- \t start \t end   (tools/Parsers.cpp:211-264)
@@ -50,7 +50,7 @@ inline void ReadRegionPairs(const std::string& filename, std::map<int, std::vect
 	if (!in.good())
 	{
 		std::cerr << "Error: Unable to open align region pairs file " << filename << std::endl;
-		exit(1);
+		ExitNow(1);
 	}
 	std::string line;
 	std::vector<std::string> f;
@@ -65,12 +65,12 @@ inline void ReadRegionPairs(const std::string& filename, std::map<int, std::vect
 		if (f.size() < 6 || !ParseInt(f[0], id) || !ParseInt(f[1], end) || !ParseInt(f[4], start) || !ParseInt(f[5], stop))
 		{
 			std::cout << "Failed to interpret region:" << std::endl << line << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		if (end != 0 && end != 1)
 		{
 			std::cerr << "Error: pairEnd == 0 || pairEnd == 1 failed for region line: " << line << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		Location loc;
 		loc.ref_name = f[2];
@@ -109,7 +109,7 @@ public:
 				if (!ParseInt(f[k - 1], e.start) || !ParseInt(f[k], e.end))
 				{
 					std::cout << "Failed to interpret exon:" << std::endl << line << std::endl;
-					exit(1);
+					ExitNow(1);
 				}
 				exons.push_back(e);
 			}
@@ -140,7 +140,7 @@ public:
 		if (it == mTranscripts.end())
 		{
 			std::cerr << "Error: Data mismatch, unable to find gene for transcript " << transcript << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		return it->second.gene;
 	}
@@ -153,7 +153,7 @@ public:
 		if (chr == mLookup.end())
 		{
 			std::cerr << "Error: Data mismatch, invalid chromosome " << chromosome << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		std::unordered_set<std::string> unique;
 		const int first_bin = region.start / kBinLength, last_bin = region.end / kBinLength;
@@ -240,7 +240,7 @@ private:
 		if (it == mTranscripts.end() || it->second.exons[kPlus].empty())
 		{
 			std::cerr << "Error: Data mismatch, unable to find transcript " << transcript << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		return it->second;
 	}
@@ -261,7 +261,7 @@ public:
 		if (!mFile)
 		{
 			std::cerr << "[fai_load] fail to open FASTA file." << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		const std::string fai = fasta + ".fai";
 		std::ifstream in(fai.c_str());
@@ -312,7 +312,7 @@ public:
 		if (it == mIndex.end())
 		{
 			std::cerr << "Error: Unable to find sequence for " << ref_name << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		const Entry& e = it->second;
 		// fai_fetch's own clamping of "name:start-end" (atoi semantics on the two numbers)

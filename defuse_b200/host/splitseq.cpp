@@ -30,7 +30,7 @@ public:
 		if (!mIndex.good())
 		{
 			std::cerr << "Error: Unable to open file " << mIndexName << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		for (int end = 0; end <= 1; end++)
 		{
@@ -39,7 +39,7 @@ public:
 			if (!mFastq[end].good())
 			{
 				std::cerr << "Error: Unable to open file " << mFastqName[end] << std::endl;
-				exit(1);
+				ExitNow(1);
 			}
 		}
 	}
@@ -64,27 +64,27 @@ public:
 		{
 			std::cerr << "Error: Unable to interpret read name " << line[0] << " when searching for fragment " << fragment
 			          << " end " << end << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		const char end_name = line[0][slash + 1];
 		if (end_name != '1' && end_name != '2')
 		{
 			std::cerr << "Error: Unable to interpret read end " << line[0] << " when searching for fragment " << fragment
 			          << " end " << end << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		const int found_fragment = IntOrDie(line[0].substr(1, slash - 1), "fragment index");
 		if (found_fragment != fragment)
 		{
 			std::cerr << "Error: Fragment index mismatch when interpreting " << line[0] << " and searching for fragment "
 			          << fragment << " end " << end << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		if ((end_name == '1' ? 0 : 1) != end)
 		{
 			std::cerr << "Error: Read end mismatch when interpreting " << line[0] << " and searching for fragment " << fragment
 			          << " end " << end << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		sequence = line[1];
 	}
@@ -95,7 +95,7 @@ private:
 		if (mIndex.fail())
 		{
 			std::cerr << "Error: Failure reading index file " << mIndexName << " when searching for fragment " << fragment << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 	}
 	void FastqFail(int fragment, int end)
@@ -104,7 +104,7 @@ private:
 		{
 			std::cerr << "Error: Failure reading fastq file " << mFastqName[end] << " when searching for fragment " << fragment
 			          << " end " << end << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 	}
 	std::string mIndexName, mFastqName[2];
@@ -140,7 +140,7 @@ int main(int argc, char* argv[])
 		if (it == regions.end())
 		{
 			std::cerr << "Error: Unable to find fusion " << query << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 		std::map<int, std::vector<Location>> only;
 		only[query] = it->second;
@@ -154,7 +154,7 @@ int main(int argc, char* argv[])
 		if (!in.good() || !exons.Read(in))
 		{
 			std::cerr << "Error: Unable to read exon regions file " << cmd.Str('e') << std::endl;
-			exit(1);
+			ExitNow(1);
 		}
 	}
 	std::unordered_map<int, ClusterTask> tasks;
@@ -167,7 +167,7 @@ int main(int argc, char* argv[])
 	if (!align_file.good())
 	{
 		std::cerr << "Error: Unable to open " << cmd.Str('a') << std::endl;
-		exit(1);
+		ExitNow(1);
 	}
 
 	// ---- every record of a fusion we hold = one task (runs of equal fusion id, SplitAlignment.cpp:319-370) ----
@@ -184,7 +184,7 @@ int main(int argc, char* argv[])
 			if (f.size() < 9)
 			{
 				std::cerr << "Error: Format error for candidate reads line:" << std::endl << line << std::endl;
-				exit(1);
+				ExitNow(1);
 			}
 			Record r;
 			r.fusion_id = IntOrDie(f[0], "fusion id");
@@ -193,7 +193,7 @@ int main(int argc, char* argv[])
 			if (f[3] != "0" && f[3] != "1")
 			{
 				std::cerr << "Error: bad lexical cast: revComp '" << f[3] << "'" << std::endl;
-				exit(1);
+				ExitNow(1);
 			}
 			r.rev_comp = f[3][0] - '0';
 			r.ref_split = std::make_pair(IntOrDie(f[4], "ref split"), IntOrDie(f[5], "ref split"));
@@ -278,7 +278,7 @@ int main(int argc, char* argv[])
 				std::cerr << "Error: false failed: no alignment of read " << r.fragment << (r.read_end == 0 ? "/1" : "/2")
 				          << " to fusion " << r.fusion_id << " has ref split " << r.ref_split.first << "," << r.ref_split.second
 				          << std::endl;
-				exit(1);
+				ExitNow(1);
 			}
 			split1[(size_t)t] = r.ref_split.first;
 			split2[(size_t)t] = r.ref_split.second;
