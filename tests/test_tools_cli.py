@@ -80,3 +80,36 @@ def test_dosplitalign_input_errors_like_the_reference(tmp_path):
         theirs = subprocess.run([ref] + a, capture_output=True)
         assert ours.returncode == theirs.returncode == 1, a
         assert ours.stdout == theirs.stdout and strip(ours.stderr) == strip(theirs.stderr), a
+
+
+def test_matealign_input_errors_like_the_reference(tmp_path):
+    """matealign's SAM checks and unreadable inputs: they come before any alignment (no GPU needed) and must give the
+    compiled reference tool's exit code, stdout and stderr -- with the SAM parsed by chunks on several threads."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from synth import files
+    from oracle import ref_tool
+    ref = ref_tool("ref_matealign")
+    if not ref:
+        pytest.skip("oracle/_ref tools not built")
+    d = str(tmp_path / "m")
+    args, sam = files.make_matealign_dataset(d, seed=4, n_pairs=50)
+    lines = sam.split(b"\n")
+
+    def swap(flag, val):
+        a = list(args)
+        a[a.index(flag) + 1] = val
+        return a
+
+    open(os.path.join(d, "reads.1.txt"), "w").write(open(os.path.join(d, "reads.1.fastq")).read())
+    hit = b"\ttr1 some description\t100\t255\t50M\t*\t0\t0\tACGT\tIIII"
+    cases = [(swap("-r", d + "/nope.fa"), sam), (swap("-1", d + "/reads.1.txt"), sam), (swap("-2", d + "/nope.fastq"), sam),
+             (args, b"\n".join(lines[:10] + [b""] + lines[10:])), (args, b"\n".join(lines[:7] + [b"a\tb\tc"] + lines[7:])),
+             (args, b"\n".join(lines[:5] + [b"7/3\t0" + hit] + lines[5:])), (args, b"\n".join(lines[:5] + [b"73\t0" + hit] + lines[5:]))]
+    for a, text in cases:
+        theirs = subprocess.run([ref] + a, input=text, capture_output=True)
+        for chunk in ("1", "65536"):
+            ours = subprocess.run([_tool("matealign")] + a, input=text, capture_output=True,
+                                  env=dict(os.environ, DFB_TOOL_CHUNK_MIN=chunk, DFB_TOOL_THREADS="8"))
+            assert ours.returncode == theirs.returncode == 1, a
+            assert ours.stdout == theirs.stdout and ours.stderr == theirs.stderr, (a, ours.stderr, theirs.stderr)
