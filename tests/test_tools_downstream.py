@@ -154,3 +154,53 @@ def test_evalsplitalign_score_ties_follow_the_reference_container_order(oracle_m
     ours, theirs = _eval(_tool("evalsplitalign"), ev, d, "ours"), _eval(ref_eval, ev, d, "ref")
     assert len(theirs["seq"].splitlines()) == 40
     assert ours == theirs
+
+
+def _eval_rc(tool, ev, d, tag, env=None):
+    names = {k: os.path.join(d, "%s.%s" % (tag, k)) for k in ("seq", "break", "predalign")}
+    p = subprocess.run([tool] + ev + ["-q", names["seq"], "-b", names["break"], "-p", names["predalign"]],
+                       capture_output=True, timeout=300, env=dict(os.environ, **(env or {})))
+    return p, {k: open(v).read() for k, v in names.items()}
+
+
+@pytest.mark.parametrize("env", [dict(DFB_TOOL_THREADS="1"), dict(DFB_TOOL_THREADS="3", DFB_TOOL_CHUNK_MIN="64"),
+                                 dict(DFB_TOOL_THREADS="7", DFB_TOOL_CHUNK_MIN="700"), dict(DFB_TOOL_THREADS="16", DFB_TOOL_CHUNK_MIN="5000")])
+def test_evalsplitalign_regions_and_blocks_reproduce_the_serial_reader(tmp_path, env):
+    """The records file is cut into blocks and per-thread regions where the fusion id changes: any cut gives the
+    golden bytes (regions of a few lines, several blocks, more threads than runs)."""
+    g, d, common, ev = _golden_dataset(tmp_path)
+    p, got = _eval_rc(_tool("evalsplitalign"), ev, d, "ours", env)
+    assert p.returncode == 0, p.stderr
+    for k in ("seq", "break", "predalign"):
+        assert got[k] == g[k], k
+
+
+def test_evalsplitalign_dies_where_the_reference_dies(oracle_mod, tmp_path):
+    """A line with too few fields ends the run of the reference at that line (tools/SplitAlignment.cpp:331-335): the
+    fusions in front of it are written, and -- because the reader looks at the first line of the NEXT fusion before it
+    evaluates the current one -- a bad first line of a fusion also drops the fusion in front of it.  Same sequence and
+    break files as the compiled tool for every cut of the file (prediction records are buffered by the reference and
+    lost at exit, so they are not compared)."""
+    ref_eval = oracle_mod.ref_tool("ref_evalsplitalign")
+    if not ref_eval:
+        pytest.skip("oracle/_ref tools not built")
+    g, d, common, ev = _golden_dataset(tmp_path)
+    lines = g["sorted"].splitlines(keepends=True)
+    ids = [l.split("\t")[0] for l in lines]
+    starts = [k for k in range(1, len(lines)) if ids[k] != ids[k - 1]]
+    inside = [k for k in range(1, len(lines) - 1) if ids[k] == ids[k - 1] == ids[k + 1]]
+    assert len(starts) > 6 and len(inside) > 6
+    cases = {"first line of a fusion": starts[len(starts) // 2], "inside a fusion": inside[len(inside) // 2],
+             "first line of the file": 0, "last line of the file": len(lines)}
+    for name, at in cases.items():
+        bad = lines[:at] + ["12\t3\t0\n"] + lines[at:]
+        open(os.path.join(d, "sorted.alignments"), "w").write("".join(bad))
+        pr, theirs = _eval_rc(ref_eval, ev, d, "ref")
+        assert pr.returncode == 1 and b"Format error" in pr.stderr, name
+        for env in (dict(DFB_TOOL_THREADS="1"), dict(DFB_TOOL_THREADS="4", DFB_TOOL_CHUNK_MIN="100"),
+                    dict(DFB_TOOL_THREADS="8", DFB_TOOL_CHUNK_MIN="1500")):
+            po, ours = _eval_rc(_tool("evalsplitalign"), ev, d, "ours", env)
+            assert po.returncode == 1, (name, env)
+            want = b"".join(l for l in pr.stderr.splitlines(keepends=True) if not l.startswith(b"[fai_load]"))  # samtools' notice
+            assert po.stderr == want, (name, env, po.stderr, want)
+            assert ours["seq"] == theirs["seq"] and ours["break"] == theirs["break"], (name, env)
