@@ -427,11 +427,11 @@ def run_ours(args):
                                  "stress_config5": measure_stress(ctx, stream, args)}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            n = args.ref_tasks_per_core * threads
+            n = args.cpu_baseline_tasks_per_core * threads   # ~10 s of CPU work on the box's host cores
             g, tps, dt, kind = cpu_split_throughput(w, n, threads)
             line["cpu_baseline"] = {"value": g, "unit": UNIT, "cores": threads, "kind": kind, "tasks_per_s": tps,
                                     "seconds": dt,
-                                    "sample": "first %d tasks of the same workload (%d per host thread)" % (n, args.ref_tasks_per_core)}
+                                    "sample": "first %d tasks of the same workload (%d per host thread)" % (min(n, w["n_tasks"]), args.cpu_baseline_tasks_per_core)}
         args.out.write(json.dumps(line) + "\n")
         args.out.flush()
     plan.close()
@@ -459,7 +459,8 @@ def main():
     ap.add_argument("--tasks-per-cluster", type=int, default=100)
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--ref-tasks-per-core", type=int, default=2000)
+    ap.add_argument("--ref-tasks-per-core", type=int, default=2000)            # reference arm: tasks per thread per step
+    ap.add_argument("--cpu-baseline-tasks-per-core", type=int, default=14000)  # cpu_baseline leg of our arm (one sample)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--local-tasks", type=int, default=1000000)
