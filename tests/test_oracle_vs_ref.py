@@ -65,3 +65,41 @@ def test_backtrace_vs_ref(ref, params):
             assert p2.shape == m2.shape and (p2 == m2).all()
             checked += 1
     assert checked > 10
+
+
+def test_random_parameters_vs_ref(ref):
+    """Random scoring triples (positive gaps, negative matches, zeros), endGaps either way, minSplitScore and minScore
+    below and above zero, alphabets from one letter to mixed case with N, empty strings: restatement == compiled
+    reference for the split tuples and the simple score.  (The same loop ran for 21 000 rounds / 630 000 tasks while the
+    oracle was being pinned; 150 rounds stay in the suite.)"""
+    import defuse_b200 as d
+    rng = np.random.default_rng(9)
+    alphabets = [util.ACGT] + [np.frombuffer(a, np.uint8) for a in (b"ACGTN", b"AC", b"ACGTacgtN", b"A")]
+    for _ in range(150):
+        m, x, g = int(rng.integers(-2, 12)), int(rng.integers(-8, 3)), int(rng.integers(-8, 3))
+        eg, mss = bool(rng.integers(0, 2)), int(rng.integers(-5, 20))
+        alpha = alphabets[int(rng.integers(0, len(alphabets)))]
+        refs, reads, tc, trd = [], [], [], []
+        for c in range(6):
+            refs += [util.rand_seq(rng, int(rng.integers(0, 120)), alpha), util.rand_seq(rng, int(rng.integers(0, 120)), alpha)]
+            for _k in range(5):
+                L = int(rng.integers(0, 70))
+                joined = refs[-2] + refs[-1]
+                if rng.random() < 0.6 and 0 < L <= len(joined):
+                    s = int(rng.integers(0, len(joined) - L + 1))
+                    read = util.mutate(rng, joined[s:s + L], 0.05, 0.02, 0.01)
+                else:
+                    read = util.rand_seq(rng, L, alpha)
+                tc.append(c)
+                trd.append(len(reads))
+                reads.append(read)
+        tc, trd = np.array(tc, np.int32), np.array(trd, np.int32)
+        rt, st = d.SeqTable.from_list(refs), d.SeqTable.from_list(reads)
+        thr = np.array([int(rng.integers(-5, max(1, m) * len(reads[r]) + 2)) for r in trd], np.int32)
+        ca, aa = ref.split_align_batch(rt.data, rt.off, st.data, st.off, tc, trd, thr, m, x, g, eg, mss, impl="port")
+        cb, ab = ref.split_align_batch(rt.data, rt.off, st.data, st.off, tc, trd, thr, m, x, g, eg, mss, impl="ref")
+        assert (ca == cb).all() and (aa == ab).all(), (m, x, g, eg, mss)
+        tr = rng.integers(0, len(refs), len(reads)).astype(np.int32)
+        sa = ref.simple_align_batch(m, x, g, rt.data, rt.off, st.data, st.off, tr, trd, impl="port")
+        sb = ref.simple_align_batch(m, x, g, rt.data, rt.off, st.data, st.off, tr, trd, impl="ref")
+        assert (sa == sb).all(), (m, x, g)
