@@ -382,3 +382,14 @@ def test_backtrace_argument_errors(gpu_ctx):
         al.backtrace_batch(rt, st, [0], [0], [4], [0], [9])   # read split beyond the read
     off, pairs = al.backtrace_batch(rt, st, [], [], [], [], [])
     assert len(off) == 1 and len(pairs) == 0
+
+
+def test_random_parameters(oracle_mod, gpu_ctx):
+    """Random scoring triples (positive gaps, negative matches, zeros: both the s16x2 and the s32 kernels get picked),
+    endGaps either way, minSplitScore and minScore either side of zero, alphabets from one letter to mixed case with N,
+    empty strings; lengths that land in several (G,S) classes (util.random_parameter_round, the generator of the
+    oracle-vs-reference loop with longer sequences every fourth round).  scripts/gpu_fuzz.py runs the same loop by the
+    clock."""
+    rng = np.random.default_rng(41)
+    for rnd in range(48):
+        util.check_random_parameter_round(rng, rnd, oracle_mod, gpu_ctx, _check_split, _check_simple)

@@ -86,3 +86,50 @@ def simple_batch(rng, n_refs, n_tasks, R, L, related=0.8, sub=0.02, indel=0.002)
         task_seq.append(len(seqs))
         seqs.append(seq)
     return refs, seqs, np.array(task_ref, np.int32), np.array(task_seq, np.int32)
+
+
+def random_parameter_round(rng, rnd):
+    """One round of the random-parameter parity loops: (params, refs, reads, task_cluster, task_read, min_score) with
+    params = (match, mismatch, gap, endGaps, minSplitScore).  Every third round stays inside the s16x2 kernels'
+    parameter range, every fourth one uses sequences long enough for several (G,S) classes."""
+    alphabets = [ACGT] + [np.frombuffer(a, np.uint8) for a in (b"ACGTN", b"AC", b"ACGTacgtN", b"A")]
+    big = rnd % 4 == 3
+    m, x, g = int(rng.integers(-2, 12)), int(rng.integers(-8, 3)), int(rng.integers(-8, 3))
+    if rnd % 3 == 0:
+        m, x, g = int(rng.integers(1, 12)), int(rng.integers(-8, 1)), int(rng.integers(-8, 1))
+    eg, mss = bool(rng.integers(0, 2)) and rnd % 3 != 0, int(rng.integers(-5, 20))
+    alpha = alphabets[int(rng.integers(0, len(alphabets)))]
+    r_hi, l_hi = (700, 300) if big else (120, 70)
+    refs, reads, tc, trd = [], [], [], []
+    for c in range(5):
+        refs += [rand_seq(rng, int(rng.integers(0, r_hi)), alpha), rand_seq(rng, int(rng.integers(0, r_hi)), alpha)]
+        for _k in range(4):
+            L = int(rng.integers(0, l_hi))
+            joined = refs[-2] + refs[-1]
+            if rng.random() < 0.6 and 0 < L <= len(joined):
+                s = int(rng.integers(0, len(joined) - L + 1))
+                read = mutate(rng, joined[s:s + L], 0.05, 0.02, 0.01)
+            else:
+                read = rand_seq(rng, L, alpha)
+            tc.append(c)
+            trd.append(len(reads))
+            reads.append(read)
+    tc, trd = np.array(tc, np.int32), np.array(trd, np.int32)
+    thr = np.array([int(rng.integers(-5, max(1, m) * len(reads[r]) + 2)) for r in trd], np.int32)
+    return (m, x, g, eg, mss), refs, reads, tc, trd, thr
+
+
+def check_random_parameter_round(rng, rnd, oracle, ctx, check_split, check_simple):
+    """CUDA path against the oracle on one random_parameter_round; returns the number of tasks compared."""
+    import defuse_b200 as d
+    params, refs, reads, tc, trd, thr = random_parameter_round(rng, rnd)
+    m, x, g, eg, mss = params
+    # (one-letter alphabets with free gaps tie everywhere: tasks with more than 20 000 tuples are left to
+    # test_split_edge_cases, expanding millions of tuples in Python is not what this loop is for)
+    rt, st = d.SeqTable.from_list(refs), d.SeqTable.from_list(reads)
+    cnt, _ = oracle.split_align_batch(rt.data, rt.off, st.data, st.off, tc, trd, thr, m, x, g, eg, mss)
+    keep = cnt <= 20000
+    check_split(oracle, ctx, refs, reads, tc[keep], trd[keep], thr[keep], params)
+    tr = rng.integers(0, len(refs), len(reads)).astype(np.int32)
+    check_simple(oracle, ctx, refs, reads, tr, trd, m, x, g)
+    return int(keep.sum()) + len(trd)
