@@ -109,7 +109,9 @@ int main(int argc, char* argv[])
 	// ---- candidates, in the reference's order (SplitAlignment.cpp:266-303): SAM record order x iteration order of
 	//      the overlap set; once per (cluster, read id, revComp).  Chunks of lines are parsed in parallel (every chunk
 	//      keeps, per record, the overlap set in its iteration order), then merged in file order. ----
-	std::vector<Candidate> candidates;
+	// (plain arrays below: a std::vector would zero hundreds of megabytes on one thread before the workers fill them)
+	std::unique_ptr<Candidate[]> candidates;
+	size_t n_candidates = 0;
 	{
 		MappedInput sam;
 		const bool opened = cmd.Str('i') == "-" ? sam.OpenStdin() : sam.OpenFile(cmd.Str('i'));
@@ -221,8 +223,7 @@ int main(int argc, char* argv[])
 			part_base[c + 1] = part_base[c] + m;
 		}
 		const size_t total = part_base.back();
-		std::vector<Candidate> all(total);
-		std::vector<uint64_t> keys(total);
+		std::unique_ptr<uint64_t[]> keys(new uint64_t[total + 1]); // key = cluster id, read id, revComp: the whole candidate
 		ParallelRun((int)parts.size(), [&](int c) {
 			const std::vector<int32_t>& st = parts[(size_t)c].stream;
 			size_t at = part_base[(size_t)c];
@@ -235,28 +236,85 @@ int main(int argc, char* argv[])
 					const int cluster_id = IdIndex(st[q]), cluster_end = IdEnd(st[q]);
 					const int read_id = PackId(fragment_index, read_end == 0 ? 1 : 0);
 					const int rev_comp = cluster_end == 0 ? 1 : 0;
-					all[at] = Candidate{cluster_id, read_id, rev_comp};
 					keys[at] = ((uint64_t)(uint32_t)cluster_id << 33) | ((uint64_t)(uint32_t)read_id << 1) | (uint64_t)rev_comp;
 				}
 			}
 		});
 		parts.clear();
+		// first occurrence of every key, in list order: the positions are dealt into P buckets by key hash (a stable
+		// counting sort: ranges of the list are scanned in parallel and write behind one another), every bucket is
+		// then resolved by one thread with its own set, and the survivors are compacted range by range
 		std::vector<uint8_t> keep(total, 0);
-		const int P = total < 100000 ? 1 : T;
-		ParallelRun(P, [&](int tid) {
-			KeySet seen(total / (size_t)P + 16);
+		const int P = total < (getenv("DFB_TOOL_CHUNK_MIN") ? (size_t)64 : (size_t)100000) ? 1 : T; // (tests shrink the chunks and this with them)
+		if (P == 1)
+		{
+			KeySet seen(total + 16);
 			for (size_t k = 0; k < total; k++)
+				if (seen.Insert(keys[k])) keep[k] = 1;
+		}
+		else
+		{
+			// (many more buckets than threads: a bucket's set then fits the cache of the core that resolves it)
+			int log_b = 1;
+			while ((1 << log_b) < P || (log_b < 10 && (total >> log_b) > 32768)) log_b++;
+			const int B = 1 << log_b;
+			auto bucket_of = [log_b](uint64_t key) { return (int)((key * 0xD6E8FEB86659FD93ull) >> (64 - log_b)); };
+			std::vector<size_t> count((size_t)P * (size_t)B, 0); // [range][bucket]
+			ParallelRun(P, [&](int r) {
+				size_t* cnt = &count[(size_t)r * (size_t)B];
+				for (size_t k = total * (size_t)r / (size_t)P; k < total * ((size_t)r + 1) / (size_t)P; k++) cnt[bucket_of(keys[k])]++;
+			});
+			// bucket b holds [bucket_begin[b], bucket_begin[b+1]) of `order`; range r writes its part of b at start[r][b]
+			std::vector<size_t> bucket_begin((size_t)B + 1, 0), start((size_t)P * (size_t)B, 0);
+			for (int b = 0; b < B; b++)
 			{
-				const uint64_t key = keys[k];
-				if ((int)(((key * 0xD6E8FEB86659FD93ull) >> 40) % (uint64_t)P) != tid) continue;
-				if (seen.Insert(key)) keep[k] = 1;
+				size_t at = bucket_begin[(size_t)b];
+				for (int r = 0; r < P; r++)
+				{
+					start[(size_t)r * (size_t)B + (size_t)b] = at;
+					at += count[(size_t)r * (size_t)B + (size_t)b];
+				}
+				bucket_begin[(size_t)b + 1] = at;
 			}
+			const bool wide = total > 0xFFFFFFFFull;
+			std::unique_ptr<uint32_t[]> order32(wide ? nullptr : new uint32_t[total + 1]);
+			std::unique_ptr<uint64_t[]> order64(wide ? new uint64_t[total + 1] : nullptr);
+			ParallelRun(P, [&](int r) {
+				size_t* at = &start[(size_t)r * (size_t)B];
+				for (size_t k = total * (size_t)r / (size_t)P; k < total * ((size_t)r + 1) / (size_t)P; k++)
+				{
+					const size_t pos = at[bucket_of(keys[k])]++;
+					if (wide) order64[pos] = k; else order32[pos] = (uint32_t)k;
+				}
+			});
+			ParallelRun(P, [&](int tid) {
+				for (int b = tid; b < B; b += P)
+				{
+					const size_t lo = bucket_begin[(size_t)b], hi = bucket_begin[(size_t)b + 1];
+					KeySet seen(hi - lo + 16);
+					for (size_t q = lo; q < hi; q++)
+					{
+						const size_t k = wide ? (size_t)order64[q] : (size_t)order32[q];
+						if (seen.Insert(keys[k])) keep[k] = 1;
+					}
+				}
+			});
+		}
+		std::vector<size_t> kept_before((size_t)P + 1, 0);
+		ParallelRun(P, [&](int r) {
+			size_t c = 0;
+			for (size_t k = total * (size_t)r / (size_t)P; k < total * ((size_t)r + 1) / (size_t)P; k++) c += keep[k];
+			kept_before[(size_t)r + 1] = c;
 		});
-		size_t kept = 0;
-		for (size_t k = 0; k < total; k++) kept += keep[k];
-		candidates.reserve(kept);
-		for (size_t k = 0; k < total; k++)
-			if (keep[k]) candidates.push_back(all[k]);
+		for (int r = 0; r < P; r++) kept_before[(size_t)r + 1] += kept_before[(size_t)r];
+		n_candidates = kept_before[(size_t)P];
+		candidates.reset(new Candidate[n_candidates + 1]);
+		ParallelRun(P, [&](int r) {
+			size_t at = kept_before[(size_t)r];
+			for (size_t k = total * (size_t)r / (size_t)P; k < total * ((size_t)r + 1) / (size_t)P; k++)
+				if (keep[k])
+					candidates[at++] = Candidate{(int)(uint32_t)(keys[k] >> 33), (int)(uint32_t)((keys[k] >> 1) & 0xFFFFFFFFull), (int)(keys[k] & 1)};
+		});
 	}
 
 	timer.Lap("candidates (dedupe)");
@@ -289,7 +347,10 @@ int main(int argc, char* argv[])
 	if (const char* e = getenv("DFB_TOOL_BATCH")) kBatch = (size_t)std::max(1, atoi(e)); // tests: force several batches
 	struct Shard
 	{
-		TableBuilder reads;
+		// the batch's reads as a CSR table; the bytes are a plain array that the worker threads touch first
+		std::unique_ptr<char[]> read_bytes;
+		size_t read_bytes_cap = 0;
+		std::vector<int64_t> read_off;
 		std::vector<int32_t> task_cluster, task_read, task_min_score, best, read_len, ref2_len;
 		std::vector<int64_t> row_begin; // first result row of each task (n_rows when it has none)
 		const dfb_split_row* rows = nullptr;
@@ -308,9 +369,9 @@ int main(int argc, char* argv[])
 	static unsigned char complement[256];
 	for (int k = 0; k < 256; k++) complement[k] = (unsigned char)k;
 	for (int k = 0; k < 8; k++) complement[(unsigned char)"ACGTacgt"[k]] = (unsigned char)"TGCAtgca"[k]; // tools/Common.cpp:32-54
-	for (size_t first = 0; first < candidates.size(); first += kBatch)
+	for (size_t first = 0; first < n_candidates; first += kBatch)
 	{
-		const size_t last = std::min(candidates.size(), first + kBatch);
+		const size_t last = std::min(n_candidates, first + kBatch);
 		const size_t n = last - first;
 		cand_seq.resize(n);
 		cand_len.resize(n);
@@ -373,24 +434,63 @@ int main(int argc, char* argv[])
 				for (int32_t k : u.members) gpu_of[k] = g;
 			}
 		}
-		// shard tables: offsets by one sequential pass, bytes (reverse-complemented where the candidate says so) in parallel
+		// shard tables: offsets by one sequential pass over arrays that keep their size from batch to batch (nothing is
+		// re-zeroed: every entry in use is written below), bytes (reverse-complemented where the candidate says so) in
+		// parallel
 		local_of.resize(n);
+		std::vector<size_t> shard_tasks((size_t)n_gpus, 0);
 		for (Shard& sh : shards)
 		{
-			sh.reads.Clear();
-			sh.task_cluster.clear();
+			if (sh.task_cluster.size() < n) sh.task_cluster.resize(n);
+			if (sh.read_off.size() < n + 1) sh.read_off.resize(n + 1);
+			sh.read_off[0] = 0;
 		}
-		for (size_t k = 0; k < n; k++)
+		if (n_gpus == 1)
 		{
-			Shard& sh = shards[gpu_of[k]];
-			local_of[k] = (int32_t)sh.task_cluster.size();
-			sh.task_cluster.push_back(cand_slot[k]);
-			sh.reads.off.push_back(sh.reads.off.back() + (int64_t)cand_len[k]);
+			// one shard: task k is candidate k, offsets are a prefix sum over ranges of candidates
+			Shard& sh = shards[0];
+			std::vector<int64_t> range_bytes((size_t)T + 1, 0);
+			ParallelRun(T, [&](int tid) {
+				int64_t sum = 0;
+				for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++) sum += (int64_t)cand_len[k];
+				range_bytes[(size_t)tid + 1] = sum;
+			});
+			for (int r = 0; r < T; r++) range_bytes[(size_t)r + 1] += range_bytes[(size_t)r];
+			ParallelRun(T, [&](int tid) {
+				int64_t at = range_bytes[(size_t)tid];
+				for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
+				{
+					local_of[k] = (int32_t)k;
+					sh.task_cluster[k] = cand_slot[k];
+					at += (int64_t)cand_len[k];
+					sh.read_off[k + 1] = at;
+				}
+			});
+			shard_tasks[0] = n;
 		}
-		for (Shard& sh : shards)
+		else
 		{
-			const size_t m = sh.task_cluster.size();
-			sh.reads.bytes.resize((size_t)sh.reads.off.back());
+			for (size_t k = 0; k < n; k++)
+			{
+				const int g = gpu_of[k];
+				Shard& sh = shards[(size_t)g];
+				const size_t t = shard_tasks[(size_t)g]++;
+				local_of[k] = (int32_t)t;
+				sh.task_cluster[t] = cand_slot[k];
+				sh.read_off[t + 1] = sh.read_off[t] + (int64_t)cand_len[k];
+			}
+		}
+		for (int g = 0; g < n_gpus; g++)
+		{
+			Shard& sh = shards[(size_t)g];
+			const size_t m = shard_tasks[(size_t)g];
+			sh.task_cluster.resize(m);
+			sh.read_off.resize(m + 1);
+			if (sh.read_bytes_cap < (size_t)sh.read_off[m] + 1)
+			{
+				sh.read_bytes_cap = (size_t)sh.read_off[m] + (size_t)sh.read_off[m] / 8 + 64;
+				sh.read_bytes.reset(new char[sh.read_bytes_cap]);
+			}
 			sh.task_read.resize(m);
 			sh.task_min_score.resize(m);
 			sh.read_len.resize(m);
@@ -403,7 +503,7 @@ int main(int argc, char* argv[])
 				Shard& sh = shards[gpu_of[k]];
 				const int32_t t = local_of[k];
 				const uint32_t len = cand_len[k];
-				char* dst = &sh.reads.bytes[0] + sh.reads.off[(size_t)t];
+				char* dst = sh.read_bytes.get() + sh.read_off[(size_t)t];
 				const char* src = cand_seq[k];
 				if (candidates[first + k].rev_comp)
 					for (uint32_t q = 0; q < len; q++) dst[q] = (char)complement[(unsigned char)src[len - 1 - q]];
@@ -421,7 +521,7 @@ int main(int argc, char* argv[])
 		timer.Add("batch: wait for gpu context");
 		auto run_shard = [&](int g) {
 			Shard& sh = shards[g];
-			const dfb_seq_table read_table = sh.reads.View();
+			const dfb_seq_table read_table{(const uint8_t*)sh.read_bytes.get(), sh.read_off.data(), (int64_t)sh.read_off.size() - 1};
 			sh.rc = dfb_split_align_batch(gpus[g]->ctx(), &params, &window_table, &read_table, sh.task_cluster.data(),
 			                              sh.task_read.data(), sh.task_min_score.data(), (int64_t)sh.task_cluster.size(),
 			                              sh.best.data());

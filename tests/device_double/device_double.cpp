@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -66,6 +67,54 @@ struct Seq
 };
 Seq At(const dfb_seq_table* t, int64_t k) { return Seq{t->bytes + t->off[k], (int)(t->off[k + 1] - t->off[k])}; }
 
+// DEVICE_DOUBLE_SKIP_DP=1: answer every call with "no alignment" at once -- for timing the tools' host phases at
+// sizes the oracle would need hours for (scripts/cpu_tool_host_phases.py)
+bool SkipDp()
+{
+	static const bool skip = getenv("DEVICE_DOUBLE_SKIP_DP") && *getenv("DEVICE_DOUBLE_SKIP_DP") == '1';
+	return skip;
+}
+
+// DEVICE_DOUBLE_DIGEST=<file>: append one line per split/simple call with a hash of everything the tool handed over
+// (task order, the window pair and the read bytes of every task, thresholds) -- two builds of a tool submit the same
+// work exactly when their digests agree, also at sizes where the DP itself is skipped
+void Digest(const char* what, const dfb_seq_table* a, const dfb_seq_table* b, const int32_t* ta, const int32_t* tb,
+            const int32_t* extra, int64_t n_tasks, bool pairs)
+{
+	const char* path = getenv("DEVICE_DOUBLE_DIGEST");
+	if (!path || !*path) return;
+	uint64_t h = 1469598103934665603ull;
+	auto mix = [&](const void* p, size_t n) {
+		const uint8_t* q = (const uint8_t*)p;
+		for (size_t k = 0; k < n; k++) h = (h ^ q[k]) * 1099511628211ull;
+	};
+	for (int64_t t = 0; t < n_tasks; t++)
+	{
+		if (pairs)
+		{
+			const Seq r1 = At(a, 2 * (int64_t)ta[t]), r2 = At(a, 2 * (int64_t)ta[t] + 1);
+			mix(r1.p, (size_t)r1.n);
+			mix("|", 1);
+			mix(r2.p, (size_t)r2.n);
+		}
+		else
+		{
+			const Seq r = At(a, ta[t]);
+			mix(r.p, (size_t)r.n);
+		}
+		mix("|", 1);
+		const Seq s = At(b, tb[t]);
+		mix(s.p, (size_t)s.n);
+		mix("|", 1);
+		if (extra) mix(&extra[t], sizeof(int32_t));
+	}
+	if (FILE* f = fopen(path, "a"))
+	{
+		fprintf(f, "%s %lld %016llx\n", what, (long long)n_tasks, (unsigned long long)h);
+		fclose(f);
+	}
+}
+
 int Fail(dfb_ctx* ctx, int code, const char* what)
 {
 	if (ctx) ctx->error = what;
@@ -104,6 +153,12 @@ int dfb_simple_align_batch(dfb_ctx* ctx, const dfb_simple_params* params, const 
 	for (int64_t t = 0; t < n_tasks; t++)
 		if (task_ref[t] < 0 || task_ref[t] >= refs->n || task_seq[t] < 0 || task_seq[t] >= seqs->n)
 			return Fail(ctx, DFB_ERR_ARG, "device double: table index out of range");
+	Digest("simple", refs, seqs, task_ref, task_seq, nullptr, n_tasks, false);
+	if (SkipDp())
+	{
+		std::fill(out_score, out_score + n_tasks, 0);
+		return DFB_OK;
+	}
 	ParallelTasks(n_tasks, [&](int64_t t) {
 		const Seq r = At(refs, task_ref[t]), s = At(seqs, task_seq[t]);
 		out_score[t] = dpo_simple_align(r.p, r.n, s.p, s.n, params->match, params->mismatch, params->gap);
@@ -129,6 +184,15 @@ int dfb_split_align_batch(dfb_ctx* ctx, const dfb_split_params* params, const df
 		std::vector<int32_t> cols;
 		int best = 0;
 	};
+	Digest("split", refs, reads, task_cluster, task_read, task_min_score, n_tasks, true);
+	if (SkipDp())
+	{
+		ctx->rows.clear();
+		ctx->cols.clear();
+		if (out_best) std::fill(out_best, out_best + n_tasks, 0);
+		ctx->have_result = true;
+		return DFB_OK;
+	}
 	std::vector<TaskOut> outs((size_t)n_tasks);
 	ParallelTasks(n_tasks, [&](int64_t t) {
 		const Seq r1 = At(refs, 2 * (int64_t)task_cluster[t]), r2 = At(refs, 2 * (int64_t)task_cluster[t] + 1), rd = At(reads, task_read[t]);

@@ -82,7 +82,8 @@ def test_dosplitalign_sharded_over_contexts(devices, device_double, tmp_path, mo
         res = os.path.join(sub, "ours.alignments")
         env = {"DFB_DEVICES": devices}
         if batch:
-            env["DFB_TOOL_BATCH"] = batch
+            # several batches; SAM chunks of a few lines and the bucketed de-duplication on every thread
+            env.update(DFB_TOOL_BATCH=batch, DFB_TOOL_CHUNK_MIN="300", DFB_TOOL_THREADS="5")
         tg._run([os.path.join(tg.BIN, "dosplitalign")] + args + ["-a", res], env=env)
         assert open(res).read() == g[name]["output"], (name, devices)
 
