@@ -235,7 +235,12 @@ int main(int argc, char* argv[])
 	size_t kBatchTasks = 1u << 19;
 	if (const char* e = getenv("DFB_TOOL_BATCH")) kBatchTasks = (size_t)std::max(1, atoi(e)); // tests: force several batches
 	const size_t kBatchBytes = (size_t)1 << 29;
-	TableBuilder windows, reads;
+	// the batch's tables (CSR; the byte arrays are plain arrays so that the worker threads touch them first)
+	std::unique_ptr<char[]> window_bytes, read_bytes;
+	size_t window_cap = 0, read_cap = 0;
+	std::vector<int64_t> window_off, read_off;
+	std::vector<const std::string*> full;
+	std::vector<WindowPlan> plan;
 	std::vector<int32_t> task_ref, task_seq, score;
 	std::vector<Task> tasks;
 	std::vector<std::string> out_parts((size_t)T);
@@ -253,57 +258,101 @@ int main(int argc, char* argv[])
 		auto flush = [&]() {
 			const size_t n = tasks.size();
 			if (n == 0) return;
-			// window lengths and read slots (a read is uploaded once, its tasks are consecutive)
-			windows.Clear();
-			reads.Clear();
+			// window lengths and read slots (a read is uploaded once, its tasks are consecutive): planned by ranges of
+			// tasks, offsets from the ranges' sums, bytes written by the same ranges into arrays that keep their size
+			// from batch to batch (nothing is zeroed first: every byte in use is written here)
 			task_ref.resize(n);
 			task_seq.resize(n);
 			score.resize(n);
-			std::vector<const std::string*> full(n);
-			std::vector<WindowPlan> plan(n);
-			int64_t bad = -1;
-			for (size_t k = 0; k < n; k++)
+			full.resize(n);
+			plan.resize(n);
+			if (window_off.size() < n + 1) window_off.resize(n + 1);
+			if (read_off.size() < n + 1) read_off.resize(n + 1);
+			struct Range
 			{
-				const SamEntry& en = entries[tasks[k].mate];
-				const std::string* seq = ref_of.find(en.ref_name)->second;
-				if (!seq)
-				{
-					std::cerr << "Error: Unable to find sequence " << en.ref_name << std::endl;
-					ExitNow(1);
-				}
-				full[k] = seq;
-				plan[k] = en.strand == 0 ? PlanWindow((long long)seq->size(), en.position, en.position + search_length)
-				                         : PlanWindow((long long)seq->size(), en.position - search_length, en.position);
-				if (plan[k].bad && bad < 0) bad = (int64_t)k;
-				windows.off.push_back(windows.off.back() + (plan[k].bad ? 0 : plan[k].Length((long long)seq->size())));
-				if (k == 0 || tasks[k].record != tasks[k - 1].record)
-				{
-					int id;
-					const char* s;
-					uint32_t len;
-					fq.Record(tasks[k].record, id, s, len);
-					reads.Add(s, len);
-				}
-				task_ref[k] = (int32_t)k;
-				task_seq[k] = (int32_t)reads.Count() - 1;
-			}
-			if (bad >= 0)
-			{
-				// std::string(n,'N') / substr would throw here in the reference (window starts beyond the sequence, or ends
-				// before position 1): it aborts; we report and fail the same way (non-zero exit)
-				const SamEntry& en = entries[tasks[(size_t)bad].mate];
-				std::cerr << "Error: window around " << en.position << " outside sequence " << en.ref_name << std::endl;
-				ExitNow(1);
-			}
-			windows.bytes.resize((size_t)windows.off.back());
+				int64_t window_bytes = 0, read_bytes = 0, reads = 0, missing = -1, bad = -1;
+			};
+			std::vector<Range> range((size_t)T + 1);
 			ParallelRun(T, [&](int tid) {
+				Range& rg = range[(size_t)tid + 1];
 				for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
 				{
+					const SamEntry& en = entries[tasks[k].mate];
+					const std::string* seq = ref_of.find(en.ref_name)->second;
+					full[k] = seq;
+					if (!seq)
+					{
+						if (rg.missing < 0) rg.missing = (int64_t)k;
+						continue;
+					}
+					plan[k] = en.strand == 0 ? PlanWindow((long long)seq->size(), en.position, en.position + search_length)
+					                         : PlanWindow((long long)seq->size(), en.position - search_length, en.position);
+					if (plan[k].bad && rg.bad < 0) rg.bad = (int64_t)k;
+					rg.window_bytes += plan[k].bad ? 0 : plan[k].Length((long long)seq->size());
+					if (k == 0 || tasks[k].record != tasks[k - 1].record)
+					{
+						int id;
+						const char* rs;
+						uint32_t len;
+						fq.Record(tasks[k].record, id, rs, len);
+						rg.reads++;
+						rg.read_bytes += (int64_t)len;
+					}
+				}
+			});
+			for (int r = 1; r <= T; r++) // (a sequential reader meets a missing sequence before it gets to cut any window)
+				if (range[(size_t)r].missing >= 0)
+				{
+					std::cerr << "Error: Unable to find sequence " << entries[tasks[(size_t)range[(size_t)r].missing].mate].ref_name << std::endl;
+					ExitNow(1);
+				}
+			for (int r = 1; r <= T; r++)
+				if (range[(size_t)r].bad >= 0)
+				{
+					// std::string(n,'N') / substr would throw here in the reference (window starts beyond the sequence, or ends
+					// before position 1): it aborts; we report and fail the same way (non-zero exit)
+					const SamEntry& en = entries[tasks[(size_t)range[(size_t)r].bad].mate];
+					std::cerr << "Error: window around " << en.position << " outside sequence " << en.ref_name << std::endl;
+					ExitNow(1);
+				}
+			for (int r = 1; r <= T; r++)
+			{
+				range[(size_t)r].window_bytes += range[(size_t)r - 1].window_bytes;
+				range[(size_t)r].read_bytes += range[(size_t)r - 1].read_bytes;
+				range[(size_t)r].reads += range[(size_t)r - 1].reads;
+			}
+			const size_t n_reads = (size_t)range[(size_t)T].reads;
+			auto grow = [](std::unique_ptr<char[]>& buf, size_t& cap, size_t need) {
+				if (cap >= need + 1) return;
+				cap = need + need / 8 + 64;
+				buf.reset(new char[cap]);
+			};
+			grow(window_bytes, window_cap, (size_t)range[(size_t)T].window_bytes);
+			grow(read_bytes, read_cap, (size_t)range[(size_t)T].read_bytes);
+			window_off[0] = read_off[0] = 0;
+			ParallelRun(T, [&](int tid) {
+				int64_t w_at = range[(size_t)tid].window_bytes, r_at = range[(size_t)tid].read_bytes, r_idx = range[(size_t)tid].reads;
+				for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
+				{
+					if (k == 0 || tasks[k].record != tasks[k - 1].record)
+					{
+						int id;
+						const char* rs;
+						uint32_t rlen;
+						fq.Record(tasks[k].record, id, rs, rlen);
+						if (rlen) memcpy(read_bytes.get() + r_at, rs, rlen);
+						r_at += (int64_t)rlen;
+						read_off[(size_t)++r_idx] = r_at;
+					}
+					task_ref[k] = (int32_t)k;
+					task_seq[k] = (int32_t)r_idx - 1; // (a range that starts inside a read's run uses the read its predecessor stored)
 					const WindowPlan& w = plan[k];
 					const std::string& seq = *full[k];
-					char* dst = &windows.bytes[0] + windows.off[k];
+					char* dst = window_bytes.get() + w_at;
 					const long long take = w.take < 0 ? (long long)seq.size() - w.from : w.take;
 					const long long len = w.prepend + take + w.append;
+					w_at += len;
+					window_off[k + 1] = w_at;
 					if (entries[tasks[k].mate].strand == 0)
 					{
 						// plus-strand mate: the window is reverse-complemented (tools/matealign.cpp:197-201)
@@ -322,7 +371,8 @@ int main(int argc, char* argv[])
 				}
 			});
 			timer.Add("tables");
-			dfb_seq_table wt = windows.View(), rt = reads.View();
+			const dfb_seq_table wt{(const uint8_t*)window_bytes.get(), window_off.data(), (int64_t)n};
+			const dfb_seq_table rt{(const uint8_t*)read_bytes.get(), read_off.data(), (int64_t)n_reads};
 			if (dfb_simple_align_batch(gpu.ctx(), &params, &wt, &rt, task_ref.data(), task_seq.data(), (int64_t)n, score.data()) != DFB_OK)
 				gpu.Die("alignment failed");
 			timer.Add("gpu");
