@@ -103,6 +103,18 @@ int main(int argc, char* argv[])
 		fastq[1].Scan(std::max(1, T / 2));
 	});
 
+	// The reference reads both fastq files to the end before it opens the SAM file (tools/dosplitalign.cpp:93-110), so
+	// whatever the fastq streams have to say -- and a fatal fragment name -- comes before any SAM error.
+	auto finish_fastq = [&]() {
+		if (!fastq_thread.joinable()) return;
+		fastq_thread.join();
+		for (int file = 0; file <= 1; file++)
+		{
+			std::cerr << fastq[file].Message();
+			if (fastq[file].Fatal()) ExitNow(1);
+		}
+	};
+
 	timer.Lap("bins");
 	const int n_gpus = (int)gpus.size();
 
@@ -117,7 +129,7 @@ int main(int argc, char* argv[])
 		const bool opened = cmd.Str('i') == "-" ? sam.OpenStdin() : sam.OpenFile(cmd.Str('i'));
 		if (!opened)
 		{
-			fastq_thread.join();
+			finish_fastq();
 			std::cerr << "Error: Unable to open sam file " << cmd.Str('i') << std::endl;
 			ExitNow(1);
 		}
@@ -206,7 +218,7 @@ int main(int argc, char* argv[])
 			if (part.error_line >= 0)
 			{
 				// (chunks are in file order: this is the first line a sequential reader would have died on)
-				fastq_thread.join();
+				finish_fastq();
 				std::cerr << part.error << std::endl;
 				ExitNow(1);
 			}
@@ -320,12 +332,7 @@ int main(int argc, char* argv[])
 	timer.Lap("candidates (dedupe)");
 	// ---- the reads the candidates need (the reference keeps every read of both files, SplitAlignment.cpp:253-264, the
 	//      second file overwriting the first; a read id that is absent aligns as the empty string, :286) ----
-	fastq_thread.join();
-	for (int file = 0; file <= 1; file++)
-	{
-		std::cerr << fastq[file].Message();
-		if (fastq[file].Fatal()) ExitNow(1);
-	}
+	finish_fastq();
 	auto find_read = [&](int id, const char*& seq, uint32_t& len) {
 		if (fastq[1].Find(id, seq, len) || fastq[0].Find(id, seq, len)) return;
 		seq = nullptr;

@@ -9,6 +9,8 @@
 #include "host_common.h"
 #include "fast_io.h"
 
+#include <sstream>
+
 #include <fstream>
 #include <string_view>
 #include <unordered_map>
@@ -256,8 +258,9 @@ int main(int argc, char* argv[])
 		const FastqIndex& fq = fastq[file];
 		// one batch: tasks [tasks of records r0..r1)
 		auto flush = [&]() {
-			const size_t n = tasks.size();
+			size_t n = tasks.size();
 			if (n == 0) return;
+			std::string fault; // what a task-by-task reader dies on; the tasks in front of that one are still aligned and printed
 			// window lengths and read slots (a read is uploaded once, its tasks are consecutive): planned by ranges of
 			// tasks, offsets from the ranges' sums, bytes written by the same ranges into arrays that keep their size
 			// from batch to batch (nothing is zeroed first: every byte in use is written here)
@@ -272,7 +275,10 @@ int main(int argc, char* argv[])
 			{
 				int64_t window_bytes = 0, read_bytes = 0, reads = 0, missing = -1, bad = -1;
 			};
-			std::vector<Range> range((size_t)T + 1);
+			std::vector<Range> range;
+			for (;;)
+			{
+			range.assign((size_t)T + 1, Range());
 			ParallelRun(T, [&](int tid) {
 				Range& rg = range[(size_t)tid + 1];
 				for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
@@ -300,21 +306,26 @@ int main(int argc, char* argv[])
 					}
 				}
 			});
-			for (int r = 1; r <= T; r++) // (a sequential reader meets a missing sequence before it gets to cut any window)
-				if (range[(size_t)r].missing >= 0)
-				{
-					std::cerr << "Error: Unable to find sequence " << entries[tasks[(size_t)range[(size_t)r].missing].mate].ref_name << std::endl;
-					ExitNow(1);
-				}
+			int64_t first = -1;
 			for (int r = 1; r <= T; r++)
-				if (range[(size_t)r].bad >= 0)
-				{
-					// std::string(n,'N') / substr would throw here in the reference (window starts beyond the sequence, or ends
-					// before position 1): it aborts; we report and fail the same way (non-zero exit)
-					const SamEntry& en = entries[tasks[(size_t)range[(size_t)r].bad].mate];
-					std::cerr << "Error: window around " << en.position << " outside sequence " << en.ref_name << std::endl;
-					ExitNow(1);
-				}
+				for (int64_t k : {range[(size_t)r].missing, range[(size_t)r].bad})
+					if (k >= 0 && (first < 0 || k < first)) first = k;
+			if (first < 0) break;
+			const SamEntry& en = entries[tasks[(size_t)first].mate];
+			std::ostringstream msg;
+			if (!full[(size_t)first])
+				msg << "Error: Unable to find sequence " << en.ref_name << std::endl;
+			else
+				// std::string(n,'N') / substr would throw here in the reference (window starts beyond the sequence, or ends
+				// before position 1): it aborts; we report and fail the same way (non-zero exit)
+				msg << "Error: window around " << en.position << " outside sequence " << en.ref_name << std::endl;
+			fault = msg.str();
+			n = (size_t)first;
+			tasks.resize(n);
+			if (n == 0) break;
+			}
+			if (n > 0)
+			{
 			for (int r = 1; r <= T; r++)
 			{
 				range[(size_t)r].window_bytes += range[(size_t)r - 1].window_bytes;
@@ -400,6 +411,12 @@ int main(int argc, char* argv[])
 			for (const std::string& part : out_parts) fwrite(part.data(), 1, part.size(), stdout);
 			fflush(stdout);
 			timer.Add("format + write");
+			}
+			if (!fault.empty())
+			{
+				std::cerr << fault;
+				ExitNow(1);
+			}
 			tasks.clear();
 		};
 		size_t batch_bytes = 0;

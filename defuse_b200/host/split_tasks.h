@@ -60,13 +60,14 @@ inline void ReadRegionPairs(const std::string& filename, std::map<int, std::vect
 		SplitChar(line, '\t', f);
 		if (f.size() < 5) continue;
 		int id = 0, end = 0, start = 0, stop = 0;
-		// the reference reads field 5 after checking for only 5 fields (Parsers.cpp:237,251): a 5-field line is
-		// undefined behaviour there; here it is a format error
-		if (f.size() < 6 || !ParseInt(f[0], id) || !ParseInt(f[1], end) || !ParseInt(f[4], start) || !ParseInt(f[5], stop))
-		{
+		auto bad_line = [&]() {
 			std::cout << "Failed to interpret region:" << std::endl << line << std::endl;
 			ExitNow(1);
-		}
+		};
+		// fields are read in the reference's order (Parsers.cpp:242-251): ids, the pairEnd check, strand, positions --
+		// a line with several faults dies on the first of them.  The reference reads field 5 after checking for only 5
+		// fields (:237,251): a 5-field line is undefined behaviour there; here it is a format error
+		if (f.size() < 6 || !ParseInt(f[0], id) || !ParseInt(f[1], end)) bad_line();
 		if (end != 0 && end != 1)
 		{
 			std::cerr << "Error: pairEnd == 0 || pairEnd == 1 failed for region line: " << line << std::endl;
@@ -75,6 +76,7 @@ inline void ReadRegionPairs(const std::string& filename, std::map<int, std::vect
 		Location loc;
 		loc.ref_name = f[2];
 		loc.strand = StrandOrDie(f[3]);
+		if (!ParseInt(f[4], start) || !ParseInt(f[5], stop)) bad_line();
 		loc.start = start;
 		loc.end = stop;
 		std::vector<Location>& v = pairs[id];
