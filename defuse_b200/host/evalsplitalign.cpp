@@ -186,14 +186,13 @@ void ProcessRegion(const char* begin, const char* region_end, const char* file_e
 		if (run.empty()) return;
 
 		const int fusion_id = first_id;
+		// a fusion id without regions: the reference default-constructs a task here (operator[], tools/evalsplitalign.cpp:102)
+		// whose windows are empty -- any split then trips the DebugChecks of Evaluate (:545-546), and a run without a
+		// split still gets its empty prediction
+		static const ClusterTask no_regions;
 		auto it = tasks.find(fusion_id);
-		if (it == tasks.end())
-		{
-			// the reference default-constructs a task here (operator[]) and trips a DebugCheck on its empty windows
-			die("Error: no fusion regions for fusion " + std::to_string(fusion_id) + "\n");
-			return;
-		}
-		const ClusterTask& task = it->second;
+		const ClusterTask& task = it == tasks.end() ? no_regions : it->second;
+		const int task_id = it == tasks.end() ? 0 : fusion_id; // what the prediction is labelled with: the task's own id (:596-612)
 
 		// ---- SplitAlignmentTask::Evaluate (tools/SplitAlignment.cpp:484-594) ----
 		// (a fresh container per fusion: its bucket count, hence its iteration order, must be the reference's)
@@ -211,7 +210,7 @@ void ProcessRegion(const char* begin, const char* region_end, const char* file_e
 		double pos_avg = -1.0, min_avg = -1.0;
 		int break_pos[2] = {0, 0};
 		support.clear();
-		AppendInt(out.seq, fusion_id);
+		AppendInt(out.seq, task_id);
 		out.seq += '\t';
 		if (max_score == -1)
 		{
@@ -227,7 +226,7 @@ void ProcessRegion(const char* begin, const char* region_end, const char* file_e
 			if (!(best.first >= 0 && (size_t)best.first <= task.window[0].length()) ||
 			    !(best.second + 1 >= 0 && (size_t)(best.second + 1) < task.window[1].length()))
 			{
-				out.seq.resize(out.seq.size() - 1 - std::to_string(fusion_id).size());
+				out.seq.resize(out.seq.size() - 1 - std::to_string(task_id).size());
 				die("Error: split outside the breakpoint windows of fusion " + std::to_string(fusion_id) + "\n");
 				return;
 			}
@@ -266,7 +265,7 @@ void ProcessRegion(const char* begin, const char* region_end, const char* file_e
 		out.seq += '\n';
 		for (int end = 0; end <= 1; end++)
 		{
-			AppendInt(out.brk, fusion_id);
+			AppendInt(out.brk, task_id);
 			out.brk += '\t';
 			AppendInt(out.brk, end);
 			out.brk += '\t';

@@ -98,3 +98,18 @@ def test_missing_device_is_an_error(device_double, tmp_path, monkeypatch):
     p = subprocess.run([os.path.join(tg.BIN, "dosplitalign")] + args + ["-a", str(tmp_path / "out")], capture_output=True,
                        env=dict(os.environ, DFB_DEVICES="0,7"))
     assert p.returncode == 1 and b"Error:" in p.stderr
+
+
+@pytest.mark.parametrize("tool", ["dosplitalign", "matealign", "localalign", "evalsplitalign"])
+def test_input_fuzz_agrees_with_the_reference_tool(tool, oracle_mod):
+    """scripts/cpu_fuzz_tools.py, a fixed number of rounds: perturbed inputs (odd but legal records and malformed ones),
+    our tool over the device double against the compiled reference tool -- exit codes, outputs, messages."""
+    import json
+    import sys
+    if not oracle_mod.ref_tool("ref_" + tool) or not os.path.exists(os.path.join(tg.BIN, tool)):
+        pytest.skip("tools not built")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "cpu_fuzz_tools.py"), tool, "5", "120", "60"],
+                       capture_output=True, timeout=600)
+    report = json.loads(p.stdout.decode())
+    assert report["rounds"] == 60 and not report["disagreements"], report["disagreements"][:2]
+    assert report["reference_exit_0"] > 5 and report["reference_exit_1"] > 5  # both kinds of outcome were exercised
