@@ -171,6 +171,10 @@ int main(int argc, char* argv[])
 	}
 
 	// ---- every record of a fusion we hold = one task (runs of equal fusion id, SplitAlignment.cpp:319-370) ----
+	// The reference handles one run at a time and prints it before it reads the next (tools/splitseq.cpp:104-124): what it
+	// dies on -- a malformed line, met while the run in front of it is still being read, or a record whose alignment
+	// does not exist -- comes after the text of the runs in front.  `fault` holds that message until they are printed.
+	std::string fault;
 	std::vector<Record> records;
 	std::vector<size_t> run_begin; // first record of each printed run
 	{
@@ -181,25 +185,48 @@ int main(int argc, char* argv[])
 		while (std::getline(align_file, line))
 		{
 			SplitChar(line, '\t', f);
+			// the run being read is lost with a line that cannot be read: the reference meets such a line while it still
+			// collects that run (it looks one line ahead, SplitAlignment.cpp:319-370)
+			auto drop_current_run = [&]() {
+				if (in_run && keep)
+				{
+					records.resize(run_begin.back());
+					run_begin.pop_back();
+				}
+			};
+			Record r;
 			if (f.size() < 9)
 			{
-				std::cerr << "Error: Format error for candidate reads line:" << std::endl << line << std::endl;
-				ExitNow(1);
+				fault = "Error: Format error for candidate reads line:\n" + line + "\n";
+				drop_current_run();
+				break;
 			}
-			Record r;
-			r.fusion_id = IntOrDie(f[0], "fusion id");
-			r.fragment = IntOrDie(f[1], "fragment index");
-			r.read_end = IntOrDie(f[2], "read end");
-			if (f[3] != "0" && f[3] != "1")
+			if (!ParseInt(f[0], r.fusion_id))
 			{
-				std::cerr << "Error: bad lexical cast: revComp '" << f[3] << "'" << std::endl;
-				ExitNow(1);
+				fault = "Error: bad lexical cast: fusion id '" + f[0] + "'\n";
+				drop_current_run();
+				break;
+			}
+			// the other fields are only read once the line belongs to the run being collected: a bad one on the first line
+			// of a new run comes after the run in front of it has been handled
+			int unused = 0;
+			const char* bad = nullptr;
+			size_t bad_field = 0;
+			if (!ParseInt(f[1], r.fragment)) bad = "fragment index", bad_field = 1;
+			else if (!ParseInt(f[2], r.read_end)) bad = "read end", bad_field = 2;
+			else if (f[3] != "0" && f[3] != "1") bad = "revComp", bad_field = 3;
+			else if (!ParseInt(f[4], r.ref_split.first)) bad = "ref split", bad_field = 4;
+			else if (!ParseInt(f[5], r.ref_split.second)) bad = "ref split", bad_field = 5;
+			else if (!ParseInt(f[6], unused)) bad = "read split", bad_field = 6;
+			else if (!ParseInt(f[7], unused)) bad = "read split", bad_field = 7;
+			else if (!ParseInt(f[8], unused)) bad = "score", bad_field = 8;
+			if (bad)
+			{
+				fault = std::string("Error: bad lexical cast: ") + bad + " '" + f[bad_field] + "'\n";
+				if (in_run && r.fusion_id == run_id) drop_current_run();
+				break;
 			}
 			r.rev_comp = f[3][0] - '0';
-			r.ref_split = std::make_pair(IntOrDie(f[4], "ref split"), IntOrDie(f[5], "ref split"));
-			IntOrDie(f[6], "read split");
-			IntOrDie(f[7], "read split");
-			IntOrDie(f[8], "score");
 			if (!in_run || r.fusion_id != run_id)
 			{
 				in_run = true;
@@ -215,7 +242,7 @@ int main(int argc, char* argv[])
 	// ---- tables: window pairs of the fusions seen, reads in the orientation the record names ----
 	TableBuilder windows, reads;
 	std::unordered_map<int, int> slot;
-	const int64_t n = (int64_t)records.size();
+	int64_t n = (int64_t)records.size();
 	std::vector<int32_t> task_cluster((size_t)n), task_read((size_t)n), task_min_score((size_t)n), best((size_t)n);
 	std::string seq;
 	for (int64_t t = 0; t < n; t++)
@@ -274,11 +301,16 @@ int main(int argc, char* argv[])
 			}
 			if (!found)
 			{
-				// DebugCheck(false) in ReAlign (SplitAlignment.cpp:462)
-				std::cerr << "Error: false failed: no alignment of read " << r.fragment << (r.read_end == 0 ? "/1" : "/2")
-				          << " to fusion " << r.fusion_id << " has ref split " << r.ref_split.first << "," << r.ref_split.second
-				          << std::endl;
-				ExitNow(1);
+				// DebugCheck(false) in ReAlign (SplitAlignment.cpp:462): the runs in front of this record's are still printed
+				std::ostringstream msg;
+				msg << "Error: false failed: no alignment of read " << r.fragment << (r.read_end == 0 ? "/1" : "/2") << " to fusion "
+				    << r.fusion_id << " has ref split " << r.ref_split.first << "," << r.ref_split.second << std::endl;
+				fault = msg.str();
+				size_t run = 0;
+				while (run + 1 < run_begin.size() && run_begin[run + 1] <= (size_t)t) run++;
+				n = (int64_t)run_begin[run];
+				run_begin.resize(run + 1);
+				break;
 			}
 			split1[(size_t)t] = r.ref_split.first;
 			split2[(size_t)t] = r.ref_split.second;
@@ -286,9 +318,9 @@ int main(int argc, char* argv[])
 		const int64_t cap = reads.off.back();
 		matches.resize((size_t)(2 * cap + 2));
 		int64_t n_pairs = 0;
-		if (dfb_split_backtrace_batch(gpu.ctx(), &params, &window_table, &read_table, task_cluster.data(), task_read.data(),
-		                              split1.data(), split2.data(), read_split.data(), n, match_off.data(), matches.data(), cap,
-		                              &n_pairs) != DFB_OK)
+		if (n > 0 && dfb_split_backtrace_batch(gpu.ctx(), &params, &window_table, &read_table, task_cluster.data(), task_read.data(),
+		                                       split1.data(), split2.data(), read_split.data(), n, match_off.data(), matches.data(),
+		                                       cap, &n_pairs) != DFB_OK)
 			gpu.Die("backtrace failed");
 	}
 
@@ -324,5 +356,11 @@ int main(int argc, char* argv[])
 		}
 	}
 	std::cout << os.str();
+	if (!fault.empty())
+	{
+		std::cout.flush();
+		std::cerr << fault;
+		ExitNow(1);
+	}
 	FinishProcess(0);
 }

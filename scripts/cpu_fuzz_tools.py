@@ -4,7 +4,7 @@ legal records, and malformed ones) and handed to our tool (device double preload
 exit code, output bytes and messages must agree.  Where the reference dies on a signal (an escaped bad_lexical_cast
 aborts it) any non-zero exit of ours is accepted -- we report and exit 1 by design; where a DebugCheck of the reference
 trips (exit 1, the message is its own source line) the exit code and the outputs must agree, not the wording.
-Usage: python scripts/cpu_fuzz_tools.py <dosplitalign|matealign|localalign|evalsplitalign> <seed> <seconds> [max rounds]"""
+Usage: python scripts/cpu_fuzz_tools.py <dosplitalign|matealign|localalign|evalsplitalign|splitseq> <seed> <seconds> [max rounds]"""
 import json
 import os
 import shutil
@@ -305,6 +305,43 @@ def fuzz_evalsplitalign(rng, d, env, rnd):
     return verdict, kw, what, ro, rr
 
 
+def fuzz_splitseq(rng, d, env, rnd):
+    sub = os.path.join(d, "q%d" % rnd)
+    kw = dict(seed=int(rng.integers(1, 10 ** 6)), n_clusters=int(rng.integers(2, 7)), pairs_per_cluster=int(rng.integers(4, 14)),
+              L=int(rng.choice([60, 76, 100])))
+    if rng.random() < 0.3:
+        kw.update(read_len_jitter=int(rng.integers(1, 9)), lower_frac=0.02, n_rate=0.01)
+    args = files.make_split_dataset(sub, **kw)
+    raw, srt = os.path.join(sub, "raw.alignments"), os.path.join(sub, "sorted.alignments")
+    subprocess.run([oracle.ref_tool("ref_dosplitalign")] + args + ["-a", raw], check=True, capture_output=True)
+    files.sort_alignments(raw, srt)
+    common, ev = files.downstream_args(args, sub)
+    pred = os.path.join(sub, "ref.pred")
+    subprocess.run([oracle.ref_tool("ref_evalsplitalign")] + ev + ["-q", os.path.join(sub, "ref.seq"), "-b", os.path.join(sub, "ref.break"), "-p", pred],
+                   check=True, capture_output=True)
+    prefix = files.write_read_index(sub)
+    source = pred if rng.random() < 0.5 else srt  # the predicted records, or every record
+    what = []
+    if rng.random() < 0.7:
+        ops = [o for o in ALIGN_OPS if o[0] in ("dup", "del", "ref_split_shift", "ref_split2_shift", "score", "read_split", "revcomp_bad",
+                                                 "fragment_bad", "fusion_other", "fusion_unknown", "cut", "no_trailing_tab", "empty_line")]
+        text, what = mutate_lines(rng, open(source).read(), ops, int(rng.integers(1, 4)))
+        open(source, "w").write(text)
+    tail = common + ["-p", prefix, "-a", source]
+    if rng.random() < 0.3:
+        tail += ["-i", str(int(rng.integers(0, kw["n_clusters"] + 2)))]
+    ro = run([os.path.join(BIN, "splitseq")] + tail, env=env)
+    rr = run([oracle.ref_tool("ref_splitseq")] + tail)
+    verdict = compare(ro, rr, None, None)
+    if verdict:
+        keep = os.path.join(ROOT, "gpurun_out", "fuzz_fail_splitseq_%d" % rnd)
+        shutil.rmtree(keep, ignore_errors=True)
+        shutil.copytree(sub, keep)
+        open(os.path.join(keep, "args.txt"), "w").write("\n".join(tail))
+    shutil.rmtree(sub, ignore_errors=True)
+    return verdict, kw, what, ro, rr
+
+
 def compare(ro, rr, fo, fr):
     """'' when the two runs agree, else what differs."""
     if rr[0] < 0:  # the reference died on a signal
@@ -331,7 +368,7 @@ def main():
     with tempfile.TemporaryDirectory() as d:
         env = dict(os.environ, LD_PRELOAD=build_double(d))
         while time.time() < t_end and (max_rounds is None or stats["rounds"] < max_rounds):
-            verdict, kw, what, ro, rr = {"dosplitalign": fuzz_dosplitalign, "matealign": fuzz_matealign, "localalign": fuzz_localalign, "evalsplitalign": fuzz_evalsplitalign}[tool](rng, d, env, stats["rounds"])
+            verdict, kw, what, ro, rr = {"dosplitalign": fuzz_dosplitalign, "matealign": fuzz_matealign, "localalign": fuzz_localalign, "evalsplitalign": fuzz_evalsplitalign, "splitseq": fuzz_splitseq}[tool](rng, d, env, stats["rounds"])
             stats["rounds"] += 1
             stats["reference_exit_0" if rr[0] == 0 else ("reference_signal" if rr[0] < 0 else "reference_exit_1")] += 1
             if verdict:

@@ -100,7 +100,7 @@ def test_missing_device_is_an_error(device_double, tmp_path, monkeypatch):
     assert p.returncode == 1 and b"Error:" in p.stderr
 
 
-@pytest.mark.parametrize("tool", ["dosplitalign", "matealign", "localalign", "evalsplitalign"])
+@pytest.mark.parametrize("tool", ["dosplitalign", "matealign", "localalign", "evalsplitalign", "splitseq"])
 def test_input_fuzz_agrees_with_the_reference_tool(tool, oracle_mod):
     """scripts/cpu_fuzz_tools.py, a fixed number of rounds: perturbed inputs (odd but legal records and malformed ones),
     our tool over the device double against the compiled reference tool -- exit codes, outputs, messages."""
