@@ -125,6 +125,22 @@ REGION_OPS = [
 ]
 
 
+EXON_OPS = [
+    ("dup", lambda r, l: [l, l]),
+    ("del", lambda r, l: None),
+    ("odd_coords", lambda r, l: l + "\t" + str(int(r.integers(1, 5000)))),
+    ("more_exons", lambda r, l: l + "\t%d\t%d" % (int(l.split("\t")[-1]) + 50, int(l.split("\t")[-1]) + 120)),
+    ("unknown_chrom", _field(2, lambda r, v: v + "_nope")),
+    ("flip_strand", _field(3, lambda r, v: "-" if v == "+" else "+")),
+    ("bad_strand", _field(3, lambda r, v: "?")),
+    ("bad_int", _field(4, lambda r, v: v + "q")),
+    ("cut", lambda r, l: "\t".join(l.split("\t")[:int(r.integers(1, 6))])),
+    ("same_transcript", _field(1, lambda r, v: "T0_0")),
+    ("empty_line", lambda r, l: [l, ""]),
+    ("shift", lambda r, l: "\t".join(l.split("\t")[:4] + [str(int(v) + 7) for v in l.split("\t")[4:]])),
+]
+
+
 def mutate_fastq(rng, text, n_ops):
     lines = text.split("\n")
     if lines and lines[-1] == "":
@@ -151,7 +167,7 @@ def fuzz_dosplitalign(rng, d, env, rnd):
         kw.update(read_len_jitter=int(rng.integers(1, 9)), lower_frac=0.02)
     args = files.make_split_dataset(sub, **kw)
     what = []
-    for name, ops, p_mut in (("improper.sam", SAM_OPS, 0.8), ("clusters.regions", REGION_OPS, 0.4)):
+    for name, ops, p_mut in (("improper.sam", SAM_OPS, 0.8), ("clusters.regions", REGION_OPS, 0.4), ("exons.regions", EXON_OPS, 0.25)):
         if rng.random() < p_mut:
             path = os.path.join(sub, name)
             text, done = mutate_lines(rng, open(path).read(), ops, int(rng.integers(1, 4)))
