@@ -103,3 +103,24 @@ def test_random_parameters_vs_ref(ref):
         sa = ref.simple_align_batch(m, x, g, rt.data, rt.off, st.data, st.off, tr, trd, impl="port")
         sb = ref.simple_align_batch(m, x, g, rt.data, rt.off, st.data, st.off, tr, trd, impl="ref")
         assert (sa == sb).all(), (m, x, g)
+
+
+def test_backtrace_random_parameters_vs_ref(ref):
+    """Match lists of GetAlignments(backtrace=True) under random scoring triples / endGaps / thresholds and odd
+    alphabets (the generator of test_random_parameters_vs_ref): restatement == compiled reference."""
+    rng = np.random.default_rng(10)
+    checked = 0
+    for rnd in range(20):
+        params, refs, reads, tc, trd, thr = util.random_parameter_round(rng, rnd if rnd % 4 != 3 else rnd + 1)  # short sequences only
+        m, x, g, eg, mss = params
+        for c, r, t in zip(tc, trd, thr):
+            read, ref1, ref2 = reads[r], refs[2 * c], refs[2 * c + 1]
+            for which in range(3):
+                n, hdr, m1, m2 = ref.ref_split_backtrace(read, ref1, ref2, int(t), which, m, x, g, eg, mss)
+                if which >= n:
+                    break
+                p1, p2 = ref.split_backtrace(read, ref1, ref2, (hdr[0], hdr[1]), hdr[2], m, x, g, eg)
+                assert p1.shape == m1.shape and (p1 == m1).all(), (params, which)
+                assert p2.shape == m2.shape and (p2 == m2).all(), (params, which)
+                checked += 1
+    assert checked > 100
