@@ -278,139 +278,139 @@ int main(int argc, char* argv[])
 			std::vector<Range> range;
 			for (;;)
 			{
-			range.assign((size_t)T + 1, Range());
-			ParallelRun(T, [&](int tid) {
-				Range& rg = range[(size_t)tid + 1];
-				for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
-				{
-					const SamEntry& en = entries[tasks[k].mate];
-					const std::string* seq = ref_of.find(en.ref_name)->second;
-					full[k] = seq;
-					if (!seq)
+				range.assign((size_t)T + 1, Range());
+				ParallelRun(T, [&](int tid) {
+					Range& rg = range[(size_t)tid + 1];
+					for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
 					{
-						if (rg.missing < 0) rg.missing = (int64_t)k;
-						continue;
+						const SamEntry& en = entries[tasks[k].mate];
+						const std::string* seq = ref_of.find(en.ref_name)->second;
+						full[k] = seq;
+						if (!seq)
+						{
+							if (rg.missing < 0) rg.missing = (int64_t)k;
+							continue;
+						}
+						plan[k] = en.strand == 0 ? PlanWindow((long long)seq->size(), en.position, en.position + search_length)
+						                         : PlanWindow((long long)seq->size(), en.position - search_length, en.position);
+						if (plan[k].bad && rg.bad < 0) rg.bad = (int64_t)k;
+						rg.window_bytes += plan[k].bad ? 0 : plan[k].Length((long long)seq->size());
+						if (k == 0 || tasks[k].record != tasks[k - 1].record)
+						{
+							int id;
+							const char* rs;
+							uint32_t len;
+							fq.Record(tasks[k].record, id, rs, len);
+							rg.reads++;
+							rg.read_bytes += (int64_t)len;
+						}
 					}
-					plan[k] = en.strand == 0 ? PlanWindow((long long)seq->size(), en.position, en.position + search_length)
-					                         : PlanWindow((long long)seq->size(), en.position - search_length, en.position);
-					if (plan[k].bad && rg.bad < 0) rg.bad = (int64_t)k;
-					rg.window_bytes += plan[k].bad ? 0 : plan[k].Length((long long)seq->size());
-					if (k == 0 || tasks[k].record != tasks[k - 1].record)
-					{
-						int id;
-						const char* rs;
-						uint32_t len;
-						fq.Record(tasks[k].record, id, rs, len);
-						rg.reads++;
-						rg.read_bytes += (int64_t)len;
-					}
-				}
-			});
-			int64_t first = -1;
-			for (int r = 1; r <= T; r++)
-				for (int64_t k : {range[(size_t)r].missing, range[(size_t)r].bad})
-					if (k >= 0 && (first < 0 || k < first)) first = k;
-			if (first < 0) break;
-			const SamEntry& en = entries[tasks[(size_t)first].mate];
-			std::ostringstream msg;
-			if (!full[(size_t)first])
-				msg << "Error: Unable to find sequence " << en.ref_name << std::endl;
-			else
-				// std::string(n,'N') / substr would throw here in the reference (window starts beyond the sequence, or ends
-				// before position 1): it aborts; we report and fail the same way (non-zero exit)
-				msg << "Error: window around " << en.position << " outside sequence " << en.ref_name << std::endl;
-			fault = msg.str();
-			n = (size_t)first;
-			tasks.resize(n);
-			if (n == 0) break;
+				});
+				int64_t first = -1;
+				for (int r = 1; r <= T; r++)
+					for (int64_t k : {range[(size_t)r].missing, range[(size_t)r].bad})
+						if (k >= 0 && (first < 0 || k < first)) first = k;
+				if (first < 0) break;
+				const SamEntry& en = entries[tasks[(size_t)first].mate];
+				std::ostringstream msg;
+				if (!full[(size_t)first])
+					msg << "Error: Unable to find sequence " << en.ref_name << std::endl;
+				else
+					// std::string(n,'N') / substr would throw here in the reference (window starts beyond the sequence, or ends
+					// before position 1): it aborts; we report and fail the same way (non-zero exit)
+					msg << "Error: window around " << en.position << " outside sequence " << en.ref_name << std::endl;
+				fault = msg.str();
+				n = (size_t)first;
+				tasks.resize(n);
+				if (n == 0) break;
 			}
 			if (n > 0)
 			{
-			for (int r = 1; r <= T; r++)
-			{
-				range[(size_t)r].window_bytes += range[(size_t)r - 1].window_bytes;
-				range[(size_t)r].read_bytes += range[(size_t)r - 1].read_bytes;
-				range[(size_t)r].reads += range[(size_t)r - 1].reads;
-			}
-			const size_t n_reads = (size_t)range[(size_t)T].reads;
-			auto grow = [](std::unique_ptr<char[]>& buf, size_t& cap, size_t need) {
-				if (cap >= need + 1) return;
-				cap = need + need / 8 + 64;
-				buf.reset(new char[cap]);
-			};
-			grow(window_bytes, window_cap, (size_t)range[(size_t)T].window_bytes);
-			grow(read_bytes, read_cap, (size_t)range[(size_t)T].read_bytes);
-			window_off[0] = read_off[0] = 0;
-			ParallelRun(T, [&](int tid) {
-				int64_t w_at = range[(size_t)tid].window_bytes, r_at = range[(size_t)tid].read_bytes, r_idx = range[(size_t)tid].reads;
-				for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
+				for (int r = 1; r <= T; r++)
 				{
-					if (k == 0 || tasks[k].record != tasks[k - 1].record)
+					range[(size_t)r].window_bytes += range[(size_t)r - 1].window_bytes;
+					range[(size_t)r].read_bytes += range[(size_t)r - 1].read_bytes;
+					range[(size_t)r].reads += range[(size_t)r - 1].reads;
+				}
+				const size_t n_reads = (size_t)range[(size_t)T].reads;
+				auto grow = [](std::unique_ptr<char[]>& buf, size_t& cap, size_t need) {
+					if (cap >= need + 1) return;
+					cap = need + need / 8 + 64;
+					buf.reset(new char[cap]);
+				};
+				grow(window_bytes, window_cap, (size_t)range[(size_t)T].window_bytes);
+				grow(read_bytes, read_cap, (size_t)range[(size_t)T].read_bytes);
+				window_off[0] = read_off[0] = 0;
+				ParallelRun(T, [&](int tid) {
+					int64_t w_at = range[(size_t)tid].window_bytes, r_at = range[(size_t)tid].read_bytes, r_idx = range[(size_t)tid].reads;
+					for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
+					{
+						if (k == 0 || tasks[k].record != tasks[k - 1].record)
+						{
+							int id;
+							const char* rs;
+							uint32_t rlen;
+							fq.Record(tasks[k].record, id, rs, rlen);
+							if (rlen) memcpy(read_bytes.get() + r_at, rs, rlen);
+							r_at += (int64_t)rlen;
+							read_off[(size_t)++r_idx] = r_at;
+						}
+						task_ref[k] = (int32_t)k;
+						task_seq[k] = (int32_t)r_idx - 1; // (a range that starts inside a read's run uses the read its predecessor stored)
+						const WindowPlan& w = plan[k];
+						const std::string& seq = *full[k];
+						char* dst = window_bytes.get() + w_at;
+						const long long take = w.take < 0 ? (long long)seq.size() - w.from : w.take;
+						const long long len = w.prepend + take + w.append;
+						w_at += len;
+						window_off[k + 1] = w_at;
+						if (entries[tasks[k].mate].strand == 0)
+						{
+							// plus-strand mate: the window is reverse-complemented (tools/matealign.cpp:197-201)
+							char* q = dst + len;
+							for (long long j = 0; j < w.prepend; j++) *--q = 'N';
+							const char* src = seq.data() + w.from;
+							for (long long j = 0; j < take; j++) *--q = (char)complement[(unsigned char)src[j]];
+							for (long long j = 0; j < w.append; j++) *--q = 'N';
+						}
+						else
+						{
+							memset(dst, 'N', (size_t)w.prepend);
+							if (take) memcpy(dst + w.prepend, seq.data() + w.from, (size_t)take);
+							memset(dst + w.prepend + take, 'N', (size_t)w.append);
+						}
+					}
+				});
+				timer.Add("tables");
+				const dfb_seq_table wt{(const uint8_t*)window_bytes.get(), window_off.data(), (int64_t)n};
+				const dfb_seq_table rt{(const uint8_t*)read_bytes.get(), read_off.data(), (int64_t)n_reads};
+				if (dfb_simple_align_batch(gpu.ctx(), &params, &wt, &rt, task_ref.data(), task_seq.data(), (int64_t)n, score.data()) != DFB_OK)
+					gpu.Die("alignment failed");
+				timer.Add("gpu");
+				ParallelRun(T, [&](int tid) {
+					std::string& os = out_parts[(size_t)tid];
+					os.clear();
+					char num[64];
+					for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
 					{
 						int id;
-						const char* rs;
-						uint32_t rlen;
-						fq.Record(tasks[k].record, id, rs, rlen);
-						if (rlen) memcpy(read_bytes.get() + r_at, rs, rlen);
-						r_at += (int64_t)rlen;
-						read_off[(size_t)++r_idx] = r_at;
+						const char* s;
+						uint32_t len;
+						fq.Record(tasks[k].record, id, s, len);
+						const int max_score = (int)len * match;                       // tools/matealign.cpp:211
+						const double percent = (double)score[k] / (double)max_score; // :212
+						if (percent < threshold) continue;
+						AppendInt(os, IdIndex(id)); // readID.fragmentIndex is a 31-bit field
+						os += '\t';
+						AppendInt(os, score[k]);
+						os += '\t';
+						os.append(num, (size_t)snprintf(num, sizeof(num), "%.6g", percent)); // ostream's default float format
+						os += '\n';
 					}
-					task_ref[k] = (int32_t)k;
-					task_seq[k] = (int32_t)r_idx - 1; // (a range that starts inside a read's run uses the read its predecessor stored)
-					const WindowPlan& w = plan[k];
-					const std::string& seq = *full[k];
-					char* dst = window_bytes.get() + w_at;
-					const long long take = w.take < 0 ? (long long)seq.size() - w.from : w.take;
-					const long long len = w.prepend + take + w.append;
-					w_at += len;
-					window_off[k + 1] = w_at;
-					if (entries[tasks[k].mate].strand == 0)
-					{
-						// plus-strand mate: the window is reverse-complemented (tools/matealign.cpp:197-201)
-						char* q = dst + len;
-						for (long long j = 0; j < w.prepend; j++) *--q = 'N';
-						const char* src = seq.data() + w.from;
-						for (long long j = 0; j < take; j++) *--q = (char)complement[(unsigned char)src[j]];
-						for (long long j = 0; j < w.append; j++) *--q = 'N';
-					}
-					else
-					{
-						memset(dst, 'N', (size_t)w.prepend);
-						if (take) memcpy(dst + w.prepend, seq.data() + w.from, (size_t)take);
-						memset(dst + w.prepend + take, 'N', (size_t)w.append);
-					}
-				}
-			});
-			timer.Add("tables");
-			const dfb_seq_table wt{(const uint8_t*)window_bytes.get(), window_off.data(), (int64_t)n};
-			const dfb_seq_table rt{(const uint8_t*)read_bytes.get(), read_off.data(), (int64_t)n_reads};
-			if (dfb_simple_align_batch(gpu.ctx(), &params, &wt, &rt, task_ref.data(), task_seq.data(), (int64_t)n, score.data()) != DFB_OK)
-				gpu.Die("alignment failed");
-			timer.Add("gpu");
-			ParallelRun(T, [&](int tid) {
-				std::string& os = out_parts[(size_t)tid];
-				os.clear();
-				char num[64];
-				for (size_t k = n * (size_t)tid / (size_t)T; k < n * ((size_t)tid + 1) / (size_t)T; k++)
-				{
-					int id;
-					const char* s;
-					uint32_t len;
-					fq.Record(tasks[k].record, id, s, len);
-					const int max_score = (int)len * match;                       // tools/matealign.cpp:211
-					const double percent = (double)score[k] / (double)max_score; // :212
-					if (percent < threshold) continue;
-					AppendInt(os, IdIndex(id)); // readID.fragmentIndex is a 31-bit field
-					os += '\t';
-					AppendInt(os, score[k]);
-					os += '\t';
-					os.append(num, (size_t)snprintf(num, sizeof(num), "%.6g", percent)); // ostream's default float format
-					os += '\n';
-				}
-			});
-			for (const std::string& part : out_parts) fwrite(part.data(), 1, part.size(), stdout);
-			fflush(stdout);
-			timer.Add("format + write");
+				});
+				for (const std::string& part : out_parts) fwrite(part.data(), 1, part.size(), stdout);
+				fflush(stdout);
+				timer.Add("format + write");
 			}
 			if (!fault.empty())
 			{
