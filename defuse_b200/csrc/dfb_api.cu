@@ -1165,6 +1165,9 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 			{
 				int c = (L <= kMaxFastRows && R1 <= 65535 && R2 <= 65535) ? class_for_rows((int)L) : -1;
 				if (c >= 0 && !pl->fast_ok[c]) c = -1;
+				// the probe sweep finds its windows by checkpoint block, 8 bits per half (255 blocks of 4G steps); a window
+				// pair too long for that is swept by the s32 kernels, which take any length
+				if (c >= 0 && std::max(R1, R2) + kClasses[c].G - 1 > 255LL * 4 * kClasses[c].G) c = -1;
 				if (c < 0)
 				{
 					bin = -2;

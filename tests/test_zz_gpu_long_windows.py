@@ -1,0 +1,52 @@
+"""Split alignment against window pairs far longer than deFuse ever cuts (hundreds of bases): beyond what the probe sweep
+of the s16x2 kernels can address by checkpoint block (255 blocks of 4G steps: 8 160 / 16 320 / 32 640 columns for the
+G = 8 / 16 / 32 classes) and beyond the 16-bit reference length of a job pair (65 535).  Such tasks are swept by the s32
+kernels; the junctions are planted near the END of the windows, where a truncated sweep would miss the arg-max columns.
+(Sorted last on purpose: the path is new in the suite.)"""
+import numpy as np
+import pytest
+
+import util
+from test_gpu_parity import _check_split
+
+pytestmark = pytest.mark.gpu
+
+
+def _late_junction_batch(rng, R1, R2, L, n_reads):
+    """One cluster whose reads span a junction in the last few hundred columns of window 1 / first columns of the
+    reversed window 2, plus reads from either side and random ones."""
+    ref1, ref2 = util.rand_seq(rng, R1), util.rand_seq(rng, R2)
+    bp1 = R1 - int(rng.integers(5, 200))
+    bp2 = int(rng.integers(5, 200))
+    fusion = ref1[:bp1] + ref2[bp2:]
+    reads = []
+    for k in range(n_reads):
+        kind = k % 4
+        if kind == 0:
+            s = bp1 - int(rng.integers(10, L - 10))
+            read = fusion[s:s + L]
+        elif kind == 1:
+            s = int(rng.integers(max(0, R1 - 3 * L), R1 - L))
+            read = ref1[s:s + L]
+        elif kind == 2:
+            s = int(rng.integers(0, min(R2 - L, 3 * L)))
+            read = ref2[s:s + L]
+        else:
+            read = util.rand_seq(rng, L)
+        reads.append(util.mutate(rng, read, 0.01, 0.002))
+    return [ref1, ref2], reads
+
+
+@pytest.mark.parametrize("R,L", [(8100, 100), (8300, 100), (9000, 100), (20000, 100), (17000, 300), (34000, 700), (70000, 100)])
+def test_split_windows_longer_than_the_probe_can_address(oracle_mod, gpu_ctx, R, L):
+    import defuse_b200 as d
+    rng = np.random.default_rng(R + L)
+    refs, reads = _late_junction_batch(rng, R, R - 37, L, 8)
+    # a second, ordinary cluster in the same batch: both kernel families run side by side
+    refs2, reads2, tc2, tr2 = util.split_batch(rng, 1, 6, L, 300, 380)
+    task_cluster = np.array([0] * len(reads) + [1] * len(reads2), np.int32)
+    all_reads = reads + reads2
+    task_read = np.arange(len(all_reads), dtype=np.int32)
+    min_score = np.array([d.split_min_score(len(r)) for r in all_reads], np.int32)
+    res = _check_split(oracle_mod, gpu_ctx, refs + refs2, all_reads, task_cluster, task_read, min_score)
+    assert (res.best[:len(reads)] > 0).sum() >= 2  # the planted junction near the window end is found
