@@ -53,3 +53,15 @@ def test_split_windows_longer_than_the_probe_can_address(oracle_mod, gpu_ctx, R,
     min_score = np.array([d.split_min_score(len(r)) for r in reads], np.int32)
     res = _check_split(oracle_mod, gpu_ctx, refs, reads, task_cluster, task_read, min_score)
     assert (res.best[:8] > 0).sum() >= 2  # the planted junction near the window end is found
+
+
+@pytest.mark.parametrize("L", [330, 400, 512, 640, 768, 900, 1024])
+def test_split_long_reads_in_the_wide_classes(oracle_mod, gpu_ctx, L):
+    """Split mode of the (16,25) (16,32) (32,24) (32,32) classes of the s16x2 kernel (reads of 321-1024 bases; deFuse's
+    reads are 50-250): first sweep with checkpoints every 64 / 128 steps, probe sweep, assembly."""
+    import defuse_b200 as d
+    rng = np.random.default_rng(L)
+    refs, reads, tc, trd = util.split_batch(rng, 3, 4, (L - 6, L), L + 150, L + 700, sub=0.02, indel=0.004, n_rate=0.003)
+    ms = np.array([d.split_min_score(len(reads[r])) for r in trd], np.int32)
+    res = _check_split(oracle_mod, gpu_ctx, refs, reads, tc, trd, ms)
+    assert (res.best > 0).sum() >= 3
