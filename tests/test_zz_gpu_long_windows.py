@@ -65,3 +65,23 @@ def test_split_long_reads_in_the_wide_classes(oracle_mod, gpu_ctx, L):
     ms = np.array([d.split_min_score(len(reads[r])) for r in trd], np.int32)
     res = _check_split(oracle_mod, gpu_ctx, refs, reads, tc, trd, ms)
     assert (res.best > 0).sum() >= 3
+
+
+@pytest.mark.parametrize("R,L", [(30000, 100), (65535, 150), (65536, 150), (100000, 600)])
+def test_simple_very_long_references(oracle_mod, gpu_ctx, R, L):
+    """SimpleAligner against references at and beyond the 16-bit length of a job pair (s16x2 up to 65 535, s32 beyond),
+    the related reads taken from the far end of the reference."""
+    from test_gpu_parity import _check_simple
+    rng = np.random.default_rng(R + L)
+    refs = [util.rand_seq(rng, R), util.rand_seq(rng, R - 1)]
+    seqs, task_ref = [], []
+    for k in range(10):
+        r = k % 2
+        if k % 5 == 4:
+            seq = util.rand_seq(rng, L)
+        else:
+            s = len(refs[r]) - L - int(rng.integers(0, 300))
+            seq = util.mutate(rng, refs[r][s:s + L], 0.03, 0.004)
+        seqs.append(seq)
+        task_ref.append(r)
+    _check_simple(oracle_mod, gpu_ctx, refs, seqs, np.array(task_ref, np.int32), np.arange(len(seqs), dtype=np.int32), 10, -5, -5)
