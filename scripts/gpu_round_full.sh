@@ -20,3 +20,4 @@ cat gpurun_out/tools_bench_$TAG.json; tail -3 gpurun_out/tools_bench_$TAG.err
 timeout 300 python scripts/gpu_tool_scale.py > gpurun_out/tool_scale_split_$TAG.json 2> gpurun_out/tool_scale_split_$TAG.err; echo scale_split_rc=$?
 timeout 300 python scripts/gpu_tool_scale.py localalign 1000000 10000 > gpurun_out/tool_scale_local_$TAG.json 2> gpurun_out/tool_scale_local_$TAG.err; echo scale_local_rc=$?
 timeout 300 python scripts/gpu_tool_scale.py matealign 300000 > gpurun_out/tool_scale_mate_$TAG.json 2> gpurun_out/tool_scale_mate_$TAG.err; echo scale_mate_rc=$?
+timeout 120 python scripts/gpu_fuzz.py 7 60 > gpurun_out/fuzz_$TAG.json 2> gpurun_out/fuzz_$TAG.err; echo fuzz_rc=$?; cat gpurun_out/fuzz_$TAG.json
