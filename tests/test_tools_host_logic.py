@@ -113,3 +113,20 @@ def test_input_fuzz_agrees_with_the_reference_tool(tool, oracle_mod):
     report = json.loads(p.stdout.decode())
     assert report["rounds"] == 60 and not report["disagreements"], report["disagreements"][:2]
     assert report["reference_exit_0"] > 5 and report["reference_exit_1"] > 5  # both kinds of outcome were exercised
+
+
+def test_dosplitalign_baseline_config_0(device_double, oracle_mod, tmp_path, monkeypatch):
+    """BASELINE.json configs[0] ("dosplitalign on synthetic 2k read pairs x 200 planted-fusion breakpoint clusters, 100 bp
+    reads"): the whole tool against the compiled reference tool, byte for byte, raw and after the pipeline's sort."""
+    from synth import files
+    ref = oracle_mod.ref_tool("ref_dosplitalign")
+    if not ref or not os.path.exists(os.path.join(tg.BIN, "dosplitalign")):
+        pytest.skip("tools not built")
+    monkeypatch.setenv("LD_PRELOAD", device_double)
+    d = str(tmp_path / "c0")
+    args = files.make_split_dataset(d, seed=1, n_clusters=200, pairs_per_cluster=10, L=100, n_chrom=4, genes_per_chrom=10)
+    ours, theirs = os.path.join(d, "ours.tmp"), os.path.join(d, "ref.tmp")
+    tg._run([os.path.join(tg.BIN, "dosplitalign")] + args + ["-a", ours])
+    tg._run([ref] + args + ["-a", theirs])
+    a, b = open(ours).read(), open(theirs).read()
+    assert len(b.splitlines()) > 200 and a == b
