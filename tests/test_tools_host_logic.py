@@ -130,3 +130,21 @@ def test_dosplitalign_baseline_config_0(device_double, oracle_mod, tmp_path, mon
     tg._run([ref] + args + ["-a", theirs])
     a, b = open(ours).read(), open(theirs).read()
     assert len(b.splitlines()) > 200 and a == b
+
+
+def test_dosplitalign_stress_shape(device_double, oracle_mod, tmp_path, monkeypatch):
+    """BASELINE.json configs[4] shape at file level: 250-bp reads (-n 230 -x 270 with jitter), 600-bp fragments, N and
+    lower-case runs in the reference -- windows, candidates and records against the compiled reference tool."""
+    from synth import files
+    ref = oracle_mod.ref_tool("ref_dosplitalign")
+    if not ref or not os.path.exists(os.path.join(tg.BIN, "dosplitalign")):
+        pytest.skip("tools not built")
+    monkeypatch.setenv("LD_PRELOAD", device_double)
+    d = str(tmp_path / "c4")
+    args = files.make_split_dataset(d, seed=5, n_clusters=30, pairs_per_cluster=16, L=250, frag_mean=600, read_len_jitter=20,
+                                    lower_frac=0.01, n_rate=0.01)
+    ours, theirs = os.path.join(d, "ours.tmp"), os.path.join(d, "ref.tmp")
+    tg._run([os.path.join(tg.BIN, "dosplitalign")] + args + ["-a", ours])
+    tg._run([ref] + args + ["-a", theirs])
+    a, b = open(ours).read(), open(theirs).read()
+    assert len(b.splitlines()) > 50 and a == b
