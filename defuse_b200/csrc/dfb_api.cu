@@ -706,7 +706,8 @@ static cudaError_t stage_layout(dfb_ctx* ctx, int stage_slot, Staging& st, int64
 	return cudaSuccess;
 }
 
-// word layout of the two tables; returns total words
+// word layout of the two tables; returns total words.  Every sequence starts on an even word: the sweep copies
+// reference words into shared memory 16 bytes at a time (cp.async)
 static uint32_t layout_words(const dfb_seq_table* a, int mode_a, const dfb_seq_table* b, int mode_b, SeqDesc* da,
                              SeqDesc* db, uint32_t* words_a_end, bool* overflow)
 {
@@ -720,6 +721,7 @@ static uint32_t layout_words(const dfb_seq_table* a, int mode_a, const dfb_seq_t
 		da[k].len = len;
 		da[k].word = (uint32_t)w;
 		w += (uint64_t)((len + 15) / 16) * (mode_a == PACK_BOTH ? 2 : 1);
+		w += w & 1;
 	}
 	*words_a_end = (uint32_t)w;
 	for (int64_t k = 0; k < b->n; k++)
@@ -729,6 +731,7 @@ static uint32_t layout_words(const dfb_seq_table* a, int mode_a, const dfb_seq_t
 		db[k].len = len;
 		db[k].word = (uint32_t)w;
 		w += (uint64_t)((len + 15) / 16) * (mode_b == PACK_BOTH ? 2 : 1);
+		w += w & 1;
 	}
 	*overflow = w >= 0xFFFFFFF0ull;
 	return (uint32_t)w;
@@ -756,8 +759,9 @@ static int upload_and_pack(dfb_plan* pl, const dfb_seq_table* a, int mode_a, con
 	const int64_t na = a->off[a->n] - a->off[0], nb = b->off[b->n] - b->off[0];
 	CK(ctx, cudaMallocAsync((void**)&pl->d_stage, std::max<size_t>(256, st.total), up));
 	CK(ctx, cudaMemcpyAsync(pl->d_stage, st.host, st.total, cudaMemcpyHostToDevice, up));
-	CK(ctx, cudaMallocAsync((void**)&pl->d_pool, ((size_t)total_words + 2) * sizeof(uint2), up));
-	CK(ctx, cudaMallocAsync((void**)&pl->d_obytes, ((size_t)total_words + 2) * 16, up));
+	// (slack: a 16-byte copy may take the word behind a sequence's last one)
+	CK(ctx, cudaMallocAsync((void**)&pl->d_pool, ((size_t)total_words + 8) * sizeof(uint2), up));
+	CK(ctx, cudaMallocAsync((void**)&pl->d_obytes, ((size_t)total_words + 8) * 16, up));
 	for (int k = 0; k < 3; k++)
 		if (!pl->ev[k]) CK(ctx, cudaEventCreate(&pl->ev[k]));
 	CK(ctx, cudaEventRecord(pl->ev[0], up));
@@ -768,11 +772,11 @@ static int upload_and_pack(dfb_plan* pl, const dfb_seq_table* a, int mode_a, con
 		if (n == 0 || w1 <= w0) return cudaSuccess;
 		const int grid = (int)std::min<uint64_t>(((uint64_t)n * 16 + 255) / 256, (uint64_t)max_grid); // sixteen lanes per sequence
 		if (mode == PACK_FWD)
-			pack_kernel<PACK_FWD><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
+			pack_kernel<PACK_FWD><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, pl->d_pool, pl->d_obytes);
 		else if (mode == PACK_REV_ODD)
-			pack_kernel<PACK_REV_ODD><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
+			pack_kernel<PACK_REV_ODD><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, pl->d_pool, pl->d_obytes);
 		else
-			pack_kernel<PACK_BOTH><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, w0, w1, pl->d_pool, pl->d_obytes);
+			pack_kernel<PACK_BOTH><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, pl->d_pool, pl->d_obytes);
 		return cudaGetLastError();
 	};
 	CK(ctx, launch(mode_a, d_da, a->n, 0, words_a_end));

@@ -10,11 +10,13 @@
 // rows (S per lane, in registers) and sweeps the reference one column per step as a skewed
 // wavefront; lane g hands the last row of its strip to lane g+1 with one SHFL per step.
 // In the s16x2 kernel every 32-bit register holds TWO independent DPs (low/high half),
-// advanced by DPX instructions (VIADDMNMX.S16x2, VIMNMX.U16x2): per register-pair of cells
-// the loop issues LOP3, VIMNMX, IMAD, VIADDMNMX, VIADDMNMX, VIADDMNMX -- the six issues
-// SURVEY.md 8(d) counts as the algorithmic work of a cell vector.
+// advanced by DPX instructions: per register pair of cells the steady-state loop issues
+// VIADDMNMX.U16x2 (mismatch indicator), IMAD (diagonal), VIADDMNMX.S16x2 x2 (the two maxima)
+// and half a VIMNMX3.S16x2 (row-maximum sink, one per two columns).  Reference words reach
+// shared memory by cp.async (LDGSTS) one ring block ahead of the wavefront.
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
@@ -46,79 +48,78 @@ enum
 	PACK_BOTH = 2     // forward copy at `word`, reversed copy right behind it (reads of the split aligner)
 };
 
-// One thread per 16-base output word: binary-search the owning sequence, fetch the 16-byte
-// source window with five aligned 32-bit loads, emit 2-bit codes + exception mask (8 B).
-// The raw copy of a word is written only when it has an exception.  The raw upload is padded
-// by 16 bytes in front and 32 behind so that the window never leaves the allocation.
+// Sixteen lanes per sequence (a 100-bp read in both orientations is 14 words, a 340-bp window 22): the owner of a
+// word is known without a search and a sequence's words are written side by side.  Per 16-base word: the 16-byte
+// source window through five aligned 32-bit loads + funnel shifts (adjacent lanes read adjacent windows, so the
+// sectors are fully used), four bytes at a time through the 2-bit code / exception test (SWAR, no per-byte loop),
+// 8 bytes written.  The raw copy of a word is written only when it has an exception.  The raw upload is padded by
+// 16 bytes in front and 32 behind so that the window never leaves the allocation.
+__device__ __forceinline__ void pack4(uint32_t w, uint32_t valid, uint32_t& codes8, uint32_t& mask4)
+{
+	// A=0x41 C=0x43 G=0x47 T=0x54: bits 2..1 are 00 01 11 10 (Gray) -> code 0..3; exact iff the code decodes back
+	const uint32_t gray = (w >> 1) & 0x03030303u;
+	const uint32_t code = gray ^ ((gray >> 1) & 0x01010101u);
+	const uint32_t c1 = code & 0x01010101u, c2 = (code >> 1) & 0x01010101u;
+	const uint32_t back = 0x41414141u + 2u * c1 + 6u * c2 + 11u * (c1 & c2); // 'A' + {0, 2, 6, 0x13}
+	const uint32_t diff = w ^ back;
+	const uint32_t bad = ((diff | ((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) >> 7) & 0x01010101u & valid; // 1 per byte that is not ACGT
+	const uint32_t good = code & (valid * 3u) & ~(bad * 3u);
+	codes8 = (good * 0x01041040u) >> 24; // byte k's two bits -> bits 2k..2k+1
+	mask4 = (bad * 0x01020408u) >> 24;   // byte k's flag -> bit k
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ raw, const SeqDesc* __restrict__ descs,
-                                                    int n_seqs, uint32_t word_begin, uint32_t word_end,
-                                                    uint2* __restrict__ pool, uint8_t* __restrict__ obytes)
+                                                    int n_seqs, uint2* __restrict__ pool, uint8_t* __restrict__ obytes)
 {
-	// sixteen lanes per sequence (a 100-bp read in both orientations is 14 words, a 340-bp window 22): the owner of a
-	// word is known without a search, a sequence's words are written side by side
-	(void)word_begin;
-	(void)word_end;
 	const uint32_t lane16 = threadIdx.x & 15u;
 	const uint32_t n_groups = (gridDim.x * blockDim.x) >> 4;
 	for (uint32_t lo = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; lo < (uint32_t)n_seqs; lo += n_groups)
-	for (uint32_t local_all = lane16, seq_words = ((descs[lo].len + 15u) >> 4) * (MODE == PACK_BOTH ? 2u : 1u); local_all < seq_words; local_all += 16u)
 	{
 		const SeqDesc sd = descs[lo];
-		const uint32_t w = sd.word + local_all;
-		uint32_t local = local_all;
-		bool rev = false;
-		if (MODE == PACK_REV_ODD) rev = (lo & 1u) != 0;
-		if (MODE == PACK_BOTH)
+		const uint32_t nw = (sd.len + 15u) >> 4;
+		const uint32_t seq_words = nw * (MODE == PACK_BOTH ? 2u : 1u);
+		for (uint32_t local_all = lane16; local_all < seq_words; local_all += 16u)
 		{
-			const uint32_t nw = (sd.len + 15u) >> 4;
-			if (local >= nw) { rev = true; local -= nw; }
-		}
-		const uint32_t first = local * 16u;
-		const uint32_t n_valid = min(16u, sd.len - first);
-		// source window: forward bytes [first, first+16); reversed bytes [len-first-16, len-first) read backwards
-		const int64_t win = sd.src + (rev ? (int64_t)sd.len - (int64_t)first - 16 : (int64_t)first);
-		const uint8_t* wp = raw + win;
-		const uintptr_t addr = reinterpret_cast<uintptr_t>(wp);
-		const uint32_t* ap = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
-		const uint32_t sh = (uint32_t)(addr & 3u) * 8u;
-		uint32_t a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2), a3 = __ldg(ap + 3), a4 = __ldg(ap + 4);
-		uint32_t b[4];
-		b[0] = __funnelshift_r(a0, a1, sh);
-		b[1] = __funnelshift_r(a1, a2, sh);
-		b[2] = __funnelshift_r(a2, a3, sh);
-		b[3] = __funnelshift_r(a3, a4, sh);
-		if (rev)
-		{
-			const uint32_t r0 = __byte_perm(b[3], 0, 0x0123), r1 = __byte_perm(b[2], 0, 0x0123);
-			const uint32_t r2 = __byte_perm(b[1], 0, 0x0123), r3 = __byte_perm(b[0], 0, 0x0123);
-			b[0] = r0; b[1] = r1; b[2] = r2; b[3] = r3;
-		}
-		uint32_t codes = 0, mask = 0;
-#pragma unroll
-		for (int n = 0; n < 16; n++)
-		{
-			const uint32_t byte = (b[n >> 2] >> (8 * (n & 3))) & 0xFFu;
-			// A=0x41 C=0x43 G=0x47 T=0x54: bits 2..1 are 00 01 11 10 -> a 2-bit code; exact iff it decodes back
-			const uint32_t gray = (byte >> 1) & 3u;
-			const uint32_t code = gray ^ (gray >> 1);                   // 00 01 11 10 -> A0 C1 G2 T3
-			const uint32_t back = (0x54474341u >> (8 * code)) & 0xFFu;  // 'A','C','G','T'
-			const bool in_seq = (uint32_t)n < n_valid;
-			const bool ok = back == byte;
-			codes |= ((ok && in_seq) ? code : 0u) << (2 * n);
-			mask |= ((!ok && in_seq) ? 1u : 0u) << n;
-		}
-		pool[w] = make_uint2(codes, mask);
-		if (mask)
-		{
+			const uint32_t w = sd.word + local_all;
+			uint32_t local = local_all;
+			bool rev = false;
+			if (MODE == PACK_REV_ODD) rev = (lo & 1u) != 0;
+			if (MODE == PACK_BOTH && local >= nw) { rev = true; local -= nw; }
+			const uint32_t first = local * 16u;
+			const uint32_t n_valid = min(16u, sd.len - first);
+			// source window: forward bytes [first, first+16); reversed bytes [len-first-16, len-first) read backwards
+			const int64_t win = sd.src + (rev ? (int64_t)sd.len - (int64_t)first - 16 : (int64_t)first);
+			const uintptr_t addr = reinterpret_cast<uintptr_t>(raw + win);
+			const uint32_t* ap = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+			const uint32_t sh = (uint32_t)(addr & 3u) * 8u;
+			const uint32_t a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2), a3 = __ldg(ap + 3), a4 = __ldg(ap + 4);
+			uint32_t b[4];
+			b[0] = __funnelshift_r(a0, a1, sh);
+			b[1] = __funnelshift_r(a1, a2, sh);
+			b[2] = __funnelshift_r(a2, a3, sh);
+			b[3] = __funnelshift_r(a3, a4, sh);
+			if (rev)
+			{
+				const uint32_t r0 = __byte_perm(b[3], 0, 0x0123), r1 = __byte_perm(b[2], 0, 0x0123);
+				const uint32_t r2 = __byte_perm(b[1], 0, 0x0123), r3 = __byte_perm(b[0], 0, 0x0123);
+				b[0] = r0; b[1] = r1; b[2] = r2; b[3] = r3;
+			}
+			uint32_t codes = 0, mask = 0;
 #pragma unroll
 			for (int q = 0; q < 4; q++)
 			{
-				// zero the bytes beyond the sequence end
+				// bytes of this quad inside the sequence: 0x01 per valid byte
 				const int keep = (int)n_valid - 4 * q;
-				if (keep < 4) b[q] = keep <= 0 ? 0u : (b[q] & (0xFFFFFFFFu >> (8 * (4 - keep))));
+				const uint32_t valid = keep >= 4 ? 0x01010101u : (keep <= 0 ? 0u : (0x01010101u >> (8 * (4 - keep))));
+				uint32_t c8, m4;
+				pack4(b[q], valid, c8, m4);
+				codes |= c8 << (8 * q);
+				mask |= m4 << (4 * q);
+				b[q] &= valid * 0xFFu; // the raw copy keeps zeros beyond the sequence end
 			}
-			reinterpret_cast<uint4*>(obytes)[w] = make_uint4(b[0], b[1], b[2], b[3]);
+			pool[w] = make_uint2(codes, mask);
+			if (mask) reinterpret_cast<uint4*>(obytes)[w] = make_uint4(b[0], b[1], b[2], b[3]);
 		}
 	}
 }
@@ -190,30 +191,39 @@ struct FastParams
 
 #define DFB_SLOT_EVENTS 8
 
+// Symbols in shared memory and registers: a base is the fp16 bit pattern of its byte value (exact for 0..255), so
+// that two symbols are equal as integers iff they are equal as fp16 numbers, and unequal ones differ by >= 1.0.
+// The integer rows of a strip test equality with one VIADDMNMX.U16x2; rows on the fp16 path use HADD2 + HFMA2.SAT.
+#define DFB_READ_PAD 0x6800u // 2048.0: read rows beyond L, never equals a reference field
+#define DFB_REF_PAD 0xE400u  // -1024.0: reference columns beyond R, never equals a read field; bit 15 doubles as the row-max mask
+
+__device__ __forceinline__ uint32_t sym_of_byte(uint32_t v)
+{
+	return (uint32_t)__half_as_ushort(__uint2half_rn(v));
+}
+
+__device__ __forceinline__ uint32_t sym_of_code(uint32_t c)
+{
+	// fp16 patterns of 'A' 65, 'C' 67, 'G' 71, 'T' 84
+	return __funnelshift_r(0x54305410u, 0x55405470u, 16u * c) & 0xFFFFu;
+}
+
 __device__ __forceinline__ uint32_t decode_base(uint2 w, uint32_t word_index, int n, const uint8_t* __restrict__ obytes)
 {
 	if ((w.y >> n) & 1u)
 	{
-		return __ldg(obytes + (size_t)word_index * 16 + n); // exception plane: raw byte
+		return sym_of_byte(__ldg(obytes + (size_t)word_index * 16 + n)); // exception plane: raw byte
 	}
-	return (0x54474341u >> (8 * ((w.x >> (2 * n)) & 3u))) & 0xFFu; // "ACGT"
+	return sym_of_code((w.x >> (2 * n)) & 3u);
 }
 
-// Decodes one pool word (16 bases) of a reference into the 16-bit fields of a shared-memory ring.
-// Out of line on purpose: three call sites per kernel x 42 kernels, and the instruction cache is what
-// the short probe jobs wait for.
-__device__ __noinline__ void fill_ring_word(uint16_t* ring16, uint32_t ring_mask, int half, uint2 pw, uint32_t widx,
-                                            uint32_t first_abs_col, uint32_t first_ring_col, uint32_t ref_len,
-                                            const uint8_t* __restrict__ obytes)
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src)
 {
-#pragma unroll 4
-	for (int n = 0; n < 16; n++)
-	{
-		uint32_t f = 0xFFFFu; // DFB_REF_PAD
-		if (first_abs_col + n < ref_len) f = decode_base(pw, widx, n, obytes);
-		ring16[2 * ((first_ring_col + n) & ring_mask) + half] = (uint16_t)f;
-	}
+	const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // One arg-max column found by the probe sweep: the task's fixed region first, the overflow list after.
 __device__ __noinline__ void emit_probe_event(const FastParams& p, int item, int task, int h, int j, int col, int score)
@@ -237,9 +247,6 @@ __device__ __noinline__ void emit_probe_event(const FastParams& p, int item, int
 	}
 }
 
-#define DFB_READ_PAD 0x7FFEu // read rows beyond L: never equals a reference field
-#define DFB_REF_PAD 0xFFFFu  // reference columns beyond R: never equals a read field; bit 15 doubles as the row-max mask
-
 // registers per thread the mode needs (arrays of S) decide how many CTAs we ask ptxas to fit per SM
 template <int S, int MODE>
 struct FastOcc
@@ -257,14 +264,18 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 	constexpr int CH = 8 * G;       // reference ring: block of CH columns, two blocks resident
 	constexpr int CK = 4 * G;       // checkpoint interval (steps): probe windows are whole CK blocks
 	constexpr int RING = 2 * CH;
+	// the groups of a warp read the same ring index in the same step: G words between their rings put them in different banks
+	constexpr int RING_STRIDE = RING + (NG > 1 ? G : 0);
 	constexpr int ROWS = G * S;
 	constexpr int RDW = (ROWS + 15) / 16;
-	constexpr int HG = G / 2;       // lanes that feed one half of the ring
-	static_assert(G >= 4 && (G & (G - 1)) == 0 && G <= 32, "group size");
+	constexpr int HG = G / 2;       // pool words of one half in a ring block
+	static_assert(G >= 8 && (G & (G - 1)) == 0 && G <= 32, "group size");
 	static_assert(S >= 1 && S <= 32, "strip height");
+	static_assert(CH == 2 * CK, "the ring is refilled at the top of every second checkpoint block");
 
-	__shared__ uint32_t s_ring[4][NG][RING];
+	__shared__ uint32_t s_ring[4][NG][RING_STRIDE];
 	__shared__ uint32_t s_rows[4][NG][ROWS + 1];
+	__shared__ __align__(16) uint2 s_raw[4][NG][2][2][HG]; // [slot][half][word]: raw pool words of the ring blocks in flight (cp.async)
 
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
@@ -272,7 +283,6 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 	const int g = lane % G;
 	uint32_t* ring = s_ring[warp][q];
 	uint32_t* rows = s_rows[warp][q];
-	uint16_t* ring16 = reinterpret_cast<uint16_t*>(ring);
 	uint16_t* rows16 = reinterpret_cast<uint16_t*>(rows);
 
 	const uint32_t B = p.bias;
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			jp = p.jobs[jid];
 		}
 
-		// ---- stage the reads: pool words -> 16-bit fields -> S registers per lane (the probe sweep gets them
+		// ---- stage the reads: pool words -> 16-bit symbols -> S registers per lane (the probe sweep gets them
 		//      from the first sweep instead) ----
 		__syncwarp();
 		if (MODE != MODE_PROBE)
@@ -352,10 +362,11 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		__syncwarp();
 
 		// ---- step window.  SIMPLE/SPLIT: the whole wavefront, steps u = 0 .. R+G-2, lane g at column
-		//      u-g.  PROBE: only the checkpoint blocks (CH steps each) in which a winning row reaches
+		//      u-g.  PROBE: only the checkpoint blocks (CK steps each) in which a winning row reaches
 		//      its maximum; unless a window starts at step 0 the wavefront state is restored from the
 		//      checkpoint in front of it, separately for the two halves ----
-		constexpr int PRE = (G <= 16) ? 16 : 32;      // ring columns kept in front of a resumed window (>= G-1, whole words)
+		constexpr int PRE = 32;                       // ring columns kept in front of a resumed window (>= G-1, two whole words)
+		static_assert(G - 1 <= PRE && PRE + CK <= CH, "ring refill schedule of a resumed window");
 		uint32_t off0 = 0, off1 = 0;                  // absolute column of relative column 0, per half
 		int pre = 0;                                  // PROBE resumed: ring index = relative column + PRE
 		int Rg = max((int)jp.R[0], (int)jp.R[1]);     // columns (from step 0) or steps (resumed) to run
@@ -400,31 +411,50 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		for (int o = 16; o >= 1; o >>= 1) T = max(T, __shfl_xor_sync(0xffffffffu, T, o));
 		const bool ck_on = p.ckpt != nullptr && T <= 255 * CK;
 
-		// ---- reference ring: two blocks of CH columns resident, next block prefetched ----
-		const int h_mine = g / HG;
-		const int sub = g % HG;
-		const uint32_t Rh = jp.R[h_mine];
-		const uint32_t offw = ((h_mine ? off1 : off0) - (uint32_t)pre) >> 4; // first ring column, in pool words
-		auto load_block = [&](int blk) -> uint2 {
-			const uint32_t wi = offw + (uint32_t)blk * HG + sub;
-			if (wi * 16u < Rh) return __ldg(p.pool + jp.ref_w[h_mine] + wi);
-			return make_uint2(0, 0);
+		// ---- reference ring: two blocks of CH columns resident as 32-bit {half 1, half 0} symbol pairs; the pool words
+		//      of the next block are copied into shared memory by cp.async while the wavefront crosses the current one ----
+		const uint32_t R0 = jp.R[0], R1 = jp.R[1];
+		const uint32_t offw0 = (off0 - (uint32_t)pre) >> 4, offw1 = (off1 - (uint32_t)pre) >> 4; // first ring column, in pool words
+		uint2(*raw)[2][HG] = s_raw[warp][q];
+		// lanes 0 .. G/2-1 copy one 16-byte chunk (two pool words) each: G/4 chunks per half
+		auto issue_block = [&](int blk) {
+			if (g < HG)
+			{
+				const int h = g / (G / 4), c = g % (G / 4);
+				const uint32_t wi = (h ? offw1 : offw0) + (uint32_t)blk * HG + 2u * c;
+				if (wi * 16u < (h ? R1 : R0)) cp_async_16(&raw[blk & 1][h][2 * c], p.pool + jp.ref_w[h] + wi);
+			}
+			cp_async_commit();
 		};
-		auto fill_block = [&](int blk, uint2 pw) {
-			const uint32_t wrel = (uint32_t)blk * HG + sub;
-			fill_ring_word(ring16, RING - 1, h_mine, pw, jp.ref_w[h_mine] + offw + wrel, (offw + wrel) * 16u, wrel * 16u, Rh,
-			               p.obytes);
+		// lane g decodes columns 8g .. 8g+7 of the block for both halves and stores them as whole 32-bit words, in an
+		// order rotated by the lane so that the 32 lanes of the warp hit 32 different banks
+		auto decode_block = [&](int blk) {
+			const uint2 w0 = raw[blk & 1][0][g >> 1], w1 = raw[blk & 1][1][g >> 1];
+			const uint32_t wrel = (uint32_t)blk * HG + (uint32_t)(g >> 1);
+			const uint32_t a0 = (offw0 + wrel) * 16u, a1 = (offw1 + wrel) * 16u; // first column of the word in its reference
+			const int bit0 = 8 * (g & 1);
+			constexpr int RSH = (G == 8) ? 0 : (G == 16 ? 1 : 2); // bank = 8 * (g + q * G / 8) + rotation (mod 32): distinct over the warp
+#pragma unroll
+			for (int n = 0; n < 8; n++)
+			{
+				const int nb = bit0 + ((n + (g >> RSH)) & 7);
+				uint32_t f0 = DFB_REF_PAD, f1 = DFB_REF_PAD;
+				if (a0 + nb < R0) f0 = decode_base(w0, jp.ref_w[0] + offw0 + wrel, nb, p.obytes);
+				if (a1 + nb < R1) f1 = decode_base(w1, jp.ref_w[1] + offw1 + wrel, nb, p.obytes);
+				ring[((uint32_t)blk * CH + 16u * (g >> 1) + nb) & (RING - 1)] = f0 | (f1 << 16);
+			}
 		};
 		// ring columns this warp will read: T steps, PRE columns in front of a resumed window
 		const int ring_blocks = min(2, (T + PRE + CH - 1) / CH);
-#pragma unroll 1
-		for (int blk = 0; blk < ring_blocks; blk++) fill_block(blk, load_block(blk));
-		uint2 pf = make_uint2(0, 0);
-		if (T + PRE > 2 * CH) pf = load_block(2);
-		int blk_next = 2;
-		// one refill schedule for every group of the warp (valid for pre = 0 and pre = PRE: G-1+PRE <= CH)
-		static_assert(G - 1 + PRE <= CH, "ring refill schedule");
+		issue_block(0);
+		if (ring_blocks > 1) issue_block(1);
+		cp_async_wait_all();
 		__syncwarp();
+		decode_block(0);
+		if (ring_blocks > 1) decode_block(1);
+		__syncwarp();
+		int blk_next = 2;
+		issue_block(2);
 
 		uint32_t acc = 0x80008000u;
 		uint32_t Y[(MODE == MODE_SPLIT) ? S : 1];    // SPLIT: row maxima inside the current checkpoint block
@@ -437,21 +467,18 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		// the sweep, one checkpoint block (CK steps) at a time so that the per-block work (checkpoint,
 		// ring refill, row-maximum bookkeeping) stays out of the per-step instruction stream
 		const int act_off = resumed ? 0 : g; // lane g joins at step g unless the wavefront was restored
-		constexpr int kEach = 0, kEven = 1, kOdd = 2;
 		// SPLIT: steps below the shorter reference of every job pair of the warp touch real columns only (lane g is at
-		// column u-g <= u), rounded down to a whole pair.  SIMPLE tolerates the padding columns: all steps.
+		// column u-g <= u).  SIMPLE tolerates the padding columns: all steps.
 		int u_paired = T;
 		if (MODE == MODE_SPLIT)
 		{
 			u_paired = have ? min((int)jp.R[0], (int)jp.R[1]) : 0x7fffffff;
 #pragma unroll
 			for (int o = 16; o >= 1; o >>= 1) u_paired = min(u_paired, __shfl_xor_sync(0xffffffffu, u_paired, o));
-			u_paired &= ~1;
 		}
-		// sink kinds: kEach = fold the new column into the row state at every step; kEven/kOdd = the two steps of a
-		// pair, where the odd step folds both columns with one three-input max (half the sink issues)
-		auto step = [&](const int u, auto sink_kind) {
-			constexpr int SINK = decltype(sink_kind)::value;
+		// one step of one lane: the next reference column against the S rows of the strip.  FOLD: the new column goes
+		// into the row state here (every step of the probe; head and tail steps of the other modes)
+		auto step = [&](const int u) {
 			uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G);
 			if (g == 0) recv = Bp;
 			const int b = u - g; // relative column; absolute column = off + b
@@ -461,7 +488,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				uint32_t left = recv;
 				uint32_t dg_in = prev;
 				uint32_t pen = 0;
-				if (MODE == MODE_SPLIT && SINK == kEach) pen = rf & 0x80008000u;
+				if (MODE == MODE_SPLIT) pen = rf & 0x80008000u;
 				if (MODE == MODE_PROBE) acc = 0x80008000u;
 #pragma unroll
 				for (int k = 0; k < S; k++)
@@ -473,16 +500,8 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 					const uint32_t e = __viaddmax_s16x2(fold, p.g2, dg);          // max(up + gap, diagonal)
 					left = __viaddmax_s16x2(left, p.gm2, e);                      // max(left + gap - m, e)
 					F[k] = left;
-					if (MODE == MODE_SPLIT)
-					{
-						if (SINK == kEach) Y[k] = __viaddmax_s16x2(left, pen, Y[k]);
-						if (SINK == kOdd) Y[k] = __vimax3_s16x2(Y[k], fold, left);
-					}
-					if (MODE == MODE_SIMPLE)
-					{
-						if (SINK == kEach) acc = __viaddmax_s16x2(left, p.ck[k], acc);
-						if (SINK == kOdd) X[k] = __vimax3_s16x2(X[k], fold, left);
-					}
+					if (MODE == MODE_SPLIT) Y[k] = __viaddmax_s16x2(left, pen, Y[k]);
+					if (MODE == MODE_SIMPLE) acc = __viaddmax_s16x2(left, p.ck[k], acc);
 					if (MODE == MODE_PROBE) acc = __viaddmax_s16x2(left, X[k], acc);
 				}
 				prev = recv;
@@ -512,6 +531,51 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				}
 			}
 		};
+		// two steps of a lane whose columns are known to be in range (every lane has joined, none has left): no
+		// activity test, and one three-input maximum folds both columns into the row state (half the sink issues)
+		auto step_pair = [&](const int u) {
+			uint32_t Fe[S];
+			{
+				uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G);
+				if (g == 0) recv = Bp;
+				const uint32_t rf = ring[(u - g) & (RING - 1)];
+				uint32_t left = recv;
+				uint32_t dg_in = prev;
+#pragma unroll
+				for (int k = 0; k < S; k++)
+				{
+					const uint32_t d = __viaddmin_u16x2(rd[k], rf, 0x00010001u);
+					const uint32_t dg = d * p.xm + dg_in;
+					dg_in = F[k];
+					const uint32_t e = __viaddmax_s16x2(F[k], p.g2, dg);
+					left = __viaddmax_s16x2(left, p.gm2, e);
+					Fe[k] = left;
+				}
+				prev = recv;
+				Flast = left;
+			}
+			{
+				uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G);
+				if (g == 0) recv = Bp;
+				const uint32_t rf = ring[(u + 1 - g) & (RING - 1)];
+				uint32_t left = recv;
+				uint32_t dg_in = prev;
+#pragma unroll
+				for (int k = 0; k < S; k++)
+				{
+					const uint32_t d = __viaddmin_u16x2(rd[k], rf, 0x00010001u);
+					const uint32_t dg = d * p.xm + dg_in;
+					dg_in = Fe[k];
+					const uint32_t e = __viaddmax_s16x2(Fe[k], p.g2, dg);
+					left = __viaddmax_s16x2(left, p.gm2, e);
+					F[k] = left;
+					if (MODE == MODE_SPLIT) Y[k] = __vimax3_s16x2(Y[k], Fe[k], left);
+					if (MODE == MODE_SIMPLE) X[k] = __vimax3_s16x2(X[k], Fe[k], left);
+				}
+				prev = recv;
+				Flast = left;
+			}
+		};
 		int u = 0;
 		for (int blkno = 0; u < T; blkno++)
 		{
@@ -527,33 +591,31 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 					p.ckpt[(cb + S + 1) * G + g] = Flast;
 				}
 			}
-			const int u_end = min(T, (blkno + 1) * CK);
-			// ring block n+1 replaces ring block n-1 once every lane is past it (G-1 steps into ring block n >= 1);
-			// a ring block is CH/CK checkpoint blocks long
-			const int u_fill = (blkno >= CH / CK && blkno % (CH / CK) == 0) ? blkno * CK + G - 1 : -1;
-			auto refill = [&]() {
+			// ring block n+1 replaces ring block n-1 half way through ring block n (n >= 1): every lane is past block
+			// n-1 by then (G-1 <= CK steps in, PRE <= CK columns ahead for a resumed window) and none has reached n+1
+			if (blkno >= 3 && (blkno & 1))
+			{
+				cp_async_wait_all();
 				__syncwarp();
-				fill_block(blk_next, pf);
+				decode_block(blk_next);
 				blk_next++;
-				pf = load_block(blk_next);
 				__syncwarp();
-			};
-			// paired steps while every lane's column is inside both references (no row-max masking needed)
-			const int u_pair_end = (MODE == MODE_PROBE) ? u : min(u_end, u_paired);
-#pragma unroll 1
-			for (; u + 1 < u_pair_end; u += 2)
+				issue_block(blk_next);
+			}
+			const int u_end = min(T, (blkno + 1) * CK);
+			if (MODE != MODE_PROBE)
 			{
-				if (u == u_fill) refill();
-				step(u, std::integral_constant<int, kEven>());
-				if (u + 1 == u_fill) refill();
-				step(u + 1, std::integral_constant<int, kOdd>());
+				// head: lanes are still joining (lane g at step g); then pairs of steps while every lane is inside the
+				// references; the steps with an activity test take the rest
+				const int u_head = min(u_end, G - 1);
+#pragma unroll 1
+				for (; u < u_head; u++) step(u);
+				const int u_pair_end = min(u_end, u_paired);
+#pragma unroll 1
+				for (; u + 1 < u_pair_end; u += 2) step_pair(u);
 			}
 #pragma unroll 1
-			for (; u < u_end; u++)
-			{
-				if (u == u_fill) refill();
-				step(u, std::integral_constant<int, kEach>());
-			}
+			for (; u < u_end; u++) step(u);
 			if (MODE == MODE_SPLIT)
 			{
 				// end of a checkpoint block (or of the sweep), same step for all lanes: fold the block
@@ -580,6 +642,8 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				}
 			}
 		}
+		// the copies of a block past the end of the sweep may still be in flight: the raw slots are reused by the next job
+		cp_async_wait_all();
 
 		// ---- epilogues ----
 		if (MODE == MODE_SIMPLE)

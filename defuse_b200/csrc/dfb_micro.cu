@@ -202,23 +202,136 @@ __global__ void __launch_bounds__(256) cell_body_kernel(const uint32_t* __restri
 	out[tid] = r;
 }
 
+
+// ---- the sweep's paired-step body in isolation (no refill, no checkpoints): what the instruction mix itself can reach ----
+__device__ __forceinline__ uint32_t f16x2_add(uint32_t a, uint32_t b)
+{
+	uint32_t d;
+	asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+	return d;
+}
+__device__ __forceinline__ uint32_t f16x2_fma(uint32_t a, uint32_t b, uint32_t c)
+{
+	uint32_t d;
+	asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+__device__ __forceinline__ uint32_t f16x2_fma_sat(uint32_t a, uint32_t b, uint32_t c)
+{
+	uint32_t d;
+	asm("fma.rn.sat.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+
+// S rows per lane, groups of 8 lanes, one SHFL.UP and one ring LDS per step like dp_fast_kernel; the last HR rows of
+// the strip take their mismatch indicator from the fp16 path (HADD2, HFMA2.SAT, HFMA2: no ALU-pipe issue), the others
+// from VIADDMNMX.U16x2 + IMAD.  SINK: 0 none (probe-like), 1 = one VIMNMX3 per row per two steps (split / simple sweeps)
+template <int S, int HR, int SINK>
+__global__ void __launch_bounds__(128, 4) sweep_body_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int pairs,
+                                                             uint32_t xm, uint32_t g2, uint32_t gm2, uint32_t c2)
+{
+	__shared__ uint32_t s_ring[4][4][128 + 8];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = lane >> 3, g = lane & 7;
+	uint32_t* ring = s_ring[warp][q];
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	for (int k = g; k < 128; k += 8)
+	{
+		const uint32_t a = in[(tid + 7 * k) & 1023], b = in[(tid + 11 * k + 5) & 1023];
+		const uint32_t sym[4] = {0x5410u, 0x5430u, 0x5470u, 0x5540u}; // fp16 bit patterns of 65, 67, 71, 84
+		ring[k] = sym[a & 3] | (sym[b & 3] << 16);
+	}
+	__syncwarp();
+	uint32_t rd[S], F[S], Fb[S], Y[S];
+#pragma unroll
+	for (int k = 0; k < S; k++)
+	{
+		const uint32_t sy = ring[(k * 5 + g) & 127];
+		rd[k] = (k >= S - HR) ? (sy ^ 0x80008000u) : ((0u - (sy & 0xFFFFu)) & 0xFFFFu) | ((0u - (sy >> 16)) << 16);
+		F[k] = 0x01900190u + 0x00010001u * (uint32_t)k;
+		Y[k] = 0;
+	}
+	uint32_t prev = 0x01900190u, Flast = F[S - 1];
+	const uint32_t Bp = 0x01A001A0u;
+	auto half_step = [&](const uint32_t* Fin, uint32_t* Fout, const int u, const bool odd) {
+		uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, 8);
+		if (g == 0) recv = Bp;
+		const uint32_t rf = ring[(u - g) & 127];
+		uint32_t left = recv, dg_in = prev;
+#pragma unroll
+		for (int k = 0; k < S; k++)
+		{
+			uint32_t dg;
+			if (k >= S - HR)
+			{
+				const uint32_t d = f16x2_add(rf, rd[k]);
+				const uint32_t r = f16x2_fma_sat(d, d, 0u);
+				dg = f16x2_fma(r, c2, dg_in);
+			}
+			else
+			{
+				const uint32_t d = __viaddmin_u16x2(rd[k], rf, 0x00010001u);
+				dg = d * xm + dg_in;
+			}
+			const uint32_t fold = Fin[k];
+			dg_in = fold;
+			const uint32_t e = __viaddmax_s16x2(fold, g2, dg);
+			left = __viaddmax_s16x2(left, gm2, e);
+			Fout[k] = left;
+			if (SINK == 1 && odd) Y[k] = __vimax3_s16x2(Y[k], fold, left);
+		}
+		prev = recv;
+		Flast = left;
+	};
+#pragma unroll 1
+	for (int it = 0, u = 8; it < pairs; it++, u += 2)
+	{
+		half_step(F, Fb, u, false);
+		half_step(Fb, F, u + 1, true);
+	}
+	uint32_t r = 0;
+#pragma unroll
+	for (int k = 0; k < S; k++) r ^= F[k] ^ Y[k];
+	out[tid] = r;
+}
+
+template <int S, int HR, int SINK>
+static void launch_body(int sm_count, const uint32_t* d_in, uint32_t* d_out, int pairs)
+{
+	// 2/-1/-2: xm = x - m = -3 as a 32-bit multiplier, gap both halves, gap - match both halves, -(m - x) as an fp16 subnormal
+	sweep_body_kernel<S, HR, SINK><<<sm_count * 4, 128>>>(d_in, d_out, pairs, 0xFFFFFFFDu, 0xFFFEFFFEu, 0xFFFCFFFCu, 0x80038003u);
+}
+
 }  // namespace
 
 extern "C" int dfb_microbench_issue_rate(dfb_ctx* ctx, int kind, int iters, double* warp_instr_per_s, double* elapsed_ms)
 {
-	if (!ctx || !warp_instr_per_s || kind < 0 || kind > 16 || iters <= 0) return DFB_ERR_ARG;
+	// kinds 0..16: one instruction kind (or a 1:1 mix) in independent chains, result = warp-instructions / s.
+	// kinds 100+HR / 200+HR: the sweep's paired-step body with S = 13 rows per lane, HR of them on the fp16 indicator
+	// path, with (100) / without (200) the row-maximum sink; `iters` = step pairs, result = warp row-steps / s
+	// (one row-step = one register pair of cells = 64 cell updates per warp)
+	const bool body = kind >= 100;
+	const int body_hr = body ? kind % 100 : 0;
+	if (!ctx || !warp_instr_per_s || kind < 0 || (!body && kind > 16) || (body && (kind >= 300 || body_hr > 13)) || iters <= 0)
+		return DFB_ERR_ARG;
 	dfb_device_info info;
 	int rc = dfb_ctx_device_info(ctx, &info);
 	if (rc) return rc;
 	if (cudaSetDevice(info.ordinal) != cudaSuccess) return DFB_ERR_CUDA;
-	const int blocks = info.sm_count * 8;
-	const int threads = 256;
+	const int blocks = body ? info.sm_count * 4 : info.sm_count * 8;
+	const int threads = body ? 128 : 256;
 	uint32_t* d_in = nullptr;
 	uint32_t* d_out = nullptr;
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	auto cleanup = [&]() {
+		if (e0) cudaEventDestroy(e0);
+		if (e1) cudaEventDestroy(e1);
+		cudaFree(d_in);
+		cudaFree(d_out);
+	};
 	if (cudaMalloc(&d_in, 1024 * sizeof(uint32_t)) != cudaSuccess) return DFB_ERR_NOMEM;
 	if (cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(uint32_t)) != cudaSuccess)
 	{
-		cudaFree(d_in);
+		cleanup();
 		return DFB_ERR_NOMEM;
 	}
 	uint32_t h_in[1024];
@@ -228,12 +341,15 @@ extern "C" int dfb_microbench_issue_rate(dfb_ctx* ctx, int kind, int iters, doub
 		s = s * 1664525u + 1013904223u;
 		h_in[k] = (s >> 4) & 0x0FFF0FFFu;
 	}
-	cudaMemcpy(d_in, h_in, sizeof(h_in), cudaMemcpyHostToDevice);
-	cudaEvent_t e0, e1;
-	cudaEventCreate(&e0);
-	cudaEventCreate(&e1);
+	if (cudaMemcpy(d_in, h_in, sizeof(h_in), cudaMemcpyHostToDevice) != cudaSuccess || cudaEventCreate(&e0) != cudaSuccess ||
+	    cudaEventCreate(&e1) != cudaSuccess)
+	{
+		cleanup();
+		return DFB_ERR_CUDA;
+	}
 	float best_ms = 1e30f;
-	for (int rep = 0; rep < 4; rep++) // first repetition is the warm-up
+	bool known = true;
+	for (int rep = 0; rep < 4 && known; rep++) // first repetition is the warm-up
 	{
 		cudaEventRecord(e0, 0);
 		switch (kind)
@@ -254,23 +370,33 @@ extern "C" int dfb_microbench_issue_rate(dfb_ctx* ctx, int kind, int iters, doub
 			case 13: issue_kernel<13><<<blocks, threads>>>(d_in, d_out, iters); break;
 			case 14: mixed_kernel<10><<<blocks, threads>>>(d_in, d_out, iters); break;
 			case 15: mixed_kernel<12><<<blocks, threads>>>(d_in, d_out, iters); break;
-			default: mixed_kernel<11><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 16: mixed_kernel<11><<<blocks, threads>>>(d_in, d_out, iters); break;
+			case 100: launch_body<13, 0, 1>(info.sm_count, d_in, d_out, iters); break;
+			case 103: launch_body<13, 3, 1>(info.sm_count, d_in, d_out, iters); break;
+			case 105: launch_body<13, 5, 1>(info.sm_count, d_in, d_out, iters); break;
+			case 107: launch_body<13, 7, 1>(info.sm_count, d_in, d_out, iters); break;
+			case 109: launch_body<13, 9, 1>(info.sm_count, d_in, d_out, iters); break;
+			case 111: launch_body<13, 11, 1>(info.sm_count, d_in, d_out, iters); break;
+			case 113: launch_body<13, 13, 1>(info.sm_count, d_in, d_out, iters); break;
+			case 200: launch_body<13, 0, 0>(info.sm_count, d_in, d_out, iters); break;
+			case 207: launch_body<13, 7, 0>(info.sm_count, d_in, d_out, iters); break;
+			case 213: launch_body<13, 13, 0>(info.sm_count, d_in, d_out, iters); break;
+			default: known = false; break;
 		}
+		if (!known) break;
 		cudaEventRecord(e1, 0);
 		if (cudaEventSynchronize(e1) != cudaSuccess) break;
 		float ms = 0;
-		cudaEventElapsedTime(&ms, e0, e1);
+		if (cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) break;
 		if (rep > 0 && ms < best_ms) best_ms = ms;
 	}
 	cudaError_t e = cudaDeviceSynchronize();
-	cudaEventDestroy(e0);
-	cudaEventDestroy(e1);
-	cudaFree(d_in);
-	cudaFree(d_out);
+	cleanup();
+	if (!known) return DFB_ERR_ARG;
 	if (e != cudaSuccess || best_ms > 1e29f) return DFB_ERR_CUDA;
 	const double warps = (double)blocks * threads / 32.0;
-	// kind 7 counts one "body" = the 6 instructions of one register-pair of cells
-	const double per_thread = (kind == 7) ? (double)iters * 6 * 8 : (double)iters * kUnroll * kChains * 3;
+	// kind 7 counts one "body" = the 6 instructions of one register-pair of cells; the sweep bodies count row-steps
+	const double per_thread = body ? (double)iters * 2 * 13 : (kind == 7) ? (double)iters * 6 * 8 : (double)iters * kUnroll * kChains * 3;
 	*warp_instr_per_s = warps * per_thread / (best_ms * 1e-3);
 	if (elapsed_ms) *elapsed_ms = best_ms;
 	return DFB_OK;
