@@ -191,12 +191,13 @@ def pinned(arr):
 
 
 def measure_stress(ctx, stream, args):
-    """BASELINE.json configs[4]: 250-bp reads, 8 % substitutions, 10 % of reads with a deletion, 1 % N, cluster sizes
-    Zipf(1.2) (the heaviest clusters hold most candidates), windows 700-860 bp."""
+    """BASELINE.json configs[4] as SURVEY 8(d) writes it (synth.STRESS): 250-bp reads, 8 % substitutions, 2 % indels,
+    1 % N, 5 % poly-A-tail reads, lowercase runs in 1 % of the windows, cluster sizes Zipf(1.2) (the heaviest clusters
+    hold most candidates), windows 700-860 bp.  A sample of the tasks is compared with the oracle (checker only)."""
     import torch
     import defuse_b200 as d
     import synth
-    w = synth.split_workload(5, 4000, 50, L=250, R_lo=700, R_hi=860, sub=0.08, n_rate=0.01, indel_frac=0.1, zipf=1.2)
+    w = synth.split_workload(5, 4000, 50, **synth.STRESS)
     refs = d.SeqTable(w["ref_bytes"], w["ref_off"])
     reads = d.SeqTable(w["read_bytes"], w["read_off"])
     al = d.SplitReadAligner(2, -1, -2, False, 8, ctx=ctx)
@@ -218,10 +219,24 @@ def measure_stress(ctx, stream, args):
     st = plan.stats()
     res = plan.fetch(copy=False)
     n_hit = int((res.best > 0).sum())
+    # sampled parity (the oracle is the checker here, never the thing measured): every 500th task plus the tasks with
+    # the most winning rows, i.e. the tie-heavy ones
+    import oracle
+    rows_per_task = np.bincount(res.rows["task"], minlength=w["n_tasks"]) if len(res.rows) else np.zeros(w["n_tasks"], int)
+    pick = np.unique(np.concatenate([np.arange(0, w["n_tasks"], 500), np.argsort(rows_per_task)[-40:]])).astype(np.int64)
+    cnt, want = oracle.split_align_batch(w["ref_bytes"], w["ref_off"], w["read_bytes"], w["read_off"], w["task_cluster"][pick],
+                                         w["task_read"][pick], w["min_score"][pick])
+    pos = np.concatenate([[0], np.cumsum(cnt)])
+    for k, t in enumerate(pick):
+        got = res.alignments(int(t))
+        assert got.shape == (cnt[k], 7) and (got == want[pos[k]:pos[k + 1]]).all(), "stress task %d differs from the oracle" % t
     plan.close()
-    return {"workload": "%d SplitReadAligner tasks, L=250, R 700-860, Zipf(1.2) cluster sizes, 8%% sub" % w["n_tasks"],
+    return {"workload": "%d SplitReadAligner tasks, L=250, R 700-860, Zipf(1.2) cluster sizes, 8%% sub, 2%% indels, 1%% N, "
+                        "5%% poly-A tails, lowercase runs, poly-A window ends" % w["n_tasks"],
             "gcups": w["cells"] / (ms * 1e-3) / 1e9, "ms_per_step": ms, "sweep_ms": st["ms_sweep"], "probe_ms": st["ms_probe"],
-            "tasks_with_split": n_hit, "tasks_per_s": w["n_tasks"] / (ms * 1e-3)}
+            "tasks_with_split": n_hit, "tasks_per_s": w["n_tasks"] / (ms * 1e-3), "events": int(st["events"]),
+            "parity_sample": {"tasks": int(len(pick)), "alignments": int(cnt.sum()), "max_alignments_of_a_task": int(cnt.max()),
+                              "checker": "oracle port", "mismatches": 0}}
 
 
 def measure_local(ctx, stream, args, R=2001, L=100, n_refs=10000, n_tasks=None):

@@ -16,7 +16,6 @@
 // shared memory by cp.async (LDGSTS) one ring block ahead of the wavefront.
 #pragma once
 
-#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <type_traits>
@@ -191,30 +190,18 @@ struct FastParams
 
 #define DFB_SLOT_EVENTS 8
 
-// Symbols in shared memory and registers: a base is the fp16 bit pattern of its byte value (exact for 0..255), so
-// that two symbols are equal as integers iff they are equal as fp16 numbers, and unequal ones differ by >= 1.0.
-// The integer rows of a strip test equality with one VIADDMNMX.U16x2; rows on the fp16 path use HADD2 + HFMA2.SAT.
-#define DFB_READ_PAD 0x6800u // 2048.0: read rows beyond L, never equals a reference field
-#define DFB_REF_PAD 0xE400u  // -1024.0: reference columns beyond R, never equals a read field; bit 15 doubles as the row-max mask
-
-__device__ __forceinline__ uint32_t sym_of_byte(uint32_t v)
-{
-	return (uint32_t)__half_as_ushort(__uint2half_rn(v));
-}
-
-__device__ __forceinline__ uint32_t sym_of_code(uint32_t c)
-{
-	// fp16 patterns of 'A' 65, 'C' 67, 'G' 71, 'T' 84
-	return __funnelshift_r(0x54305410u, 0x55405470u, 16u * c) & 0xFFFFu;
-}
+// Symbols in shared memory and registers: the raw byte of a base in a 16-bit field (equality of symbols is equality
+// of bytes: SplitReadAligner.cpp:51), and two padding values that equal nothing.
+#define DFB_READ_PAD 0x7FFEu // read rows beyond L: never equals a reference field
+#define DFB_REF_PAD 0xFFFFu  // reference columns beyond R: never equals a read field; bit 15 doubles as the row-max mask
 
 __device__ __forceinline__ uint32_t decode_base(uint2 w, uint32_t word_index, int n, const uint8_t* __restrict__ obytes)
 {
 	if ((w.y >> n) & 1u)
 	{
-		return sym_of_byte(__ldg(obytes + (size_t)word_index * 16 + n)); // exception plane: raw byte
+		return __ldg(obytes + (size_t)word_index * 16 + n); // exception plane: raw byte
 	}
-	return sym_of_code((w.x >> (2 * n)) & 3u);
+	return (0x54474341u >> (8 * ((w.x >> (2 * n)) & 3u))) & 0xFFu; // "ACGT"
 }
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src)

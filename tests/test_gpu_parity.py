@@ -21,6 +21,24 @@ def _check_simple(oracle, ctx, refs, seqs, task_ref, task_seq, m, x, g):
     bad = np.nonzero(got != want)[0]
     assert bad.size == 0, "first mismatch task %d: got %d want %d (R=%d L=%d)" % (
         bad[0], got[bad[0]], want[bad[0]], len(refs[task_ref[bad[0]]]), len(seqs[task_seq[bad[0]]]))
+    # the compiled reference class itself as the checker (oracle/_ref travels to the GPU box), on a bounded sample
+    if oracle.have_ref():
+        pick = _ref_sample(len(task_ref), lambda t: len(refs[task_ref[t]]) * len(seqs[task_seq[t]]))
+        ref = oracle.simple_align_batch(m, x, g, rt.data, rt.off, st.data, st.off, np.asarray(task_ref)[pick],
+                                        np.asarray(task_seq)[pick], impl="ref")
+        assert (got[pick] == ref).all(), "CUDA path differs from the compiled reference SimpleAligner"
+
+
+def _ref_sample(n, cells_of, budget=4.0e8):
+    """Tasks the unmodified reference classes re-check directly: evenly spread, about `budget` DP cells in total
+    (a few seconds at the reference's rate)."""
+    if n == 0:
+        return np.zeros(0, np.int64)
+    step = 1
+    total = sum(cells_of(t) for t in range(0, n, max(1, n // 64))) * max(1, n // 64)
+    if total > budget:
+        step = int(np.ceil(total / budget))
+    return np.arange(0, n, step, dtype=np.int64)
 
 
 def _check_split(oracle, ctx, refs, reads, task_cluster, task_read, min_score, params=(2, -1, -2, False, 8)):
@@ -39,6 +57,18 @@ def _check_split(oracle, ctx, refs, reads, task_cluster, task_read, min_score, p
         rec = res.records(t)
         wrec = oracle.split_dedupe(w)
         assert rec.shape == wrec.shape and (rec == wrec).all()
+    # the compiled reference class itself as the checker, on a bounded sample of the tasks
+    if oracle.have_ref():
+        tc, tr, mn = np.asarray(task_cluster), np.asarray(task_read), np.asarray(min_score)
+        pick = _ref_sample(len(tc), lambda t: len(reads[tr[t]]) * (len(refs[2 * tc[t]]) + len(refs[2 * tc[t] + 1])))
+        pick = pick[cnt[pick] <= 20000]  # (tie-heavy tasks: millions of tuples through the reference's vectors)
+        rcnt, rwant = oracle.split_align_batch(rt.data, rt.off, st.data, st.off, tc[pick], tr[pick], mn[pick],
+                                               m, x, g, eg, ms, impl="ref")
+        rpos = np.concatenate([[0], np.cumsum(rcnt)])
+        for k, t in enumerate(pick):
+            w = rwant[rpos[k]:rpos[k + 1]]
+            a = res.alignments(int(t))
+            assert a.shape == w.shape and (a == w).all(), "task %d differs from the compiled reference SplitReadAligner" % t
     return res
 
 
@@ -221,6 +251,38 @@ def test_large_batch_properties_and_sampled_parity(oracle_mod, gpu_ctx):
         a = res.alignments(int(t))
         b = want[pos[k]:pos[k + 1]]
         assert a.shape == b.shape and (a == b).all(), t
+
+
+def test_split_stress_config_as_specified(oracle_mod, gpu_ctx):
+    """SURVEY 8(d) config 5 as written (synth.STRESS): 250-bp reads, 8 % substitutions, 2 % indels, 1 % N, 5 % poly-A
+    tails, lowercase runs in the windows, poly-A window ends, Zipf(1.2) cluster sizes.  Every task against the oracle,
+    a sample against the compiled reference class; the exception plane (N, lowercase) and the tie-heavy overflow path
+    (poly-A read tail against a poly-A window end) must both occur."""
+    import defuse_b200 as d
+    import synth
+    w = synth.split_workload(5, 150, 40, **synth.STRESS)
+    n = w["n_tasks"]
+    refs, reads = d.SeqTable(w["ref_bytes"], w["ref_off"]), d.SeqTable(w["read_bytes"], w["read_off"])
+    res = d.SplitReadAligner(ctx=gpu_ctx).align_batch(refs, reads, w["task_cluster"], w["task_read"], w["min_score"])
+    cnt, want = oracle_mod.split_align_batch(w["ref_bytes"], w["ref_off"], w["read_bytes"], w["read_off"],
+                                             w["task_cluster"], w["task_read"], w["min_score"])
+    pos = np.concatenate([[0], np.cumsum(cnt)])
+    for t in range(n):
+        a = res.alignments(t)
+        b = want[pos[t]:pos[t + 1]]
+        assert a.shape == b.shape and (a == b).all(), t
+    assert (cnt > 0).sum() > n // 50                      # junctions are still found at this error rate
+    assert cnt.max() > 64                                  # a tie-heavy task went through the overflow list
+    assert (w["ref_bytes"] >= 97).any() and (w["read_bytes"] == ord("N")).any()
+    if oracle_mod.have_ref():
+        pick = np.unique(np.concatenate([np.arange(0, n, 40), np.argsort(cnt)[-5:]])).astype(np.int32)
+        rcnt, rwant = oracle_mod.split_align_batch(w["ref_bytes"], w["ref_off"], w["read_bytes"], w["read_off"],
+                                                   w["task_cluster"][pick], w["task_read"][pick], w["min_score"][pick], impl="ref")
+        rpos = np.concatenate([[0], np.cumsum(rcnt)])
+        for k, t in enumerate(pick):
+            a = res.alignments(int(t))
+            b = rwant[rpos[k]:rpos[k + 1]]
+            assert a.shape == b.shape and (a == b).all(), t
 
 
 def _expand_cols(res):
