@@ -415,14 +415,14 @@ static const int kNumClasses = (int)(sizeof(kClasses) / sizeof(kClasses[0]));
 static const int kMaxFastRows = 1024;
 static const int kRBins = 1024; // job order inside a class: reference length / 16, longest first
 
-template <int G, int S, int MODE>
-static cudaError_t launch_fast_t(const FastParams& p, int sm_count, cudaStream_t stream, int n_items_bound)
+// persistent grid: one CTA per resident slot of every SM (or fewer when the work is less), warps pull job pairs from a queue
+template <class K>
+static cudaError_t launch_persistent(K kernel, int& occ, int G, const FastParams& p, int sm_count, cudaStream_t stream, int n_items_bound)
 {
-	static int occ = 0;
 	if (occ == 0)
 	{
 		int o = 0;
-		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, dp_fast_kernel<G, S, MODE>, 128, 0);
+		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, 128, 0);
 		if (e != cudaSuccess) return e;
 		occ = o > 0 ? o : 1;
 	}
@@ -430,8 +430,22 @@ static cudaError_t launch_fast_t(const FastParams& p, int sm_count, cudaStream_t
 	long long want = ((long long)n_items_bound + per_block - 1) / per_block;
 	long long cap = (long long)sm_count * occ;
 	int grid = (int)std::max(1LL, std::min(want, cap));
-	dp_fast_kernel<G, S, MODE><<<grid, 128, 0, stream>>>(p);
+	kernel<<<grid, 128, 0, stream>>>(p);
 	return cudaGetLastError();
+}
+
+template <int G, int S, int MODE>
+static cudaError_t launch_fast_t(const FastParams& p, int sm_count, cudaStream_t stream, int n_items_bound)
+{
+	static int occ = 0;
+	return launch_persistent(dp_fast_kernel<G, S, MODE>, occ, G, p, sm_count, stream, n_items_bound);
+}
+
+template <int G, int S>
+static cudaError_t launch_probe_t(const FastParams& p, int sm_count, cudaStream_t stream, int n_items_bound)
+{
+	static int occ = 0;
+	return launch_persistent(dp_probe_kernel<G, S>, occ, G, p, sm_count, stream, n_items_bound);
 }
 
 static cudaError_t launch_fast(int cls, int mode, const FastParams& p, int sm_count, cudaStream_t stream, int bound)
@@ -442,7 +456,7 @@ static cudaError_t launch_fast(int cls, int mode, const FastParams& p, int sm_co
 	{                                                                                             \
 		if (mode == MODE_SIMPLE) return launch_fast_t<g, s, MODE_SIMPLE>(p, sm_count, stream, bound); \
 		if (mode == MODE_SPLIT) return launch_fast_t<g, s, MODE_SPLIT>(p, sm_count, stream, bound);   \
-		return launch_fast_t<g, s, MODE_PROBE>(p, sm_count, stream, bound);                           \
+		return launch_probe_t<g, s>(p, sm_count, stream, bound);                                      \
 	}
 	DFB_CLASSES(X)
 #undef X
@@ -822,6 +836,9 @@ static void fill_fast_params(dfb_plan* pl, int c, int m, int x, int g, int min_s
 	fp.rdq = cw.d_rdq;
 	fp.ckpt = cw.d_ckpt;
 	fp.ckpt_blocks = cw.ckpt_blocks;
+	// probe granules: 16 mask bits per half cover checkpoint blocks 0 .. ckpt_blocks
+	fp.gran_shift = 0;
+	while ((cw.ckpt_blocks >> fp.gran_shift) > 15) fp.gran_shift++;
 	fp.slot_rng = cw.d_slot_rng;
 	fp.events = pl->d_events;
 	fp.ev_count = pl->d_ev_count;
@@ -858,7 +875,7 @@ static int alloc_work(dfb_plan* pl, const Staging& st, const int64_t* n_jobs_cls
 			const int G = kClasses[c].G, CK = 4 * G;
 			cw.ckpt_blocks = (int)(((int64_t)cw.max_R + G - 2) / CK);
 			const size_t ck_bytes = n * (size_t)cw.ckpt_blocks * (size_t)(kClasses[c].S + 2) * G * sizeof(uint32_t);
-			if (cw.ckpt_blocks > 0 && cw.max_R + G - 1 <= 255u * CK && ck_bytes <= (size_t)ctx->prop.totalGlobalMem / 4)
+			if (cw.ckpt_blocks > 0 && ck_bytes <= (size_t)ctx->prop.totalGlobalMem / 4)
 				DALLOC(ctx, cw.d_ckpt, ck_bytes);
 			else
 				cw.ckpt_blocks = 0;
@@ -1169,9 +1186,6 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 			{
 				int c = (L <= kMaxFastRows && R1 <= 65535 && R2 <= 65535) ? class_for_rows((int)L) : -1;
 				if (c >= 0 && !pl->fast_ok[c]) c = -1;
-				// the probe sweep finds its windows by checkpoint block, 8 bits per half (255 blocks of 4G steps); a window
-				// pair too long for that is swept by the s32 kernels, which take any length
-				if (c >= 0 && std::max(R1, R2) + kClasses[c].G - 1 > 255LL * 4 * kClasses[c].G) c = -1;
 				if (c < 0)
 				{
 					bin = -2;

@@ -176,8 +176,9 @@ struct FastParams
 	uint32_t* rdq;   // [slot][S][G] the lanes' (negated) read symbols, so that the probe does not decode them again
 	uint32_t* ckpt;  // [job][ckpt_blocks][S+2][G] wavefront state (F[S], prev, Flast) in front of every CH-th step (null: off)
 	int ckpt_blocks; // checkpoints per job in this launch
+	int gran_shift;  // a probe granule is 1 << gran_shift checkpoint blocks (so that a class' longest wavefront has <= 16 granules)
 	int slot_base;   // SPLIT: first global slot number of this class (slots are numbered class by class)
-	uint32_t* slot_rng; // per queue slot: checkpoint blocks to re-sweep, first/last per half
+	uint32_t* slot_rng; // per queue slot: granules to re-sweep, a 16-bit mask per half
 	int32_t* slot_task; // SPLIT (write): task index per queue slot
 	int32_t* task_slot; // SPLIT (write): queue slot per task, -1 when the task needs no second sweep
 	uint2* slot_ev;     // PROBE: [slot][DFB_SLOT_EVENTS] {key = half<<27 | row<<16 | col, score}
@@ -238,10 +239,9 @@ __device__ __noinline__ void emit_probe_event(const FastParams& p, int item, int
 template <int S, int MODE>
 struct FastOcc
 {
-	static constexpr int kArrays = (MODE == MODE_SPLIT) ? 5 : (MODE == MODE_PROBE ? 3 : 2);
+	static constexpr int kArrays = (MODE == MODE_SPLIT) ? 5 : 2;
 	static constexpr int kEst = kArrays * S + 48;
-	static constexpr int kMinBlocks =
-	    (MODE == MODE_PROBE && kEst <= 96) ? 5 : (kEst <= 128 ? 4 : (kEst <= 168 ? 3 : (kEst <= 255 ? 2 : 1)));
+	static constexpr int kMinBlocks = kEst <= 128 ? 4 : (kEst <= 168 ? 3 : (kEst <= 255 ? 2 : 1));
 };
 
 template <int G, int S, int MODE>
@@ -276,13 +276,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 	const uint32_t Bp = B | (B << 16);
 	const uint32_t gm16 = p.gm2 & 0xFFFFu;
 
-	int n_items = p.n_jobs;
-	int n_short = 0;
-	if (MODE == MODE_PROBE)
-	{
-		n_short = *p.hit_count;
-		n_items = n_short + *p.hit_count_long;
-	}
+	const int n_items = p.n_jobs;
 
 	for (;;)
 	{
@@ -291,23 +285,15 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= n_items) break;
 		const bool have = base + q < n_items;
-		// PROBE: queue position -> slot (short windows were queued from the front, long ones from the back)
-		const int item = (MODE == MODE_PROBE && base + q >= n_short) ? p.n_jobs - 1 - (base + q - n_short) : base + q;
-		int jid = 0;
+		const int jid = base + q;
 		JobPair jp;
 		jp.ref_w[0] = jp.ref_w[1] = jp.read_w[0] = jp.read_w[1] = 0;
 		jp.R[0] = jp.R[1] = jp.L[0] = jp.L[1] = 0;
 		jp.out0 = jp.out1 = -1;
-		if (have)
-		{
-			jid = (MODE == MODE_PROBE) ? p.hitq[item] : item;
-			jp = p.jobs[jid];
-		}
+		if (have) jp = p.jobs[jid];
 
-		// ---- stage the reads: pool words -> 16-bit symbols -> S registers per lane (the probe sweep gets them
-		//      from the first sweep instead) ----
+		// ---- stage the reads: pool words -> 16-bit symbols -> S registers per lane ----
 		__syncwarp();
-		if (MODE != MODE_PROBE)
 		{
 			for (int w = g; w < 2 * RDW; w += G)
 			{
@@ -338,7 +324,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 #pragma unroll
 		for (int k = 0; k < S; k++)
 		{
-			rd[k] = (MODE == MODE_PROBE) ? (have ? p.rdq[((size_t)item * S + k) * G + g] : 0u) : rows[j0 + k];
+			rd[k] = rows[j0 + k];
 			// column i = 0: H(0,j) = j*gap  ->  stored value B + j*(gap - match)
 			const uint32_t v = (B + (uint32_t)(j0 + k + 1) * gm16) & 0xFFFFu;
 			F[k] = v | (v << 16);
@@ -348,67 +334,25 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		uint32_t prev = v0 | (v0 << 16); // stored value of (i-1, j0); lane 0: row 0 is H = 0 -> B
 		__syncwarp();
 
-		// ---- step window.  SIMPLE/SPLIT: the whole wavefront, steps u = 0 .. R+G-2, lane g at column
-		//      u-g.  PROBE: only the checkpoint blocks (CK steps each) in which a winning row reaches
-		//      its maximum; unless a window starts at step 0 the wavefront state is restored from the
-		//      checkpoint in front of it, separately for the two halves ----
-		constexpr int PRE = 32;                       // ring columns kept in front of a resumed window (>= G-1, two whole words)
-		static_assert(G - 1 <= PRE && PRE + CK <= CH, "ring refill schedule of a resumed window");
-		uint32_t off0 = 0, off1 = 0;                  // absolute column of relative column 0, per half
-		int pre = 0;                                  // PROBE resumed: ring index = relative column + PRE
-		int Rg = max((int)jp.R[0], (int)jp.R[1]);     // columns (from step 0) or steps (resumed) to run
+		// ---- the whole wavefront: steps u = 0 .. R+G-2, lane g at column u-g ----
+		const int Rg = max((int)jp.R[0], (int)jp.R[1]);
 		uint32_t Flast = F[S - 1];
-		bool resumed = false;
-		uint32_t en_lo = 0, en_hi = 0; // PROBE: rows of this lane that are being enumerated, per half
-		if (MODE == MODE_PROBE)
-		{
-			const uint32_t rng = have ? p.slot_rng[item] : 0u;
-			const int f0 = rng & 0xFF, l0 = (rng >> 8) & 0xFF, f1 = (rng >> 16) & 0xFF, l1 = rng >> 24;
-#pragma unroll
-			for (int k = 0; k < S; k++)
-			{
-				X[k] = have ? p.ntg[((size_t)item * S + k) * G + g] : 0x80018001u;
-				if ((X[k] & 0xFFFFu) != 0x8001u) en_lo |= 1u << k;
-				if ((X[k] >> 16) != 0x8001u) en_hi |= 1u << k;
-			}
-			if (f0 > 0 && f1 > 0)
-			{
-				resumed = true;
-				pre = PRE;
-				off0 = (uint32_t)f0 * CK;
-				off1 = (uint32_t)f1 * CK;
-				Rg = max(l0 - f0 + 1, l1 - f1 + 1) * CK; // steps
-				const size_t cb0 = ((size_t)jid * p.ckpt_blocks + (size_t)(f0 - 1)) * (S + 2);
-				const size_t cb1 = ((size_t)jid * p.ckpt_blocks + (size_t)(f1 - 1)) * (S + 2);
-#pragma unroll
-				for (int k = 0; k < S; k++)
-					F[k] = (p.ckpt[(cb0 + k) * G + g] & 0x0000FFFFu) | (p.ckpt[(cb1 + k) * G + g] & 0xFFFF0000u);
-				prev = (p.ckpt[(cb0 + S) * G + g] & 0x0000FFFFu) | (p.ckpt[(cb1 + S) * G + g] & 0xFFFF0000u);
-				Flast = (p.ckpt[(cb0 + S + 1) * G + g] & 0x0000FFFFu) | (p.ckpt[(cb1 + S + 1) * G + g] & 0xFFFF0000u);
-			}
-			else
-			{
-				// from step 0: columns up to the end of the last needed block (lane g is at column u-g)
-				Rg = have ? max(min((int)jp.R[0], (l0 + 1) * CK), min((int)jp.R[1], (l1 + 1) * CK)) : 0;
-			}
-		}
 		// steps this warp runs: the longest of its groups (every lane takes part in the shuffles)
-		int T = resumed ? Rg : Rg + G - 1;
+		int T = Rg + G - 1;
 #pragma unroll
 		for (int o = 16; o >= 1; o >>= 1) T = max(T, __shfl_xor_sync(0xffffffffu, T, o));
-		const bool ck_on = p.ckpt != nullptr && T <= 255 * CK;
+		const bool ck_on = p.ckpt != nullptr;
 
 		// ---- reference ring: two blocks of CH columns resident as 32-bit {half 1, half 0} symbol pairs; the pool words
 		//      of the next block are copied into shared memory by cp.async while the wavefront crosses the current one ----
 		const uint32_t R0 = jp.R[0], R1 = jp.R[1];
-		const uint32_t offw0 = (off0 - (uint32_t)pre) >> 4, offw1 = (off1 - (uint32_t)pre) >> 4; // first ring column, in pool words
 		uint2(*raw)[2][HG] = s_raw[warp][q];
 		// lanes 0 .. G/2-1 copy one 16-byte chunk (two pool words) each: G/4 chunks per half
 		auto issue_block = [&](int blk) {
 			if (g < HG)
 			{
 				const int h = g / (G / 4), c = g % (G / 4);
-				const uint32_t wi = (h ? offw1 : offw0) + (uint32_t)blk * HG + 2u * c;
+				const uint32_t wi = (uint32_t)blk * HG + 2u * c;
 				if (wi * 16u < (h ? R1 : R0)) cp_async_16(&raw[blk & 1][h][2 * c], p.pool + jp.ref_w[h] + wi);
 			}
 			cp_async_commit();
@@ -418,7 +362,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		auto decode_block = [&](int blk) {
 			const uint2 w0 = raw[blk & 1][0][g >> 1], w1 = raw[blk & 1][1][g >> 1];
 			const uint32_t wrel = (uint32_t)blk * HG + (uint32_t)(g >> 1);
-			const uint32_t a0 = (offw0 + wrel) * 16u, a1 = (offw1 + wrel) * 16u; // first column of the word in its reference
+			const uint32_t a0 = wrel * 16u; // first column of the word in its reference
 			const int bit0 = 8 * (g & 1);
 			constexpr int RSH = (G == 8) ? 0 : (G == 16 ? 1 : 2); // bank = 8 * (g + q * G / 8) + rotation (mod 32): distinct over the warp
 #pragma unroll
@@ -426,13 +370,12 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			{
 				const int nb = bit0 + ((n + (g >> RSH)) & 7);
 				uint32_t f0 = DFB_REF_PAD, f1 = DFB_REF_PAD;
-				if (a0 + nb < R0) f0 = decode_base(w0, jp.ref_w[0] + offw0 + wrel, nb, p.obytes);
-				if (a1 + nb < R1) f1 = decode_base(w1, jp.ref_w[1] + offw1 + wrel, nb, p.obytes);
+				if (a0 + nb < R0) f0 = decode_base(w0, jp.ref_w[0] + wrel, nb, p.obytes);
+				if (a0 + nb < R1) f1 = decode_base(w1, jp.ref_w[1] + wrel, nb, p.obytes);
 				ring[((uint32_t)blk * CH + 16u * (g >> 1) + nb) & (RING - 1)] = f0 | (f1 << 16);
 			}
 		};
-		// ring columns this warp will read: T steps, PRE columns in front of a resumed window
-		const int ring_blocks = min(2, (T + PRE + CH - 1) / CH);
+		const int ring_blocks = min(2, (T + CH - 1) / CH); // ring columns this warp will read: T steps
 		issue_block(0);
 		if (ring_blocks > 1) issue_block(1);
 		cp_async_wait_all();
@@ -445,7 +388,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 
 		uint32_t acc = 0x80008000u;
 		uint32_t Y[(MODE == MODE_SPLIT) ? S : 1];    // SPLIT: row maxima inside the current checkpoint block
-		uint32_t info[(MODE == MODE_SPLIT) ? S : 1]; // SPLIT: first/last block attaining X, per half: f_lo | l_lo<<8 | f_hi<<16 | l_hi<<24
+		uint32_t info[(MODE == MODE_SPLIT) ? S : 1]; // SPLIT: granules in which the row attains its maximum X, a 16-bit mask per half
 		if (MODE == MODE_SPLIT)
 		{
 #pragma unroll
@@ -453,7 +396,6 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		}
 		// the sweep, one checkpoint block (CK steps) at a time so that the per-block work (checkpoint,
 		// ring refill, row-maximum bookkeeping) stays out of the per-step instruction stream
-		const int act_off = resumed ? 0 : g; // lane g joins at step g unless the wavefront was restored
 		// SPLIT: steps below the shorter reference of every job pair of the warp touch real columns only (lane g is at
 		// column u-g <= u).  SIMPLE tolerates the padding columns: all steps.
 		int u_paired = T;
@@ -463,20 +405,20 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 #pragma unroll
 			for (int o = 16; o >= 1; o >>= 1) u_paired = min(u_paired, __shfl_xor_sync(0xffffffffu, u_paired, o));
 		}
-		// one step of one lane: the next reference column against the S rows of the strip.  FOLD: the new column goes
-		// into the row state here (every step of the probe; head and tail steps of the other modes)
+		// one step of one lane: the next reference column against the S rows of the strip, with an activity test (lane g
+		// joins at step g and leaves after its last column) and the new column folded into the row state at once:
+		// head and tail steps
 		auto step = [&](const int u) {
 			uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G);
 			if (g == 0) recv = Bp;
-			const int b = u - g; // relative column; absolute column = off + b
-			if ((unsigned)(u - act_off) < (unsigned)Rg)
+			const int b = u - g; // column
+			if ((unsigned)b < (unsigned)Rg)
 			{
-				const uint32_t rf = ring[(b + pre) & (RING - 1)];
+				const uint32_t rf = ring[b & (RING - 1)];
 				uint32_t left = recv;
 				uint32_t dg_in = prev;
 				uint32_t pen = 0;
-				if (MODE == MODE_SPLIT) pen = rf & 0x80008000u;
-				if (MODE == MODE_PROBE) acc = 0x80008000u;
+				if (MODE == MODE_SPLIT) pen = rf & 0x80008000u; // -32768 in a half that is past its reference end
 #pragma unroll
 				for (int k = 0; k < S; k++)
 				{
@@ -489,33 +431,9 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 					F[k] = left;
 					if (MODE == MODE_SPLIT) Y[k] = __viaddmax_s16x2(left, pen, Y[k]);
 					if (MODE == MODE_SIMPLE) acc = __viaddmax_s16x2(left, p.ck[k], acc);
-					if (MODE == MODE_PROBE) acc = __viaddmax_s16x2(left, X[k], acc);
 				}
 				prev = recv;
 				Flast = left;
-				if (MODE == MODE_PROBE)
-				{
-					// a half of acc is >= 0 only when some enabled row reached its target here
-					if ((~acc) & 0x80008000u)
-					{
-#pragma unroll
-						for (int k = 0; k < S; k++)
-						{
-							if (!(((en_lo | en_hi) >> k) & 1u)) continue;
-#pragma unroll
-							for (int h = 0; h < 2; h++)
-							{
-								if (!(((h ? en_hi : en_lo) >> k) & 1u)) continue;
-								const int f = (int)((F[k] >> (16 * h)) & 0xFFFFu);
-								const int t = (int)(short)((X[k] >> (16 * h)) & 0xFFFFu);
-								const int j = j0 + k + 1;
-								const int col = (int)(h ? off1 : off0) + b; // 0-based column in the reference
-								if (f + t == 0 && col >= 0 && col < (int)jp.R[h] && j <= (int)jp.L[h])
-									emit_probe_event(p, item, jp.out0, h, j, col, f - (int)B + p.m * j);
-							}
-						}
-					}
-				}
 			}
 		};
 		// two steps of a lane whose columns are known to be in range (every lane has joined, none has left): no
@@ -579,7 +497,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				}
 			}
 			// ring block n+1 replaces ring block n-1 half way through ring block n (n >= 1): every lane is past block
-			// n-1 by then (G-1 <= CK steps in, PRE <= CK columns ahead for a resumed window) and none has reached n+1
+			// n-1 by then (G-1 <= CK steps in) and none has reached n+1
 			if (blkno >= 3 && (blkno & 1))
 			{
 				cp_async_wait_all();
@@ -590,24 +508,21 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				issue_block(blk_next);
 			}
 			const int u_end = min(T, (blkno + 1) * CK);
-			if (MODE != MODE_PROBE)
-			{
-				// head: lanes are still joining (lane g at step g); then pairs of steps while every lane is inside the
-				// references; the steps with an activity test take the rest
-				const int u_head = min(u_end, G - 1);
+			// head: lanes are still joining (lane g at step g); then pairs of steps while every lane is inside the
+			// references; the steps with an activity test take the rest
+			const int u_head = min(u_end, G - 1);
 #pragma unroll 1
-				for (; u < u_head; u++) step(u);
-				const int u_pair_end = min(u_end, u_paired);
+			for (; u < u_head; u++) step(u);
+			const int u_pair_end = min(u_end, u_paired);
 #pragma unroll 1
-				for (; u + 1 < u_pair_end; u += 2) step_pair(u);
-			}
+			for (; u + 1 < u_pair_end; u += 2) step_pair(u);
 #pragma unroll 1
 			for (; u < u_end; u++) step(u);
 			if (MODE == MODE_SPLIT)
 			{
-				// end of a checkpoint block (or of the sweep), same step for all lanes: fold the block
-				// maxima into the row maxima and remember in which blocks each row maximum occurs
-				const uint32_t blk = (uint32_t)blkno & 0xFFu;
+				// end of a checkpoint block (or of the sweep), same step for all lanes: fold the block maxima into the
+				// row maxima and remember in which granules each row maximum occurs
+				const uint32_t bit = 1u << (blkno >> p.gran_shift);
 #pragma unroll
 				for (int k = 0; k < S; k++)
 				{
@@ -618,10 +533,10 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 					{
 						const uint32_t grew = X[k] ^ xn; // half != 0: the block maximum beats the row maximum
 						uint32_t inf = info[k];
-						if (grew & 0x0000FFFFu) inf = (inf & 0xFFFF0000u) | blk | (blk << 8);
-						else if (!(same & 0x0000FFFFu)) inf = (inf & 0xFFFF00FFu) | (blk << 8);
-						if (grew & 0xFFFF0000u) inf = (inf & 0x0000FFFFu) | (blk << 16) | (blk << 24);
-						else if (!(same & 0xFFFF0000u)) inf = (inf & 0x00FFFFFFu) | (blk << 24);
+						if (grew & 0x0000FFFFu) inf = (inf & 0xFFFF0000u) | bit;
+						else if (!(same & 0x0000FFFFu)) inf |= bit;
+						if (grew & 0xFFFF0000u) inf = (inf & 0x0000FFFFu) | (bit << 16);
+						else if (!(same & 0xFFFF0000u)) inf |= bit << 16;
 						info[k] = inf;
 					}
 					X[k] = xn;
@@ -689,7 +604,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			// second sweep (SplitReadAligner.cpp:233-269); the others emit nothing.
 			bool en_any = false;
 			uint32_t ntg[S];
-			int f0 = 255, l0 = 0, f1 = 255, l1 = 0; // checkpoint blocks the second sweep has to visit, per half
+			uint32_t gr0 = 0, gr1 = 0; // granules the second sweep has to visit, per half
 #pragma unroll
 			for (int k = 0; k < S; k++)
 			{
@@ -703,15 +618,13 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 					{
 						tlo = (0u - (X[k] & 0xFFFFu)) & 0xFFFFu;
 						en_any = true;
-						f0 = min(f0, (int)(info[k] & 0xFF));
-						l0 = max(l0, (int)((info[k] >> 8) & 0xFF));
+						gr0 |= info[k] & 0xFFFFu;
 					}
 					if (b1 > 0 && b2 > 0 && b1 + b2 == best)
 					{
 						thi = (0u - (X[k] >> 16)) & 0xFFFFu;
 						en_any = true;
-						f1 = min(f1, (int)((info[k] >> 16) & 0xFF));
-						l1 = max(l1, (int)(info[k] >> 24));
+						gr1 |= info[k] >> 16;
 					}
 				}
 				ntg[k] = tlo | (thi << 16);
@@ -719,10 +632,8 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 #pragma unroll
 			for (int o = G / 2; o >= 1; o >>= 1)
 			{
-				f0 = min(f0, __shfl_xor_sync(0xffffffffu, f0, o, G));
-				f1 = min(f1, __shfl_xor_sync(0xffffffffu, f1, o, G));
-				l0 = max(l0, __shfl_xor_sync(0xffffffffu, l0, o, G));
-				l1 = max(l1, __shfl_xor_sync(0xffffffffu, l1, o, G));
+				gr0 |= __shfl_xor_sync(0xffffffffu, gr0, o, G);
+				gr1 |= __shfl_xor_sync(0xffffffffu, gr1, o, G);
 			}
 			const uint32_t ballot = __ballot_sync(0xffffffffu, en_any);
 			const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (q * G));
@@ -733,22 +644,14 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				p.out[jp.out0] = hit ? best : 0;
 				if (group_en)
 				{
-					// one checkpoint block per half is the common case; longer windows go to the other end of the
-					// queue so that the job pairs of a probe warp sweep windows of similar length
-					f0 = min(f0, l0);
-					f1 = min(f1, l1);
-					const bool short_window = ck_on && f0 > 0 && f1 > 0 && l0 == f0 && l1 == f1;
-					slot = (short_window ? atomicAdd(p.hit_count, 1) : p.n_jobs - 1 - atomicAdd(p.hit_count_long, 1)) + p.slot_base;
+					// one granule per half is the common case; jobs with more rounds go to the other end of the queue so
+					// that the job pairs of a probe warp run equally many rounds
+					const bool one_round = ck_on && __popc(gr0) <= 1 && __popc(gr1) <= 1;
+					slot = (one_round ? atomicAdd(p.hit_count, 1) : p.n_jobs - 1 - atomicAdd(p.hit_count_long, 1)) + p.slot_base;
 					p.hitq[slot - p.slot_base] = jid;
 					p.slot_task[slot - p.slot_base] = jp.out0;
 					p.task_slot[jp.out0] = slot;
-					uint32_t rng = 0xFF00FF00u; // no checkpoints: sweep everything
-					if (ck_on)
-					{
-						if (f0 == 0 || f1 == 0) f0 = f1 = 0; // a window that starts at step 0 starts both halves there
-						rng = (uint32_t)f0 | ((uint32_t)l0 << 8) | ((uint32_t)f1 << 16) | ((uint32_t)l1 << 24);
-					}
-					p.slot_rng[slot - p.slot_base] = rng;
+					p.slot_rng[slot - p.slot_base] = gr0 | (gr1 << 16);
 					slot -= p.slot_base;
 				}
 			}
@@ -762,6 +665,255 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 					p.rdq[((size_t)slot * S + k) * G + g] = rd[k];
 				}
 			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// Probe sweep: the arg-max column sets of the winning split rows (second half of GetAlignments,
+// SplitReadAligner.cpp:229-269).  The first sweep left, per winning task, the negated row maxima of
+// its winning rows (ntg), the lanes' read symbols (rdq) and, per half, a 16-bit mask of the
+// checkpoint granules in which those rows attain their maxima.  A job is swept in rounds: round r
+// visits the r-th marked granule of either half -- the two halves of the registers resume from two
+// different checkpoints -- and records every column at which an enabled row reaches its target.
+// ------------------------------------------------------------------------------------------
+template <int S>
+struct ProbeOcc
+{
+	static constexpr int kEst = 3 * S + 44;
+	static constexpr int kMinBlocks = kEst <= 60 ? 6 : (kEst <= 100 ? 5 : (kEst <= 128 ? 4 : (kEst <= 168 ? 3 : 2)));
+};
+
+template <int G, int S>
+__global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(const __grid_constant__ FastParams p)
+{
+	constexpr int NG = 32 / G;
+	constexpr int CH = 8 * G;
+	constexpr int CK = 4 * G;
+	constexpr int RING = 2 * CH;
+	constexpr int RING_STRIDE = RING + (NG > 1 ? G : 0);
+	constexpr int HG = G / 2;
+	constexpr int PRE = 32; // ring columns in front of a round's first step (>= G-1, two whole pool words)
+	static_assert(G >= 8 && (G & (G - 1)) == 0 && G <= 32, "group size");
+	static_assert(G - 1 <= PRE && PRE + CK <= CH, "a one-block round fits one ring block");
+
+	__shared__ uint32_t s_ring[4][NG][RING_STRIDE];
+	__shared__ __align__(16) uint2 s_raw[4][NG][2][2][HG];
+
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int q = lane / G;
+	const int g = lane % G;
+	uint32_t* ring = s_ring[warp][q];
+	uint2(*raw)[2][HG] = s_raw[warp][q];
+
+	const uint32_t B = p.bias;
+	const uint32_t Bp = B | (B << 16);
+	const uint32_t gm16 = p.gm2 & 0xFFFFu;
+	const int gs = p.gran_shift;
+	const int n_short = *p.hit_count;
+	const int n_items = n_short + *p.hit_count_long;
+	const int j0 = g * S; // rows owned: j0+1 .. j0+S
+
+	for (;;)
+	{
+		int base = 0;
+		if (lane == 0) base = atomicAdd(p.cursor, NG);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (base >= n_items) break;
+		const bool have = base + q < n_items;
+		// queue position -> slot (one-round jobs were queued from the front, the others from the back)
+		const int item = (base + q >= n_short) ? p.n_jobs - 1 - (base + q - n_short) : base + q;
+		int jid = 0;
+		JobPair jp;
+		jp.ref_w[0] = jp.ref_w[1] = jp.read_w[0] = jp.read_w[1] = 0;
+		jp.R[0] = jp.R[1] = jp.L[0] = jp.L[1] = 0;
+		jp.out0 = jp.out1 = -1;
+		uint32_t m0 = 0, m1 = 0;
+		if (have)
+		{
+			jid = p.hitq[item];
+			jp = p.jobs[jid];
+			const uint32_t rng = p.slot_rng[item];
+			m0 = rng & 0xFFFFu;
+			m1 = rng >> 16;
+		}
+		uint32_t rd[S], X[S]; // read symbols; negated targets of the rows being enumerated (0x8001: row not enumerated)
+#pragma unroll
+		for (int k = 0; k < S; k++)
+		{
+			rd[k] = have ? p.rdq[((size_t)item * S + k) * G + g] : 0u;
+			X[k] = have ? p.ntg[((size_t)item * S + k) * G + g] : 0x80018001u;
+		}
+		// without checkpoints (the class' references are too long to keep them): one round over the whole wavefront
+		const bool whole = p.ckpt == nullptr;
+		int Tr = CK << gs; // steps per round
+		if (whole)
+		{
+			m0 = m1 = have ? 1u : 0u;
+			Tr = max((int)jp.R[0], (int)jp.R[1]) + G - 1;
+		}
+		int rounds = max(__popc(m0), __popc(m1));
+#pragma unroll
+		for (int o = 16; o >= 1; o >>= 1)
+		{
+			rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, o));
+			Tr = max(Tr, __shfl_xor_sync(0xffffffffu, Tr, o));
+		}
+
+		for (int r = 0; r < rounds; r++)
+		{
+			// the granule either half visits in this round; a half that has none left idles on padding
+			const bool on0 = r < __popc(m0), on1 = r < __popc(m1);
+			const int b0 = on0 ? (int)(__fns(m0, 0, r + 1) << gs) : 0; // first checkpoint block of the granule
+			const int b1 = on1 ? (int)(__fns(m1, 0, r + 1) << gs) : 0;
+			const uint32_t R0 = on0 ? jp.R[0] : 0u, R1 = on1 ? jp.R[1] : 0u;
+			// ring index = relative column + PRE; relative column 0 = absolute column b * CK of the half
+			const int c0 = b0 * CK - PRE, c1 = b1 * CK - PRE; // absolute column of ring column 0 (negative in block 0)
+			auto issue_block = [&](int blk) {
+				if (g < HG)
+				{
+					const int h = g / (G / 4), c = g % (G / 4);
+					const int wi = ((h ? c1 : c0) >> 4) + blk * HG + 2 * c; // (c0, c1 are multiples of 32: arithmetic shift is exact)
+					if (wi >= 0 && (uint32_t)wi * 16u < (h ? R1 : R0)) cp_async_16(&raw[blk & 1][h][2 * c], p.pool + jp.ref_w[h] + wi);
+				}
+				cp_async_commit();
+			};
+			auto decode_block = [&](int blk) {
+				const uint2 w0 = raw[blk & 1][0][g >> 1], w1 = raw[blk & 1][1][g >> 1];
+				const int wrel = blk * HG + (g >> 1);
+				const int wi0 = (c0 >> 4) + wrel, wi1 = (c1 >> 4) + wrel;
+				const int bit0 = 8 * (g & 1);
+				constexpr int RSH = (G == 8) ? 0 : (G == 16 ? 1 : 2);
+#pragma unroll
+				for (int n = 0; n < 8; n++)
+				{
+					const int nb = bit0 + ((n + (g >> RSH)) & 7);
+					uint32_t f0 = DFB_REF_PAD, f1 = DFB_REF_PAD;
+					if (wi0 >= 0 && (uint32_t)(wi0 * 16 + nb) < R0) f0 = decode_base(w0, jp.ref_w[0] + (uint32_t)wi0, nb, p.obytes);
+					if (wi1 >= 0 && (uint32_t)(wi1 * 16 + nb) < R1) f1 = decode_base(w1, jp.ref_w[1] + (uint32_t)wi1, nb, p.obytes);
+					ring[((uint32_t)blk * CH + 16u * (g >> 1) + nb) & (RING - 1)] = f0 | (f1 << 16);
+				}
+			};
+			__syncwarp(); // (the previous round's ring reads are over)
+			const int ring_blocks = min(2, (Tr + PRE + CH - 1) / CH);
+			issue_block(0);
+			if (ring_blocks > 1) issue_block(1);
+
+			// wavefront state in front of the round's first step: the checkpoint of the block before it, or the
+			// boundary column H(0,j) = j*gap (stored B + j*(gap - match)) in block 0 -- per half
+			uint32_t F[S], prev, Flast;
+			const uint32_t keep0 = (on0 && b0 > 0) ? 0x0000FFFFu : 0u, keep1 = (on1 && b1 > 0) ? 0xFFFF0000u : 0u;
+			const uint32_t init0 = (on0 && b0 == 0) ? 0x0000FFFFu : 0u, init1 = (on1 && b1 == 0) ? 0xFFFF0000u : 0u;
+			const uint32_t jm = whole ? 0u : (init0 | init1); // halves whose lanes join one by one (lane g at step g)
+			const size_t cb0 = ((size_t)jid * p.ckpt_blocks + (size_t)max(b0 - 1, 0)) * (S + 2);
+			const size_t cb1 = ((size_t)jid * p.ckpt_blocks + (size_t)max(b1 - 1, 0)) * (S + 2);
+			auto boundary = [&](int j) -> uint32_t { // stored value of column 0, row j, in both halves
+				const uint32_t v = (B + (uint32_t)j * gm16) & 0xFFFFu;
+				return v | (v << 16);
+			};
+#pragma unroll
+			for (int k = 0; k < S + 2; k++)
+			{
+				uint32_t v = 0;
+				if (keep0) v |= p.ckpt[(cb0 + k) * G + g] & keep0;
+				if (keep1) v |= p.ckpt[(cb1 + k) * G + g] & keep1;
+				// k < S: row j0+k+1; k = S: the diagonal input (row j0); k = S+1: the hand-off value (row j0+S)
+				v |= boundary(k < S ? j0 + k + 1 : (k == S ? j0 : j0 + S)) & (init0 | init1);
+				if (k < S) F[k] = v;
+				else if (k == S) prev = v;
+				else Flast = v;
+			}
+			cp_async_wait_all();
+			__syncwarp();
+			decode_block(0);
+			if (ring_blocks > 1) decode_block(1);
+			__syncwarp();
+			int blk_next = 2;
+			if (Tr + PRE > 2 * CH) issue_block(2);
+
+			// whole-wavefront rounds: lane g joins at step g and leaves after its last column (activity test);
+			// checkpointed rounds: every lane runs every step, a half that starts in block 0 is put back to the
+			// boundary column after each step its lane has not joined yet
+			const int act_off = whole ? g : 0;
+			const int Rg = whole ? max((int)jp.R[0], (int)jp.R[1]) : Tr;
+			auto step = [&](const int u) {
+				uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G);
+				if (g == 0) recv = Bp;
+				const int b = u - g;
+				if ((unsigned)(u - act_off) < (unsigned)Rg)
+				{
+					const uint32_t rf = ring[(b + PRE) & (RING - 1)];
+					uint32_t left = recv;
+					uint32_t dg_in = prev;
+					uint32_t acc = 0x80008000u;
+#pragma unroll
+					for (int k = 0; k < S; k++)
+					{
+						const uint32_t d = __viaddmin_u16x2(rd[k], rf, 0x00010001u);
+						const uint32_t dg = d * p.xm + dg_in;
+						dg_in = F[k];
+						const uint32_t e = __viaddmax_s16x2(F[k], p.g2, dg);
+						left = __viaddmax_s16x2(left, p.gm2, e);
+						F[k] = left;
+						acc = __viaddmax_s16x2(left, X[k], acc);
+					}
+					prev = recv;
+					Flast = left;
+					// a half of acc is >= 0 only when some enabled row reached its target here
+					if ((~acc) & 0x80008000u)
+					{
+#pragma unroll
+						for (int k = 0; k < S; k++)
+						{
+							if (X[k] == 0x80018001u) continue;
+#pragma unroll
+							for (int h = 0; h < 2; h++)
+							{
+								const int f = (int)((F[k] >> (16 * h)) & 0xFFFFu);
+								const int t = (int)(short)((X[k] >> (16 * h)) & 0xFFFFu);
+								if (t == -32767 || !(h ? on1 : on0)) continue;
+								const int j = j0 + k + 1;
+								const int col = (h ? b1 : b0) * CK + b; // 0-based column in the reference
+								if (f + t == 0 && col >= 0 && col < (int)jp.R[h] && j <= (int)jp.L[h])
+									emit_probe_event(p, item, jp.out0, h, j, col, f - (int)B + p.m * j);
+							}
+						}
+					}
+				}
+			};
+			int u = 0;
+			for (int blkno = 0; u < Tr; blkno++)
+			{
+				if (blkno >= 3 && (blkno & 1))
+				{
+					cp_async_wait_all();
+					__syncwarp();
+					decode_block(blk_next);
+					blk_next++;
+					__syncwarp();
+					issue_block(blk_next);
+				}
+				const int u_end = min(Tr, (blkno + 1) * CK);
+				if (blkno == 0 && jm)
+				{
+#pragma unroll 1
+					for (; u < min(u_end, G - 1); u++)
+					{
+						step(u);
+						if (u < g)
+						{
+#pragma unroll
+							for (int k = 0; k < S; k++) F[k] = (F[k] & ~jm) | (boundary(j0 + k + 1) & jm);
+							prev = (prev & ~jm) | (boundary(j0) & jm);
+							Flast = (Flast & ~jm) | (boundary(j0 + S) & jm);
+						}
+					}
+				}
+#pragma unroll 1
+				for (; u < u_end; u++) step(u);
+			}
+			cp_async_wait_all();
 		}
 	}
 }
