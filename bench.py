@@ -182,6 +182,25 @@ def run_reference_arm(args):
 # our arm
 # --------------------------------------------------------------------------------------------
 
+def exception_words(seq_bytes, seq_off, reverse=False):
+    """16-base words of a CSR byte table that hold a byte other than A, C, G, T (the pack kernel writes a 16-byte raw
+    copy only for those).  `reverse`: words of the reversed copies."""
+    off = np.asarray(seq_off, dtype=np.int64)
+    lens = off[1:] - off[:-1]
+    if lens.size == 0 or int(lens.max()) == 0:
+        return 0
+    bad = ~np.isin(np.asarray(seq_bytes), np.frombuffer(b"ACGT", dtype=np.uint8))
+    if not bad.any():
+        return 0
+    idx = np.nonzero(bad)[0]
+    seq = np.searchsorted(off, idx, side="right") - 1
+    pos = idx - off[seq]
+    if reverse:
+        pos = lens[seq] - 1 - pos
+    words_before = np.concatenate([[0], np.cumsum((lens + 15) // 16)])
+    return int(np.unique(words_before[seq] + pos // 16).size)
+
+
 def pinned(arr):
     import torch
     t = torch.empty(arr.shape, dtype=getattr(torch, str(arr.dtype)), pin_memory=True)
@@ -275,6 +294,143 @@ def measure_local(ctx, stream, args, R=2001, L=100, n_refs=10000, n_tasks=None):
             "e2e_ms": e2e_ms, "first_call_ms": (t1 - t0) * 1e3, "kernel_launches": int(st["kernel_launches"])}
 
 
+def measure_sharded(aligner, args, rank, world, barrier):
+    """The path as the north star partitions it: ONE fixed batch (strong scaling), its tasks dealt to the ranks by
+    candidate cluster (defuse_b200.sharding, LPT on DP cells, window table replicated), every rank aligns its shard
+    through the C ABI from pinned host buffers, rank 0 gathers and merges the rows back into the batch's task order --
+    the reference's emission order (SplitAlignment.cpp:271-301; fan-out + ordered merge: defuse_run.pl:518-533).
+    The digest of the merged result does not depend on the number of shards: compare it across the N of a scaling run."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    import defuse_b200 as d
+    import synth
+    from defuse_b200 import sharding
+    n_clusters, per = args.shard_clusters, args.tasks_per_cluster
+    w = synth.split_workload(args.seed + 77, n_clusters, per, 100, 320, 360)   # the same batch on every rank
+    n, L = w["n_tasks"], w["L"]
+    tc64 = w["task_cluster"].astype(np.int64)
+    cost = L * (w["ref_off"][2 * tc64 + 2] - w["ref_off"][2 * tc64])
+    shards, _ = sharding.shard_tasks(w["task_cluster"], cost, n_clusters, world)
+    mine = shards[rank]
+    reads2d = w["read_bytes"].reshape(n, L)
+    keep, host = [], {}
+    for k, a in (("ref_bytes", w["ref_bytes"]), ("ref_off", w["ref_off"]),
+                 ("read_bytes", np.ascontiguousarray(reads2d[mine]).reshape(-1)),
+                 ("read_off", np.arange(len(mine) + 1, dtype=np.int64) * L),
+                 ("task_cluster", w["task_cluster"][mine]), ("task_read", np.arange(len(mine), dtype=np.int32)),
+                 ("min_score", w["min_score"][mine])):
+        host[k], t = pinned(a)
+        keep.append(t)
+    refs = d.SeqTable(host["ref_bytes"], host["ref_off"])
+    reads = d.SeqTable(host["read_bytes"], host["read_off"])
+    times = []
+    res = None
+    for rep in range(3):   # first one warms the pools up
+        barrier()
+        t0 = time.perf_counter()
+        res = aligner.align_batch(refs, reads, host["task_cluster"], host["task_read"], host["min_score"], copy=False)
+        torch.cuda.synchronize()
+        times.append((time.perf_counter() - t0) * 1e3)
+    align_ms = min(times[1:])
+    # gather on rank 0: best per task, rows (task renumbered to the batch's numbering), columns
+    t0 = time.perf_counter()
+    rows = np.array(res.rows, copy=True)
+    rows["task"] = mine[rows["task"]]
+    cols = np.asarray(res.cols)
+    parts = {"idx": mine.astype(np.int64), "best": np.asarray(res.best, dtype=np.int32), "rows": rows.view(np.uint8).reshape(-1), "cols": cols.astype(np.int32)}
+    gathered = {}
+    for key, a in parts.items():
+        a = np.ascontiguousarray(a)
+        if world == 1:
+            gathered[key] = [a]
+            continue
+        size = torch.tensor([a.nbytes], dtype=torch.int64, device="cuda")
+        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(sizes, size)
+        sizes = [int(x.item()) for x in sizes]
+        buf = torch.zeros(max(max(sizes), 1), dtype=torch.uint8, device="cuda")
+        buf[:a.nbytes] = torch.from_numpy(a.view(np.uint8).reshape(-1)).cuda()
+        out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, out, dst=0)
+        if rank == 0:
+            gathered[key] = [out[r][:sizes[r]].cpu().numpy().view(a.dtype) for r in range(world)]
+    result = None
+    if rank == 0:
+        best = sharding.merge_by_task(n, zip(gathered["idx"], gathered["best"]))
+        all_rows = [g.view(rows.dtype) for g in gathered["rows"]]
+        col_base = np.concatenate([[0], np.cumsum([len(c) for c in gathered["cols"]])])
+        for r, g in enumerate(all_rows):
+            g["col_begin"] += col_base[r]
+        merged = np.concatenate(all_rows)
+        all_cols = np.concatenate(gathered["cols"])
+        order = np.argsort(merged["task"], kind="stable")   # rows of a task stay in their (ascending split row) order
+        merged = merged[order]
+        h = hashlib.sha1()
+        h.update(best.tobytes())
+        for f in ("task", "read_split", "score1", "score2", "n1", "n2"):
+            h.update(np.ascontiguousarray(merged[f]).tobytes())
+        # columns in merged row order
+        width = merged["n1"].astype(np.int64) + merged["n2"]
+        starts = np.repeat(merged["col_begin"].astype(np.int64), width)
+        within = np.arange(int(width.sum())) - np.repeat(np.concatenate([[0], np.cumsum(width)[:-1]]), width)
+        h.update(np.ascontiguousarray(all_cols[starts + within]).tobytes())
+        merge_ms = (time.perf_counter() - t0) * 1e3
+        loads = np.array([cost[g].sum() for g in gathered["idx"]], dtype=np.float64)
+        result = {"digest": h.hexdigest(), "merge_ms": merge_ms, "rows": int(len(merged)), "tasks": int(n),
+                  "load_imbalance": float(loads.max() / loads.mean())}
+    t = torch.tensor([align_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        result.update({"workload": "one batch of %d clusters x %d candidate reads = %d tasks in total, dealt to %d rank(s) by cluster"
+                                   % (n_clusters, per, n, world),
+                       "scaling": "strong", "align_ms_max_over_ranks": float(t[0]),
+                       "e2e_gcups": w["cells"] / (float(t[0]) * 1e-3) / 1e9,
+                       "e2e_gcups_incl_merge": w["cells"] / ((float(t[0]) + result["merge_ms"]) * 1e-3) / 1e9})
+    return result
+
+
+def measure_tool(args):
+    """BASELINE's second unit, input read pairs per second of process wall time: the dosplitalign drop-in on
+    generated files of one (scaled-down) fastq split, and the compiled reference tool on a stated sample of the same
+    generator; outputs compared byte for byte on the sample."""
+    from synth import files
+    import oracle  # baseline leg: the compiled reference tool
+    bin_dir = os.path.join(ROOT, "defuse_b200", "bin")
+    ours = os.path.join(bin_dir, "dosplitalign")
+    if not os.path.exists(ours):
+        return {"unavailable": "defuse_b200/bin/dosplitalign not built"}
+    out = {"read_pairs": args.tool_clusters * 100, "clusters": args.tool_clusters}
+    with tempfile.TemporaryDirectory() as d:
+        a = files.make_split_dataset(os.path.join(d, "s"), seed=3, n_clusters=args.tool_clusters, pairs_per_cluster=100,
+                                     n_chrom=8, genes_per_chrom=40)
+        res = os.path.join(d, "s", "ours.tmp")
+        runs = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            p = subprocess.run([ours] + a + ["-a", res], capture_output=True)
+            runs.append(time.perf_counter() - t0)
+            if p.returncode != 0:
+                return {"unavailable": "dosplitalign failed: " + p.stderr.decode()[-300:]}
+        out.update({"seconds": min(runs), "runs_s": runs, "read_pairs_per_s": out["read_pairs"] / min(runs),
+                    "records": sum(1 for _ in open(res))})
+        ref = oracle.ref_tool("ref_dosplitalign")
+        if ref:
+            sub_c = max(20, args.tool_clusters // 50)
+            sa = files.make_split_dataset(os.path.join(d, "r"), seed=3, n_clusters=sub_c, pairs_per_cluster=100, n_chrom=8,
+                                          genes_per_chrom=40)
+            rres, ores = os.path.join(d, "r", "ref.tmp"), os.path.join(d, "r", "ours.tmp")
+            t0 = time.perf_counter()
+            subprocess.run([ref] + sa + ["-a", rres], check=True, capture_output=True)
+            ref_s = time.perf_counter() - t0
+            subprocess.run([ours] + sa + ["-a", ores], check=True, capture_output=True)
+            out["reference_tool"] = {"read_pairs": sub_c * 100, "seconds": ref_s, "read_pairs_per_s": sub_c * 100 / ref_s,
+                                     "cores": 1, "identical_output": open(rres, "rb").read() == open(ores, "rb").read(),
+                                     "sample": "%d of the %d clusters of the same generator" % (sub_c, args.tool_clusters)}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -355,7 +511,7 @@ def run_ours(args):
 
     # ---- end to end through the C ABI with host buffers ----
     e2e_ms = []
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = max(1, min(args.steps, args.e2e_steps or args.steps))
     import resource
     cpu_ms = []
     for s in range(1 + e2e_steps):  # first one is the warm-up
@@ -371,6 +527,7 @@ def run_ours(args):
             cpu_ms.append(((ru1.ru_utime - ru0.ru_utime) + (ru1.ru_stime - ru0.ru_stime)) * 1e3)  # all threads of this rank
     assert (r2.best == best_resident).all() and len(r2.rows) == n_rows
     clocks = sampler.stop() if rank == 0 else None
+    sharded = None if args.no_sharded else measure_sharded(aligner, args, rank, world, barrier)
 
     t = torch.tensor([ms_total, float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -391,11 +548,12 @@ def run_ours(args):
         peak_gcups = p_int_lane * 2.0 / 6.0 / 1e9      # 6 INT issues per s16x2 vector of 2 cells
         k_ms = float(np.mean(sweep_ms))
         achieved = cells_rank / (k_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, ncu = None, {}
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             try:
-                per_task = json.load(open(tpath)).get("dp_fast_kernel_split_dram_bytes_per_task")
+                ncu = json.load(open(tpath))
+                per_task = ncu.get("dp_fast_kernel_split_dram_bytes_per_task")
                 traffic = per_task * st["n_tasks"] if per_task else None  # ncu capture scaled to this launch's task count
             except Exception:
                 traffic = None
@@ -405,7 +563,11 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        pack_bytes = st["raw_bytes"] + st["packed_bytes"] * 3   # read raw; write 8 B codes+mask and 16 B raw copy per 16 bases
+        # what the pack kernels move: every raw byte read once per stored copy (window 2 of a cluster reversed, reads
+        # forward and reversed), 8 B {codes, mask} written per 16-base word, 16 B raw copy only for words with an exception
+        n_exc = (exception_words(w["ref_bytes"], w["ref_off"]) + exception_words(w["read_bytes"], w["read_off"])
+                 + exception_words(w["read_bytes"], w["read_off"], reverse=True))
+        pack_bytes = st["raw_bytes"] + st["packed_bytes"] + 16 * n_exc
         pack_gbs = pack_bytes / (st["ms_pack"] * 1e-3) / 1e9 if st["ms_pack"] > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -425,16 +587,28 @@ def run_ours(args):
                          "peak_source": "measured now: VIADDMNMX.S16x2 issue rate %.1f Gwarp-instr/s x 32 lanes x 2 cells / 6 issues"
                                         % (rate / 1e9),
                          "kernel_ms": k_ms, "probe_sweep_ms": float(np.mean(probe_ms)),
-                         "step_frac_incl_probe": value / world / peak_gcups},
+                         "step_frac_incl_probe": value / world / peak_gcups,
+                         # the survey's 6-issue definition is generous: the steady-state loop needs 3.5 ALU-pipe issues per
+                         # register pair of cells (indicator, two maxima, half a three-input sink), so this is the fraction
+                         # of the kernel's own floor -- the number that says how much is left
+                         "frac_own_minimum": achieved / (p_int_lane * 2.0 / 3.5 / 1e9),
+                         "own_minimum_gcups": p_int_lane * 2.0 / 3.5 / 1e9,
+                         "ncu_alu_pipe_pct": ncu.get("dp_fast_kernel_split_alu_pipe_pct"),
+                         "ncu_capture": ncu.get("capture")},
             "roofline_staging": {"bound": "hbm", "kernel": "pack_kernel", "achieved": pack_gbs, "peak": hbm_peak,
                                  "unit": "GB/s", "frac": (pack_gbs / hbm_peak) if pack_gbs else None,
                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                                 "bytes": pack_bytes, "ms": st["ms_pack"]},
+                                 "bytes": pack_bytes, "ms": st["ms_pack"], "exception_words": n_exc,
+                                 "bytes_are": "raw bytes read once per stored copy + 8 B per 16-base word + 16 B per exception word"},
             "clocks": clocks,
             "results": {"tasks_with_split": n_hit, "winning_rows": n_rows, "probe_jobs": int(st["probe_jobs"]),
                         "events": int(st["events"])},
             "device": info["name"],
         }
+        if sharded:
+            line["sharded_merge"] = sharded
+        if world == 1 and not args.no_secondary:
+            line["tool_dosplitalign"] = measure_tool(args)
         if world == 1 and not args.no_secondary:
             line["secondary"] = {"localalign_config2": measure_local(ctx, stream, args),
                                  "matealign_config4": measure_local(ctx, stream, args, R=1001, L=150, n_refs=200000,
@@ -447,6 +621,10 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": g, "unit": UNIT, "cores": threads, "kind": kind, "tasks_per_s": tps,
                                     "seconds": dt,
                                     "sample": "first %d tasks of the same workload (%d per host thread)" % (min(n, w["n_tasks"]), args.cpu_baseline_tasks_per_core)}
+            # also one process on one core (the reference tools are single-threaded)
+            g1, tps1, dt1, _ = cpu_split_throughput(w, max(1, args.cpu_baseline_tasks_per_core // 3), 1)
+            line["cpu_baseline"]["one_core"] = {"value": g1, "unit": UNIT, "cores": 1, "tasks_per_s": tps1, "seconds": dt1,
+                                                "sample": "first %d tasks of the same workload" % max(1, args.cpu_baseline_tasks_per_core // 3)}
         args.out.write(json.dumps(line) + "\n")
         args.out.flush()
     plan.close()
@@ -473,12 +651,15 @@ def main():
     ap.add_argument("--clusters", type=int, default=20000)
     ap.add_argument("--tasks-per-cluster", type=int, default=100)
     ap.add_argument("--seed", type=int, default=3)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=0)                        # 0: as many as --steps
     ap.add_argument("--ref-tasks-per-core", type=int, default=2000)            # reference arm: tasks per thread per step
     ap.add_argument("--cpu-baseline-tasks-per-core", type=int, default=14000)  # cpu_baseline leg of our arm (one sample)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--local-tasks", type=int, default=1000000)
+    ap.add_argument("--no-sharded", action="store_true")
+    ap.add_argument("--shard-clusters", type=int, default=8000)                # sharded_merge leg: clusters of the ONE batch all ranks share
+    ap.add_argument("--tool-clusters", type=int, default=2000)                 # tool leg: clusters (x 100 read pairs) of the generated split
     args = ap.parse_args()
     args.out = _claim_stdout()
     if args.impl == "reference":

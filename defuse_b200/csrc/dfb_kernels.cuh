@@ -765,8 +765,10 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 		{
 			// the granule either half visits in this round; a half that has none left idles on padding
 			const bool on0 = r < __popc(m0), on1 = r < __popc(m1);
-			const int b0 = on0 ? (int)(__fns(m0, 0, r + 1) << gs) : 0; // first checkpoint block of the granule
-			const int b1 = on1 ? (int)(__fns(m1, 0, r + 1) << gs) : 0;
+			uint32_t mr0 = m0, mr1 = m1; // masks without their r lowest set bits
+			for (int i = 0; i < r; i++) { mr0 &= mr0 - 1; mr1 &= mr1 - 1; }
+			const int b0 = on0 ? ((__ffs(mr0) - 1) << gs) : 0; // first checkpoint block of the granule
+			const int b1 = on1 ? ((__ffs(mr1) - 1) << gs) : 0;
 			const uint32_t R0 = on0 ? jp.R[0] : 0u, R1 = on1 ? jp.R[1] : 0u;
 			// ring index = relative column + PRE; relative column 0 = absolute column b * CK of the half
 			const int c0 = b0 * CK - PRE, c1 = b1 * CK - PRE; // absolute column of ring column 0 (negative in block 0)
@@ -803,9 +805,12 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 			// wavefront state in front of the round's first step: the checkpoint of the block before it, or the
 			// boundary column H(0,j) = j*gap (stored B + j*(gap - match)) in block 0 -- per half
 			uint32_t F[S], prev, Flast;
+			// (an idle half starts from the boundary column too: every field must stay a valid stored value, the 32-bit
+			// diagonal IMAD borrows from the other half otherwise)
 			const uint32_t keep0 = (on0 && b0 > 0) ? 0x0000FFFFu : 0u, keep1 = (on1 && b1 > 0) ? 0xFFFF0000u : 0u;
-			const uint32_t init0 = (on0 && b0 == 0) ? 0x0000FFFFu : 0u, init1 = (on1 && b1 == 0) ? 0xFFFF0000u : 0u;
-			const uint32_t jm = whole ? 0u : (init0 | init1); // halves whose lanes join one by one (lane g at step g)
+			const uint32_t init0 = keep0 ^ 0x0000FFFFu, init1 = keep1 ^ 0xFFFF0000u;
+			// halves whose lanes join one by one (lane g at step g)
+			const uint32_t jm = whole ? 0u : (((on0 && b0 == 0) ? 0x0000FFFFu : 0u) | ((on1 && b1 == 0) ? 0xFFFF0000u : 0u));
 			const size_t cb0 = ((size_t)jid * p.ckpt_blocks + (size_t)max(b0 - 1, 0)) * (S + 2);
 			const size_t cb1 = ((size_t)jid * p.ckpt_blocks + (size_t)max(b1 - 1, 0)) * (S + 2);
 			auto boundary = [&](int j) -> uint32_t { // stored value of column 0, row j, in both halves

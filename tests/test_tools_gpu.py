@@ -116,6 +116,44 @@ def test_dosplitalign_sharded_over_contexts(oracle_mod, tmp_path, devices):
         assert open(ours).read() == open(theirs).read()
 
 
+def _n_gpus():
+    import defuse_b200
+    return max(0, defuse_b200.load_library().dfb_device_count())
+
+
+@pytest.mark.parametrize("devices", ["0,1", "all"])
+def test_dosplitalign_sharded_over_distinct_gpus(oracle_mod, tmp_path, devices):
+    """The partition-by-cluster + host-merge path on MORE THAN ONE physical GPU (needs `gpurun --gpus 2` or more; skipped
+    on a one-GPU box): a fastq split large enough for every device to get work, its output compared byte for byte with
+    the one-GPU run and, on a sample of the same generator, with the compiled reference tool
+    (fan-out + ordered merge: scripts/defuse_run.pl:518-533; emission order: tools/SplitAlignment.cpp:271-301)."""
+    from synth import files
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip("one GPU visible: the distinct-ordinal path needs at least two")
+    d = str(tmp_path / "big")
+    args = files.make_split_dataset(d, seed=51, n_clusters=1500, pairs_per_cluster=100, n_chrom=8, genes_per_chrom=40)
+    one, many = os.path.join(d, "one.tmp"), os.path.join(d, "many.tmp")
+    _run([os.path.join(BIN, "dosplitalign")] + args + ["-a", one], env={"DFB_DEVICES": "0"})
+    p = subprocess.run([os.path.join(BIN, "dosplitalign")] + args + ["-a", many], env=dict(os.environ, DFB_DEVICES=devices, DFB_TRACE="1"),
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    a, b = open(one, "rb").read(), open(many, "rb").read()
+    assert a.count(b"\n") > 50000
+    assert a == b
+    # every named device did work (the tool's trace names the contexts it created)
+    trace = p.stderr.decode()
+    assert ("%d device" % (2 if devices == "0,1" else n)) in trace or "devices" in trace, trace[-1500:]
+    ref = oracle_mod.ref_tool("ref_dosplitalign")
+    if ref:
+        s = str(tmp_path / "sample")
+        sargs = files.make_split_dataset(s, seed=52, n_clusters=200, pairs_per_cluster=80, n_chrom=8, genes_per_chrom=40)
+        ours, theirs = os.path.join(s, "ours.tmp"), os.path.join(s, "ref.tmp")
+        _run([os.path.join(BIN, "dosplitalign")] + sargs + ["-a", ours], env={"DFB_DEVICES": devices})
+        _run([ref] + sargs + ["-a", theirs])
+        assert open(ours, "rb").read() == open(theirs, "rb").read()
+
+
 def test_tools_with_many_small_batches(oracle_mod, tmp_path):
     """The tools flush work to the GPU in batches (1 M tasks by default); DFB_TOOL_BATCH forces many small batches on
     small inputs.  Output bytes must not depend on the batch size."""
