@@ -7,7 +7,7 @@
 //    back to the driver between batches); host-built arrays are written straight into a
 //    grow-only pinned staging buffer, results land in another one;
 //  * jobs are ordered by one counting sort (kernel class, reference length), O(n);
-//  * the probe sweep leaves its arg-max columns in fixed 64-byte regions per winning task,
+//  * the probe sweep leaves its arg-max columns in fixed 128-byte regions per winning task,
 //    so the host only has to order a handful of entries per task; that assembly is
 //    spread over host threads.
 #include "../../include/defuse_b200.h"
@@ -1921,7 +1921,7 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
                                  const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
                                  const int32_t* task_min_score, int64_t n_tasks, int32_t* out_best)
 {
-	const int K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), n_tasks / 280000));
+	const int K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), n_tasks / 250000));
 	std::vector<dfb_plan*> plans((size_t)K, nullptr);
 	// chunk boundaries: short chunks in front put the GPU to work early, chunks that taper off at the end keep the part
 	// of the result assembly that nothing overlaps small (lane 2 finishes chunk k while the GPU runs chunk k+1); the
@@ -1929,7 +1929,18 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	std::vector<int64_t> t0((size_t)K + 1);
 	{
 		std::vector<double> weight((size_t)K, 1.0);
-		if (K >= 6)
+		if (K >= 8)
+		{
+			// the fetch lane needs about 0.8 of a chunk's GPU time for that chunk: a tail that shrinks by no more than
+			// that factor per chunk keeps it from falling behind, so only the last, smallest chunk's fetch is left uncovered
+			weight[0] = 0.3;
+			weight[1] = 0.7;
+			weight[(size_t)K - 4] = 0.8;
+			weight[(size_t)K - 3] = 0.62;
+			weight[(size_t)K - 2] = 0.48;
+			weight[(size_t)K - 1] = 0.36;
+		}
+		else if (K >= 6)
 		{
 			weight[0] = 0.25;
 			weight[1] = 0.6;

@@ -1,15 +1,15 @@
 // Result assembly on the GPU: the second half of SplitReadAligner::GetAlignments (tools/SplitReadAligner.cpp:229-285)
-// for the common task -- at most DFB_SLOT_EVENTS arg-max columns, all of them in the task's fixed 64-byte region
+// for the common task -- at most DFB_SLOT_EVENTS arg-max columns, all of them in the task's fixed 128-byte region
 // left by the probe sweep.  The kernels order those columns the way GetAlignments walks them (matrix, row, column),
 // pair every winning row a of matrix 1 with row L-a of matrix 2 and write the dfb_split_row records and their column
 // lists in TASK ORDER into two dense arrays, so that the host only copies them back.  Tasks whose columns spilled into
-// the overflow list (tie-heavy ones; about 1 % of a dosplitalign batch) are left to the host: their region entries
+// the overflow list (tie-heavy ones; a fraction of a percent of a dosplitalign batch) are left to the host: their region entries
 // are appended to that list here, which makes the list self-contained.
 //
 //   asm_count_kernel   rows / columns per task -> sums per block of 256 tasks
 //   asm_scan_kernel    exclusive scan of the block sums (one block), totals
 //   asm_write_kernel   per-task offsets by an in-block scan, records written
-// HBM-bound and tiny next to the sweeps: 64 B read and <= 160 B written per winning task.
+// HBM-bound and tiny next to the sweeps: 128 B read and <= 320 B written per winning task.
 #pragma once
 
 namespace dfb

@@ -189,7 +189,7 @@ struct FastParams
 	uint32_t ck[32]; // SIMPLE: m*(k+1) in both halves
 };
 
-#define DFB_SLOT_EVENTS 8
+#define DFB_SLOT_EVENTS 16
 
 // Symbols in shared memory and registers: the raw byte of a base in a 16-bit field (equality of symbols is equality
 // of bytes: SplitReadAligner.cpp:51), and two padding values that equal nothing.
@@ -232,6 +232,56 @@ __device__ __noinline__ void emit_probe_event(const FastParams& p, int item, int
 		ev.col = col + 1;
 		ev.score = score;
 		p.events[idx] = ev;
+	}
+}
+
+// Decodes one ring block (8G reference columns of both halves) from the raw pool words cp.async left in shared memory
+// into 32-bit {half 1, half 0} symbol pairs.  Lane g owns columns 8g .. 8g+7 of the block and stores them in an order
+// rotated by the lane, so that the 32 lanes of the warp hit 32 different banks.  cw0 / cw1: pool word of ring column 0
+// in either half's reference (negative in front of the reference: those columns are padding).  Out of line: three call
+// sites per kernel, and the instruction cache is what short probe rounds wait for.
+template <int G>
+__device__ __noinline__ void ring_decode_block(uint32_t* ring, const uint2* raw_slot, int blk, int cw0, int cw1, uint32_t R0, uint32_t R1,
+                                               uint32_t ref_w0, uint32_t ref_w1, const uint8_t* __restrict__ obytes, int g)
+{
+	constexpr int HG = G / 2, CH = 8 * G, RING = 2 * CH;
+	constexpr int RSH = (G == 8) ? 0 : (G == 16 ? 1 : 2); // bank = 8 * (g + q * G / 8) + rotation (mod 32): distinct over the warp
+	const uint2 w0 = raw_slot[g >> 1], w1 = raw_slot[HG + (g >> 1)];
+	const int wrel = blk * HG + (g >> 1);
+	const int wi0 = cw0 + wrel, wi1 = cw1 + wrel;
+	const int bit0 = 8 * (g & 1);
+#pragma unroll
+	for (int n = 0; n < 8; n++)
+	{
+		const int nb = bit0 + ((n + (g >> RSH)) & 7);
+		uint32_t f0 = DFB_REF_PAD, f1 = DFB_REF_PAD;
+		if (wi0 >= 0 && (uint32_t)(wi0 * 16 + nb) < R0) f0 = decode_base(w0, ref_w0 + (uint32_t)wi0, nb, obytes);
+		if (wi1 >= 0 && (uint32_t)(wi1 * 16 + nb) < R1) f1 = decode_base(w1, ref_w1 + (uint32_t)wi1, nb, obytes);
+		ring[((uint32_t)blk * CH + 16u * (g >> 1) + nb) & (RING - 1)] = f0 | (f1 << 16);
+	}
+}
+
+// Probe sweep, rare path: rows of this lane (bit k of hm0 / hm1: row j0+k+1 of half 0 / 1) reached their targets in the
+// column the lane has just computed.  Out of line and loop-shaped: the unrolled form of this test was most of the probe
+// kernel's code.  The score of an event is the row's target, read back from the list the first sweep wrote.
+__device__ __noinline__ void emit_probe_hits(const FastParams& p, int item, int task, uint32_t hm0, uint32_t hm1, int j0, int col0, int col1,
+                                             uint32_t R0, uint32_t R1, int L, int S, int G, int g)
+{
+	for (int h = 0; h < 2; h++)
+	{
+		uint32_t hm = h ? hm1 : hm0;
+		const int col = h ? col1 : col0;
+		if (col < 0 || col >= (int)(h ? R1 : R0)) continue;
+		while (hm)
+		{
+			const int k = __ffs(hm) - 1;
+			hm &= hm - 1;
+			const int j = j0 + k + 1;
+			if (j > L) continue;
+			const uint32_t x = p.ntg[((size_t)item * S + k) * G + g];
+			const int target = (int)((0u - (h ? (x >> 16) : x)) & 0xFFFFu); // stored value of the row maximum
+			emit_probe_event(p, item, task, h, j, col, target - (int)p.bias + p.m * j);
+		}
 	}
 }
 
@@ -357,23 +407,8 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			}
 			cp_async_commit();
 		};
-		// lane g decodes columns 8g .. 8g+7 of the block for both halves and stores them as whole 32-bit words, in an
-		// order rotated by the lane so that the 32 lanes of the warp hit 32 different banks
 		auto decode_block = [&](int blk) {
-			const uint2 w0 = raw[blk & 1][0][g >> 1], w1 = raw[blk & 1][1][g >> 1];
-			const uint32_t wrel = (uint32_t)blk * HG + (uint32_t)(g >> 1);
-			const uint32_t a0 = wrel * 16u; // first column of the word in its reference
-			const int bit0 = 8 * (g & 1);
-			constexpr int RSH = (G == 8) ? 0 : (G == 16 ? 1 : 2); // bank = 8 * (g + q * G / 8) + rotation (mod 32): distinct over the warp
-#pragma unroll
-			for (int n = 0; n < 8; n++)
-			{
-				const int nb = bit0 + ((n + (g >> RSH)) & 7);
-				uint32_t f0 = DFB_REF_PAD, f1 = DFB_REF_PAD;
-				if (a0 + nb < R0) f0 = decode_base(w0, jp.ref_w[0] + wrel, nb, p.obytes);
-				if (a0 + nb < R1) f1 = decode_base(w1, jp.ref_w[1] + wrel, nb, p.obytes);
-				ring[((uint32_t)blk * CH + 16u * (g >> 1) + nb) & (RING - 1)] = f0 | (f1 << 16);
-			}
+			ring_decode_block<G>(ring, &raw[blk & 1][0][0], blk, 0, 0, R0, R1, jp.ref_w[0], jp.ref_w[1], p.obytes, g);
 		};
 		const int ring_blocks = min(2, (T + CH - 1) / CH); // ring columns this warp will read: T steps
 		issue_block(0);
@@ -782,20 +817,7 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 				cp_async_commit();
 			};
 			auto decode_block = [&](int blk) {
-				const uint2 w0 = raw[blk & 1][0][g >> 1], w1 = raw[blk & 1][1][g >> 1];
-				const int wrel = blk * HG + (g >> 1);
-				const int wi0 = (c0 >> 4) + wrel, wi1 = (c1 >> 4) + wrel;
-				const int bit0 = 8 * (g & 1);
-				constexpr int RSH = (G == 8) ? 0 : (G == 16 ? 1 : 2);
-#pragma unroll
-				for (int n = 0; n < 8; n++)
-				{
-					const int nb = bit0 + ((n + (g >> RSH)) & 7);
-					uint32_t f0 = DFB_REF_PAD, f1 = DFB_REF_PAD;
-					if (wi0 >= 0 && (uint32_t)(wi0 * 16 + nb) < R0) f0 = decode_base(w0, jp.ref_w[0] + (uint32_t)wi0, nb, p.obytes);
-					if (wi1 >= 0 && (uint32_t)(wi1 * 16 + nb) < R1) f1 = decode_base(w1, jp.ref_w[1] + (uint32_t)wi1, nb, p.obytes);
-					ring[((uint32_t)blk * CH + 16u * (g >> 1) + nb) & (RING - 1)] = f0 | (f1 << 16);
-				}
+				ring_decode_block<G>(ring, &raw[blk & 1][0][0], blk, c0 >> 4, c1 >> 4, R0, R1, jp.ref_w[0], jp.ref_w[1], p.obytes, g);
 			};
 			__syncwarp(); // (the previous round's ring reads are over)
 			const int ring_blocks = min(2, (Tr + PRE + CH - 1) / CH);
@@ -865,25 +887,21 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 					}
 					prev = recv;
 					Flast = left;
-					// a half of acc is >= 0 only when some enabled row reached its target here
+					// a half of acc is >= 0 only when some enumerated row reached its target here (a row that is not
+					// enumerated has the target 0x8001, which no stored value cancels)
 					if ((~acc) & 0x80008000u)
 					{
+						uint32_t hm0 = 0, hm1 = 0;
 #pragma unroll
 						for (int k = 0; k < S; k++)
 						{
-							if (X[k] == 0x80018001u) continue;
-#pragma unroll
-							for (int h = 0; h < 2; h++)
-							{
-								const int f = (int)((F[k] >> (16 * h)) & 0xFFFFu);
-								const int t = (int)(short)((X[k] >> (16 * h)) & 0xFFFFu);
-								if (t == -32767 || !(h ? on1 : on0)) continue;
-								const int j = j0 + k + 1;
-								const int col = (h ? b1 : b0) * CK + b; // 0-based column in the reference
-								if (f + t == 0 && col >= 0 && col < (int)jp.R[h] && j <= (int)jp.L[h])
-									emit_probe_event(p, item, jp.out0, h, j, col, f - (int)B + p.m * j);
-							}
+							if (((F[k] + X[k]) & 0xFFFFu) == 0) hm0 |= 1u << k;
+							if ((((F[k] >> 16) + (X[k] >> 16)) & 0xFFFFu) == 0) hm1 |= 1u << k;
 						}
+						if (!on0) hm0 = 0;
+						if (!on1) hm1 = 0;
+						if (hm0 | hm1)
+							emit_probe_hits(p, item, jp.out0, hm0, hm1, j0, b0 * CK + b, b1 * CK + b, jp.R[0], jp.R[1], (int)jp.L[0], S, G, g);
 					}
 				}
 			};
@@ -900,23 +918,19 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 					issue_block(blk_next);
 				}
 				const int u_end = min(Tr, (blkno + 1) * CK);
-				if (blkno == 0 && jm)
-				{
 #pragma unroll 1
-					for (; u < min(u_end, G - 1); u++)
+				for (; u < u_end; u++)
+				{
+					step(u);
+					if (jm && u < g)
 					{
-						step(u);
-						if (u < g)
-						{
+						// this lane has not joined the half that starts in block 0 yet: back to the boundary column
 #pragma unroll
-							for (int k = 0; k < S; k++) F[k] = (F[k] & ~jm) | (boundary(j0 + k + 1) & jm);
-							prev = (prev & ~jm) | (boundary(j0) & jm);
-							Flast = (Flast & ~jm) | (boundary(j0 + S) & jm);
-						}
+						for (int k = 0; k < S; k++) F[k] = (F[k] & ~jm) | (boundary(j0 + k + 1) & jm);
+						prev = (prev & ~jm) | (boundary(j0) & jm);
+						Flast = (Flast & ~jm) | (boundary(j0 + S) & jm);
 					}
 				}
-#pragma unroll 1
-				for (; u < u_end; u++) step(u);
 			}
 			cp_async_wait_all();
 		}
