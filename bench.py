@@ -366,6 +366,7 @@ def measure_sharded(aligner, args, rank, world, barrier):
         all_cols = np.concatenate(gathered["cols"])
         order = np.argsort(merged["task"], kind="stable")   # rows of a task stay in their (ascending split row) order
         merged = merged[order]
+        merge_ms = (time.perf_counter() - t0) * 1e3   # gather + merge into task order; the digest below is bookkeeping
         h = hashlib.sha1()
         h.update(best.tobytes())
         for f in ("task", "read_split", "score1", "score2", "n1", "n2"):
@@ -375,7 +376,6 @@ def measure_sharded(aligner, args, rank, world, barrier):
         starts = np.repeat(merged["col_begin"].astype(np.int64), width)
         within = np.arange(int(width.sum())) - np.repeat(np.concatenate([[0], np.cumsum(width)[:-1]]), width)
         h.update(np.ascontiguousarray(all_cols[starts + within]).tobytes())
-        merge_ms = (time.perf_counter() - t0) * 1e3
         loads = np.array([cost[g].sum() for g in gathered["idx"]], dtype=np.float64)
         result = {"digest": h.hexdigest(), "merge_ms": merge_ms, "rows": int(len(merged)), "tasks": int(n),
                   "load_imbalance": float(loads.max() / loads.mean())}

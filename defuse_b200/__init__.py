@@ -18,7 +18,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdefuse_b200.so")
+# (DFB_LIB_PATH: another build of the same CUDA library, for A/B runs of kernel variants; never a fallback)
+LIB_PATH = os.environ.get("DFB_LIB_PATH") or os.path.join(_HERE, "libdefuse_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "defuse_b200.h")
 
 DFB_OK = 0

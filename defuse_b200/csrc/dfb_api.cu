@@ -13,6 +13,7 @@
 #include "../../include/defuse_b200.h"
 #include "dfb_kernels.cuh"
 #include "dfb_assemble.cuh"
+#include "dfb_build.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -497,6 +498,11 @@ struct dfb_plan
 	// device
 	uint8_t* d_raw = nullptr;
 	uint8_t* d_stage = nullptr; // descriptors + fast jobs + generic jobs (one upload)
+	uint8_t* d_build = nullptr; // job build on the device: offsets, task arrays, descriptors, bins, jobs (one arena)
+	// (device-built plans look a task's read length up in the caller's arrays, which outlive the one-call batch)
+	const int64_t* h_read_off = nullptr;
+	const int32_t* h_task_read = nullptr;
+	int32_t h_read_base = 0;
 	uint2* d_pool = nullptr;
 	uint8_t* d_obytes = nullptr;
 	int32_t* d_out = nullptr; // score / best per task
@@ -560,6 +566,7 @@ static void release_device(dfb_plan* plan)
 	dfb_ctx* ctx = plan->ctx;
 	dfree(ctx, plan->d_raw);
 	dfree(ctx, plan->d_stage);
+	dfree(ctx, plan->d_build);
 	dfree(ctx, plan->d_pool);
 	dfree(ctx, plan->d_obytes);
 	dfree(ctx, plan->d_out);
@@ -847,7 +854,7 @@ static void fill_fast_params(dfb_plan* pl, int c, int m, int x, int g, int min_s
 }
 
 // device-side bookkeeping common to both plan kinds, after the job counts are known
-static int alloc_work(dfb_plan* pl, const Staging& st, const int64_t* n_jobs_cls, bool split, uint32_t gen_max_R)
+static int alloc_work(dfb_plan* pl, JobPair* d_jobs_base, GenJob* d_gen_base, const int64_t* n_jobs_cls, bool split, uint32_t gen_max_R)
 {
 	dfb_ctx* ctx = pl->ctx;
 	DALLOC(ctx, pl->d_ctrl, kNumClasses * 4 * sizeof(int));
@@ -856,7 +863,7 @@ static int alloc_work(dfb_plan* pl, const Staging& st, const int64_t* n_jobs_cls
 	{
 		ClassWork& cw = pl->cls[c];
 		cw.n_jobs = n_jobs_cls[c];
-		cw.d_jobs = (JobPair*)(pl->d_stage + st.off_jobs) + first;
+		cw.d_jobs = d_jobs_base + first;
 		cw.d_ctrl = pl->d_ctrl + 4 * c;
 		pl->job_base[c] = first;
 		first += cw.n_jobs;
@@ -884,7 +891,7 @@ static int alloc_work(dfb_plan* pl, const Staging& st, const int64_t* n_jobs_cls
 	if (pl->n_gen_jobs)
 	{
 		const size_t n = (size_t)pl->n_gen_jobs;
-		pl->d_gen_jobs = (GenJob*)(pl->d_stage + st.off_gen);
+		pl->d_gen_jobs = d_gen_base;
 		DALLOC(ctx, pl->d_gen_ctrl, 4 * sizeof(int));
 		pl->gen_bnd_stride = (int64_t)gen_max_R + 2;
 		pl->gen_grid = (int)std::min<size_t>((n + 3) / 4, (size_t)ctx->prop.multiProcessorCount * 4);
@@ -1102,7 +1109,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 
 	rc = upload_and_pack(pl, refs, PACK_FWD, seqs, PACK_FWD, st, words_a_end, total_words);
 	tr.lap("simple.create: enqueue pack");
-	if (!rc) rc = alloc_work(pl, st, n_jobs_cls, false, gen_max_R);
+	if (!rc) rc = alloc_work(pl, (JobPair*)(pl->d_stage + st.off_jobs), (GenJob*)(pl->d_stage + st.off_gen), n_jobs_cls, false, gen_max_R);
 	tr.lap("simple.create: alloc");
 	if (!rc)
 	{
@@ -1320,7 +1327,7 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 		}
 		if (e2 != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "output allocation failed: %s", cudaGetErrorString(e2));
 	}
-	if (!rc) rc = alloc_work(pl, st, n_jobs_cls, true, gen_max_R);
+	if (!rc) rc = alloc_work(pl, (JobPair*)(pl->d_stage + st.off_jobs), (GenJob*)(pl->d_stage + st.off_gen), n_jobs_cls, true, gen_max_R);
 	if (!rc)
 	{
 		for (int c = 0; c < kNumClasses; c++)
@@ -1335,6 +1342,199 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 		dfb_plan_destroy(pl);
 		return rc;
 	}
+	*out = pl;
+	return DFB_OK;
+}
+
+// ---- SplitReadAligner plan, job lists built on the device (dfb_build.cuh) ---------------------------------------
+// Chunks of a pipelined batch: the caller's offsets and task arrays are uploaded as they are; descriptors, class /
+// length bins and the 32-byte job records are made by kernels on the upload stream.  One small read-back (jobs per
+// class, longest reference per class, total pool words) separates the classify pass from the allocations that
+// depend on it.  Returns DFB_BUILD_ON_HOST when the chunk holds tasks only the s32 kernels can take: the caller
+// builds that chunk on the host instead.
+static const int DFB_BUILD_ON_HOST = 1000;
+
+static int split_plan_create_device(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
+                                    const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
+                                    const int32_t* task_min_score, int64_t n_tasks, int32_t read_base, int stage_slot, dfb_plan** out)
+{
+	static_assert(kNumClasses <= DFB_BUILD_MAX_CLASSES && kRBins == DFB_BUILD_RBINS, "dfb_build.cuh tables");
+	*out = nullptr;
+	int rc;
+	CK(ctx, cudaSetDevice(ctx->device));
+	dfb_plan* pl = new (std::nothrow) dfb_plan();
+	if (!pl) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
+	pl->ctx = ctx;
+	pl->split = true;
+	pl->sp = *params;
+	pl->n_tasks = n_tasks;
+	pl->stats.n_tasks = n_tasks;
+	pl->h_read_off = reads->off;
+	pl->h_task_read = task_read;
+	pl->h_read_base = read_base;
+	classify_params(pl, params->match, params->mismatch, params->gap, params->end_gaps == 0 && params->min_split_score >= 1);
+	pl->up = ctx->upload_stream;
+	cudaStream_t up = pl->up;
+	auto fail = [&](int code) {
+		dfb_plan_destroy(pl);
+		return code;
+	};
+	Trace tr;
+	if ((rc = upload_raw(pl, refs, reads))) return fail(rc);
+
+	// arena
+	const int64_t na = refs->n, nb = reads->n;
+	const size_t n_bins = (size_t)kNumClasses * kRBins;
+	const int64_t blocks_a = (na + DFB_BUILD_BLOCK * DFB_BUILD_ITEMS - 1) / (DFB_BUILD_BLOCK * DFB_BUILD_ITEMS);
+	const int64_t blocks_b = (nb + DFB_BUILD_BLOCK * DFB_BUILD_ITEMS - 1) / (DFB_BUILD_BLOCK * DFB_BUILD_ITEMS);
+	size_t at = 0;
+	auto take = [&](size_t bytes) {
+		const size_t o = at;
+		at = align_up(at + bytes, 256);
+		return o;
+	};
+	const size_t o_off_a = take((size_t)(na + 1) * 8), o_off_b = take((size_t)(nb + 1) * 8);
+	const size_t o_tc = take((size_t)n_tasks * 4), o_tr = take((size_t)n_tasks * 4), o_tm = take((size_t)n_tasks * 4);
+	const size_t o_desc_a = take((size_t)na * sizeof(SeqDesc)), o_desc_b = take((size_t)nb * sizeof(SeqDesc));
+	const size_t o_bin_of = take((size_t)n_tasks * 4);
+	const size_t o_bins = take(2 * n_bins * 4);
+	const size_t o_sums_a = take((size_t)(blocks_a + 1) * 8), o_sums_b = take((size_t)(blocks_b + 1) * 8);
+	const size_t o_stats = take(sizeof(BuildStats) + 64);
+	const size_t o_jobs = take((size_t)n_tasks * sizeof(JobPair));
+	CK(ctx, cudaMallocAsync((void**)&pl->d_build, std::max<size_t>(at, 256), up));
+	uint8_t* base = pl->d_build;
+	BuildStats* d_stats = (BuildStats*)(base + o_stats);
+	unsigned long long* d_words_a_end = (unsigned long long*)(base + o_stats + sizeof(BuildStats));
+	int* d_bad_table = &d_stats->bad_table;
+	// pinned scratch: the initial statistics go up from it, the final ones come back into it
+	PinnedBuf& hin = ctx->h_in[stage_slot];
+	{
+		cudaError_t e = hin.ensure(2 * sizeof(BuildStats) + 64);
+		if (e != cudaSuccess) return fail(set_err(ctx, DFB_ERR_NOMEM, "pinned staging buffer: %s", cudaGetErrorString(e)));
+	}
+	BuildStats* h_init = (BuildStats*)hin.p;
+	BuildStats* h_stats = h_init + 1;
+	memset(h_init, 0, sizeof(*h_init));
+	h_init->bad_task = ~0ull;
+	auto cuda_fail = [&](cudaError_t e, const char* what) {
+		return fail(set_err(ctx, DFB_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e)));
+	};
+	cudaError_t e;
+	if ((e = cudaMemcpyAsync(d_stats, h_init, sizeof(BuildStats), cudaMemcpyHostToDevice, up)) != cudaSuccess) return cuda_fail(e, "statistics upload");
+	if ((e = cudaMemsetAsync(base + o_bins, 0, 2 * n_bins * 4, up)) != cudaSuccess) return cuda_fail(e, "bin reset");
+	if ((e = cudaMemcpyAsync(base + o_off_a, refs->off, (size_t)(na + 1) * 8, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
+	    (e = cudaMemcpyAsync(base + o_off_b, reads->off, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
+	    (e = cudaMemcpyAsync(base + o_tc, task_cluster, (size_t)n_tasks * 4, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
+	    (e = cudaMemcpyAsync(base + o_tr, task_read, (size_t)n_tasks * 4, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
+	    (e = cudaMemcpyAsync(base + o_tm, task_min_score, (size_t)n_tasks * 4, cudaMemcpyHostToDevice, up)) != cudaSuccess)
+		return cuda_fail(e, "task upload");
+	const int64_t raw_a = refs->off[refs->n] - refs->off[0];
+	// descriptors: windows (one stored copy each), then reads (forward + reversed copy)
+	DescParams da;
+	da.off = (const int64_t*)(base + o_off_a);
+	da.n = na;
+	da.copies = 1;
+	da.src_base = 0;
+	da.desc = (SeqDesc*)(base + o_desc_a);
+	da.block_sums = (unsigned long long*)(base + o_sums_a);
+	da.word_base = nullptr;
+	da.total = d_words_a_end;
+	da.bad = d_bad_table;
+	DescParams db = da;
+	db.off = (const int64_t*)(base + o_off_b);
+	db.n = nb;
+	db.copies = 2;
+	db.src_base = raw_a;
+	db.desc = (SeqDesc*)(base + o_desc_b);
+	db.block_sums = (unsigned long long*)(base + o_sums_b);
+	db.word_base = d_words_a_end;
+	db.total = &d_stats->total_words;
+	if (na)
+	{
+		desc_count_kernel<<<(unsigned)blocks_a, DFB_BUILD_BLOCK, 0, up>>>(da);
+		desc_scan_kernel<<<1, DFB_BUILD_BLOCK, 0, up>>>(da.block_sums, blocks_a, da.word_base, da.total);
+		desc_write_kernel<<<(unsigned)blocks_a, DFB_BUILD_BLOCK, 0, up>>>(da);
+	}
+	else if ((e = cudaMemsetAsync(d_words_a_end, 0, 8, up)) != cudaSuccess) return cuda_fail(e, "memset");
+	if (nb)
+	{
+		desc_count_kernel<<<(unsigned)blocks_b, DFB_BUILD_BLOCK, 0, up>>>(db);
+		desc_scan_kernel<<<1, DFB_BUILD_BLOCK, 0, up>>>(db.block_sums, blocks_b, db.word_base, db.total);
+		desc_write_kernel<<<(unsigned)blocks_b, DFB_BUILD_BLOCK, 0, up>>>(db);
+	}
+	else if ((e = cudaMemcpyAsync(&d_stats->total_words, d_words_a_end, 8, cudaMemcpyDeviceToDevice, up)) != cudaSuccess) return cuda_fail(e, "copy");
+	SplitBuildParams bp;
+	memset(&bp, 0, sizeof(bp));
+	bp.desc_a = da.desc;
+	bp.n_clusters = na / 2;
+	bp.desc_b = db.desc;
+	bp.n_reads = nb;
+	bp.task_cluster = (const int32_t*)(base + o_tc);
+	bp.task_read = (const int32_t*)(base + o_tr);
+	bp.task_min_score = (const int32_t*)(base + o_tm);
+	bp.n_tasks = n_tasks;
+	bp.read_base = read_base;
+	bp.bin_of = (int32_t*)(base + o_bin_of);
+	bp.bin_count = (unsigned int*)(base + o_bins);
+	bp.bin_fill = bp.bin_count + n_bins;
+	bp.n_classes = kNumClasses;
+	for (int c = 0; c < kNumClasses; c++)
+	{
+		bp.cls_rows[c] = kClasses[c].G * kClasses[c].S;
+		bp.cls_ok[c] = pl->fast_ok[c] ? 1 : 0;
+	}
+	bp.max_fast_rows = kMaxFastRows;
+	bp.stats = d_stats;
+	bp.jobs = (JobPair*)(base + o_jobs);
+	const unsigned task_blocks = (unsigned)((n_tasks + DFB_BUILD_BLOCK - 1) / DFB_BUILD_BLOCK);
+	if (n_tasks) split_classify_kernel<<<task_blocks, DFB_BUILD_BLOCK, 0, up>>>(bp);
+	bin_scan_kernel<<<1, 1024, 0, up>>>(bp.bin_count, kNumClasses, d_stats);
+	if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "job build kernels");
+	if ((e = cudaMemcpyAsync(h_stats, d_stats, sizeof(BuildStats), cudaMemcpyDeviceToHost, up)) != cudaSuccess) return cuda_fail(e, "statistics read-back");
+	tr.lap("split.create(dev): enqueue");
+	if ((e = cudaStreamSynchronize(up)) != cudaSuccess) return cuda_fail(e, "job build");
+	tr.lap("split.create(dev): classify done");
+	if (h_stats->bad_table) return fail(set_err(ctx, DFB_ERR_ARG, "a table's offsets decrease or a sequence is too long"));
+	if (h_stats->bad_task != ~0ull) return fail(set_err(ctx, DFB_ERR_ARG, "task %llu: table index out of range", h_stats->bad_task));
+	if (h_stats->n_gen) return fail(DFB_BUILD_ON_HOST);
+	if (h_stats->total_words >= 0xFFFFFFF0ull) return fail(set_err(ctx, DFB_ERR_ARG, "batch too large: more than 2^32 packed words; split it"));
+	pl->stats.cells = (int64_t)h_stats->cells;
+	const uint32_t total_words = (uint32_t)h_stats->total_words;
+	int64_t n_jobs_cls[kNumClasses];
+	for (int c = 0; c < kNumClasses; c++)
+	{
+		n_jobs_cls[c] = h_stats->cls_jobs[c];
+		pl->cls[c].max_R = h_stats->cls_max_R[c];
+	}
+	// pool, packing, job scatter: still on the upload stream, underneath the previous chunk's sweeps
+	if ((e = cudaMallocAsync((void**)&pl->d_pool, ((size_t)total_words + 8) * sizeof(uint2), up)) != cudaSuccess ||
+	    (e = cudaMallocAsync((void**)&pl->d_obytes, ((size_t)total_words + 8) * 16, up)) != cudaSuccess)
+		return fail(set_err(ctx, DFB_ERR_NOMEM, "packed pool of %u words: %s", total_words, cudaGetErrorString(e)));
+	for (int k = 0; k < 3; k++)
+		if (!pl->ev[k] && (e = cudaEventCreate(&pl->ev[k])) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+	cudaEventRecord(pl->ev[0], up);
+	const int max_grid = ctx->prop.multiProcessorCount * 16;
+	if (na) pack_kernel<PACK_REV_ODD><<<(int)std::min<uint64_t>(((uint64_t)na * 16 + 255) / 256, (uint64_t)max_grid), 256, 0, up>>>(pl->d_raw, da.desc, (int)na, pl->d_pool, pl->d_obytes);
+	if (nb) pack_kernel<PACK_BOTH><<<(int)std::min<uint64_t>(((uint64_t)nb * 16 + 255) / 256, (uint64_t)max_grid), 256, 0, up>>>(pl->d_raw, db.desc, (int)nb, pl->d_pool, pl->d_obytes);
+	cudaEventRecord(pl->ev[1], up);
+	pl->pack_timed = true;
+	if (n_tasks) split_scatter_kernel<<<task_blocks, DFB_BUILD_BLOCK, 0, up>>>(bp);
+	if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "pack / scatter kernels");
+	if (!pl->packed_ev && (e = cudaEventCreateWithFlags(&pl->packed_ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+	cudaEventRecord(pl->packed_ev, up);
+	const int64_t raw_b = reads->off[reads->n] - reads->off[0];
+	pl->stats.h2d_bytes += raw_a + raw_b + (na + 1 + nb + 1) * 8 + n_tasks * 12 + (int64_t)sizeof(BuildStats);
+	pl->stats.raw_bytes = raw_a + 2 * raw_b;
+	pl->stats.packed_bytes = (int64_t)total_words * 8;
+
+	pl->ev_cap = (unsigned long long)std::max<int64_t>(n_tasks, 1 << 20);
+	if ((e = dalloc(ctx, (void**)&pl->d_events, (size_t)pl->ev_cap * sizeof(Event))) != cudaSuccess ||
+	    (e = dalloc(ctx, (void**)&pl->d_ev_count, sizeof(unsigned long long))) != cudaSuccess)
+		return fail(set_err(ctx, DFB_ERR_CUDA, "output allocation failed: %s", cudaGetErrorString(e)));
+	if ((rc = alloc_work(pl, bp.jobs, nullptr, n_jobs_cls, true, 0))) return fail(rc);
+	for (int c = 0; c < kNumClasses; c++)
+		if (pl->cls[c].n_jobs) fill_fast_params(pl, c, params->match, params->mismatch, params->gap, params->min_split_score);
+	tr.lap("split.create(dev): pack, scatter, alloc");
 	*out = pl;
 	return DFB_OK;
 }
@@ -1766,7 +1966,14 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 					key.push_back(wide_key(ov->half_row >> 30, ov->half_row & 0x3fffffff, ov->col));
 					score.push_back(ov->score);
 				}
-				emit_task_rows((int)t, pl->task_L[(size_t)t], key.data(), score.data(), (int)key.size(), out);
+				int L_t;
+				if (pl->h_read_off)
+				{
+					const int64_t rd = (int64_t)pl->h_task_read[t] - pl->h_read_base;
+					L_t = (int)(pl->h_read_off[rd + 1] - pl->h_read_off[rd]);
+				}
+				else L_t = pl->task_L[(size_t)t];
+				emit_task_rows((int)t, L_t, key.data(), score.data(), (int)key.size(), out);
 			}
 		});
 	}
@@ -1963,6 +2170,16 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	}
 	int rc = DFB_OK;
 	Trace trp;
+	// job lists are built on the device unless no class of the s16x2 kernels takes this scoring (then every task is
+	// generic and the host path lists them) or DFB_HOST_BUILD asks for the host path (A/B runs, tests)
+	bool device_build = false;
+	{
+		dfb_plan probe;
+		classify_params(&probe, params->match, params->mismatch, params->gap, params->end_gaps == 0 && params->min_split_score >= 1);
+		for (int c = 0; c < kNumClasses; c++) device_build = device_build || probe.fast_ok[c];
+		if (const char* e = getenv("DFB_HOST_BUILD"))
+			if (*e && *e != '0') device_build = false;
+	}
 	// the batch's result holder: every chunk's rows go straight behind the previous chunk's
 	dfb_plan* holder = new (std::nothrow) dfb_plan();
 	if (!holder) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
@@ -2015,8 +2232,11 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 		}
 		dfb_seq_table view{reads->bytes, reads->off + r_lo, (int64_t)(r_hi - r_lo)};
 		dfb_plan* pk = nullptr;
-		rc = split_plan_create_impl(ctx, params, refs, &view, task_cluster + a, task_read + a, task_min_score + a, b - a, r_lo, k,
-		                            true, &pk);
+		rc = device_build ? split_plan_create_device(ctx, params, refs, &view, task_cluster + a, task_read + a, task_min_score + a, b - a, r_lo, k, &pk)
+		                  : DFB_BUILD_ON_HOST;
+		if (rc == DFB_BUILD_ON_HOST)
+			rc = split_plan_create_impl(ctx, params, refs, &view, task_cluster + a, task_read + a, task_min_score + a, b - a, r_lo, k,
+			                            true, &pk);
 		if (rc) break;
 		pk->result_slot = k;
 		rc = dfb_plan_run(pk);

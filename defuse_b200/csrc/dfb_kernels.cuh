@@ -291,7 +291,10 @@ struct FastOcc
 {
 	static constexpr int kArrays = (MODE == MODE_SPLIT) ? 5 : 2;
 	static constexpr int kEst = kArrays * S + 48;
-	static constexpr int kMinBlocks = kEst <= 128 ? 4 : (kEst <= 168 ? 3 : (kEst <= 255 ? 2 : 1));
+#ifndef DFB_OCC_SMALL
+#define DFB_OCC_SMALL 4 // CTAs per SM asked of ptxas for the classes with short strips (build-time knob for A/B runs)
+#endif
+	static constexpr int kMinBlocks = kEst <= 128 ? DFB_OCC_SMALL : (kEst <= 168 ? 3 : (kEst <= 255 ? 2 : 1));
 };
 
 template <int G, int S, int MODE>
