@@ -200,11 +200,13 @@ struct dfb_ctx
 	cudaStream_t stream = nullptr;
 	cudaDeviceProp prop;
 	mutable std::string err;
+	mutable std::mutex err_mu; // the two lanes of a pipelined batch may both report
 	static const int kStageSlots = 8;
 	PinnedBuf h_in[kStageSlots]; // host-built descriptors and job lists, on their way to the device (one per batch chunk in flight)
 	PinnedBuf h_out;             // results on their way back
 	cudaStream_t copy_stream = nullptr; // device->host result copies, ordered after a plan's kernels by an event
 	cudaStream_t upload_stream = nullptr; // uploads + packing of the next chunk of a pipelined batch
+	cudaStream_t upload_stream2 = nullptr; // device-built chunks alternate between the two: chunk k+1's uploads do not hold up chunk k's packing
 	cudaEvent_t copied_ev = nullptr;      // blocking-sync event behind the result copies of a fetch
 	HostPool* pool = nullptr;       // plan building (and everything else on the caller's thread)
 	HostPool* pool_fetch = nullptr; // result assembly when it runs on the pipelining helper thread
@@ -251,7 +253,12 @@ static int set_err(const dfb_ctx* ctx, int code, const char* fmt, ...)
 	va_start(ap, fmt);
 	vsnprintf(buf, sizeof(buf), fmt, ap);
 	va_end(ap);
-	if (ctx) ctx->err = buf; else g_create_err = buf;
+	if (ctx)
+	{
+		std::lock_guard<std::mutex> lk(ctx->err_mu);
+		ctx->err = buf;
+	}
+	else g_create_err = buf;
 	return code;
 }
 
@@ -263,6 +270,29 @@ static int set_err(const dfb_ctx* ctx, int code, const char* fmt, ...)
 			return set_err(ctx, DFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
 			               __FILE__, __LINE__);                                                        \
 	} while (0)
+
+// Nothing may unwind through the C ABI: allocation failures of the batch-sized host arrays (std::vector, std::thread)
+// become DFB_ERR_NOMEM / DFB_ERR_STATE like every other failure.
+template <class F>
+static int guarded(dfb_ctx* ctx, F f)
+{
+	try
+	{
+		return f();
+	}
+	catch (const std::bad_alloc&)
+	{
+		return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
+	}
+	catch (const std::exception& e)
+	{
+		return set_err(ctx, DFB_ERR_STATE, "%s", e.what());
+	}
+	catch (...)
+	{
+		return set_err(ctx, DFB_ERR_STATE, "unexpected exception");
+	}
+}
 
 extern "C" int dfb_abi_version(void) { return DFB_ABI_VERSION; }
 
@@ -320,7 +350,8 @@ extern "C" int dfb_ctx_create(int device_ordinal, dfb_ctx** out)
 	}
 	ctx->stream = ctx->own_stream;
 	if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-	    (e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking)) != cudaSuccess)
+	    (e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaStreamCreateWithFlags(&ctx->upload_stream2, cudaStreamNonBlocking)) != cudaSuccess)
 	{
 		cudaStreamDestroy(ctx->own_stream);
 		delete ctx;
@@ -356,6 +387,7 @@ extern "C" void dfb_ctx_destroy(dfb_ctx* ctx)
 	ctx->h_out.release();
 	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+	if (ctx->upload_stream2) cudaStreamDestroy(ctx->upload_stream2);
 	if (ctx->copied_ev) cudaEventDestroy(ctx->copied_ev);
 	delete ctx->pool;
 	delete ctx->pool_fetch;
@@ -503,6 +535,18 @@ struct dfb_plan
 	const int64_t* h_read_off = nullptr;
 	const int32_t* h_task_read = nullptr;
 	int32_t h_read_base = 0;
+	// between the two halves of a device build (enqueue: uploads + descriptor / classify kernels; finish: allocations,
+	// packing, job scatter once the class counts are back)
+	struct BuildPending
+	{
+		bool active = false;
+		SplitBuildParams bp;
+		const SeqDesc* d_desc_a = nullptr;
+		const SeqDesc* d_desc_b = nullptr;
+		int64_t na = 0, nb = 0, raw_a = 0, raw_b = 0;
+		BuildStats* h_stats = nullptr;
+		cudaEvent_t ready = nullptr; // behind the read-back of the statistics (blocking-sync: the waiting thread sleeps)
+	} pending;
 	uint2* d_pool = nullptr;
 	uint8_t* d_obytes = nullptr;
 	int32_t* d_out = nullptr; // score / best per task
@@ -564,6 +608,9 @@ static void dfree(dfb_ctx* ctx, T*& p)
 static void release_device(dfb_plan* plan)
 {
 	dfb_ctx* ctx = plan->ctx;
+	// blocks filled on the plan's upload stream go back to the pool on the compute stream: nothing of this plan may
+	// still be in flight there (a plan that failed half way through its creation, for one)
+	if (plan->up) cudaStreamSynchronize(plan->up);
 	dfree(ctx, plan->d_raw);
 	dfree(ctx, plan->d_stage);
 	dfree(ctx, plan->d_build);
@@ -620,6 +667,7 @@ extern "C" void dfb_plan_destroy(dfb_plan* plan)
 			if (plan->cols.cap > plan->ctx->spare_cols.cap) plan->cols.swap(plan->ctx->spare_cols);
 		}
 	}
+	if (plan->pending.ready) cudaEventDestroy(plan->pending.ready);
 	if (plan->done_ev) cudaEventDestroy(plan->done_ev);
 	if (plan->packed_ev) cudaEventDestroy(plan->packed_ev);
 	plan->rows.release();
@@ -934,17 +982,15 @@ static int finish_create(dfb_plan* pl)
 
 // ---- SimpleAligner plan ------------------------------------------------------------------
 
-extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* params, const dfb_seq_table* refs,
-                                      const dfb_seq_table* seqs, const int32_t* task_ref, const int32_t* task_seq,
-                                      int64_t n_tasks, dfb_plan** out)
+// `refs` / `seqs` may be views into larger tables (off[0] != 0) whose first entries are reference `ref_base` / sequence
+// `seq_base` of the caller's numbering; `async` skips the final stream synchronisation and uploads on the upload
+// stream (chunks of a pipelined batch).
+static int simple_plan_create_impl(dfb_ctx* ctx, const dfb_simple_params* params, const dfb_seq_table* refs,
+                                   const dfb_seq_table* seqs, const int32_t* task_ref, const int32_t* task_seq,
+                                   int64_t n_tasks, int32_t ref_base, int32_t seq_base, int stage_slot, bool async, dfb_plan** out)
 {
-	if (!ctx) return DFB_ERR_ARG;
-	if (!params || !out || n_tasks < 0 || (n_tasks > 0 && (!task_ref || !task_seq)))
-		return set_err(ctx, DFB_ERR_ARG, "dfb_simple_plan_create: null argument");
 	*out = nullptr;
 	int rc;
-	if ((rc = check_table(ctx, refs, "refs")) || (rc = check_table(ctx, seqs, "seqs"))) return rc;
-	if (n_tasks > 0x7fffff00LL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
 	CK(ctx, cudaSetDevice(ctx->device));
 	dfb_plan* pl = new (std::nothrow) dfb_plan();
 	if (!pl) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
@@ -956,6 +1002,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 	pl->sp.mismatch = params->mismatch;
 	pl->sp.gap = params->gap;
 	classify_params(pl, params->match, params->mismatch, params->gap, true);
+	pl->up = async ? ctx->upload_stream : nullptr;
 	Trace tr;
 	if ((rc = upload_raw(pl, refs, seqs)))
 	{
@@ -980,7 +1027,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 		int64_t* cnt = bin_pos.data() + n_bins * (size_t)tid;
 		for (int64_t t = n_tasks * tid / T; t < n_tasks * (tid + 1) / T; t++)
 		{
-			const int32_t r = task_ref[t], sq = task_seq[t];
+			const int32_t r = task_ref[t] - ref_base, sq = task_seq[t] - seq_base;
 			if (r < 0 || r >= refs->n || sq < 0 || sq >= seqs->n)
 			{
 				if (pt.bad < 0) pt.bad = t;
@@ -1046,7 +1093,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 
 	tr.lap("simple.create: classify");
 	Staging st;
-	cudaError_t e = stage_layout(ctx, 0, st, refs->n, seqs->n, n_fast_jobs, n_gen);
+	cudaError_t e = stage_layout(ctx, stage_slot, st, refs->n, seqs->n, n_fast_jobs, n_gen);
 	if (e != cudaSuccess)
 	{
 		dfb_plan_destroy(pl);
@@ -1076,7 +1123,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 		{
 			const int32_t bin = bin_of[t];
 			if (bin < 0) continue;
-			const int32_t r = task_ref[t], sq = task_seq[t];
+			const int32_t r = task_ref[t] - ref_base, sq = task_seq[t] - seq_base;
 			const int64_t p = pos[bin]++;
 			JobPair& jp = st.jobs[job_base[bin / kRBins] + (p >> 1)];
 			const int h = (int)(p & 1);
@@ -1093,7 +1140,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 		for (int64_t t = 0; t < n_tasks; t++)
 		{
 			if (bin_of[t] != -2) continue;
-			const int32_t r = task_ref[t], sq = task_seq[t];
+			const int32_t r = task_ref[t] - ref_base, sq = task_seq[t] - seq_base;
 			GenJob& j = st.gen[gi++];
 			j.ref_w = st.desc_a[r].word;
 			j.read_w = st.desc_b[sq].word;
@@ -1115,7 +1162,7 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 	{
 		for (int c = 0; c < kNumClasses; c++)
 			if (pl->cls[c].n_jobs) fill_fast_params(pl, c, params->match, params->mismatch, params->gap, 0);
-		rc = finish_create(pl);
+		if (!async) rc = finish_create(pl);
 	}
 	tr.lap("simple.create: sync");
 	if (rc)
@@ -1125,6 +1172,20 @@ extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* par
 	}
 	*out = pl;
 	return DFB_OK;
+}
+
+static int dfb_simple_plan_create_body(dfb_ctx* ctx, const dfb_simple_params* params, const dfb_seq_table* refs,
+                                      const dfb_seq_table* seqs, const int32_t* task_ref, const int32_t* task_seq,
+                                      int64_t n_tasks, dfb_plan** out)
+{
+	if (!ctx) return DFB_ERR_ARG;
+	if (!params || !out || n_tasks < 0 || (n_tasks > 0 && (!task_ref || !task_seq)))
+		return set_err(ctx, DFB_ERR_ARG, "dfb_simple_plan_create: null argument");
+	*out = nullptr;
+	int rc;
+	if ((rc = check_table(ctx, refs, "refs")) || (rc = check_table(ctx, seqs, "seqs"))) return rc;
+	if (n_tasks > 0x7fffff00LL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
+	return simple_plan_create_impl(ctx, params, refs, seqs, task_ref, task_seq, n_tasks, 0, 0, 0, false, out);
 }
 
 // ---- SplitReadAligner plan ------------------------------------------------------------------
@@ -1354,9 +1415,10 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 // builds that chunk on the host instead.
 static const int DFB_BUILD_ON_HOST = 1000;
 
-static int split_plan_create_device(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
-                                    const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
-                                    const int32_t* task_min_score, int64_t n_tasks, int32_t read_base, int stage_slot, dfb_plan** out)
+static int split_build_enqueue(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
+                               const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
+                               const int32_t* task_min_score, int64_t n_tasks, int32_t read_base, int stage_slot, cudaStream_t up_stream,
+                               dfb_plan** out)
 {
 	static_assert(kNumClasses <= DFB_BUILD_MAX_CLASSES && kRBins == DFB_BUILD_RBINS, "dfb_build.cuh tables");
 	*out = nullptr;
@@ -1373,7 +1435,7 @@ static int split_plan_create_device(dfb_ctx* ctx, const dfb_split_params* params
 	pl->h_task_read = task_read;
 	pl->h_read_base = read_base;
 	classify_params(pl, params->match, params->mismatch, params->gap, params->end_gaps == 0 && params->min_split_score >= 1);
-	pl->up = ctx->upload_stream;
+	pl->up = up_stream;
 	cudaStream_t up = pl->up;
 	auto fail = [&](int code) {
 		dfb_plan_destroy(pl);
@@ -1491,8 +1553,43 @@ static int split_plan_create_device(dfb_ctx* ctx, const dfb_split_params* params
 	bin_scan_kernel<<<1, 1024, 0, up>>>(bp.bin_count, kNumClasses, d_stats);
 	if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "job build kernels");
 	if ((e = cudaMemcpyAsync(h_stats, d_stats, sizeof(BuildStats), cudaMemcpyDeviceToHost, up)) != cudaSuccess) return cuda_fail(e, "statistics read-back");
+	if ((e = cudaEventCreateWithFlags(&pl->pending.ready, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess ||
+	    (e = cudaEventRecord(pl->pending.ready, up)) != cudaSuccess)
+		return cuda_fail(e, "cudaEventRecord");
+	pl->pending.active = true;
+	pl->pending.bp = bp;
+	pl->pending.d_desc_a = da.desc;
+	pl->pending.d_desc_b = db.desc;
+	pl->pending.na = na;
+	pl->pending.nb = nb;
+	pl->pending.raw_a = raw_a;
+	pl->pending.raw_b = reads->off[reads->n] - reads->off[0];
+	pl->pending.h_stats = h_stats;
 	tr.lap("split.create(dev): enqueue");
-	if ((e = cudaStreamSynchronize(up)) != cudaSuccess) return cuda_fail(e, "job build");
+	*out = pl;
+	return DFB_OK;
+}
+
+// second half: the class counts are back (or will be: the wait sleeps); everything that depends on them
+static int split_build_finish(dfb_plan* pl)
+{
+	dfb_ctx* ctx = pl->ctx;
+	const dfb_split_params* params = &pl->sp;
+	cudaStream_t up = pl->up;
+	auto fail = [&](int code) { return code; }; // (the caller destroys the plan)
+	auto cuda_fail = [&](cudaError_t e, const char* what) {
+		return set_err(ctx, DFB_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+	};
+	Trace tr;
+	cudaError_t e;
+	if ((e = cudaEventSynchronize(pl->pending.ready)) != cudaSuccess) return cuda_fail(e, "job build");
+	pl->pending.active = false;
+	const SplitBuildParams bp = pl->pending.bp;
+	const int64_t na = pl->pending.na, nb = pl->pending.nb, raw_a = pl->pending.raw_a, raw_b = pl->pending.raw_b;
+	const int64_t n_tasks = pl->n_tasks;
+	const BuildStats* h_stats = pl->pending.h_stats;
+	const unsigned task_blocks = (unsigned)((n_tasks + DFB_BUILD_BLOCK - 1) / DFB_BUILD_BLOCK);
+	int rc;
 	tr.lap("split.create(dev): classify done");
 	if (h_stats->bad_table) return fail(set_err(ctx, DFB_ERR_ARG, "a table's offsets decrease or a sequence is too long"));
 	if (h_stats->bad_task != ~0ull) return fail(set_err(ctx, DFB_ERR_ARG, "task %llu: table index out of range", h_stats->bad_task));
@@ -1514,15 +1611,14 @@ static int split_plan_create_device(dfb_ctx* ctx, const dfb_split_params* params
 		if (!pl->ev[k] && (e = cudaEventCreate(&pl->ev[k])) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
 	cudaEventRecord(pl->ev[0], up);
 	const int max_grid = ctx->prop.multiProcessorCount * 16;
-	if (na) pack_kernel<PACK_REV_ODD><<<(int)std::min<uint64_t>(((uint64_t)na * 16 + 255) / 256, (uint64_t)max_grid), 256, 0, up>>>(pl->d_raw, da.desc, (int)na, pl->d_pool, pl->d_obytes);
-	if (nb) pack_kernel<PACK_BOTH><<<(int)std::min<uint64_t>(((uint64_t)nb * 16 + 255) / 256, (uint64_t)max_grid), 256, 0, up>>>(pl->d_raw, db.desc, (int)nb, pl->d_pool, pl->d_obytes);
+	if (na) pack_kernel<PACK_REV_ODD><<<(int)std::min<uint64_t>(((uint64_t)na * 16 + 255) / 256, (uint64_t)max_grid), 256, 0, up>>>(pl->d_raw, pl->pending.d_desc_a, (int)na, pl->d_pool, pl->d_obytes);
+	if (nb) pack_kernel<PACK_BOTH><<<(int)std::min<uint64_t>(((uint64_t)nb * 16 + 255) / 256, (uint64_t)max_grid), 256, 0, up>>>(pl->d_raw, pl->pending.d_desc_b, (int)nb, pl->d_pool, pl->d_obytes);
 	cudaEventRecord(pl->ev[1], up);
 	pl->pack_timed = true;
 	if (n_tasks) split_scatter_kernel<<<task_blocks, DFB_BUILD_BLOCK, 0, up>>>(bp);
 	if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "pack / scatter kernels");
 	if (!pl->packed_ev && (e = cudaEventCreateWithFlags(&pl->packed_ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
 	cudaEventRecord(pl->packed_ev, up);
-	const int64_t raw_b = reads->off[reads->n] - reads->off[0];
 	pl->stats.h2d_bytes += raw_a + raw_b + (na + 1 + nb + 1) * 8 + n_tasks * 12 + (int64_t)sizeof(BuildStats);
 	pl->stats.raw_bytes = raw_a + 2 * raw_b;
 	pl->stats.packed_bytes = (int64_t)total_words * 8;
@@ -1535,11 +1631,10 @@ static int split_plan_create_device(dfb_ctx* ctx, const dfb_split_params* params
 	for (int c = 0; c < kNumClasses; c++)
 		if (pl->cls[c].n_jobs) fill_fast_params(pl, c, params->match, params->mismatch, params->gap, params->min_split_score);
 	tr.lap("split.create(dev): pack, scatter, alloc");
-	*out = pl;
 	return DFB_OK;
 }
 
-extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
+static int dfb_split_plan_create_body(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
                                      const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
                                      const int32_t* task_min_score, int64_t n_tasks, dfb_plan** out)
 {
@@ -1646,7 +1741,7 @@ static int run_assemble(dfb_plan* pl)
 	return DFB_OK;
 }
 
-extern "C" int dfb_plan_run(dfb_plan* pl)
+static int dfb_plan_run_body(dfb_plan* pl)
 {
 	if (!pl) return DFB_ERR_ARG;
 	dfb_ctx* ctx = pl->ctx;
@@ -1822,7 +1917,7 @@ struct ResultSink
 
 static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols, HostPool* pool, ResultSink* sink = nullptr);
 
-extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols)
+static int dfb_split_plan_fetch_body(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols)
 {
 	if (!pl) return DFB_ERR_ARG;
 	return split_fetch_impl(pl, out_best, n_rows, n_cols, pl->ctx->pool);
@@ -2102,10 +2197,90 @@ extern "C" int dfb_plan_get_stats(const dfb_plan* pl, dfb_plan_stats* stats)
 
 // ---- one-call forms -------------------------------------------------------------------------------
 
-extern "C" int dfb_simple_align_batch(dfb_ctx* ctx, const dfb_simple_params* params, const dfb_seq_table* refs,
+// Large batches whose task_seq is non-decreasing are cut into chunks: chunk k+1 is uploaded and packed (upload stream)
+// underneath chunk k's sweep, the scores of chunk k-1 go back on the copy stream meanwhile.  A chunk takes a view of
+// the sequences it names; of the references too when task_ref is non-decreasing as well (matealign: one window per
+// task), else the whole reference table (localalign: few references, named in any order).
+static int simple_align_pipelined(dfb_ctx* ctx, const dfb_simple_params* params, const dfb_seq_table* refs,
+                                  const dfb_seq_table* seqs, const int32_t* task_ref, const int32_t* task_seq,
+                                  int64_t n_tasks, bool refs_monotone, int32_t* out_score)
+{
+	const int K = (int)std::max<int64_t>(2, std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks / 150000));
+	std::vector<dfb_plan*> plans((size_t)K, nullptr);
+	std::vector<double> weight((size_t)K, 1.0);
+	weight[0] = 0.4; // a short first chunk puts the GPU to work early
+	double total = 0, run = 0;
+	for (double w : weight) total += w;
+	int rc = DFB_OK;
+	int64_t a = 0;
+	for (int k = 0; k < K && !rc; k++)
+	{
+		run += weight[(size_t)k];
+		const int64_t b = k + 1 == K ? n_tasks : (int64_t)((double)n_tasks * run / total);
+		if (b <= a) continue;
+		const int32_t s_lo = task_seq[a], s_hi = task_seq[b - 1] + 1;
+		int32_t r_lo = 0, r_hi = (int32_t)refs->n;
+		if (refs_monotone) { r_lo = task_ref[a]; r_hi = task_ref[b - 1] + 1; }
+		if (s_lo < 0 || s_hi > seqs->n || r_lo < 0 || r_hi > refs->n || s_hi < s_lo || r_hi < r_lo)
+		{
+			rc = set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)a);
+			break;
+		}
+		dfb_seq_table sview{seqs->bytes, seqs->off + s_lo, (int64_t)(s_hi - s_lo)};
+		dfb_seq_table rview{refs->bytes, refs->off + r_lo, (int64_t)(r_hi - r_lo)};
+		dfb_plan* pk = nullptr;
+		rc = simple_plan_create_impl(ctx, params, &rview, &sview, task_ref + a, task_seq + a, b - a, r_lo, s_lo, k, true, &pk);
+		if (rc) break;
+		plans[(size_t)k] = pk;
+		rc = dfb_plan_run(pk);
+		if (!rc)
+		{
+			// scores straight into the caller's array, behind this chunk's kernels only
+			cudaError_t e = cudaStreamWaitEvent(ctx->copy_stream, pk->done_ev, 0);
+			if (e == cudaSuccess)
+				e = cudaMemcpyAsync(out_score + a, pk->d_out, (size_t)(b - a) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
+			if (e != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "score copy failed: %s", cudaGetErrorString(e));
+		}
+		a = b;
+	}
+	cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (!rc && e != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "pipelined batch failed: %s", cudaGetErrorString(e));
+	for (dfb_plan* pk : plans)
+		if (pk) dfb_plan_destroy(pk);
+	return rc;
+}
+
+static int dfb_simple_align_batch_body(dfb_ctx* ctx, const dfb_simple_params* params, const dfb_seq_table* refs,
                                       const dfb_seq_table* seqs, const int32_t* task_ref, const int32_t* task_seq,
                                       int64_t n_tasks, int32_t* out_score)
 {
+	if (!ctx) return DFB_ERR_ARG;
+	int64_t pipeline_min = 1 << 18;
+	if (const char* e = getenv("DFB_PIPELINE_MIN_TASKS")) pipeline_min = std::max<long long>(2, atoll(e)); // tests
+	if (n_tasks >= pipeline_min && params && refs && seqs && task_ref && task_seq && out_score)
+	{
+		int rc;
+		if ((rc = check_table_parallel(ctx, refs, "refs")) || (rc = check_table_parallel(ctx, seqs, "seqs"))) return rc;
+		if (n_tasks > 0x7fffff00LL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
+		const int T = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->host_threads, n_tasks / 262144 + 1));
+		std::vector<char> ok_s((size_t)T, 1), ok_r((size_t)T, 1);
+		parallel_for(ctx->pool, T, [&](int tid) {
+			const int64_t a = std::max<int64_t>(1, n_tasks * tid / T), b = n_tasks * (tid + 1) / T;
+			bool ms = true, mr = true;
+			for (int64_t t = a; t < b && ms; t++)
+			{
+				ms = task_seq[t] >= task_seq[t - 1];
+				mr = mr && task_ref[t] >= task_ref[t - 1];
+			}
+			ok_s[(size_t)tid] = ms;
+			ok_r[(size_t)tid] = mr;
+		});
+		bool seq_monotone = true, ref_monotone = true;
+		for (char c : ok_s) seq_monotone = seq_monotone && c;
+		for (char c : ok_r) ref_monotone = ref_monotone && c;
+		if (seq_monotone) return simple_align_pipelined(ctx, params, refs, seqs, task_ref, task_seq, n_tasks, ref_monotone, out_score);
+	}
 	dfb_plan* pl = nullptr;
 	Trace tr;
 	int rc = dfb_simple_plan_create(ctx, params, refs, seqs, task_ref, task_seq, n_tasks, &pl);
@@ -2198,6 +2373,8 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	bool abort = false;  // lane 1 failed: lane 2 stops after the chunks already queued
 	int fetch_rc = DFB_OK;
 	std::thread lane2([&] {
+		try
+		{
 		for (int k = 0; k < K; k++)
 		{
 			{
@@ -2215,28 +2392,59 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 				return;
 			}
 		}
+		}
+		catch (...)
+		{
+			fetch_rc = set_err(ctx, DFB_ERR_NOMEM, "out of host memory in the fetch lane");
+		}
 	});
+	// lane 1 is itself a two-stage pipeline when the job lists are built on the device: the uploads and classify kernels
+	// of chunk k+1 are queued (stage A) before chunk k is finished and launched (stage B), so that the wait for a
+	// chunk's class counts -- its kernels slip into the next gap between two sweeps -- is never on the critical path
+	std::vector<dfb_plan*> staged((size_t)K, nullptr);
+	auto chunk_of = [&](int k, dfb_seq_table& view, int32_t& r_lo) -> int {
+		const int64_t a = t0[k], b = t0[k + 1];
+		if (b <= a) return set_err(ctx, DFB_ERR_STATE, "empty chunk in a pipelined batch");
+		r_lo = task_read[a];
+		const int32_t r_hi = task_read[b - 1] + 1;
+		if (r_lo < 0 || r_hi > reads->n) return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)a);
+		view = dfb_seq_table{reads->bytes, reads->off + r_lo, (int64_t)(r_hi - r_lo)};
+		return DFB_OK;
+	};
+	auto stage_a = [&](int k) -> int {
+		dfb_seq_table view;
+		int32_t r_lo = 0;
+		int arc = chunk_of(k, view, r_lo);
+		if (arc) return arc;
+		const int64_t a = t0[k], b = t0[k + 1];
+		return split_build_enqueue(ctx, params, refs, &view, task_cluster + a, task_read + a, task_min_score + a, b - a, r_lo, k,
+		                           (k & 1) ? ctx->upload_stream2 : ctx->upload_stream, &staged[(size_t)k]);
+	};
+	if (device_build) rc = stage_a(0);
 	for (int k = 0; k < K && !rc; k++)
 	{
+		if (device_build && k + 1 < K && (rc = stage_a(k + 1))) break;
 		const int64_t a = t0[k], b = t0[k + 1];
-		if (b <= a)
+		dfb_plan* pk = staged[(size_t)k];
+		staged[(size_t)k] = nullptr;
+		rc = DFB_BUILD_ON_HOST;
+		if (pk)
 		{
-			rc = set_err(ctx, DFB_ERR_STATE, "empty chunk in a pipelined batch");
-			break;
+			rc = split_build_finish(pk);
+			if (rc)
+			{
+				dfb_plan_destroy(pk);
+				pk = nullptr;
+			}
 		}
-		const int32_t r_lo = task_read[a], r_hi = task_read[b - 1] + 1;
-		if (r_lo < 0 || r_hi > reads->n)
-		{
-			rc = set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)a);
-			break;
-		}
-		dfb_seq_table view{reads->bytes, reads->off + r_lo, (int64_t)(r_hi - r_lo)};
-		dfb_plan* pk = nullptr;
-		rc = device_build ? split_plan_create_device(ctx, params, refs, &view, task_cluster + a, task_read + a, task_min_score + a, b - a, r_lo, k, &pk)
-		                  : DFB_BUILD_ON_HOST;
 		if (rc == DFB_BUILD_ON_HOST)
-			rc = split_plan_create_impl(ctx, params, refs, &view, task_cluster + a, task_read + a, task_min_score + a, b - a, r_lo, k,
-			                            true, &pk);
+		{
+			dfb_seq_table view;
+			int32_t r_lo = 0;
+			if (!(rc = chunk_of(k, view, r_lo)))
+				rc = split_plan_create_impl(ctx, params, refs, &view, task_cluster + a, task_read + a, task_min_score + a, b - a, r_lo, k,
+				                            true, &pk);
+		}
 		if (rc) break;
 		pk->result_slot = k;
 		rc = dfb_plan_run(pk);
@@ -2247,6 +2455,12 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 		}
 		cv.notify_all();
 	}
+	for (dfb_plan* sp : staged)
+		if (sp)
+		{
+			cudaStreamSynchronize(sp->up); // (its uploads read the caller's arrays)
+			dfb_plan_destroy(sp);
+		}
 	{
 		std::lock_guard<std::mutex> lk(mu);
 		if (rc) abort = true;
@@ -2279,7 +2493,7 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	return DFB_OK;
 }
 
-extern "C" int dfb_split_align_batch(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
+static int dfb_split_align_batch_body(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
                                      const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
                                      const int32_t* task_min_score, int64_t n_tasks, int32_t* out_best)
 {
@@ -2350,6 +2564,47 @@ extern "C" int dfb_split_result_view(const dfb_ctx* ctx, const dfb_split_row** r
 	if (!ctx) return DFB_ERR_ARG;
 	if (!ctx->last_split) return set_err(ctx, DFB_ERR_STATE, "no split result on this context");
 	return dfb_split_plan_view(ctx->last_split, rows, n_rows, cols, n_cols);
+}
+
+
+// ---- exception barrier of the entry points that allocate batch-sized host memory --------------------------------
+
+extern "C" int dfb_simple_plan_create(dfb_ctx* ctx, const dfb_simple_params* params, const dfb_seq_table* refs,
+                                      const dfb_seq_table* seqs, const int32_t* task_ref, const int32_t* task_seq,
+                                      int64_t n_tasks, dfb_plan** out)
+{
+	return guarded(ctx, [&] { return dfb_simple_plan_create_body(ctx, params, refs, seqs, task_ref, task_seq, n_tasks, out); });
+}
+
+extern "C" int dfb_split_plan_create(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
+                                     const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
+                                     const int32_t* task_min_score, int64_t n_tasks, dfb_plan** out)
+{
+	return guarded(ctx, [&] { return dfb_split_plan_create_body(ctx, params, refs, reads, task_cluster, task_read, task_min_score, n_tasks, out); });
+}
+
+extern "C" int dfb_plan_run(dfb_plan* pl)
+{
+	return guarded(pl ? pl->ctx : nullptr, [&] { return dfb_plan_run_body(pl); });
+}
+
+extern "C" int dfb_split_plan_fetch(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, int64_t* n_cols)
+{
+	return guarded(pl ? pl->ctx : nullptr, [&] { return dfb_split_plan_fetch_body(pl, out_best, n_rows, n_cols); });
+}
+
+extern "C" int dfb_simple_align_batch(dfb_ctx* ctx, const dfb_simple_params* params, const dfb_seq_table* refs,
+                                      const dfb_seq_table* seqs, const int32_t* task_ref, const int32_t* task_seq,
+                                      int64_t n_tasks, int32_t* out_score)
+{
+	return guarded(ctx, [&] { return dfb_simple_align_batch_body(ctx, params, refs, seqs, task_ref, task_seq, n_tasks, out_score); });
+}
+
+extern "C" int dfb_split_align_batch(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
+                                     const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
+                                     const int32_t* task_min_score, int64_t n_tasks, int32_t* out_best)
+{
+	return guarded(ctx, [&] { return dfb_split_align_batch_body(ctx, params, refs, reads, task_cluster, task_read, task_min_score, n_tasks, out_best); });
 }
 
 #include "dfb_trace.cuh"

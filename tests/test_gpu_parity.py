@@ -344,6 +344,29 @@ def test_large_simple_batch_sampled_parity(oracle_mod, gpu_ctx):
     assert np.array_equal(got[sample], want)
 
 
+def test_pipelined_simple_batch(oracle_mod, gpu_ctx, monkeypatch):
+    """dfb_simple_align_batch cuts large batches (non-decreasing task_seq) into chunks: forced here on small batches,
+    with references named in any order (localalign: the whole table per chunk), references in task order (matealign:
+    a view per chunk), empty sequences and the generic (s32) kernels.  Same scores as the single plan and the oracle."""
+    import defuse_b200 as d
+    rng = np.random.default_rng(41)
+    refs, seqs, tr, ts = util.simple_batch(rng, 30, 700, (1, 600), (0, 260))
+    for scoring in [(10, -5, -5), (2, 1, -1)]:
+        monkeypatch.delenv("DFB_PIPELINE_MIN_TASKS", raising=False)
+        rt, st = _tables(refs, seqs)
+        al = d.SimpleAligner(*scoring, ctx=gpu_ctx)
+        single = al.align_batch(rt, st, tr, ts)
+        monkeypatch.setenv("DFB_PIPELINE_MIN_TASKS", "16")
+        assert np.array_equal(al.align_batch(rt, st, tr, ts), single)
+        _check_simple(oracle_mod, gpu_ctx, refs, seqs, tr, ts, *scoring)
+        # one reference per task, in task order
+        refs2 = [refs[r] for r in tr]
+        tr2 = np.arange(len(tr), dtype=np.int32)
+        _check_simple(oracle_mod, gpu_ctx, refs2, seqs, tr2, ts, *scoring)
+        # decreasing task_seq: single plan
+        assert np.array_equal(al.align_batch(rt, st, tr[::-1].copy(), ts[::-1].copy()), single[::-1])
+
+
 def test_pipelined_one_call_path(oracle_mod, gpu_ctx, monkeypatch):
     """dfb_split_align_batch cuts large batches (non-decreasing task_read) into chunks that overlap host and GPU work;
     forced here on a small batch.  Results must equal the single-plan path and the oracle, including shared reads
