@@ -115,6 +115,7 @@ def load_library():
         "dfb_plan_get_stats": ([vp, P(_PlanStats)], ctypes.c_int),
         "dfb_plan_destroy": ([vp], None),
         "dfb_microbench_issue_rate": ([vp, ctypes.c_int, ctypes.c_int, P(ctypes.c_double), P(ctypes.c_double)], ctypes.c_int),
+        "dfb_ctx_memory_info": ([vp, ctypes.c_int, P(i64), P(i64), P(i64)], ctypes.c_int),
         "dfb_split_backtrace_batch": ([vp, P(_SplitParams), P(_SeqTable), P(_SeqTable), vp, vp, vp, vp, vp, i64, vp, vp, i64,
                                        P(i64)], ctypes.c_int),
     }
@@ -132,7 +133,7 @@ ABI_SYMBOLS = (
     "dfb_split_result_copy", "dfb_split_result_view", "dfb_split_plan_view", "dfb_simple_plan_create", "dfb_split_plan_create", "dfb_plan_run", "dfb_plan_sync",
     "dfb_plan_set_timing",
     "dfb_simple_plan_fetch", "dfb_split_plan_fetch", "dfb_split_plan_copy", "dfb_plan_get_stats", "dfb_plan_destroy",
-    "dfb_microbench_issue_rate", "dfb_split_backtrace_batch",
+    "dfb_microbench_issue_rate", "dfb_split_backtrace_batch", "dfb_ctx_memory_info",
 )
 
 
@@ -215,6 +216,12 @@ class Context:
         self._check(self._lib.dfb_ctx_device_info(self._h, ctypes.byref(info)))
         return {"name": info.name.decode(), "ordinal": info.ordinal, "sm_count": info.sm_count,
                 "cc": (info.cc_major, info.cc_minor), "clock_khz": info.clock_khz, "total_mem": info.total_mem}
+
+    def memory_info(self, reset=False):
+        """Device memory of the context's pool: (reserved now, reserved high-water mark, used high-water mark) in bytes."""
+        a, b, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        self._check(self._lib.dfb_ctx_memory_info(self._h, int(bool(reset)), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
 
     def microbench_issue_rate(self, kind, iters=2000):
         rate = ctypes.c_double()

@@ -349,9 +349,13 @@ extern "C" int dfb_ctx_create(int device_ordinal, dfb_ctx** out)
 		return set_err(nullptr, DFB_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(e));
 	}
 	ctx->stream = ctx->own_stream;
+	// the upload streams outrank the compute stream: their small kernels (packing, job build) take the first SM slots
+	// that a persistent sweep kernel gives back, instead of queueing behind the next sweep's whole grid
+	int prio_lo = 0, prio_hi = 0;
+	cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
 	if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-	    (e = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-	    (e = cudaStreamCreateWithFlags(&ctx->upload_stream2, cudaStreamNonBlocking)) != cudaSuccess)
+	    (e = cudaStreamCreateWithPriority(&ctx->upload_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
+	    (e = cudaStreamCreateWithPriority(&ctx->upload_stream2, cudaStreamNonBlocking, prio_hi)) != cudaSuccess)
 	{
 		cudaStreamDestroy(ctx->own_stream);
 		delete ctx;
@@ -426,6 +430,27 @@ extern "C" int dfb_ctx_device_info(const dfb_ctx* ctx, dfb_device_info* info)
 	cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
 	info->clock_khz = khz;
 	info->total_mem = (int64_t)ctx->prop.totalGlobalMem;
+	return DFB_OK;
+}
+
+extern "C" int dfb_ctx_memory_info(dfb_ctx* ctx, int reset, int64_t* reserved_now, int64_t* reserved_high, int64_t* used_high)
+{
+	if (!ctx) return DFB_ERR_ARG;
+	cudaMemPool_t pool;
+	CK(ctx, cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+	unsigned long long now = 0, rhigh = 0, uhigh = 0;
+	CK(ctx, cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &now));
+	CK(ctx, cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemHigh, &rhigh));
+	CK(ctx, cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &uhigh));
+	if (reserved_now) *reserved_now = (int64_t)now;
+	if (reserved_high) *reserved_high = (int64_t)rhigh;
+	if (used_high) *used_high = (int64_t)uhigh;
+	if (reset)
+	{
+		unsigned long long zero = 0;
+		CK(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReservedMemHigh, &zero));
+		CK(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &zero));
+	}
 	return DFB_OK;
 }
 
@@ -987,8 +1012,9 @@ static int finish_create(dfb_plan* pl)
 // stream (chunks of a pipelined batch).
 static int simple_plan_create_impl(dfb_ctx* ctx, const dfb_simple_params* params, const dfb_seq_table* refs,
                                    const dfb_seq_table* seqs, const int32_t* task_ref, const int32_t* task_seq,
-                                   int64_t n_tasks, int32_t ref_base, int32_t seq_base, int stage_slot, bool async, dfb_plan** out)
+                                   int64_t n_tasks, int32_t ref_base, int32_t seq_base, int stage_slot, cudaStream_t up_stream, dfb_plan** out)
 {
+	const bool async = up_stream != nullptr;
 	*out = nullptr;
 	int rc;
 	CK(ctx, cudaSetDevice(ctx->device));
@@ -1002,7 +1028,7 @@ static int simple_plan_create_impl(dfb_ctx* ctx, const dfb_simple_params* params
 	pl->sp.mismatch = params->mismatch;
 	pl->sp.gap = params->gap;
 	classify_params(pl, params->match, params->mismatch, params->gap, true);
-	pl->up = async ? ctx->upload_stream : nullptr;
+	pl->up = up_stream;
 	Trace tr;
 	if ((rc = upload_raw(pl, refs, seqs)))
 	{
@@ -1185,7 +1211,7 @@ static int dfb_simple_plan_create_body(dfb_ctx* ctx, const dfb_simple_params* pa
 	int rc;
 	if ((rc = check_table(ctx, refs, "refs")) || (rc = check_table(ctx, seqs, "seqs"))) return rc;
 	if (n_tasks > 0x7fffff00LL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
-	return simple_plan_create_impl(ctx, params, refs, seqs, task_ref, task_seq, n_tasks, 0, 0, 0, false, out);
+	return simple_plan_create_impl(ctx, params, refs, seqs, task_ref, task_seq, n_tasks, 0, 0, 0, nullptr, out);
 }
 
 // ---- SplitReadAligner plan ------------------------------------------------------------------
@@ -1209,7 +1235,7 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 	pl->n_tasks = n_tasks;
 	pl->stats.n_tasks = n_tasks;
 	classify_params(pl, params->match, params->mismatch, params->gap, params->end_gaps == 0 && params->min_split_score >= 1);
-	pl->up = async ? ctx->upload_stream : nullptr;
+	pl->up = async ? ((stage_slot & 1) ? ctx->upload_stream2 : ctx->upload_stream) : nullptr;
 	if ((rc = upload_raw(pl, refs, reads)))
 	{
 		dfb_plan_destroy(pl);
@@ -2229,7 +2255,9 @@ static int simple_align_pipelined(dfb_ctx* ctx, const dfb_simple_params* params,
 		dfb_seq_table sview{seqs->bytes, seqs->off + s_lo, (int64_t)(s_hi - s_lo)};
 		dfb_seq_table rview{refs->bytes, refs->off + r_lo, (int64_t)(r_hi - r_lo)};
 		dfb_plan* pk = nullptr;
-		rc = simple_plan_create_impl(ctx, params, &rview, &sview, task_ref + a, task_seq + a, b - a, r_lo, s_lo, k, true, &pk);
+		// (alternating upload streams: chunk k+1's copies do not queue behind chunk k's pack kernels)
+		rc = simple_plan_create_impl(ctx, params, &rview, &sview, task_ref + a, task_seq + a, b - a, r_lo, s_lo, k,
+		                             (k & 1) ? ctx->upload_stream2 : ctx->upload_stream, &pk);
 		if (rc) break;
 		plans[(size_t)k] = pk;
 		rc = dfb_plan_run(pk);
@@ -2382,8 +2410,6 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 				cv.wait(lk, [&] { return queued > k || abort; });
 				if (queued <= k) return;
 			}
-			// (the chunk's device buffers are released with the others at the end: a stream-ordered free in the middle
-			// of the pipeline cannot be reused by the chunks still being built and only makes the pool grow)
 			sink.task_shift = (int32_t)t0[(size_t)k];
 			int frc = split_fetch_impl(plans[k], out_best ? out_best + t0[k] : nullptr, nullptr, nullptr, ctx->pool_fetch, &sink);
 			if (frc)
@@ -2391,6 +2417,10 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 				fetch_rc = frc;
 				return;
 			}
+			// the chunk's device buffers go back to the pool now (stream-ordered): lane 1 stays about two chunks ahead
+			// of the GPU, so the chunks still to be built reuse them and a batch never holds more than about half of
+			// its chunks' checkpoints at a time
+			release_device(plans[k]);
 		}
 		}
 		catch (...)

@@ -240,6 +240,12 @@ DFB_API void dfb_plan_destroy(dfb_plan* plan);
 
 /* ---- measurement support --------------------------------------------------------------- */
 
+/* Device memory of the context's stream-ordered pool: bytes reserved from the driver now, and the
+ * high-water marks of reserved and used bytes since the context was created (or since the last
+ * call with reset != 0).  What a batch holds on the GPU at most. */
+DFB_API int dfb_ctx_memory_info(dfb_ctx* ctx, int reset, int64_t* reserved_now, int64_t* reserved_high,
+                                int64_t* used_high);
+
 /* Integer/DPX issue-rate microbenchmark (the denominator of the DP roofline).
  * Runs dependent-free streams of one instruction kind on every SM and returns
  * warp-instructions issued per second (whole chip).  `kind`:
