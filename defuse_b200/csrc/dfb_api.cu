@@ -566,11 +566,15 @@ struct dfb_plan
 	{
 		bool active = false;
 		SplitBuildParams bp;
+		DescParams da, db;
 		const SeqDesc* d_desc_a = nullptr;
 		const SeqDesc* d_desc_b = nullptr;
-		int64_t na = 0, nb = 0, raw_a = 0, raw_b = 0;
+		int64_t na = 0, nb = 0, raw_a = 0, raw_b = 0, blocks_a = 0, blocks_b = 0;
+		BuildStats* d_stats = nullptr;
+		unsigned long long* d_words_a_end = nullptr;
 		BuildStats* h_stats = nullptr;
-		cudaEvent_t ready = nullptr; // behind the read-back of the statistics (blocking-sync: the waiting thread sleeps)
+		cudaEvent_t uploaded = nullptr; // behind the chunk's uploads (upload stream)
+		cudaEvent_t ready = nullptr;    // behind the read-back of the statistics (blocking-sync: the waiting thread sleeps)
 	} pending;
 	uint2* d_pool = nullptr;
 	uint8_t* d_obytes = nullptr;
@@ -693,6 +697,7 @@ extern "C" void dfb_plan_destroy(dfb_plan* plan)
 		}
 	}
 	if (plan->pending.ready) cudaEventDestroy(plan->pending.ready);
+	if (plan->pending.uploaded) cudaEventDestroy(plan->pending.uploaded);
 	if (plan->done_ev) cudaEventDestroy(plan->done_ev);
 	if (plan->packed_ev) cudaEventDestroy(plan->packed_ev);
 	plan->rows.release();
@@ -1537,20 +1542,6 @@ static int split_build_enqueue(dfb_ctx* ctx, const dfb_split_params* params, con
 	db.block_sums = (unsigned long long*)(base + o_sums_b);
 	db.word_base = d_words_a_end;
 	db.total = &d_stats->total_words;
-	if (na)
-	{
-		desc_count_kernel<<<(unsigned)blocks_a, DFB_BUILD_BLOCK, 0, up>>>(da);
-		desc_scan_kernel<<<1, DFB_BUILD_BLOCK, 0, up>>>(da.block_sums, blocks_a, da.word_base, da.total);
-		desc_write_kernel<<<(unsigned)blocks_a, DFB_BUILD_BLOCK, 0, up>>>(da);
-	}
-	else if ((e = cudaMemsetAsync(d_words_a_end, 0, 8, up)) != cudaSuccess) return cuda_fail(e, "memset");
-	if (nb)
-	{
-		desc_count_kernel<<<(unsigned)blocks_b, DFB_BUILD_BLOCK, 0, up>>>(db);
-		desc_scan_kernel<<<1, DFB_BUILD_BLOCK, 0, up>>>(db.block_sums, blocks_b, db.word_base, db.total);
-		desc_write_kernel<<<(unsigned)blocks_b, DFB_BUILD_BLOCK, 0, up>>>(db);
-	}
-	else if ((e = cudaMemcpyAsync(&d_stats->total_words, d_words_a_end, 8, cudaMemcpyDeviceToDevice, up)) != cudaSuccess) return cuda_fail(e, "copy");
 	SplitBuildParams bp;
 	memset(&bp, 0, sizeof(bp));
 	bp.desc_a = da.desc;
@@ -1574,25 +1565,60 @@ static int split_build_enqueue(dfb_ctx* ctx, const dfb_split_params* params, con
 	bp.max_fast_rows = kMaxFastRows;
 	bp.stats = d_stats;
 	bp.jobs = (JobPair*)(base + o_jobs);
-	const unsigned task_blocks = (unsigned)((n_tasks + DFB_BUILD_BLOCK - 1) / DFB_BUILD_BLOCK);
-	if (n_tasks) split_classify_kernel<<<task_blocks, DFB_BUILD_BLOCK, 0, up>>>(bp);
-	bin_scan_kernel<<<1, 1024, 0, up>>>(bp.bin_count, kNumClasses, d_stats);
-	if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "job build kernels");
-	if ((e = cudaMemcpyAsync(h_stats, d_stats, sizeof(BuildStats), cudaMemcpyDeviceToHost, up)) != cudaSuccess) return cuda_fail(e, "statistics read-back");
-	if ((e = cudaEventCreateWithFlags(&pl->pending.ready, cudaEventDisableTiming | cudaEventBlockingSync)) != cudaSuccess ||
-	    (e = cudaEventRecord(pl->pending.ready, up)) != cudaSuccess)
+	if ((e = cudaEventCreateWithFlags(&pl->pending.uploaded, cudaEventDisableTiming)) != cudaSuccess ||
+	    (e = cudaEventRecord(pl->pending.uploaded, up)) != cudaSuccess)
 		return cuda_fail(e, "cudaEventRecord");
 	pl->pending.active = true;
 	pl->pending.bp = bp;
+	pl->pending.da = da;
+	pl->pending.db = db;
 	pl->pending.d_desc_a = da.desc;
 	pl->pending.d_desc_b = db.desc;
 	pl->pending.na = na;
 	pl->pending.nb = nb;
+	pl->pending.blocks_a = blocks_a;
+	pl->pending.blocks_b = blocks_b;
 	pl->pending.raw_a = raw_a;
 	pl->pending.raw_b = reads->off[reads->n] - reads->off[0];
+	pl->pending.d_stats = d_stats;
+	pl->pending.d_words_a_end = d_words_a_end;
 	pl->pending.h_stats = h_stats;
-	tr.lap("split.create(dev): enqueue");
+	tr.lap("split.create(dev): uploads queued");
 	*out = pl;
+	return DFB_OK;
+}
+
+// The build kernels of a chunk, on the COMPUTE stream: the sweeps are persistent grids that fill every SM, so a chain
+// of small dependent kernels on another stream would wait for a kernel boundary per link.  Queued between the first
+// sweep and the probe sweep of the previous chunk, the chain costs the GPU a few tens of microseconds and its class
+// counts are back on the host long before that chunk's probe sweep ends.
+static int split_build_kernels(dfb_plan* pl)
+{
+	dfb_ctx* ctx = pl->ctx;
+	cudaStream_t cs = ctx->stream;
+	auto& pd = pl->pending;
+	CK(ctx, cudaStreamWaitEvent(cs, pd.uploaded, 0));
+	if (pd.na)
+	{
+		desc_count_kernel<<<(unsigned)pd.blocks_a, DFB_BUILD_BLOCK, 0, cs>>>(pd.da);
+		desc_scan_kernel<<<1, DFB_BUILD_BLOCK, 0, cs>>>(pd.da.block_sums, pd.blocks_a, pd.da.word_base, pd.da.total);
+		desc_write_kernel<<<(unsigned)pd.blocks_a, DFB_BUILD_BLOCK, 0, cs>>>(pd.da);
+	}
+	else CK(ctx, cudaMemsetAsync(pd.d_words_a_end, 0, 8, cs));
+	if (pd.nb)
+	{
+		desc_count_kernel<<<(unsigned)pd.blocks_b, DFB_BUILD_BLOCK, 0, cs>>>(pd.db);
+		desc_scan_kernel<<<1, DFB_BUILD_BLOCK, 0, cs>>>(pd.db.block_sums, pd.blocks_b, pd.db.word_base, pd.db.total);
+		desc_write_kernel<<<(unsigned)pd.blocks_b, DFB_BUILD_BLOCK, 0, cs>>>(pd.db);
+	}
+	else CK(ctx, cudaMemcpyAsync(&pd.d_stats->total_words, pd.d_words_a_end, 8, cudaMemcpyDeviceToDevice, cs));
+	const unsigned task_blocks = (unsigned)((pl->n_tasks + DFB_BUILD_BLOCK - 1) / DFB_BUILD_BLOCK);
+	if (pl->n_tasks) split_classify_kernel<<<task_blocks, DFB_BUILD_BLOCK, 0, cs>>>(pd.bp);
+	bin_scan_kernel<<<1, 1024, 0, cs>>>(pd.bp.bin_count, kNumClasses, pd.d_stats);
+	CK(ctx, cudaGetLastError());
+	CK(ctx, cudaMemcpyAsync(pd.h_stats, pd.d_stats, sizeof(BuildStats), cudaMemcpyDeviceToHost, cs));
+	if (!pd.ready) CK(ctx, cudaEventCreateWithFlags(&pd.ready, cudaEventDisableTiming | cudaEventBlockingSync));
+	CK(ctx, cudaEventRecord(pd.ready, cs));
 	return DFB_OK;
 }
 
@@ -1601,7 +1627,7 @@ static int split_build_finish(dfb_plan* pl)
 {
 	dfb_ctx* ctx = pl->ctx;
 	const dfb_split_params* params = &pl->sp;
-	cudaStream_t up = pl->up;
+	cudaStream_t up = ctx->stream; // (packing and the job scatter run on the compute stream, in front of the chunk's sweeps)
 	auto fail = [&](int code) { return code; }; // (the caller destroys the plan)
 	auto cuda_fail = [&](cudaError_t e, const char* what) {
 		return set_err(ctx, DFB_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
@@ -1643,8 +1669,6 @@ static int split_build_finish(dfb_plan* pl)
 	pl->pack_timed = true;
 	if (n_tasks) split_scatter_kernel<<<task_blocks, DFB_BUILD_BLOCK, 0, up>>>(bp);
 	if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "pack / scatter kernels");
-	if (!pl->packed_ev && (e = cudaEventCreateWithFlags(&pl->packed_ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
-	cudaEventRecord(pl->packed_ev, up);
 	pl->stats.h2d_bytes += raw_a + raw_b + (na + 1 + nb + 1) * 8 + n_tasks * 12 + (int64_t)sizeof(BuildStats);
 	pl->stats.raw_bytes = raw_a + 2 * raw_b;
 	pl->stats.packed_bytes = (int64_t)total_words * 8;
@@ -1767,7 +1791,9 @@ static int run_assemble(dfb_plan* pl)
 	return DFB_OK;
 }
 
-static int dfb_plan_run_body(dfb_plan* pl)
+// `between_sweeps`: work queued on the compute stream behind the first sweep and in front of the probe sweep (the
+// pipelined batch puts the next chunk's job-build kernels there)
+static int plan_run_impl(dfb_plan* pl, const std::function<int()>* between_sweeps)
 {
 	if (!pl) return DFB_ERR_ARG;
 	dfb_ctx* ctx = pl->ctx;
@@ -1824,6 +1850,11 @@ static int dfb_plan_run_body(dfb_plan* pl)
 		}
 	}
 	if (pl->timing) CK(ctx, cudaEventRecord(pl->ev[1], ctx->stream));
+	if (between_sweeps)
+	{
+		int rc = (*between_sweeps)();
+		if (rc) return rc;
+	}
 	if (pl->split)
 	{
 		int rc = run_probe(pl);
@@ -1842,6 +1873,8 @@ static int dfb_plan_run_body(dfb_plan* pl)
 	pl->ran = true;
 	return DFB_OK;
 }
+
+static int dfb_plan_run_body(dfb_plan* pl) { return plan_run_impl(pl, nullptr); }
 
 extern "C" int dfb_plan_sync(dfb_plan* pl)
 {
@@ -2428,9 +2461,10 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 			fetch_rc = set_err(ctx, DFB_ERR_NOMEM, "out of host memory in the fetch lane");
 		}
 	});
-	// lane 1 is itself a two-stage pipeline when the job lists are built on the device: the uploads and classify kernels
-	// of chunk k+1 are queued (stage A) before chunk k is finished and launched (stage B), so that the wait for a
-	// chunk's class counts -- its kernels slip into the next gap between two sweeps -- is never on the critical path
+	// Device-built chunks (lane 1 in three beats per chunk): the uploads of chunk k+1 are queued on an upload stream
+	// while chunk k is finished -- allocations, packing and job scatter once its class counts are back -- and launched;
+	// the job-build kernels of chunk k+1 ride on the compute stream between chunk k's two sweeps, so their counts are
+	// on the host before chunk k's probe sweep ends and the GPU never waits for this thread.
 	std::vector<dfb_plan*> staged((size_t)K, nullptr);
 	auto chunk_of = [&](int k, dfb_seq_table& view, int32_t& r_lo) -> int {
 		const int64_t a = t0[k], b = t0[k + 1];
@@ -2441,7 +2475,7 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 		view = dfb_seq_table{reads->bytes, reads->off + r_lo, (int64_t)(r_hi - r_lo)};
 		return DFB_OK;
 	};
-	auto stage_a = [&](int k) -> int {
+	auto upload = [&](int k) -> int {
 		dfb_seq_table view;
 		int32_t r_lo = 0;
 		int arc = chunk_of(k, view, r_lo);
@@ -2450,10 +2484,14 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 		return split_build_enqueue(ctx, params, refs, &view, task_cluster + a, task_read + a, task_min_score + a, b - a, r_lo, k,
 		                           (k & 1) ? ctx->upload_stream2 : ctx->upload_stream, &staged[(size_t)k]);
 	};
-	if (device_build) rc = stage_a(0);
+	if (device_build)
+	{
+		rc = upload(0);
+		if (!rc) rc = split_build_kernels(staged[0]); // (the GPU is idle: straight away)
+	}
 	for (int k = 0; k < K && !rc; k++)
 	{
-		if (device_build && k + 1 < K && (rc = stage_a(k + 1))) break;
+		if (device_build && k + 1 < K && (rc = upload(k + 1))) break;
 		const int64_t a = t0[k], b = t0[k + 1];
 		dfb_plan* pk = staged[(size_t)k];
 		staged[(size_t)k] = nullptr;
@@ -2477,7 +2515,9 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 		}
 		if (rc) break;
 		pk->result_slot = k;
-		rc = dfb_plan_run(pk);
+		dfb_plan* next = (k + 1 < K) ? staged[(size_t)k + 1] : nullptr;
+		const std::function<int()> hook = [&]() -> int { return next ? split_build_kernels(next) : DFB_OK; };
+		rc = plan_run_impl(pk, &hook);
 		{
 			std::lock_guard<std::mutex> lk(mu);
 			plans[k] = pk;
