@@ -7,8 +7,19 @@
 // cluster ends) are the same std containers filled by the same sequence of inserts.
 // SplitReadAligner::Align + GetAlignments (tools/SplitAlignment.cpp:376-379) run on the GPU through
 // dfb_split_align_batch; de-duplication and min(score1,score2) (:381-400) stay on the host.
+//
+// Built with -DDFB_FUSED_EVAL the same source is dosplitalign_eval, the fused align -> evaluate tool:
+//   dosplitalign_eval <the flags above, -a optional> -q out.seq -b out.break -p out.predalign
+// The records stay in memory, are put into the order the pipeline's `sort -n -k 1` gives the alignments file
+// (scripts/defuse_run.pl:528,533: numeric on the fusion id, whole line bytewise among equals, C locale) and go straight
+// into evalsplitalign's evaluation (eval_core.h): the three outputs are byte-identical to
+// dosplitalign | sort | evalsplitalign, without the multi-gigabyte intermediate file, the sort and the second parse.
+// One process must see every read of the fusions it evaluates (one fastq split, or all of them).
 #include "split_tasks.h"
 #include "fast_io.h"
+#ifdef DFB_FUSED_EVAL
+#include "eval_core.h"
+#endif
 
 #include <algorithm>
 #include <fstream>
@@ -29,6 +40,65 @@ struct Candidate
 	int rev_comp;
 };
 
+#ifdef DFB_FUSED_EVAL
+// `sort -n -k 1` in the C locale over the lines of `text`: by leading integer, lines with equal numbers bytewise
+// (sort's last-resort comparison).  Counting sort on the fusion id, the lines of a fusion ordered by one thread.
+std::string SortRecordsLikeThePipeline(const std::string& text)
+{
+	struct Line
+	{
+		const char* b;
+		uint32_t len; // without the newline
+		int id;
+	};
+	std::vector<Line> lines;
+	for (const char *a = text.data(), *end = a + text.size(); a < end;)
+	{
+		const char* nl = (const char*)memchr(a, '\n', (size_t)(end - a));
+		const char* e = nl ? nl : end;
+		int id = 0;
+		const char* t = (const char*)memchr(a, '\t', (size_t)(e - a));
+		ParseIntRange(a, t ? t : e, id);
+		lines.push_back(Line{a, (uint32_t)(e - a), id});
+		a = nl ? nl + 1 : end;
+	}
+	std::vector<int> ids;
+	ids.reserve(lines.size());
+	for (const Line& l : lines) ids.push_back(l.id);
+	std::sort(ids.begin(), ids.end());
+	ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+	std::vector<size_t> begin(ids.size() + 1, 0);
+	std::vector<uint32_t> rank(lines.size());
+	for (size_t k = 0; k < lines.size(); k++)
+	{
+		rank[k] = (uint32_t)(std::lower_bound(ids.begin(), ids.end(), lines[k].id) - ids.begin());
+		begin[rank[k] + 1]++;
+	}
+	for (size_t k = 0; k < ids.size(); k++) begin[k + 1] += begin[k];
+	std::vector<Line> sorted(lines.size());
+	{
+		std::vector<size_t> at(begin.begin(), begin.end() - 1);
+		for (size_t k = 0; k < lines.size(); k++) sorted[at[rank[k]]++] = lines[k];
+	}
+	const int T = ToolThreads();
+	ParallelRun(T, [&](int tid) {
+		for (size_t f = (size_t)tid; f < ids.size(); f += (size_t)T)
+			std::sort(sorted.begin() + (ptrdiff_t)begin[f], sorted.begin() + (ptrdiff_t)begin[f + 1], [](const Line& x, const Line& y) {
+				const int c = memcmp(x.b, y.b, std::min(x.len, y.len));
+				return c != 0 ? c < 0 : x.len < y.len;
+			});
+	});
+	std::string out;
+	out.reserve(text.size() + 1);
+	for (const Line& l : sorted)
+	{
+		out.append(l.b, l.len);
+		out += '\n';
+	}
+	return out;
+}
+#endif
+
 }  // namespace
 
 int main(int argc, char* argv[])
@@ -44,7 +114,14 @@ int main(int argc, char* argv[])
 	    {'i', "improper", "Improper Alignments Sam Filename", true, "string", "", false},
 	    {'1', "seq1", "End 1 Sequences", true, "string", "", false},
 	    {'2', "seq2", "End 2 Sequences", true, "string", "", false},
+#ifdef DFB_FUSED_EVAL
+	    {'a', "align", "Split Alignments Filename (optional here)", false, "string", "", false},
+	    {'q', "seq", "Sequences Filename", true, "string", "", false},
+	    {'b', "break", "Break Positions Filename", true, "string", "", false},
+	    {'p', "predalign", "Prediction Split Alignments Filename", true, "string", "", false},
+#else
 	    {'a', "align", "Split Alignments Filename", true, "string", "", false},
+#endif
 	});
 	cmd.Parse(argc, argv);
 	PhaseTimer timer;
@@ -340,8 +417,16 @@ int main(int argc, char* argv[])
 	};
 
 	timer.Lap("fastq (wait)");
+#ifdef DFB_FUSED_EVAL
+	const bool write_align = cmd.IsSet('a');
+	std::ofstream out;
+	if (write_align) out.open(cmd.Str('a').c_str());
+	std::string fused_text; // every record of the run, in emission order
+#else
+	const bool write_align = true;
 	std::ofstream out(cmd.Str('a').c_str());
-	if (!out.good())
+#endif
+	if (write_align && !out.good())
 	{
 		std::cerr << "Error: Unable to open " << cmd.Str('a') << std::endl;
 		ExitNow(1);
@@ -618,11 +703,35 @@ int main(int argc, char* argv[])
 			}
 		});
 		timer.Add("batch: format");
-		for (const std::string& part : out_parts) out.write(part.data(), (std::streamsize)part.size());
+		if (write_align)
+			for (const std::string& part : out_parts) out.write(part.data(), (std::streamsize)part.size());
+#ifdef DFB_FUSED_EVAL
+		for (const std::string& part : out_parts) fused_text += part;
+#endif
 		timer.Add("batch: write");
 	}
-	out.flush();
-	out.close();
+	if (write_align)
+	{
+		out.flush();
+		out.close();
+	}
+#ifdef DFB_FUSED_EVAL
+	{
+		// align -> evaluate without the file in between (tools/evalsplitalign.cpp:96-114 on the sorted records)
+		std::ofstream seq_file(cmd.Str('q').c_str()), break_file(cmd.Str('b').c_str()), pred_file(cmd.Str('p').c_str());
+		for (const char f : {'q', 'b', 'p'})
+			if (!(f == 'q' ? seq_file : (f == 'b' ? break_file : pred_file)).good())
+			{
+				std::cerr << "Error: Unable to open " << cmd.Str(f) << std::endl;
+				ExitNow(1);
+			}
+		const std::string sorted = SortRecordsLikeThePipeline(fused_text);
+		timer.Lap("fused: sort records");
+		const bool ok = EvaluateSortedRecords(sorted.data(), sorted.data() + sorted.size(), tasks, seq_file, break_file, pred_file);
+		timer.Lap("fused: evaluate");
+		if (!ok) ExitNow(1);
+	}
+#endif
 	timer.Report();
 	timer.Lap("close");
 	FinishProcess(0);
