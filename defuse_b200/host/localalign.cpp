@@ -7,6 +7,12 @@
 // helper thread when it is a pipe), a block is parsed in place by line-aligned chunks on all host threads, and the
 // 2 001-bp references the pipeline repeats on ~100 consecutive lines (scripts/prep_local_alignment_seqs.pl:120) are
 // uploaded once per batch.
+//
+// Built with -DDFB_COMPACT_INPUT the same source is localalign_dedup: same flags and output, but
+// a reference field that is the single character '=' stands for the reference of the line before it.  The pipeline
+// repeats each 2 001-bp reference on about a hundred consecutive lines (scripts/prep_local_alignment_seqs.pl:92-156), so
+// this form carries every reference once: stdin shrinks from ~2.1 kB to ~120 B per line (INTEGRATION.md shows the
+// one-line change on the Perl side).  The stock form stays what it was: a separate binary, not a changed grammar.
 #include "host_common.h"
 #include "fast_io.h"
 
@@ -65,6 +71,11 @@ int main(int argc, char* argv[])
 	std::vector<int32_t> task_ref, task_seq, score, remap;
 	std::vector<std::string> out_parts((size_t)T);
 	int64_t lines_before = 0; // lines of the blocks already handled (for the 1-based line numbers of the messages)
+#ifdef DFB_COMPACT_INPUT
+	std::string carry_store;  // the reference of the last line seen, across chunks and blocks
+	std::string_view carry;
+	bool have_carry = false;
+#endif
 	const char* block = nullptr;
 	size_t block_len = 0;
 	while (input.Next(block, block_len))
@@ -108,7 +119,22 @@ int main(int argc, char* argv[])
 				ln.ref_len = (uint32_t)(t2 - t1 - 1);
 				ln.seq = t2 + 1;
 				ln.seq_len = (uint32_t)((t3 ? t3 : e) - t2 - 1);
-				if (!out.lines.empty() && out.lines.back().ref_len == ln.ref_len && memcmp(out.lines.back().ref, ln.ref, ln.ref_len) == 0)
+#ifdef DFB_COMPACT_INPUT
+				if (ln.ref_len == 1 && ln.ref[0] == '=')
+				{
+					// the reference of the line before; the first line of a chunk is resolved when the chunks are put together
+					if (out.lines.empty()) ln.ref_index = -1;
+					else
+					{
+						ln.ref = out.lines.back().ref;
+						ln.ref_len = out.lines.back().ref_len;
+						ln.ref_index = out.lines.back().ref_index;
+					}
+				}
+				else
+#endif
+				if (!out.lines.empty() && out.lines.back().ref_index >= 0 && out.lines.back().ref_len == ln.ref_len &&
+				    memcmp(out.lines.back().ref, ln.ref, ln.ref_len) == 0)
 				{
 					ln.ref_index = out.lines.back().ref_index;
 				}
@@ -148,7 +174,40 @@ int main(int argc, char* argv[])
 					if (ins.second) block_refs.push_back(parsed[c].refs[r]);
 					to_block[r] = ins.first->second;
 				}
-				for (Line& ln : parsed[c].lines) ln.ref_index = to_block[(size_t)ln.ref_index];
+#ifdef DFB_COMPACT_INPUT
+				// leading '=' lines of the chunk: the reference of the last line in front of them (of the previous chunk, or
+				// of the previous block); with nothing in front of them the line is malformed
+				for (Line& ln : parsed[c].lines)
+				{
+					if (ln.ref_index >= 0) break;
+					if (!have_carry)
+					{
+						error_line = chunks[c].first_line + (int64_t)(&ln - parsed[c].lines.data());
+						error = "Error: Format error for line ";
+						break;
+					}
+					ln.ref = carry.data();
+					ln.ref_len = (uint32_t)carry.size();
+					auto ins = lookup.emplace(carry, (int32_t)block_refs.size());
+					if (ins.second) block_refs.push_back(carry);
+					ln.ref_index = -2 - ins.first->second; // already a block-level index (encoded: the loop below skips it)
+				}
+				if (error && error_line >= chunks[c].first_line && !have_carry && !parsed[c].lines.empty() && parsed[c].lines[0].ref_index == -1)
+				{
+					// keep only the lines in front of the malformed one
+					parsed[c].lines.resize((size_t)(error_line - chunks[c].first_line));
+					usable_chunks = c + 1;
+				}
+#endif
+				for (Line& ln : parsed[c].lines) ln.ref_index = ln.ref_index <= -2 ? -2 - ln.ref_index : to_block[(size_t)ln.ref_index];
+#ifdef DFB_COMPACT_INPUT
+				if (!parsed[c].lines.empty())
+				{
+					carry = std::string_view(parsed[c].lines.back().ref, parsed[c].lines.back().ref_len);
+					have_carry = true;
+				}
+				if (c + 1 == usable_chunks) break;
+#endif
 			}
 		}
 		std::vector<size_t> chunk_base(usable_chunks + 1, 0);
@@ -230,6 +289,16 @@ int main(int argc, char* argv[])
 			ExitNow(1);
 		}
 		if (!chunks.empty()) lines_before += chunks.back().first_line + (int64_t)parsed.back().lines.size();
+#ifdef DFB_COMPACT_INPUT
+		// the block's memory goes away with the next one: keep the last reference (only now: lines of this block may
+		// still have pointed at the previous block's copy)
+		if (have_carry && carry.data() != carry_store.data())
+		{
+			std::string keep(carry.data(), carry.size());
+			carry_store.swap(keep);
+			carry = carry_store;
+		}
+#endif
 	}
 	timer.Report();
 	FinishProcess(0);

@@ -119,6 +119,39 @@ def test_splitseq_vs_reference_tool(oracle_mod, tmp_path, kw):
         assert a == b, name
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(seed=71, n_clusters=70, pairs_per_cluster=50),
+                                dict(seed=72, n_clusters=30, pairs_per_cluster=40, read_len_jitter=20, lower_frac=0.02, n_rate=0.01)])
+def test_fused_align_evaluate_vs_reference_pipeline(oracle_mod, tmp_path, kw):
+    """dosplitalign_eval (align -> evaluate without the alignments file, the sort and the second parse in between) against
+    the reference pipeline on the same files: ref dosplitalign | sort -n -k 1 (C locale) | ref evalsplitalign.  The three
+    outputs must be byte-identical; with -a the alignments file is still written and equals the reference's; several
+    small GPU batches and small evaluation regions give the same bytes."""
+    from synth import files
+    ref_split, ref_eval = oracle_mod.ref_tool("ref_dosplitalign"), oracle_mod.ref_tool("ref_evalsplitalign")
+    if not ref_split or not ref_eval:
+        pytest.skip("oracle/_ref tools not built")
+    d = str(tmp_path / "d")
+    args = files.make_split_dataset(d, **kw)
+    _run([ref_split] + args + ["-a", os.path.join(d, "raw.alignments")])
+    p = subprocess.run("LC_ALL=C sort -n -k 1 %s > %s" % (os.path.join(d, "raw.alignments"), os.path.join(d, "sorted.alignments")), shell=True)
+    assert p.returncode == 0
+    common, ev = files.downstream_args(args, d)
+    theirs = _eval(ref_eval, ev, d, "ref")
+    assert len(theirs["seq"].splitlines()) > 10
+
+    def fused(tag, extra=(), env=None):
+        names = {k: os.path.join(d, "%s.%s" % (tag, k)) for k in ("seq", "break", "predalign")}
+        _run([_tool("dosplitalign_eval")] + args + list(extra) + ["-q", names["seq"], "-b", names["break"], "-p", names["predalign"]],
+             env=dict(os.environ, **env) if env else None)
+        return {k: open(v).read() for k, v in names.items()}
+
+    assert fused("fused") == theirs
+    assert fused("fused_a", ["-a", os.path.join(d, "fused.alignments")]) == theirs
+    assert open(os.path.join(d, "fused.alignments"), "rb").read() == open(os.path.join(d, "raw.alignments"), "rb").read()
+    assert fused("fused_small", env={"DFB_TOOL_BATCH": "700", "DFB_TOOL_CHUNK_MIN": "400"}) == theirs
+
+
 def test_evalsplitalign_score_ties_follow_the_reference_container_order(oracle_mod, tmp_path):
     """Evaluate picks the first split with the highest summed score in the ITERATION order of an
     unordered_map<pair<int,int>,int> (tools/SplitAlignment.cpp:505-528).  Engineered records: many distinct refSplits

@@ -207,3 +207,37 @@ def test_matealign_chunked_ingest(oracle_mod, tmp_path):
         got = _run([os.path.join(BIN, "matealign")] + args, sam,
                    env={"DFB_TOOL_CHUNK_MIN": chunk, "DFB_TOOL_THREADS": threads, "DFB_TOOL_BATCH": batch})
         assert got == want
+
+
+def _compact_localalign_input(data):
+    """The input form of localalign_dedup: '=' where a line's reference equals the one on the line before."""
+    out, prev = [], None
+    for line in data.split(b"\n"):
+        f = line.split(b"\t")
+        if len(f) >= 3 and f[1] == prev:
+            f[1] = b"="
+        elif len(f) >= 3:
+            prev = f[1]
+        out.append(b"\t".join(f))
+    return b"\n".join(out)
+
+
+@pytest.mark.parametrize("env", [None, {"DFB_TOOL_BATCH": "37", "DFB_TOOL_BLOCK": "30000", "DFB_TOOL_THREADS": "5"}])
+def test_localalign_dedup_input_form(oracle_mod, env):
+    """localalign_dedup reads the input form that carries every reference once: same output bytes as the
+    reference tool on the expanded input, with blocks and chunks cut in the middle of runs of '=' lines, too."""
+    from synth import files
+    ref = _ref(oracle_mod, "ref_localalign")
+    lines = files.make_localalign_input(seed=9, n_refs=25, n_lines=900).splitlines()
+    lines.sort(key=lambda l: l.split(b"\t")[1])   # the pipeline lists the reads of a cluster together: runs of one reference
+    data = b"\n".join(lines) + b"\n"
+    compact = _compact_localalign_input(data)
+    assert len(compact) < len(data) // 8
+    sc = ["-m", "10", "-x", "-5", "-g", "-5", "-t", "0.8"]
+    want = _run([ref] + sc, data)
+    assert _run([os.path.join(BIN, "localalign_dedup")] + sc, compact, env) == want
+    assert _run([os.path.join(BIN, "localalign_dedup")] + sc, data, env) == want      # the stock form is still understood
+    # a leading '=' has no reference to stand for
+    p = subprocess.run([os.path.join(BIN, "localalign_dedup")] + sc, input=b"a\t=\tACGT\n", stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       env=dict(os.environ, **env) if env else None)
+    assert p.returncode == 1 and b"Format error for line 1" in p.stderr

@@ -40,8 +40,10 @@ def _cases():
                                 "test_localalign_vs_reference_tool", "test_localalign_errors_like_reference",
                                 "test_matealign_vs_reference_tool", "test_dosplitalign_vs_reference_tool",
                                 "test_tools_with_many_small_batches",
-                                "test_localalign_blocks_pipe_and_mapped_file", "test_matealign_chunked_ingest")]
-    bodies += [(td, n) for n in ("test_splitseq_golden", "test_splitseq_vs_reference_tool")]
+                                "test_localalign_blocks_pipe_and_mapped_file", "test_matealign_chunked_ingest",
+                                "test_localalign_dedup_input_form")]
+    bodies += [(td, n) for n in ("test_splitseq_golden", "test_splitseq_vs_reference_tool",
+                                 "test_fused_align_evaluate_vs_reference_pipeline")]
     for mod, name in bodies:
         fn = getattr(mod, name)
         marks = [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]
