@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(DFB_BUILD_BLOCK) split_classify_kernel(SplitBu
 {
 	const long long t = (long long)blockIdx.x * DFB_BUILD_BLOCK + threadIdx.x;
 	int bin = -1;
+	unsigned int fast_R = 0;
 	unsigned long long cells = 0;
 	if (t < p.n_tasks)
 	{
@@ -196,25 +197,32 @@ __global__ void __launch_bounds__(DFB_BUILD_BLOCK) split_classify_kernel(SplitBu
 				if (c < 0)
 				{
 					bin = -2;
-					atomicAdd(&p.stats->n_gen, 1u);
+					atomicAdd(&p.stats->n_gen, 1u); // (rare: these tasks send the chunk to the host path)
 					atomicMax(&p.stats->gen_max_R, (unsigned int)(Rm > 0xffffffffLL ? 0xffffffffLL : Rm));
 				}
 				else
 				{
 					const long long rb = Rm >> 4;
 					bin = c * DFB_BUILD_RBINS + (DFB_BUILD_RBINS - 1 - (int)(rb < DFB_BUILD_RBINS - 1 ? rb : DFB_BUILD_RBINS - 1));
-					atomicMax(&p.stats->cls_max_R[c], (unsigned int)Rm);
+					fast_R = (unsigned int)Rm;
 				}
 			}
 		}
 		p.bin_of[t] = bin;
 	}
-	// histogram: the tasks of a cluster are neighbours and share a bin, one atomic per group of equal bins in a warp
+	// histogram and longest reference per class: the tasks of a cluster are neighbours and share a bin, one atomic per
+	// group of equal bins in a warp (every task on its own would serialise on a handful of addresses)
 	const unsigned active = __ballot_sync(0xffffffffu, bin >= 0);
 	if (bin >= 0)
 	{
 		const unsigned same = __match_any_sync(active, bin);
-		if ((int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&p.bin_count[bin], (unsigned)__popc(same));
+		const unsigned int group_R = __reduce_max_sync(same, fast_R);
+		if ((int)(threadIdx.x & 31) == __ffs(same) - 1)
+		{
+			atomicAdd(&p.bin_count[bin], (unsigned)__popc(same));
+			const int c = bin / DFB_BUILD_RBINS;
+			if (group_R > p.stats->cls_max_R[c]) atomicMax(&p.stats->cls_max_R[c], group_R);
+		}
 	}
 	// cells: block sum, one atomic per block
 	unsigned long long all = 0;
