@@ -350,6 +350,13 @@ def measure_sharded(aligner, args, rank, world, barrier):
         times.append((time.perf_counter() - t0) * 1e3)
     align_ms = min(times[1:])
     # gather on rank 0: best per task, rows (task renumbered to the batch's numbering), columns
+    if world > 1:
+        # (the first collective of a process sets the communicator's channels up: not part of the merge)
+        warm = torch.zeros(1, dtype=torch.uint8, device="cuda")
+        dist.gather(warm, [torch.empty_like(warm) for _ in range(world)] if rank == 0 else None, dst=0)
+        dist.all_gather([torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)], torch.zeros(1, dtype=torch.int64, device="cuda"))
+        torch.cuda.synchronize()
+        barrier()
     t0 = time.perf_counter()
     rows = np.array(res.rows, copy=True)
     rows["task"] = mine[rows["task"]]

@@ -139,11 +139,12 @@ def test_dosplitalign_sharded_over_distinct_gpus(oracle_mod, tmp_path, devices):
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
     assert p.returncode == 0, p.stderr.decode()[-2000:]
     a, b = open(one, "rb").read(), open(many, "rb").read()
-    assert a.count(b"\n") > 50000
+    assert a.count(b"\n") > 20000
     assert a == b
-    # every named device did work (the tool's trace names the contexts it created)
+    # one context per named device (the library's trace reports every context it creates), and every one of them ran batches
     trace = p.stderr.decode()
-    assert ("%d device" % (2 if devices == "0,1" else n)) in trace or "devices" in trace, trace[-1500:]
+    want = 2 if devices == "0,1" else n
+    assert trace.count("ctx: context, streams, pools") == want, trace[-1500:]
     ref = oracle_mod.ref_tool("ref_dosplitalign")
     if ref:
         s = str(tmp_path / "sample")
