@@ -44,7 +44,7 @@ struct PinnedBuf
 		p = nullptr;
 		cap = 0;
 		size_t want = n + n / 4 + 4096;
-		cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+		cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped); // (kernels store the build statistics into it)
 		if (e == cudaSuccess) cap = want;
 		return e;
 	}
@@ -1615,8 +1615,8 @@ static int split_build_kernels(dfb_plan* pl)
 	const unsigned task_blocks = (unsigned)((pl->n_tasks + DFB_BUILD_BLOCK - 1) / DFB_BUILD_BLOCK);
 	if (pl->n_tasks) split_classify_kernel<<<task_blocks, DFB_BUILD_BLOCK, 0, cs>>>(pd.bp);
 	bin_scan_kernel<<<1, 1024, 0, cs>>>(pd.bp.bin_count, kNumClasses, pd.d_stats);
+	stats_to_host_kernel<<<1, 64, 0, cs>>>(pd.d_stats, pd.h_stats); // (pinned host memory is device-accessible under UVA)
 	CK(ctx, cudaGetLastError());
-	CK(ctx, cudaMemcpyAsync(pd.h_stats, pd.d_stats, sizeof(BuildStats), cudaMemcpyDeviceToHost, cs));
 	if (!pd.ready) CK(ctx, cudaEventCreateWithFlags(&pd.ready, cudaEventDisableTiming | cudaEventBlockingSync));
 	CK(ctx, cudaEventRecord(pd.ready, cs));
 	return DFB_OK;

@@ -268,6 +268,17 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(unsigned int* bin_count,
 	if (tid < n_classes) stats->cls_jobs[tid] = s_cls[tid + 1] - s_cls[tid];
 }
 
+// The statistics go to the host through a store into pinned host memory, not through a copy: the copy engine may be
+// busy for a millisecond or two with a previous chunk's result rows, and the host is waiting for these 200 bytes to
+// launch the next chunk.
+__global__ void stats_to_host_kernel(const BuildStats* __restrict__ d_stats, BuildStats* __restrict__ h_stats)
+{
+	const unsigned int* src = reinterpret_cast<const unsigned int*>(d_stats);
+	unsigned int* dst = reinterpret_cast<unsigned int*>(h_stats);
+	for (unsigned k = threadIdx.x; k < sizeof(BuildStats) / sizeof(unsigned int); k += blockDim.x) dst[k] = src[k];
+	__threadfence_system();
+}
+
 __global__ void __launch_bounds__(DFB_BUILD_BLOCK) split_scatter_kernel(SplitBuildParams p)
 {
 	const long long t = (long long)blockIdx.x * DFB_BUILD_BLOCK + threadIdx.x;
