@@ -604,6 +604,7 @@ def run_ours(args):
             "tasks_per_s": tasks_all / (ms_step * 1e-3),
             "e2e": {"value": cells_all / (e2e_mean * 1e-3) / 1e9, "unit": UNIT,
                     "tasks_per_s": tasks_all / (e2e_mean * 1e-3), "ms_per_step": e2e_mean,
+                    "ms_per_step_min_rank0": float(np.min(e2e_ms)), "ms_per_step_median_rank0": float(np.median(e2e_ms)),
                     "h2d_bytes_per_step": st["h2d_bytes"] + 3 * 4 * st["n_tasks"],
                     "d2h_bytes_per_step": st["d2h_bytes"], "steps": e2e_steps,
                     "host_cpu_ms_per_step": float(np.mean(cpu_ms)),   # user+sys of all threads of rank 0 during the call

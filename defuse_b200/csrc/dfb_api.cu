@@ -2364,7 +2364,9 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
                                  const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
                                  const int32_t* task_min_score, int64_t n_tasks, int32_t* out_best)
 {
-	const int K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), n_tasks / 250000));
+	int K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), n_tasks / 250000));
+	if (const char* e = getenv("DFB_PIPELINE_CHUNKS")) // tuning runs
+		K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), atoi(e)));
 	std::vector<dfb_plan*> plans((size_t)K, nullptr);
 	// chunk boundaries: short chunks in front put the GPU to work early, chunks that taper off at the end keep the part
 	// of the result assembly that nothing overlaps small (lane 2 finishes chunk k while the GPU runs chunk k+1); the

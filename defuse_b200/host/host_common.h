@@ -347,10 +347,24 @@ private:
 // ---------------------------------------------------------------------------------------------
 // A context on one GPU.  CUDA start-up costs 2-3 s on a B200 box, so the context is created on a helper thread
 // the moment the tool starts and only joined at the first use: parsing the inputs runs underneath it.
+// The one device of a single-GPU tool run (DFB_DEVICE, default 0).  Nothing has touched CUDA yet: show the runtime only
+// that device.  On a multi-GPU host the first CUDA call otherwise initialises every GPU of the box, which is most of a
+// short tool run's wall time.
+inline int SingleDevice()
+{
+	int dev = getenv("DFB_DEVICE") ? atoi(getenv("DFB_DEVICE")) : 0;
+	if (dev >= 0 && !getenv("CUDA_VISIBLE_DEVICES"))
+	{
+		setenv("CUDA_VISIBLE_DEVICES", std::to_string(dev).c_str(), 1);
+		dev = 0;
+	}
+	return dev;
+}
+
 class Gpu
 {
 public:
-	Gpu() : Gpu(getenv("DFB_DEVICE") ? atoi(getenv("DFB_DEVICE")) : 0) {}
+	Gpu() : Gpu(SingleDevice()) {}
 	explicit Gpu(int device) : mDevice(device)
 	{
 		mThread = std::thread([this] {
@@ -422,7 +436,7 @@ inline std::vector<int> DeviceList()
 			}
 		}
 	}
-	if (out.empty()) out.push_back(getenv("DFB_DEVICE") ? atoi(getenv("DFB_DEVICE")) : 0);
+	if (out.empty()) out.push_back(SingleDevice());
 	return out;
 }
 

@@ -1,8 +1,11 @@
-# usage: bash scripts/gpu_ncu.sh <tag>   -- ncu --set full of the DP kernels on the small bench config
+# usage: bash scripts/gpu_ncu.sh <tag>   -- the one ncu session of a gpurun call: launch list + ncu --set full of the two sweeps
+# on the small bench config, after the same command has exited 0 without ncu
 TAG=${1:-x}
 mkdir -p gpurun_out
-SMALL="python bench.py --steps 2 --warmup 1 --clusters 2000 --no-cpu-baseline --no-secondary --e2e-steps 1"
+SMALL="python bench.py --steps 2 --warmup 1 --clusters 2000 --no-cpu-baseline --no-secondary --no-sharded --e2e-steps 1"
 timeout 200 $SMALL > gpurun_out/plain_$TAG.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:dp_fast_kernel -s 2 -c 2 -o gpurun_out/prof_$TAG $SMALL > gpurun_out/ncu_full_$TAG.log 2>&1
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $SMALL > gpurun_out/ncu_launch_$TAG.log 2>&1
+echo ncu_launch_rc=$?
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'dp_(fast|probe)_kernel' -s 2 -c 2 -o gpurun_out/prof_$TAG $SMALL > gpurun_out/ncu_full_$TAG.log 2>&1
 echo ncu_full_rc=$?
 tail -3 gpurun_out/ncu_full_$TAG.log

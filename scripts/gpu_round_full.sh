@@ -1,4 +1,4 @@
-# one full GPU pass with evidence: smoke, tests, bench (+reference arm), ncu launch list, ncu --set full, tool-level bench
+# one full GPU pass without profilers: smoke, tests, bench (+reference arm), tool-level bench
 # usage: bash scripts/gpu_round_full.sh <tag>
 TAG=${1:-r}
 mkdir -p gpurun_out
@@ -8,13 +8,7 @@ tail -4 gpurun_out/pytest_$TAG.log
 timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo bench_rc=$?
 tail -3 gpurun_out/bench_$TAG.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/benchref_$TAG.json 2> gpurun_out/benchref_$TAG.err; echo benchref_rc=$?
-SMALL="python bench.py --steps 2 --warmup 1 --clusters 2000 --no-cpu-baseline --no-secondary --e2e-steps 1"
-timeout 200 $SMALL > gpurun_out/plain_$TAG.log 2>&1 &&
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $SMALL > gpurun_out/ncu_launch_$TAG.log 2>&1
-echo ncu_launch_rc=$?
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:dp_fast_kernel -s 2 -c 2 -o gpurun_out/prof_$TAG $SMALL > gpurun_out/ncu_full_$TAG.log 2>&1
-echo ncu_full_rc=$?
-tail -3 gpurun_out/ncu_full_$TAG.log
+# (profilers run in their own gpurun calls: scripts/gpu_ncu.sh for ncu, scripts/gpu_sanitize.sh <tool> for compute-sanitizer)
 timeout 600 python scripts/gpu_tools_bench.py > gpurun_out/tools_bench_$TAG.json 2> gpurun_out/tools_bench_$TAG.err; echo tools_rc=$?
 cat gpurun_out/tools_bench_$TAG.json; tail -3 gpurun_out/tools_bench_$TAG.err
 timeout 300 python scripts/gpu_tool_scale.py > gpurun_out/tool_scale_split_$TAG.json 2> gpurun_out/tool_scale_split_$TAG.err; echo scale_split_rc=$?
