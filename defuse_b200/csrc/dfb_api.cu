@@ -2364,7 +2364,7 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
                                  const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
                                  const int32_t* task_min_score, int64_t n_tasks, int32_t* out_best)
 {
-	int K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), n_tasks / 250000));
+	int K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), n_tasks / 330000));
 	if (const char* e = getenv("DFB_PIPELINE_CHUNKS")) // tuning runs
 		K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), atoi(e)));
 	std::vector<dfb_plan*> plans((size_t)K, nullptr);
@@ -2408,13 +2408,25 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	}
 	int rc = DFB_OK;
 	Trace trp;
-	// job lists are built on the device unless no class of the s16x2 kernels takes this scoring (then every task is
-	// generic and the host path lists them) or DFB_HOST_BUILD asks for the host path (A/B runs, tests)
+	// Where the job lists are built.  On the device: 31 ms of host CPU time per 2 M-task batch, but the build kernels sit
+	// on the compute stream (0.2 ms per chunk with their launch gaps).  On the host: 72 ms of CPU time over the context's
+	// workers, fully hidden under the GPU when the host has the threads -- 1.7 ms per batch faster then (A/B on one box,
+	// profiles/r03l_ab_e2e.txt).  So: the device unless this context has 16 or more host threads to itself (one process
+	// per GPU on a shared host caps them with DFB_HOST_THREADS; bench.py does under torchrun); never when no class of the
+	// s16x2 kernels takes this scoring (every task is generic then and the host path lists them).  DFB_HOST_BUILD /
+	// DFB_DEVICE_BUILD force either (A/B runs, tests).
 	bool device_build = false;
 	{
 		dfb_plan probe;
 		classify_params(&probe, params->match, params->mismatch, params->gap, params->end_gaps == 0 && params->min_split_score >= 1);
 		for (int c = 0; c < kNumClasses; c++) device_build = device_build || probe.fast_ok[c];
+		if (ctx->host_threads >= 16) device_build = false;
+		if (const char* e = getenv("DFB_DEVICE_BUILD"))
+			if (*e && *e != '0')
+			{
+				device_build = false;
+				for (int c = 0; c < kNumClasses; c++) device_build = device_build || probe.fast_ok[c];
+			}
 		if (const char* e = getenv("DFB_HOST_BUILD"))
 			if (*e && *e != '0') device_build = false;
 	}

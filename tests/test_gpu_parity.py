@@ -296,12 +296,15 @@ def _expand_cols(res):
     return out
 
 
-def test_full_size_batch_pipelined_equals_resident(oracle_mod, gpu_ctx):
-    """BASELINE.json configs[2] at the size bench.py runs (2 M tasks): the one-call path cuts it into seven tapered chunks
-    whose rows go straight into the batch's result arrays; the resident plan assembles the same batch in one piece.
-    Same rows, same column lists, task by task; size-independent properties on every row; sampled oracle parity."""
+@pytest.mark.parametrize("build", ["device", "host"])
+def test_full_size_batch_pipelined_equals_resident(oracle_mod, gpu_ctx, monkeypatch, build):
+    """BASELINE.json configs[2] at the size bench.py runs (2 M tasks): the one-call path cuts it into eight tapered chunks
+    whose rows go straight into the batch's result arrays -- job lists built on the device or on the host --; the resident
+    plan assembles the same batch in one piece.  Same rows, same column lists, task by task; size-independent properties
+    on every row; sampled oracle parity."""
     import defuse_b200 as d
     import synth
+    monkeypatch.setenv("DFB_DEVICE_BUILD" if build == "device" else "DFB_HOST_BUILD", "1")
     w = synth.split_workload(21, 20000, 100)
     refs, reads = d.SeqTable(w["ref_bytes"], w["ref_off"]), d.SeqTable(w["read_bytes"], w["read_off"])
     al = d.SplitReadAligner(ctx=gpu_ctx)
@@ -384,7 +387,16 @@ def test_pipelined_one_call_path(oracle_mod, gpu_ctx, monkeypatch):
     al = d.SplitReadAligner(ctx=gpu_ctx)
     single = al.align_batch(rt, st, tc, trd, ms)
     monkeypatch.setenv("DFB_PIPELINE_MIN_TASKS", "16")
+    # job lists built on the device (forced: a context with 16 host threads of its own builds them on the host) ...
+    monkeypatch.setenv("DFB_DEVICE_BUILD", "1")
     piped = al.align_batch(rt, st, tc, trd, ms)
+    # ... and on the host
+    monkeypatch.delenv("DFB_DEVICE_BUILD")
+    monkeypatch.setenv("DFB_HOST_BUILD", "1")
+    piped_host = al.align_batch(rt, st, tc, trd, ms)
+    monkeypatch.delenv("DFB_HOST_BUILD")
+    monkeypatch.setenv("DFB_DEVICE_BUILD", "1")
+    assert np.array_equal(piped_host.best, single.best) and np.array_equal(piped_host.rows["task"], single.rows["task"])
     assert np.array_equal(piped.best, single.best)
     # the column pool may be laid out differently (col_begin is explicit); rows and their column lists must agree
     assert len(piped.rows) == len(single.rows)
