@@ -539,6 +539,7 @@ struct ClassWork
 	uint32_t* d_ckpt = nullptr;    // wavefront checkpoints of the first sweep (probe windows resume from them)
 	uint32_t* d_slot_rng = nullptr;
 	int ckpt_blocks = 0;
+	unsigned long long ckpt_words = 0;
 	uint32_t max_R = 0;            // longest reference in the class
 	FastParams fp;
 };
@@ -555,6 +556,7 @@ struct dfb_plan
 	// device
 	uint8_t* d_raw = nullptr;
 	uint8_t* d_stage = nullptr; // descriptors + fast jobs + generic jobs (one upload)
+	unsigned long long pool_words = 0, raw_bytes = 0; // allocated sizes of d_pool / d_obytes (entries) and d_raw (bytes)
 	uint8_t* d_build = nullptr; // job build on the device: offsets, task arrays, descriptors, bins, jobs (one arena)
 	// (device-built plans look a task's read length up in the caller's arrays, which outlive the one-call batch)
 	const int64_t* h_read_off = nullptr;
@@ -620,6 +622,19 @@ struct dfb_plan
 	int result_slot = -1;          // chunk of a pipelined batch: which recycled result arrays of the ctx to use
 	dfb_plan_stats stats{};
 };
+
+// -DDFB_BOUNDS_CHECK builds: a range violation recorded by a kernel becomes an error of the call that waits for it
+static int bounds_check_status(dfb_ctx* ctx)
+{
+#ifdef DFB_BOUNDS_CHECK
+	int code = 0;
+	if (cudaMemcpyFromSymbol(&code, dfb::g_dfb_bounds_err, sizeof(int)) == cudaSuccess && code != 0)
+		return set_err(ctx, DFB_ERR_STATE, "device bounds check %d failed", code);
+#else
+	(void)ctx;
+#endif
+	return DFB_OK;
+}
 
 static cudaError_t dalloc(dfb_ctx* ctx, void** p, size_t bytes)
 {
@@ -845,6 +860,7 @@ static int upload_raw(dfb_plan* pl, const dfb_seq_table* a, const dfb_seq_table*
 	const int64_t na = a->off[a->n] - a->off[0], nb = b->off[b->n] - b->off[0];
 	// 16 bytes of slack in front, 32 behind (the pack kernel reads whole 16-byte windows)
 	CK(ctx, cudaMallocAsync((void**)&pl->d_raw, std::max<size_t>(256, (size_t)(na + nb + 48)), up));
+	pl->raw_bytes = (unsigned long long)(na + nb + 48);
 	if (na) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16, a->bytes + a->off[0], (size_t)na, cudaMemcpyHostToDevice, up));
 	if (nb) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16 + na, b->bytes + b->off[0], (size_t)nb, cudaMemcpyHostToDevice, up));
 	return DFB_OK;
@@ -861,6 +877,7 @@ static int upload_and_pack(dfb_plan* pl, const dfb_seq_table* a, int mode_a, con
 	// (slack: a 16-byte copy may take the word behind a sequence's last one)
 	CK(ctx, cudaMallocAsync((void**)&pl->d_pool, ((size_t)total_words + 8) * sizeof(uint2), up));
 	CK(ctx, cudaMallocAsync((void**)&pl->d_obytes, ((size_t)total_words + 8) * 16, up));
+	pl->pool_words = (unsigned long long)total_words + 8;
 	for (int k = 0; k < 3; k++)
 		if (!pl->ev[k]) CK(ctx, cudaEventCreate(&pl->ev[k]));
 	CK(ctx, cudaEventRecord(pl->ev[0], up));
@@ -871,11 +888,11 @@ static int upload_and_pack(dfb_plan* pl, const dfb_seq_table* a, int mode_a, con
 		if (n == 0 || w1 <= w0) return cudaSuccess;
 		const int grid = (int)std::min<uint64_t>(((uint64_t)n * 16 + 255) / 256, (uint64_t)max_grid); // sixteen lanes per sequence
 		if (mode == PACK_FWD)
-			pack_kernel<PACK_FWD><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, pl->d_pool, pl->d_obytes);
+			pack_kernel<PACK_FWD><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, pl->d_pool, pl->d_obytes, pl->pool_words, pl->raw_bytes);
 		else if (mode == PACK_REV_ODD)
-			pack_kernel<PACK_REV_ODD><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, pl->d_pool, pl->d_obytes);
+			pack_kernel<PACK_REV_ODD><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, pl->d_pool, pl->d_obytes, pl->pool_words, pl->raw_bytes);
 		else
-			pack_kernel<PACK_BOTH><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, pl->d_pool, pl->d_obytes);
+			pack_kernel<PACK_BOTH><<<grid, 256, 0, up>>>(pl->d_raw, d, (int)n, pl->d_pool, pl->d_obytes, pl->pool_words, pl->raw_bytes);
 		return cudaGetLastError();
 	};
 	CK(ctx, launch(mode_a, d_da, a->n, 0, words_a_end));
@@ -921,6 +938,9 @@ static void fill_fast_params(dfb_plan* pl, int c, int m, int x, int g, int min_s
 	fp.rdq = cw.d_rdq;
 	fp.ckpt = cw.d_ckpt;
 	fp.ckpt_blocks = cw.ckpt_blocks;
+	fp.ckpt_words = cw.ckpt_words;
+	fp.pool_words = pl->pool_words;
+	fp.n_tasks = pl->n_tasks;
 	// probe granules: 16 mask bits per half cover checkpoint blocks 0 .. ckpt_blocks
 	fp.gran_shift = 0;
 	while ((cw.ckpt_blocks >> fp.gran_shift) > 15) fp.gran_shift++;
@@ -961,7 +981,10 @@ static int alloc_work(dfb_plan* pl, JobPair* d_jobs_base, GenJob* d_gen_base, co
 			cw.ckpt_blocks = (int)(((int64_t)cw.max_R + G - 2) / CK);
 			const size_t ck_bytes = n * (size_t)cw.ckpt_blocks * (size_t)(kClasses[c].S + 2) * G * sizeof(uint32_t);
 			if (cw.ckpt_blocks > 0 && ck_bytes <= (size_t)ctx->prop.totalGlobalMem / 4)
+			{
 				DALLOC(ctx, cw.d_ckpt, ck_bytes);
+				cw.ckpt_words = ck_bytes / sizeof(uint32_t);
+			}
 			else
 				cw.ckpt_blocks = 0;
 		}
@@ -1659,12 +1682,13 @@ static int split_build_finish(dfb_plan* pl)
 	if ((e = cudaMallocAsync((void**)&pl->d_pool, ((size_t)total_words + 8) * sizeof(uint2), up)) != cudaSuccess ||
 	    (e = cudaMallocAsync((void**)&pl->d_obytes, ((size_t)total_words + 8) * 16, up)) != cudaSuccess)
 		return fail(set_err(ctx, DFB_ERR_NOMEM, "packed pool of %u words: %s", total_words, cudaGetErrorString(e)));
+	pl->pool_words = (unsigned long long)total_words + 8;
 	for (int k = 0; k < 3; k++)
 		if (!pl->ev[k] && (e = cudaEventCreate(&pl->ev[k])) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
 	cudaEventRecord(pl->ev[0], up);
 	const int max_grid = ctx->prop.multiProcessorCount * 16;
-	if (na) pack_kernel<PACK_REV_ODD><<<(int)std::min<uint64_t>(((uint64_t)na * 16 + 255) / 256, (uint64_t)max_grid), 256, 0, up>>>(pl->d_raw, pl->pending.d_desc_a, (int)na, pl->d_pool, pl->d_obytes);
-	if (nb) pack_kernel<PACK_BOTH><<<(int)std::min<uint64_t>(((uint64_t)nb * 16 + 255) / 256, (uint64_t)max_grid), 256, 0, up>>>(pl->d_raw, pl->pending.d_desc_b, (int)nb, pl->d_pool, pl->d_obytes);
+	if (na) pack_kernel<PACK_REV_ODD><<<(int)std::min<uint64_t>(((uint64_t)na * 16 + 255) / 256, (uint64_t)max_grid), 256, 0, up>>>(pl->d_raw, pl->pending.d_desc_a, (int)na, pl->d_pool, pl->d_obytes, pl->pool_words, pl->raw_bytes);
+	if (nb) pack_kernel<PACK_BOTH><<<(int)std::min<uint64_t>(((uint64_t)nb * 16 + 255) / 256, (uint64_t)max_grid), 256, 0, up>>>(pl->d_raw, pl->pending.d_desc_b, (int)nb, pl->d_pool, pl->d_obytes, pl->pool_words, pl->raw_bytes);
 	cudaEventRecord(pl->ev[1], up);
 	pl->pack_timed = true;
 	if (n_tasks) split_scatter_kernel<<<task_blocks, DFB_BUILD_BLOCK, 0, up>>>(bp);
@@ -1783,6 +1807,8 @@ static int run_assemble(dfb_plan* pl)
 	ap.events = pl->d_events;
 	ap.ev_count = pl->d_ev_count;
 	ap.ev_cap = pl->ev_cap;
+	ap.rows_cap = (unsigned long long)pl->n_fast_tasks * (DFB_SLOT_EVENTS / 2);
+	ap.cols_cap = (unsigned long long)pl->n_fast_tasks * DFB_SLOT_EVENTS;
 	asm_count_kernel<<<(unsigned)pl->asm_blocks, DFB_ASM_BLOCK, 0, ctx->stream>>>(ap);
 	asm_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ap.block_sums, pl->asm_blocks, ap.totals);
 	asm_write_kernel<<<(unsigned)pl->asm_blocks, DFB_ASM_BLOCK, 0, ctx->stream>>>(ap);
@@ -1882,6 +1908,7 @@ extern "C" int dfb_plan_sync(dfb_plan* pl)
 	dfb_ctx* ctx = pl->ctx;
 	CK(ctx, cudaSetDevice(ctx->device));
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	if (int brc = bounds_check_status(ctx)) return brc;
 	if (pl->run_timed)
 	{
 		float a = 0, b = 0;
@@ -1911,6 +1938,7 @@ extern "C" int dfb_simple_plan_fetch(dfb_plan* pl, int32_t* out_score)
 	if (pl->n_tasks)
 		CK(ctx, cudaMemcpyAsync(out_score, pl->d_out, (size_t)pl->n_tasks * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	if (int brc = bounds_check_status(ctx)) return brc;
 	pl->stats.d2h_bytes = pl->n_tasks * (int64_t)sizeof(int32_t);
 	pl->fetched = true;
 	return DFB_OK;
@@ -2023,6 +2051,7 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 	for (int c = 0; c < kNumClasses; c++)
 		if (pl->cls[c].n_jobs) n_slots += (int64_t)h_ctrl[4 * c + 1] + h_ctrl[4 * c + 3]; // short- and long-window queue slots
 
+	if (int brc = bounds_check_status(ctx)) return brc;
 	tr.lap("split.fetch: wait kernels");
 	// 2. bulk copy into pinned staging: best | device-assembled rows | their columns | overflow events
 	const size_t g_rows = (size_t)asm_totals[0], g_cols = (size_t)asm_totals[1];
@@ -2307,6 +2336,7 @@ static int simple_align_pipelined(dfb_ctx* ctx, const dfb_simple_params* params,
 	cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
 	if (!rc && e != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "pipelined batch failed: %s", cudaGetErrorString(e));
+	if (!rc) rc = bounds_check_status(ctx);
 	for (dfb_plan* pk : plans)
 		if (pk) dfb_plan_destroy(pk);
 	return rc;
@@ -2589,6 +2619,8 @@ static int dfb_split_align_batch_body(dfb_ctx* ctx, const dfb_split_params* para
 	}
 	int64_t pipeline_min = kPipelineMinTasks;
 	if (const char* e = getenv("DFB_PIPELINE_MIN_TASKS")) pipeline_min = std::max<long long>(2, atoll(e)); // tests
+	Trace tre;
+	tre.lap("split: entry");
 	if (n_tasks >= pipeline_min && params && refs && reads && task_cluster && task_read && task_min_score)
 	{
 		int rc;
@@ -2607,6 +2639,7 @@ static int dfb_split_align_batch_body(dfb_ctx* ctx, const dfb_split_params* para
 			});
 			for (char c : ok) monotone = monotone && c;
 		}
+		tre.lap("split: validated");
 		if (monotone)
 			return split_align_pipelined(ctx, params, refs, reads, task_cluster, task_read, task_min_score, n_tasks, out_best);
 	}

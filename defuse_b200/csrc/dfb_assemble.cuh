@@ -34,6 +34,7 @@ struct AsmParams
 	Event* events; // overflow list (append)
 	unsigned long long* ev_count;
 	unsigned long long ev_cap;
+	unsigned long long rows_cap, cols_cap; // entries allocated (bounds-check builds)
 };
 
 // the task's region entries ordered by key (matrix << 27 | row << 16 | column); returns their number, -1 for a task
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(DFB_ASM_BLOCK) asm_write_kernel(AsmParams p)
 			row.col_begin = (int64_t)col_at;
 			row.n1 = i_end - i;
 			row.n2 = j_end - j;
+			DFB_BC(row_at < p.rows_cap && col_at + (unsigned)(row.n1 + row.n2) <= p.cols_cap, 501);
 			p.rows[row_at++] = row;
 			for (int k = i; k < i_end; k++) p.cols[col_at++] = (int32_t)(e[k].x & 0xffff);
 			for (int k = j; k < j_end; k++) p.cols[col_at++] = (int32_t)(e[k].x & 0xffff);

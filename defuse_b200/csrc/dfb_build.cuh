@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(DFB_BUILD_BLOCK) split_scatter_kernel(SplitBui
 	jp.L[0] = jp.L[1] = (uint16_t)rdd.len;
 	jp.out0 = (int32_t)t;
 	jp.out1 = p.task_min_score[t];
+	DFB_BC((long long)pos < p.n_tasks && bin < p.n_classes * DFB_BUILD_RBINS, 401);
 	p.jobs[pos] = jp;
 }
 

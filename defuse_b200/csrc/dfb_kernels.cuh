@@ -23,6 +23,23 @@
 namespace dfb
 {
 
+// -DDFB_BOUNDS_CHECK: every indexed global-memory access of the kernels is range-checked against the size of its buffer
+// (compute-sanitizer is closed on the GPU pool this was developed on).  The first violation is recorded -- the access
+// still happens -- and the host turns it into an error at the next fetch / sync.  Compiled out otherwise.
+#ifdef DFB_BOUNDS_CHECK
+__device__ int g_dfb_bounds_err = 0;
+#define DFB_BC(cond, code)                                      \
+	do                                                          \
+	{                                                           \
+		if (!(cond)) atomicCAS(&g_dfb_bounds_err, 0, (code));   \
+	} while (0)
+#else
+#define DFB_BC(cond, code) \
+	do                     \
+	{                      \
+	} while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // HBM layout of sequences
 // ------------------------------------------------------------------------------------------
@@ -69,8 +86,11 @@ __device__ __forceinline__ void pack4(uint32_t w, uint32_t valid, uint32_t& code
 
 template <int MODE>
 __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ raw, const SeqDesc* __restrict__ descs,
-                                                    int n_seqs, uint2* __restrict__ pool, uint8_t* __restrict__ obytes)
+                                                    int n_seqs, uint2* __restrict__ pool, uint8_t* __restrict__ obytes,
+                                                    unsigned long long pool_words, unsigned long long raw_bytes)
 {
+	(void)pool_words;
+	(void)raw_bytes;
 	const uint32_t lane16 = threadIdx.x & 15u;
 	const uint32_t n_groups = (gridDim.x * blockDim.x) >> 4;
 	for (uint32_t lo = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; lo < (uint32_t)n_seqs; lo += n_groups)
@@ -117,6 +137,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ r
 				mask |= m4 << (4 * q);
 				b[q] &= valid * 0xFFu; // the raw copy keeps zeros beyond the sequence end
 			}
+			DFB_BC((unsigned long long)w < pool_words && win >= 0 && (unsigned long long)(win + 20) <= raw_bytes, 101);
 			pool[w] = make_uint2(codes, mask);
 			if (mask) reinterpret_cast<uint4*>(obytes)[w] = make_uint4(b[0], b[1], b[2], b[3]);
 		}
@@ -187,6 +208,10 @@ struct FastParams
 	unsigned long long* ev_count;
 	unsigned long long ev_cap;
 	uint32_t ck[32]; // SIMPLE: m*(k+1) in both halves
+	// buffer sizes (bounds-check builds)
+	unsigned long long pool_words; // pool / obytes entries allocated
+	unsigned long long ckpt_words; // ckpt entries allocated
+	long long n_tasks;             // entries of out / task_slot
 };
 
 #define DFB_SLOT_EVENTS 16
@@ -216,6 +241,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // One arg-max column found by the probe sweep: the task's fixed region first, the overflow list after.
 __device__ __noinline__ void emit_probe_event(const FastParams& p, int item, int task, int h, int j, int col, int score)
 {
+	DFB_BC(item >= 0 && item < p.n_jobs && task >= 0 && task < p.n_tasks && col >= 0 && col < 65535 && j >= 1 && j <= 1024, 305);
 	const int n = atomicAdd(p.slot_n + item, 1);
 	if (n < DFB_SLOT_EVENTS)
 	{
@@ -242,8 +268,10 @@ __device__ __noinline__ void emit_probe_event(const FastParams& p, int item, int
 // sites per kernel, and the instruction cache is what short probe rounds wait for.
 template <int G>
 __device__ __noinline__ void ring_decode_block(uint32_t* ring, const uint2* raw_slot, int blk, int cw0, int cw1, uint32_t R0, uint32_t R1,
-                                               uint32_t ref_w0, uint32_t ref_w1, const uint8_t* __restrict__ obytes, int g)
+                                               uint32_t ref_w0, uint32_t ref_w1, const uint8_t* __restrict__ obytes, int g,
+                                               unsigned long long pool_words)
 {
+	(void)pool_words;
 	constexpr int HG = G / 2, CH = 8 * G, RING = 2 * CH;
 	constexpr int RSH = (G == 8) ? 0 : (G == 16 ? 1 : 2); // bank = 8 * (g + q * G / 8) + rotation (mod 32): distinct over the warp
 	const uint2 w0 = raw_slot[g >> 1], w1 = raw_slot[HG + (g >> 1)];
@@ -257,6 +285,8 @@ __device__ __noinline__ void ring_decode_block(uint32_t* ring, const uint2* raw_
 		uint32_t f0 = DFB_REF_PAD, f1 = DFB_REF_PAD;
 		if (wi0 >= 0 && (uint32_t)(wi0 * 16 + nb) < R0) f0 = decode_base(w0, ref_w0 + (uint32_t)wi0, nb, obytes);
 		if (wi1 >= 0 && (uint32_t)(wi1 * 16 + nb) < R1) f1 = decode_base(w1, ref_w1 + (uint32_t)wi1, nb, obytes);
+		DFB_BC(wi0 < 0 || (uint32_t)(wi0 * 16) >= R0 || (unsigned long long)ref_w0 + (unsigned long long)wi0 < pool_words, 201);
+		DFB_BC(wi1 < 0 || (uint32_t)(wi1 * 16) >= R1 || (unsigned long long)ref_w1 + (unsigned long long)wi1 < pool_words, 202);
 		ring[((uint32_t)blk * CH + 16u * (g >> 1) + nb) & (RING - 1)] = f0 | (f1 << 16);
 	}
 }
@@ -355,6 +385,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				const uint32_t len = jp.L[h];
 				uint2 pw = make_uint2(0, 0);
 				const uint32_t widx = jp.read_w[h] + wi;
+				DFB_BC((uint32_t)wi * 16u >= len || widx < p.pool_words, 205);
 				if ((uint32_t)wi * 16u < len) pw = __ldg(p.pool + widx);
 #pragma unroll 4
 				for (int n = 0; n < 16; n++)
@@ -406,12 +437,16 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			{
 				const int h = g / (G / 4), c = g % (G / 4);
 				const uint32_t wi = (uint32_t)blk * HG + 2u * c;
-				if (wi * 16u < (h ? R1 : R0)) cp_async_16(&raw[blk & 1][h][2 * c], p.pool + jp.ref_w[h] + wi);
+				if (wi * 16u < (h ? R1 : R0))
+				{
+					DFB_BC((unsigned long long)jp.ref_w[h] + wi + 2 <= p.pool_words && ((jp.ref_w[h] + wi) & 1u) == 0, 203);
+					cp_async_16(&raw[blk & 1][h][2 * c], p.pool + jp.ref_w[h] + wi);
+				}
 			}
 			cp_async_commit();
 		};
 		auto decode_block = [&](int blk) {
-			ring_decode_block<G>(ring, &raw[blk & 1][0][0], blk, 0, 0, R0, R1, jp.ref_w[0], jp.ref_w[1], p.obytes, g);
+			ring_decode_block<G>(ring, &raw[blk & 1][0][0], blk, 0, 0, R0, R1, jp.ref_w[0], jp.ref_w[1], p.obytes, g, p.pool_words);
 		};
 		const int ring_blocks = min(2, (T + CH - 1) / CH); // ring columns this warp will read: T steps
 		issue_block(0);
@@ -528,6 +563,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				if (ck_on && blkno > 0 && have)
 				{
 					const size_t cb = ((size_t)jid * p.ckpt_blocks + (size_t)(blkno - 1)) * (S + 2);
+					DFB_BC(blkno - 1 < p.ckpt_blocks && (cb + S + 2) * G <= p.ckpt_words, 206);
 #pragma unroll
 					for (int k = 0; k < S; k++) p.ckpt[(cb + k) * G + g] = F[k];
 					p.ckpt[(cb + S) * G + g] = prev;
@@ -604,6 +640,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			}
 			if (g == 0 && have)
 			{
+				DFB_BC(jp.out0 < p.n_tasks && jp.out1 < p.n_tasks, 209);
 				if (jp.out0 >= 0) p.out[jp.out0] = max(lo, 0);
 				if (jp.out1 >= 0) p.out[jp.out1] = max(hi, 0);
 			}
@@ -679,6 +716,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			int slot = -1;
 			if (g == 0 && have)
 			{
+				DFB_BC(jp.out0 >= 0 && jp.out0 < p.n_tasks, 207);
 				p.out[jp.out0] = hit ? best : 0;
 				if (group_en)
 				{
@@ -686,6 +724,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 					// that the job pairs of a probe warp run equally many rounds
 					const bool one_round = ck_on && __popc(gr0) <= 1 && __popc(gr1) <= 1;
 					slot = (one_round ? atomicAdd(p.hit_count, 1) : p.n_jobs - 1 - atomicAdd(p.hit_count_long, 1)) + p.slot_base;
+					DFB_BC(slot - p.slot_base >= 0 && slot - p.slot_base < p.n_jobs, 208);
 					p.hitq[slot - p.slot_base] = jid;
 					p.slot_task[slot - p.slot_base] = jp.out0;
 					p.task_slot[jp.out0] = slot;
@@ -770,7 +809,9 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 		uint32_t m0 = 0, m1 = 0;
 		if (have)
 		{
+			DFB_BC(item >= 0 && item < p.n_jobs, 301);
 			jid = p.hitq[item];
+			DFB_BC(jid >= 0 && jid < p.n_jobs, 302);
 			jp = p.jobs[jid];
 			const uint32_t rng = p.slot_rng[item];
 			m0 = rng & 0xFFFFu;
@@ -815,12 +856,16 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 				{
 					const int h = g / (G / 4), c = g % (G / 4);
 					const int wi = ((h ? c1 : c0) >> 4) + blk * HG + 2 * c; // (c0, c1 are multiples of 32: arithmetic shift is exact)
-					if (wi >= 0 && (uint32_t)wi * 16u < (h ? R1 : R0)) cp_async_16(&raw[blk & 1][h][2 * c], p.pool + jp.ref_w[h] + wi);
+					if (wi >= 0 && (uint32_t)wi * 16u < (h ? R1 : R0))
+					{
+						DFB_BC((unsigned long long)jp.ref_w[h] + (unsigned)wi + 2 <= p.pool_words && ((jp.ref_w[h] + (unsigned)wi) & 1u) == 0, 204);
+						cp_async_16(&raw[blk & 1][h][2 * c], p.pool + jp.ref_w[h] + wi);
+					}
 				}
 				cp_async_commit();
 			};
 			auto decode_block = [&](int blk) {
-				ring_decode_block<G>(ring, &raw[blk & 1][0][0], blk, c0 >> 4, c1 >> 4, R0, R1, jp.ref_w[0], jp.ref_w[1], p.obytes, g);
+				ring_decode_block<G>(ring, &raw[blk & 1][0][0], blk, c0 >> 4, c1 >> 4, R0, R1, jp.ref_w[0], jp.ref_w[1], p.obytes, g, p.pool_words);
 			};
 			__syncwarp(); // (the previous round's ring reads are over)
 			const int ring_blocks = min(2, (Tr + PRE + CH - 1) / CH);
@@ -842,6 +887,8 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 				const uint32_t v = (B + (uint32_t)j * gm16) & 0xFFFFu;
 				return v | (v << 16);
 			};
+			DFB_BC(!keep0 || (b0 - 1 < p.ckpt_blocks && (cb0 + S + 2) * G <= p.ckpt_words), 303);
+			DFB_BC(!keep1 || (b1 - 1 < p.ckpt_blocks && (cb1 + S + 2) * G <= p.ckpt_words), 304);
 #pragma unroll
 			for (int k = 0; k < S + 2; k++)
 			{
