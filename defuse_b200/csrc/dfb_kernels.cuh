@@ -596,23 +596,21 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			{
 				// end of a checkpoint block (or of the sweep), same step for all lanes: fold the block maxima into the
 				// row maxima and remember in which granules each row maximum occurs
-				const uint32_t bit = 1u << (blkno >> p.gran_shift);
+				// (branch-free: two DPX maxima with predicate outputs per row say, per half, whether the block maximum
+				// ties or beats the row maximum -- the block then joins or replaces the row's granule set)
+				const uint32_t bit_lo = 1u << (blkno >> p.gran_shift), bit_hi = bit_lo << 16;
 #pragma unroll
 				for (int k = 0; k < S; k++)
 				{
-					const uint32_t xn = __vmaxs2(X[k], Y[k]);
-					const uint32_t same = Y[k] ^ xn; // half == 0: the block attains the (new) row maximum
-					// common case: neither half of the row did anything in this block
-					if (!(same & 0x0000FFFFu) || !(same & 0xFFFF0000u))
-					{
-						const uint32_t grew = X[k] ^ xn; // half != 0: the block maximum beats the row maximum
-						uint32_t inf = info[k];
-						if (grew & 0x0000FFFFu) inf = (inf & 0xFFFF0000u) | bit;
-						else if (!(same & 0x0000FFFFu)) inf |= bit;
-						if (grew & 0xFFFF0000u) inf = (inf & 0x0000FFFFu) | (bit << 16);
-						else if (!(same & 0xFFFF0000u)) inf |= bit << 16;
-						info[k] = inf;
-					}
+					bool ge_hi, ge_lo, old_ge_hi, old_ge_lo;
+					const uint32_t xn = __vibmax_s16x2(Y[k], X[k], &ge_hi, &ge_lo);   // ge: block maximum >= row maximum
+					(void)__vibmax_s16x2(X[k], Y[k], &old_ge_hi, &old_ge_lo);          // !old_ge: block maximum > row maximum
+					uint32_t inf = info[k];
+					if (!old_ge_lo) inf &= 0xFFFF0000u;
+					if (ge_lo) inf |= bit_lo;
+					if (!old_ge_hi) inf &= 0x0000FFFFu;
+					if (ge_hi) inf |= bit_hi;
+					info[k] = inf;
 					X[k] = xn;
 					Y[k] = 0;
 				}
@@ -758,7 +756,10 @@ template <int S>
 struct ProbeOcc
 {
 	static constexpr int kEst = 3 * S + 44;
-	static constexpr int kMinBlocks = kEst <= 60 ? 6 : (kEst <= 100 ? 5 : (kEst <= 128 ? 4 : (kEst <= 168 ? 3 : 2)));
+#ifndef DFB_PROBE_OCC6_EST
+#define DFB_PROBE_OCC6_EST 60 // strips up to this register estimate ask ptxas for six CTAs per SM (build-time knob for A/B runs)
+#endif
+	static constexpr int kMinBlocks = kEst <= DFB_PROBE_OCC6_EST ? 6 : (kEst <= 100 ? 5 : (kEst <= 128 ? 4 : (kEst <= 168 ? 3 : 2)));
 };
 
 template <int G, int S>
