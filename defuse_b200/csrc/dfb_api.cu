@@ -208,6 +208,13 @@ struct dfb_ctx
 	cudaStream_t upload_stream = nullptr; // uploads + packing of the next chunk of a pipelined batch
 	cudaStream_t upload_stream2 = nullptr; // device-built chunks alternate between the two: chunk k+1's uploads do not hold up chunk k's packing
 	cudaEvent_t copied_ev = nullptr;      // blocking-sync event behind the result copies of a fetch
+	// pageable caller buffers are staged through a small ring of pinned blocks by the context's workers (the driver's own
+	// staging copies with one thread and blocks the caller for the whole transfer)
+	static const int kRingSlots = 4;
+	static const size_t kRingBlock = (size_t)8 << 20;
+	PinnedBuf h_ring;
+	cudaEvent_t ring_ev[kRingSlots] = {nullptr, nullptr, nullptr, nullptr};
+	unsigned long long ring_next = 0;
 	HostPool* pool = nullptr;       // plan building (and everything else on the caller's thread)
 	HostPool* pool_fetch = nullptr; // result assembly when it runs on the pipelining helper thread
 	dfb_plan* last_split = nullptr; // result holder of dfb_split_align_batch
@@ -388,6 +395,9 @@ extern "C" void dfb_ctx_destroy(dfb_ctx* ctx)
 	if (ctx->last_split) dfb_plan_destroy(ctx->last_split);
 	cudaStreamSynchronize(ctx->stream);
 	for (auto& b : ctx->h_in) b.release();
+	ctx->h_ring.release();
+	for (auto& ev : ctx->ring_ev)
+		if (ev) cudaEventDestroy(ev);
 	ctx->h_out.release();
 	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
@@ -822,33 +832,82 @@ static cudaError_t stage_layout(dfb_ctx* ctx, int stage_slot, Staging& st, int64
 
 // word layout of the two tables; returns total words.  Every sequence starts on an even word: the sweep copies
 // reference words into shared memory 16 bytes at a time (cp.async)
-static uint32_t layout_words(const dfb_seq_table* a, int mode_a, const dfb_seq_table* b, int mode_b, SeqDesc* da,
+static uint32_t layout_words(dfb_ctx* ctx, const dfb_seq_table* a, int mode_a, const dfb_seq_table* b, int mode_b, SeqDesc* da,
                              SeqDesc* db, uint32_t* words_a_end, bool* overflow)
 {
-	uint64_t w = 0;
-	const int64_t a0 = a->off[0], b0 = b->off[0];
-	const int64_t b_src_base = a->off[a->n] - a0;
-	for (int64_t k = 0; k < a->n; k++)
-	{
-		const uint32_t len = (uint32_t)(a->off[k + 1] - a->off[k]);
-		da[k].src = 16 + (a->off[k] - a0);
-		da[k].len = len;
-		da[k].word = (uint32_t)w;
-		w += (uint64_t)((len + 15) / 16) * (mode_a == PACK_BOTH ? 2 : 1);
-		w += w & 1;
-	}
-	*words_a_end = (uint32_t)w;
-	for (int64_t k = 0; k < b->n; k++)
-	{
-		const uint32_t len = (uint32_t)(b->off[k + 1] - b->off[k]);
-		db[k].src = 16 + b_src_base + (b->off[k] - b0);
-		db[k].len = len;
-		db[k].word = (uint32_t)w;
-		w += (uint64_t)((len + 15) / 16) * (mode_b == PACK_BOTH ? 2 : 1);
-		w += w & 1;
-	}
+	// one table: words per range of sequences on every worker, a prefix over the ranges, then the descriptors
+	auto one = [&](const dfb_seq_table* t, int mode, SeqDesc* d, int64_t src_base, uint64_t w0) -> uint64_t {
+		const int copies = mode == PACK_BOTH ? 2 : 1;
+		const int64_t o0 = t->off[0];
+		auto words_of = [copies](uint32_t len) -> uint64_t {
+			const uint64_t w = (uint64_t)((len + 15) / 16) * (unsigned)copies;
+			return w + (w & 1);
+		};
+		const int T = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->host_threads, t->n / 65536 + 1));
+		std::vector<uint64_t> before((size_t)T + 1, 0);
+		parallel_for(ctx->pool, T, [&](int tid) {
+			uint64_t w = 0;
+			for (int64_t k = t->n * tid / T; k < t->n * (tid + 1) / T; k++) w += words_of((uint32_t)(t->off[k + 1] - t->off[k]));
+			before[(size_t)tid + 1] = w;
+		});
+		before[0] = w0;
+		for (int k = 0; k < T; k++) before[(size_t)k + 1] += before[(size_t)k];
+		parallel_for(ctx->pool, T, [&](int tid) {
+			uint64_t w = before[(size_t)tid];
+			for (int64_t k = t->n * tid / T; k < t->n * (tid + 1) / T; k++)
+			{
+				const uint32_t len = (uint32_t)(t->off[k + 1] - t->off[k]);
+				d[k].src = 16 + src_base + (t->off[k] - o0);
+				d[k].len = len;
+				d[k].word = (uint32_t)w;
+				w += words_of(len);
+			}
+		});
+		return before[(size_t)T];
+	};
+	const uint64_t wa = one(a, mode_a, da, 0, 0);
+	*words_a_end = (uint32_t)wa;
+	const uint64_t w = one(b, mode_b, db, a->off[a->n] - a->off[0], wa);
 	*overflow = w >= 0xFFFFFFF0ull;
 	return (uint32_t)w;
+}
+
+// Host -> device copy of a caller buffer on stream `up`.  Pinned (or registered) memory goes straight to the copy engine;
+// pageable memory of a megabyte or more is copied block by block into a ring of pinned blocks by the context's workers,
+// each block's transfer queued behind its copy -- the transfer of block i runs under the host copy of block i+1.
+static cudaError_t h2d_any(dfb_ctx* ctx, cudaStream_t up, void* dst, const void* src, size_t bytes)
+{
+	if (bytes == 0) return cudaSuccess;
+	bool pageable = false;
+	if (bytes >= ((size_t)1 << 20))
+	{
+		cudaPointerAttributes attr;
+		if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+		else cudaGetLastError();
+	}
+	if (!pageable) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, up);
+	cudaError_t e = ctx->h_ring.ensure(dfb_ctx::kRingSlots * dfb_ctx::kRingBlock);
+	if (e != cudaSuccess) return e;
+	for (size_t off = 0; off < bytes; off += dfb_ctx::kRingBlock)
+	{
+		const size_t n = std::min(dfb_ctx::kRingBlock, bytes - off);
+		const int slot = (int)(ctx->ring_next++ % dfb_ctx::kRingSlots);
+		if (!ctx->ring_ev[slot])
+		{
+			if ((e = cudaEventCreateWithFlags(&ctx->ring_ev[slot], cudaEventDisableTiming)) != cudaSuccess) return e;
+		}
+		else if ((e = cudaEventSynchronize(ctx->ring_ev[slot])) != cudaSuccess) return e; // the block's last transfer is over
+		uint8_t* stage = (uint8_t*)ctx->h_ring.p + (size_t)slot * dfb_ctx::kRingBlock;
+		const uint8_t* from = (const uint8_t*)src + off;
+		const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->host_threads, n >> 20));
+		parallel_for(ctx->pool, T, [&](int tid) {
+			const size_t a = n * (size_t)tid / (size_t)T, b = n * ((size_t)tid + 1) / (size_t)T;
+			memcpy(stage + a, from + a, b - a);
+		});
+		if ((e = cudaMemcpyAsync((uint8_t*)dst + off, stage, n, cudaMemcpyHostToDevice, up)) != cudaSuccess) return e;
+		if ((e = cudaEventRecord(ctx->ring_ev[slot], up)) != cudaSuccess) return e;
+	}
+	return cudaSuccess;
 }
 
 // Starts the copy of the raw sequence bytes before the host builds descriptors and jobs: with pinned
@@ -861,8 +920,8 @@ static int upload_raw(dfb_plan* pl, const dfb_seq_table* a, const dfb_seq_table*
 	// 16 bytes of slack in front, 32 behind (the pack kernel reads whole 16-byte windows)
 	CK(ctx, cudaMallocAsync((void**)&pl->d_raw, std::max<size_t>(256, (size_t)(na + nb + 48)), up));
 	pl->raw_bytes = (unsigned long long)(na + nb + 48);
-	if (na) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16, a->bytes + a->off[0], (size_t)na, cudaMemcpyHostToDevice, up));
-	if (nb) CK(ctx, cudaMemcpyAsync(pl->d_raw + 16 + na, b->bytes + b->off[0], (size_t)nb, cudaMemcpyHostToDevice, up));
+	if (na) CK(ctx, h2d_any(ctx, up, pl->d_raw + 16, a->bytes + a->off[0], (size_t)na));
+	if (nb) CK(ctx, h2d_any(ctx, up, pl->d_raw + 16 + na, b->bytes + b->off[0], (size_t)nb));
 	return DFB_OK;
 }
 
@@ -1156,7 +1215,7 @@ static int simple_plan_create_impl(dfb_ctx* ctx, const dfb_simple_params* params
 	tr.lap("simple.create: staging");
 	uint32_t words_a_end = 0;
 	bool overflow = false;
-	const uint32_t total_words = layout_words(refs, PACK_FWD, seqs, PACK_FWD, st.desc_a, st.desc_b, &words_a_end, &overflow);
+	const uint32_t total_words = layout_words(ctx, refs, PACK_FWD, seqs, PACK_FWD, st.desc_a, st.desc_b, &words_a_end, &overflow);
 	if (overflow)
 	{
 		dfb_plan_destroy(pl);
@@ -1371,7 +1430,7 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 	// every read forward and reversed (:84-85)
 	uint32_t words_a_end = 0;
 	bool overflow = false;
-	const uint32_t total_words = layout_words(refs, PACK_REV_ODD, reads, PACK_BOTH, st.desc_a, st.desc_b, &words_a_end, &overflow);
+	const uint32_t total_words = layout_words(ctx, refs, PACK_REV_ODD, reads, PACK_BOTH, st.desc_a, st.desc_b, &words_a_end, &overflow);
 	if (overflow)
 	{
 		dfb_plan_destroy(pl);
@@ -1469,10 +1528,12 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 // builds that chunk on the host instead.
 static const int DFB_BUILD_ON_HOST = 1000;
 
+// (`simple`: a SimpleAligner batch -- task_cluster names the reference, task_min_score is null, `params` carries the scoring
+// triple only, `ref_base` is the first reference of the view)
 static int split_build_enqueue(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
                                const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
                                const int32_t* task_min_score, int64_t n_tasks, int32_t read_base, int stage_slot, cudaStream_t up_stream,
-                               dfb_plan** out)
+                               dfb_plan** out, bool simple = false, int32_t ref_base = 0)
 {
 	static_assert(kNumClasses <= DFB_BUILD_MAX_CLASSES && kRBins == DFB_BUILD_RBINS, "dfb_build.cuh tables");
 	*out = nullptr;
@@ -1481,14 +1542,14 @@ static int split_build_enqueue(dfb_ctx* ctx, const dfb_split_params* params, con
 	dfb_plan* pl = new (std::nothrow) dfb_plan();
 	if (!pl) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
 	pl->ctx = ctx;
-	pl->split = true;
+	pl->split = !simple;
 	pl->sp = *params;
 	pl->n_tasks = n_tasks;
 	pl->stats.n_tasks = n_tasks;
 	pl->h_read_off = reads->off;
 	pl->h_task_read = task_read;
 	pl->h_read_base = read_base;
-	classify_params(pl, params->match, params->mismatch, params->gap, params->end_gaps == 0 && params->min_split_score >= 1);
+	classify_params(pl, params->match, params->mismatch, params->gap, simple || (params->end_gaps == 0 && params->min_split_score >= 1));
 	pl->up = up_stream;
 	cudaStream_t up = pl->up;
 	auto fail = [&](int code) {
@@ -1516,7 +1577,7 @@ static int split_build_enqueue(dfb_ctx* ctx, const dfb_split_params* params, con
 	const size_t o_bins = take(2 * n_bins * 4);
 	const size_t o_sums_a = take((size_t)(blocks_a + 1) * 8), o_sums_b = take((size_t)(blocks_b + 1) * 8);
 	const size_t o_stats = take(sizeof(BuildStats) + 64);
-	const size_t o_jobs = take((size_t)n_tasks * sizeof(JobPair));
+	const size_t o_jobs = take(((size_t)n_tasks + 2 * kNumClasses) * sizeof(JobPair)); // (simple: ceil(tasks / 2) per class)
 	CK(ctx, cudaMallocAsync((void**)&pl->d_build, std::max<size_t>(at, 256), up));
 	uint8_t* base = pl->d_build;
 	BuildStats* d_stats = (BuildStats*)(base + o_stats);
@@ -1542,7 +1603,7 @@ static int split_build_enqueue(dfb_ctx* ctx, const dfb_split_params* params, con
 	    (e = cudaMemcpyAsync(base + o_off_b, reads->off, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
 	    (e = cudaMemcpyAsync(base + o_tc, task_cluster, (size_t)n_tasks * 4, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
 	    (e = cudaMemcpyAsync(base + o_tr, task_read, (size_t)n_tasks * 4, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
-	    (e = cudaMemcpyAsync(base + o_tm, task_min_score, (size_t)n_tasks * 4, cudaMemcpyHostToDevice, up)) != cudaSuccess)
+	    (!simple && (e = cudaMemcpyAsync(base + o_tm, task_min_score, (size_t)n_tasks * 4, cudaMemcpyHostToDevice, up)) != cudaSuccess))
 		return cuda_fail(e, "task upload");
 	const int64_t raw_a = refs->off[refs->n] - refs->off[0];
 	// descriptors: windows (one stored copy each), then reads (forward + reversed copy)
@@ -1559,7 +1620,7 @@ static int split_build_enqueue(dfb_ctx* ctx, const dfb_split_params* params, con
 	DescParams db = da;
 	db.off = (const int64_t*)(base + o_off_b);
 	db.n = nb;
-	db.copies = 2;
+	db.copies = simple ? 1 : 2;
 	db.src_base = raw_a;
 	db.desc = (SeqDesc*)(base + o_desc_b);
 	db.block_sums = (unsigned long long*)(base + o_sums_b);
@@ -1568,7 +1629,9 @@ static int split_build_enqueue(dfb_ctx* ctx, const dfb_split_params* params, con
 	SplitBuildParams bp;
 	memset(&bp, 0, sizeof(bp));
 	bp.desc_a = da.desc;
-	bp.n_clusters = na / 2;
+	bp.n_clusters = simple ? na : na / 2;
+	bp.simple = simple ? 1 : 0;
+	bp.ref_base = ref_base;
 	bp.desc_b = db.desc;
 	bp.n_reads = nb;
 	bp.task_cluster = (const int32_t*)(base + o_tc);
@@ -1687,23 +1750,47 @@ static int split_build_finish(dfb_plan* pl)
 		if (!pl->ev[k] && (e = cudaEventCreate(&pl->ev[k])) != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
 	cudaEventRecord(pl->ev[0], up);
 	const int max_grid = ctx->prop.multiProcessorCount * 16;
-	if (na) pack_kernel<PACK_REV_ODD><<<(int)std::min<uint64_t>(((uint64_t)na * 16 + 255) / 256, (uint64_t)max_grid), 256, 0, up>>>(pl->d_raw, pl->pending.d_desc_a, (int)na, pl->d_pool, pl->d_obytes, pl->pool_words, pl->raw_bytes);
-	if (nb) pack_kernel<PACK_BOTH><<<(int)std::min<uint64_t>(((uint64_t)nb * 16 + 255) / 256, (uint64_t)max_grid), 256, 0, up>>>(pl->d_raw, pl->pending.d_desc_b, (int)nb, pl->d_pool, pl->d_obytes, pl->pool_words, pl->raw_bytes);
+	const bool simple = bp.simple != 0;
+	const int grid_a = (int)std::min<uint64_t>(((uint64_t)na * 16 + 255) / 256, (uint64_t)max_grid);
+	const int grid_b = (int)std::min<uint64_t>(((uint64_t)nb * 16 + 255) / 256, (uint64_t)max_grid);
+	if (na && simple) pack_kernel<PACK_FWD><<<grid_a, 256, 0, up>>>(pl->d_raw, pl->pending.d_desc_a, (int)na, pl->d_pool, pl->d_obytes, pl->pool_words, pl->raw_bytes);
+	if (na && !simple) pack_kernel<PACK_REV_ODD><<<grid_a, 256, 0, up>>>(pl->d_raw, pl->pending.d_desc_a, (int)na, pl->d_pool, pl->d_obytes, pl->pool_words, pl->raw_bytes);
+	if (nb && simple) pack_kernel<PACK_FWD><<<grid_b, 256, 0, up>>>(pl->d_raw, pl->pending.d_desc_b, (int)nb, pl->d_pool, pl->d_obytes, pl->pool_words, pl->raw_bytes);
+	if (nb && !simple) pack_kernel<PACK_BOTH><<<grid_b, 256, 0, up>>>(pl->d_raw, pl->pending.d_desc_b, (int)nb, pl->d_pool, pl->d_obytes, pl->pool_words, pl->raw_bytes);
 	cudaEventRecord(pl->ev[1], up);
 	pl->pack_timed = true;
-	if (n_tasks) split_scatter_kernel<<<task_blocks, DFB_BUILD_BLOCK, 0, up>>>(bp);
+	if (simple)
+	{
+		// two tasks per job: jobs per class = ceil(tasks / 2); the scatter needs the first task position and first job of a class
+		SplitBuildParams sb = bp;
+		unsigned int first_task = 0, first_job = 0;
+		for (int c = 0; c < kNumClasses; c++)
+		{
+			sb.cls_first_task[c] = first_task;
+			sb.cls_first_job[c] = first_job;
+			first_task += h_stats->cls_jobs[c];
+			n_jobs_cls[c] = ((int64_t)h_stats->cls_jobs[c] + 1) / 2;
+			first_job += (unsigned int)n_jobs_cls[c];
+		}
+		if (first_job) jobs_init_kernel<<<(unsigned)((first_job + DFB_BUILD_BLOCK - 1) / DFB_BUILD_BLOCK), DFB_BUILD_BLOCK, 0, up>>>(bp.jobs, (long long)first_job);
+		if (n_tasks) simple_scatter_kernel<<<task_blocks, DFB_BUILD_BLOCK, 0, up>>>(sb);
+	}
+	else if (n_tasks) split_scatter_kernel<<<task_blocks, DFB_BUILD_BLOCK, 0, up>>>(bp);
 	if ((e = cudaGetLastError()) != cudaSuccess) return cuda_fail(e, "pack / scatter kernels");
 	pl->stats.h2d_bytes += raw_a + raw_b + (na + 1 + nb + 1) * 8 + n_tasks * 12 + (int64_t)sizeof(BuildStats);
-	pl->stats.raw_bytes = raw_a + 2 * raw_b;
+	pl->stats.raw_bytes = raw_a + (simple ? 1 : 2) * raw_b;
 	pl->stats.packed_bytes = (int64_t)total_words * 8;
 
-	pl->ev_cap = (unsigned long long)std::max<int64_t>(n_tasks, 1 << 20);
-	if ((e = dalloc(ctx, (void**)&pl->d_events, (size_t)pl->ev_cap * sizeof(Event))) != cudaSuccess ||
-	    (e = dalloc(ctx, (void**)&pl->d_ev_count, sizeof(unsigned long long))) != cudaSuccess)
-		return fail(set_err(ctx, DFB_ERR_CUDA, "output allocation failed: %s", cudaGetErrorString(e)));
-	if ((rc = alloc_work(pl, bp.jobs, nullptr, n_jobs_cls, true, 0))) return fail(rc);
+	if (!simple)
+	{
+		pl->ev_cap = (unsigned long long)std::max<int64_t>(n_tasks, 1 << 20);
+		if ((e = dalloc(ctx, (void**)&pl->d_events, (size_t)pl->ev_cap * sizeof(Event))) != cudaSuccess ||
+		    (e = dalloc(ctx, (void**)&pl->d_ev_count, sizeof(unsigned long long))) != cudaSuccess)
+			return fail(set_err(ctx, DFB_ERR_CUDA, "output allocation failed: %s", cudaGetErrorString(e)));
+	}
+	if ((rc = alloc_work(pl, bp.jobs, nullptr, n_jobs_cls, !simple, 0))) return fail(rc);
 	for (int c = 0; c < kNumClasses; c++)
-		if (pl->cls[c].n_jobs) fill_fast_params(pl, c, params->match, params->mismatch, params->gap, params->min_split_score);
+		if (pl->cls[c].n_jobs) fill_fast_params(pl, c, params->match, params->mismatch, params->gap, simple ? 0 : params->min_split_score);
 	tr.lap("split.create(dev): pack, scatter, alloc");
 	return DFB_OK;
 }
@@ -2294,35 +2381,94 @@ static int simple_align_pipelined(dfb_ctx* ctx, const dfb_simple_params* params,
                                   int64_t n_tasks, bool refs_monotone, int32_t* out_score)
 {
 	const int K = (int)std::max<int64_t>(2, std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks / 150000));
-	std::vector<dfb_plan*> plans((size_t)K, nullptr);
-	std::vector<double> weight((size_t)K, 1.0);
-	weight[0] = 0.4; // a short first chunk puts the GPU to work early
-	double total = 0, run = 0;
-	for (double w : weight) total += w;
-	int rc = DFB_OK;
-	int64_t a = 0;
-	for (int k = 0; k < K && !rc; k++)
+	std::vector<dfb_plan*> plans((size_t)K, nullptr), staged((size_t)K, nullptr);
+	std::vector<int64_t> t0((size_t)K + 1, 0);
 	{
-		run += weight[(size_t)k];
-		const int64_t b = k + 1 == K ? n_tasks : (int64_t)((double)n_tasks * run / total);
-		if (b <= a) continue;
+		std::vector<double> weight((size_t)K, 1.0);
+		weight[0] = 0.4; // a short first chunk puts the GPU to work early
+		double total = 0, run = 0;
+		for (double w : weight) total += w;
+		for (int k = 0; k < K; k++)
+		{
+			run += weight[(size_t)k];
+			t0[(size_t)k + 1] = k + 1 == K ? n_tasks : (int64_t)((double)n_tasks * run / total);
+		}
+	}
+	// Job lists on the device (dfb_build.cuh) whenever the s16x2 kernels take this scoring: a simple batch is host-bound
+	// otherwise (one pass over the tasks and two over the tables per chunk against 4 ms of sweep).  DFB_HOST_BUILD forces
+	// the host path (A/B runs, tests).
+	dfb_split_params sp{params->match, params->mismatch, params->gap, 0, 0};
+	bool device_build = false;
+	{
+		dfb_plan probe;
+		classify_params(&probe, params->match, params->mismatch, params->gap, true);
+		for (int c = 0; c < kNumClasses; c++) device_build = device_build || probe.fast_ok[c];
+		if (const char* e = getenv("DFB_HOST_BUILD"))
+			if (*e && *e != '0') device_build = false;
+	}
+	struct View
+	{
+		dfb_seq_table refs, seqs;
+		int32_t r_lo, s_lo;
+	};
+	auto chunk_of = [&](int k, View& v) -> int {
+		const int64_t a = t0[(size_t)k], b = t0[(size_t)k + 1];
+		if (b <= a) return set_err(ctx, DFB_ERR_STATE, "empty chunk in a pipelined batch");
 		const int32_t s_lo = task_seq[a], s_hi = task_seq[b - 1] + 1;
 		int32_t r_lo = 0, r_hi = (int32_t)refs->n;
 		if (refs_monotone) { r_lo = task_ref[a]; r_hi = task_ref[b - 1] + 1; }
 		if (s_lo < 0 || s_hi > seqs->n || r_lo < 0 || r_hi > refs->n || s_hi < s_lo || r_hi < r_lo)
+			return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)a);
+		v.seqs = dfb_seq_table{seqs->bytes, seqs->off + s_lo, (int64_t)(s_hi - s_lo)};
+		v.refs = dfb_seq_table{refs->bytes, refs->off + r_lo, (int64_t)(r_hi - r_lo)};
+		v.r_lo = r_lo;
+		v.s_lo = s_lo;
+		return DFB_OK;
+	};
+	auto upload = [&](int k) -> int {
+		View v;
+		int arc = chunk_of(k, v);
+		if (arc) return arc;
+		const int64_t a = t0[(size_t)k], b = t0[(size_t)k + 1];
+		// (alternating upload streams: chunk k+1's copies do not queue behind chunk k's)
+		return split_build_enqueue(ctx, &sp, &v.refs, &v.seqs, task_ref + a, task_seq + a, nullptr, b - a, v.s_lo, k,
+		                           (k & 1) ? ctx->upload_stream2 : ctx->upload_stream, &staged[(size_t)k], true, v.r_lo);
+	};
+	int rc = DFB_OK;
+	if (device_build)
+	{
+		rc = upload(0);
+		if (!rc) rc = split_build_kernels(staged[0]);
+	}
+	for (int k = 0; k < K && !rc; k++)
+	{
+		if (device_build && k + 1 < K && (rc = upload(k + 1))) break;
+		const int64_t a = t0[(size_t)k], b = t0[(size_t)k + 1];
+		dfb_plan* pk = staged[(size_t)k];
+		staged[(size_t)k] = nullptr;
+		rc = DFB_BUILD_ON_HOST;
+		if (pk)
 		{
-			rc = set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)a);
-			break;
+			rc = split_build_finish(pk);
+			if (rc)
+			{
+				dfb_plan_destroy(pk);
+				pk = nullptr;
+			}
 		}
-		dfb_seq_table sview{seqs->bytes, seqs->off + s_lo, (int64_t)(s_hi - s_lo)};
-		dfb_seq_table rview{refs->bytes, refs->off + r_lo, (int64_t)(r_hi - r_lo)};
-		dfb_plan* pk = nullptr;
-		// (alternating upload streams: chunk k+1's copies do not queue behind chunk k's pack kernels)
-		rc = simple_plan_create_impl(ctx, params, &rview, &sview, task_ref + a, task_seq + a, b - a, r_lo, s_lo, k,
-		                             (k & 1) ? ctx->upload_stream2 : ctx->upload_stream, &pk);
+		if (rc == DFB_BUILD_ON_HOST)
+		{
+			View v;
+			if (!(rc = chunk_of(k, v)))
+				rc = simple_plan_create_impl(ctx, params, &v.refs, &v.seqs, task_ref + a, task_seq + a, b - a, v.r_lo, v.s_lo, k,
+				                             (k & 1) ? ctx->upload_stream2 : ctx->upload_stream, &pk);
+		}
 		if (rc) break;
 		plans[(size_t)k] = pk;
-		rc = dfb_plan_run(pk);
+		// the next chunk's build kernels ride behind this chunk's sweep on the compute stream
+		dfb_plan* next = (k + 1 < K) ? staged[(size_t)k + 1] : nullptr;
+		const std::function<int()> hook = [&]() -> int { return next ? split_build_kernels(next) : DFB_OK; };
+		rc = plan_run_impl(pk, &hook);
 		if (!rc)
 		{
 			// scores straight into the caller's array, behind this chunk's kernels only
@@ -2331,12 +2477,17 @@ static int simple_align_pipelined(dfb_ctx* ctx, const dfb_simple_params* params,
 				e = cudaMemcpyAsync(out_score + a, pk->d_out, (size_t)(b - a) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream);
 			if (e != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "score copy failed: %s", cudaGetErrorString(e));
 		}
-		a = b;
 	}
 	cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
 	if (!rc && e != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "pipelined batch failed: %s", cudaGetErrorString(e));
 	if (!rc) rc = bounds_check_status(ctx);
+	for (dfb_plan* sp2 : staged)
+		if (sp2)
+		{
+			cudaStreamSynchronize(sp2->up); // (its uploads read the caller's arrays)
+			dfb_plan_destroy(sp2);
+		}
 	for (dfb_plan* pk : plans)
 		if (pk) dfb_plan_destroy(pk);
 	return rc;

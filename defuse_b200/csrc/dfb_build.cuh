@@ -155,7 +155,11 @@ struct SplitBuildParams
 	const int32_t* task_read;
 	const int32_t* task_min_score;
 	long long n_tasks;
-	int32_t read_base;
+	int32_t read_base;        // first entry of table b in the caller's numbering (a chunk sees a view of it)
+	int32_t ref_base;         // simple batches: the same for table a
+	int simple;               // 0: split tasks (cluster, read, minScore); 1: SimpleAligner tasks (reference, sequence), two per job
+	unsigned int cls_first_task[DFB_BUILD_MAX_CLASSES]; // simple scatter: first task position / first job of every class
+	unsigned int cls_first_job[DFB_BUILD_MAX_CLASSES];
 	int32_t* bin_of;          // [n_tasks]: class * RBINS + bin, -1: no work (empty read), -2: generic path
 	unsigned int* bin_count;  // [classes * RBINS], zeroed; the scan turns it into the first job of every bin
 	unsigned int* bin_fill;   // [classes * RBINS], zeroed
@@ -175,16 +179,19 @@ __global__ void __launch_bounds__(DFB_BUILD_BLOCK) split_classify_kernel(SplitBu
 	unsigned long long cells = 0;
 	if (t < p.n_tasks)
 	{
-		const long long c0 = p.task_cluster[t], rd = (long long)p.task_read[t] - p.read_base;
+		const long long c0 = (long long)p.task_cluster[t] - p.ref_base, rd = (long long)p.task_read[t] - p.read_base;
 		if (c0 < 0 || c0 >= p.n_clusters || rd < 0 || rd >= p.n_reads)
 		{
 			atomicMin(&p.stats->bad_task, (unsigned long long)t);
 		}
 		else
 		{
-			const long long R1 = p.desc_a[2 * c0].len, R2 = p.desc_a[2 * c0 + 1].len, L = p.desc_b[rd].len;
+			// split: the two windows of cluster c0; simple: reference c0 alone
+			const long long R1 = p.simple ? p.desc_a[c0].len : p.desc_a[2 * c0].len;
+			const long long R2 = p.simple ? 0 : p.desc_a[2 * c0 + 1].len, L = p.desc_b[rd].len;
 			cells = (unsigned long long)((R1 + R2) * L);
-			if (L > 0) // an empty read has no split (SplitReadAligner.cpp:224-227)
+			// an empty read has no split (SplitReadAligner.cpp:224-227); no interior cell: score 0 (SimpleAligner.cpp:30)
+			if (L > 0 && (!p.simple || R1 > 0))
 			{
 				const long long Rm = max(R1, R2);
 				int c = -1;
@@ -305,6 +312,45 @@ __global__ void __launch_bounds__(DFB_BUILD_BLOCK) split_scatter_kernel(SplitBui
 	jp.out1 = p.task_min_score[t];
 	DFB_BC((long long)pos < p.n_tasks && bin < p.n_classes * DFB_BUILD_RBINS, 401);
 	p.jobs[pos] = jp;
+}
+
+// SimpleAligner batches: two tasks share a job (low / high half of the registers); the task at position q inside its
+// class goes to job q/2, half q%2.  The last job of a class with an odd number of tasks keeps an empty half.
+__global__ void __launch_bounds__(DFB_BUILD_BLOCK) jobs_init_kernel(JobPair* jobs, long long n_jobs)
+{
+	const long long j = (long long)blockIdx.x * DFB_BUILD_BLOCK + threadIdx.x;
+	if (j >= n_jobs) return;
+	JobPair jp;
+	jp.ref_w[0] = jp.ref_w[1] = jp.read_w[0] = jp.read_w[1] = 0;
+	jp.R[0] = jp.R[1] = jp.L[0] = jp.L[1] = 0;
+	jp.out0 = jp.out1 = -1;
+	jobs[j] = jp;
+}
+
+__global__ void __launch_bounds__(DFB_BUILD_BLOCK) simple_scatter_kernel(SplitBuildParams p)
+{
+	const long long t = (long long)blockIdx.x * DFB_BUILD_BLOCK + threadIdx.x;
+	const int bin = t < p.n_tasks ? p.bin_of[t] : -1;
+	const unsigned active = __ballot_sync(0xffffffffu, bin >= 0);
+	if (bin < 0) return;
+	const unsigned same = __match_any_sync(active, bin);
+	const int lane = threadIdx.x & 31, leader = __ffs(same) - 1;
+	unsigned int base = 0;
+	if (lane == leader) base = atomicAdd(&p.bin_fill[bin], (unsigned)__popc(same));
+	base = __shfl_sync(same, base, leader);
+	const unsigned int pos = p.bin_count[bin] + base + (unsigned)__popc(same & ((1u << lane) - 1u)); // among all fast tasks
+	const int c = bin / DFB_BUILD_RBINS;
+	const unsigned int q = pos - p.cls_first_task[c];
+	const SeqDesc r = p.desc_a[(long long)p.task_cluster[t] - p.ref_base], sq = p.desc_b[(long long)p.task_read[t] - p.read_base];
+	JobPair* jp = p.jobs + p.cls_first_job[c] + (q >> 1);
+	DFB_BC((long long)(p.cls_first_job[c] + (q >> 1)) < (p.n_tasks + DFB_BUILD_MAX_CLASSES) / 2 + DFB_BUILD_MAX_CLASSES, 402);
+	const int h = (int)(q & 1u);
+	jp->ref_w[h] = r.word;
+	jp->read_w[h] = sq.word;
+	jp->R[h] = (uint16_t)r.len;
+	jp->L[h] = (uint16_t)sq.len;
+	if (h == 0) jp->out0 = (int32_t)t;
+	else jp->out1 = (int32_t)t;
 }
 
 }  // namespace dfb
