@@ -278,16 +278,34 @@ __device__ __noinline__ void ring_decode_block(uint32_t* ring, const uint2* raw_
 	const int wrel = blk * HG + (g >> 1);
 	const int wi0 = cw0 + wrel, wi1 = cw1 + wrel;
 	const int bit0 = 8 * (g & 1);
+	// the lane's eight bases of either half: 2-bit codes, exception flags, and how many of them lie inside the reference
+	const uint32_t c0 = w0.x >> (2 * bit0), c1 = w1.x >> (2 * bit0);
+	const int nv0 = wi0 < 0 ? 0 : min(8, max(0, (int)R0 - (wi0 * 16 + bit0)));
+	const int nv1 = wi1 < 0 ? 0 : min(8, max(0, (int)R1 - (wi1 * 16 + bit0)));
+	const uint32_t m0 = (w0.y >> bit0) & ((1u << nv0) - 1u), m1 = (w1.y >> bit0) & ((1u << nv1) - 1u);
+	DFB_BC(nv0 == 0 || (unsigned long long)ref_w0 + (unsigned long long)wi0 < pool_words, 201);
+	DFB_BC(nv1 == 0 || (unsigned long long)ref_w1 + (unsigned long long)wi1 < pool_words, 202);
+	const int rot = g >> RSH;
+	const uint32_t first = (uint32_t)blk * CH + 16u * (g >> 1) + bit0;
 #pragma unroll
 	for (int n = 0; n < 8; n++)
 	{
-		const int nb = bit0 + ((n + (g >> RSH)) & 7);
-		uint32_t f0 = DFB_REF_PAD, f1 = DFB_REF_PAD;
-		if (wi0 >= 0 && (uint32_t)(wi0 * 16 + nb) < R0) f0 = decode_base(w0, ref_w0 + (uint32_t)wi0, nb, obytes);
-		if (wi1 >= 0 && (uint32_t)(wi1 * 16 + nb) < R1) f1 = decode_base(w1, ref_w1 + (uint32_t)wi1, nb, obytes);
-		DFB_BC(wi0 < 0 || (uint32_t)(wi0 * 16) >= R0 || (unsigned long long)ref_w0 + (unsigned long long)wi0 < pool_words, 201);
-		DFB_BC(wi1 < 0 || (uint32_t)(wi1 * 16) >= R1 || (unsigned long long)ref_w1 + (unsigned long long)wi1 < pool_words, 202);
-		ring[((uint32_t)blk * CH + 16u * (g >> 1) + nb) & (RING - 1)] = f0 | (f1 << 16);
+		const int nn = (n + rot) & 7;
+		uint32_t f0 = (0x54474341u >> (8 * ((c0 >> (2 * nn)) & 3u))) & 0xFFu; // "ACGT"
+		uint32_t f1 = (0x54474341u >> (8 * ((c1 >> (2 * nn)) & 3u))) & 0xFFu;
+		if (nn >= nv0) f0 = DFB_REF_PAD;
+		if (nn >= nv1) f1 = DFB_REF_PAD;
+		ring[(first + nn) & (RING - 1)] = f0 | (f1 << 16);
+	}
+	if (m0 | m1)
+	{
+		// exception plane (rare): the raw byte replaces the decoded code
+		uint16_t* ring16 = reinterpret_cast<uint16_t*>(ring);
+		for (int nn = 0; nn < 8; nn++)
+		{
+			if ((m0 >> nn) & 1u) ring16[2 * ((first + nn) & (RING - 1))] = __ldg(obytes + ((size_t)ref_w0 + (size_t)wi0) * 16 + bit0 + nn);
+			if ((m1 >> nn) & 1u) ring16[2 * ((first + nn) & (RING - 1)) + 1] = __ldg(obytes + ((size_t)ref_w1 + (size_t)wi1) * 16 + bit0 + nn);
+		}
 	}
 }
 
