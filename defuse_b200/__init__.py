@@ -113,6 +113,7 @@ def load_library():
         "dfb_split_plan_fetch": ([vp, vp, P(i64), P(i64)], ctypes.c_int),
         "dfb_split_plan_copy": ([vp, vp, vp], ctypes.c_int),
         "dfb_plan_get_stats": ([vp, P(_PlanStats)], ctypes.c_int),
+        "dfb_split_result_stats": ([vp, P(_PlanStats)], ctypes.c_int),
         "dfb_plan_destroy": ([vp], None),
         "dfb_microbench_issue_rate": ([vp, ctypes.c_int, ctypes.c_int, P(ctypes.c_double), P(ctypes.c_double)], ctypes.c_int),
         "dfb_ctx_memory_info": ([vp, ctypes.c_int, P(i64), P(i64), P(i64)], ctypes.c_int),
@@ -134,6 +135,7 @@ ABI_SYMBOLS = (
     "dfb_plan_set_timing",
     "dfb_simple_plan_fetch", "dfb_split_plan_fetch", "dfb_split_plan_copy", "dfb_plan_get_stats", "dfb_plan_destroy",
     "dfb_microbench_issue_rate", "dfb_split_backtrace_batch", "dfb_ctx_memory_info",
+    "dfb_split_result_stats",
 )
 
 
@@ -216,6 +218,12 @@ class Context:
         self._check(self._lib.dfb_ctx_device_info(self._h, ctypes.byref(info)))
         return {"name": info.name.decode(), "ordinal": info.ordinal, "sm_count": info.sm_count,
                 "cc": (info.cc_major, info.cc_minor), "clock_khz": info.clock_khz, "total_mem": info.total_mem}
+
+    def split_result_stats(self):
+        """Accounting of the last one-call split batch on this context (what the call itself copied and launched)."""
+        st = _PlanStats()
+        self._check(self._lib.dfb_split_result_stats(self._h, ctypes.byref(st)))
+        return {n: getattr(st, n) for n, _ in _PlanStats._fields_}
 
     def memory_info(self, reset=False):
         """Device memory of the context's pool: (reserved now, reserved high-water mark, used high-water mark) in bytes."""

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 #include <condition_variable>
 #include <cstring>
 #include <functional>
@@ -26,6 +27,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <time.h>
 
 using namespace dfb;
 
@@ -253,6 +255,31 @@ struct Trace
 	}
 };
 
+// Waiting for an event on a pipeline's critical path.  A blocking-sync wait sleeps until the driver's interrupt wakes the
+// thread: 0.4-0.9 ms late on the VMs this was measured on (DFB_TRACE device timeline against the host laps), three or four
+// times per batch where nothing else covers it.  So: poll, sleeping 30 us between queries (a few per cent of one core,
+// which matters when eight ranks share a host).  DFB_WAIT=block restores the blocking wait.
+static cudaError_t wait_event(cudaEvent_t ev)
+{
+	static int mode = -1;
+	if (mode < 0)
+	{
+		const char* e = getenv("DFB_WAIT");
+		mode = (e && !strcmp(e, "block")) ? 1 : 0;
+	}
+	if (mode == 1) return cudaEventSynchronize(ev);
+	for (int spins = 0;; spins++)
+	{
+		const cudaError_t q = cudaEventQuery(ev);
+		if (q != cudaErrorNotReady) return q;
+		if (spins < 8) continue;
+		struct timespec ts = {0, 30000};
+		nanosleep(&ts, nullptr);
+	}
+}
+
+static void presize_pool(dfb_ctx* ctx, size_t want);
+
 static int set_err(const dfb_ctx* ctx, int code, const char* fmt, ...)
 {
 	char buf[512];
@@ -383,6 +410,8 @@ extern "C" int dfb_ctx_create(int device_ordinal, dfb_ctx** out)
 		if (atoi(e) > 0) ctx->host_threads = std::min(atoi(e), 64);
 	ctx->pool = new (std::nothrow) HostPool(ctx->host_threads);
 	ctx->pool_fetch = new (std::nothrow) HostPool(std::max(2, ctx->host_threads / 2));
+	if (const char* e = getenv("DFB_POOL_PRESIZE_MB"))
+		if (atoll(e) > 0) presize_pool(ctx, (size_t)atoll(e) << 20);
 	tr.lap("ctx: context, streams, pools");
 	*out = ctx;
 	return DFB_OK;
@@ -597,6 +626,10 @@ struct dfb_plan
 	Event* d_events = nullptr;
 	unsigned long long* d_ev_count = nullptr;
 	unsigned long long ev_cap = 0;
+	// chunks of a pipelined batch hand the first sweep's state (checkpoints, probe targets, read symbols: 6.5 KB per task
+	// at dosplitalign's shape) back to the pool right behind their probe sweep, so that the next chunk's allocation reuses it
+	bool early_release = false;
+	bool sweep_state_released = false;
 	ClassWork cls[kNumClasses];
 	// generic path
 	int64_t n_gen_jobs = 0;
@@ -644,6 +677,31 @@ static int bounds_check_status(dfb_ctx* ctx)
 	(void)ctx;
 #endif
 	return DFB_OK;
+}
+
+// Grows the context's stream-ordered pool to `want` reserved bytes in one step (an allocation of the difference, freed at
+// once: the release threshold keeps it).  Opt-in (DFB_POOL_PRESIZE_MB, read when the context is created -- the tools
+// create theirs on a background thread while they parse their inputs): what a first batch pays for device memory is
+// per byte and depends on the box's state -- 5 GB cost 30 ms in one process and 1.1 s in the next on the same box
+// (profiles/r04f_first_batch_pool_presize.txt) --, so sizing the pool inside the first call only moves the cost.
+static void presize_pool(dfb_ctx* ctx, size_t want)
+{
+	cudaMemPool_t pool;
+	unsigned long long now = 0;
+	size_t free_b = 0, total_b = 0;
+	if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) != cudaSuccess ||
+	    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &now) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return;
+	}
+	want = std::min<size_t>(want, (size_t)now + free_b / 2);
+	if (want <= (size_t)now + ((size_t)64 << 20)) return;
+	Trace tr;
+	void* p = nullptr;
+	if (cudaMallocAsync(&p, want - (size_t)now, ctx->stream) == cudaSuccess) cudaFreeAsync(p, ctx->stream);
+	else cudaGetLastError();
+	tr.lap("pool presized");
 }
 
 static cudaError_t dalloc(dfb_ctx* ctx, void** p, size_t bytes)
@@ -885,6 +943,8 @@ static cudaError_t h2d_any(dfb_ctx* ctx, cudaStream_t up, void* dst, const void*
 		if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
 		else cudaGetLastError();
 	}
+	// (one copy engine carries 50 of the link's 55 GB/s on the boxes measured -- scripts/gpu_h2d_rate.py --, so a large
+	// pinned upload stays one copy)
 	if (!pageable) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, up);
 	cudaError_t e = ctx->h_ring.ensure(dfb_ctx::kRingSlots * dfb_ctx::kRingBlock);
 	if (e != cudaSuccess) return e;
@@ -1304,11 +1364,12 @@ static int dfb_simple_plan_create_body(dfb_ctx* ctx, const dfb_simple_params* pa
 // ---- SplitReadAligner plan ------------------------------------------------------------------
 
 // `reads` may be a view into a larger table (off[0] != 0) whose first entry is read `read_base` of the caller's
-// numbering; `async` skips the final stream synchronisation (chunks of a pipelined batch).
+// numbering, `refs` likewise a view whose first window pair is cluster `cluster_base`; `async` skips the final
+// stream synchronisation (chunks of a pipelined batch).
 static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
                                   const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
                                   const int32_t* task_min_score, int64_t n_tasks, int32_t read_base, int stage_slot,
-                                  bool async, dfb_plan** out)
+                                  bool async, dfb_plan** out, int32_t cluster_base = 0)
 {
 	*out = nullptr;
 	int rc;
@@ -1349,7 +1410,7 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 		int64_t* cnt = bin_pos.data() + n_bins * (size_t)tid;
 		for (int64_t t = t0; t < t1; t++)
 		{
-			const int32_t c0 = task_cluster[t], rd = task_read[t] - read_base;
+			const int64_t c0 = (int64_t)task_cluster[t] - cluster_base, rd = (int64_t)task_read[t] - read_base;
 			if (c0 < 0 || c0 >= n_clusters || rd < 0 || rd >= reads->n)
 			{
 				if (pt.bad < 0) pt.bad = t;
@@ -1445,7 +1506,7 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 		{
 			const int32_t bin = bin_of[t];
 			if (bin < 0) continue;
-			const int64_t c2 = 2 * (int64_t)task_cluster[t];
+			const int64_t c2 = 2 * ((int64_t)task_cluster[t] - cluster_base);
 			const SeqDesc& rdd = st.desc_b[task_read[t] - read_base];
 			JobPair& jp = st.jobs[pos[bin]++];
 			jp.ref_w[0] = st.desc_a[c2].word;
@@ -1465,7 +1526,7 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 		for (int64_t t = 0; t < n_tasks; t++)
 		{
 			if (bin_of[t] != -2) continue;
-			const int64_t c2 = 2 * (int64_t)task_cluster[t];
+			const int64_t c2 = 2 * ((int64_t)task_cluster[t] - cluster_base);
 			const SeqDesc& rdd = st.desc_b[task_read[t] - read_base];
 			const uint32_t rev_w = rdd.word + (rdd.len + 15) / 16;
 			for (int h = 0; h < 2; h++)
@@ -1527,6 +1588,20 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 // depend on it.  Returns DFB_BUILD_ON_HOST when the chunk holds tasks only the s32 kernels can take: the caller
 // builds that chunk on the host instead.
 static const int DFB_BUILD_ON_HOST = 1000;
+
+// Upload stream of device-built chunk k.  These streams carry copies only, so one stream serves every chunk in order
+// and chunk 0's upload has the link to itself (two alternating streams share it: the first sweep of a batch started
+// 0.4 ms later on the split path, 5 ms later at the matealign shape).  DFB_UPLOAD_STREAMS=2 alternates (A/B runs).
+static cudaStream_t device_build_upload_stream(dfb_ctx* ctx, int k)
+{
+	static int n = -1;
+	if (n < 0)
+	{
+		const char* e = getenv("DFB_UPLOAD_STREAMS");
+		n = (e && atoi(e) == 2) ? 2 : 1;
+	}
+	return (n == 2 && (k & 1)) ? ctx->upload_stream2 : ctx->upload_stream;
+}
 
 // (`simple`: a SimpleAligner batch -- task_cluster names the reference, task_min_score is null, `params` carries the scoring
 // triple only, `ref_base` is the first reference of the view)
@@ -1598,7 +1673,6 @@ static int split_build_enqueue(dfb_ctx* ctx, const dfb_split_params* params, con
 	};
 	cudaError_t e;
 	if ((e = cudaMemcpyAsync(d_stats, h_init, sizeof(BuildStats), cudaMemcpyHostToDevice, up)) != cudaSuccess) return cuda_fail(e, "statistics upload");
-	if ((e = cudaMemsetAsync(base + o_bins, 0, 2 * n_bins * 4, up)) != cudaSuccess) return cuda_fail(e, "bin reset");
 	if ((e = cudaMemcpyAsync(base + o_off_a, refs->off, (size_t)(na + 1) * 8, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
 	    (e = cudaMemcpyAsync(base + o_off_b, reads->off, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
 	    (e = cudaMemcpyAsync(base + o_tc, task_cluster, (size_t)n_tasks * 4, cudaMemcpyHostToDevice, up)) != cudaSuccess ||
@@ -1651,7 +1725,7 @@ static int split_build_enqueue(dfb_ctx* ctx, const dfb_split_params* params, con
 	bp.max_fast_rows = kMaxFastRows;
 	bp.stats = d_stats;
 	bp.jobs = (JobPair*)(base + o_jobs);
-	if ((e = cudaEventCreateWithFlags(&pl->pending.uploaded, cudaEventDisableTiming)) != cudaSuccess ||
+	if ((e = cudaEventCreateWithFlags(&pl->pending.uploaded, trace_on() ? cudaEventDefault : cudaEventDisableTiming)) != cudaSuccess ||
 	    (e = cudaEventRecord(pl->pending.uploaded, up)) != cudaSuccess)
 		return cuda_fail(e, "cudaEventRecord");
 	pl->pending.active = true;
@@ -1684,6 +1758,9 @@ static int split_build_kernels(dfb_plan* pl)
 	cudaStream_t cs = ctx->stream;
 	auto& pd = pl->pending;
 	CK(ctx, cudaStreamWaitEvent(cs, pd.uploaded, 0));
+	// (a memset is a kernel: on the upload stream it would wait for an SM the persistent sweeps hold, and the copies
+	// queued behind it with it -- the upload streams carry copies only)
+	CK(ctx, cudaMemsetAsync(pd.bp.bin_count, 0, 2 * (size_t)kNumClasses * kRBins * 4, cs));
 	if (pd.na)
 	{
 		desc_count_kernel<<<(unsigned)pd.blocks_a, DFB_BUILD_BLOCK, 0, cs>>>(pd.da);
@@ -1720,7 +1797,7 @@ static int split_build_finish(dfb_plan* pl)
 	};
 	Trace tr;
 	cudaError_t e;
-	if ((e = cudaEventSynchronize(pl->pending.ready)) != cudaSuccess) return cuda_fail(e, "job build");
+	if ((e = wait_event(pl->pending.ready)) != cudaSuccess) return cuda_fail(e, "job build");
 	pl->pending.active = false;
 	const SplitBuildParams bp = pl->pending.bp;
 	const int64_t na = pl->pending.na, nb = pl->pending.nb, raw_a = pl->pending.raw_a, raw_b = pl->pending.raw_b;
@@ -1971,6 +2048,18 @@ static int plan_run_impl(dfb_plan* pl, const std::function<int()>* between_sweep
 	if (pl->split)
 	{
 		int rc = run_probe(pl);
+		if (!rc && pl->early_release)
+		{
+			for (int c = 0; c < kNumClasses; c++)
+			{
+				ClassWork& cw = pl->cls[c];
+				dfree(ctx, cw.d_ckpt);
+				dfree(ctx, cw.d_ntg);
+				dfree(ctx, cw.d_rdq);
+				cw.fp.ckpt = cw.fp.ntg = cw.fp.rdq = nullptr;
+			}
+			pl->sweep_state_released = true;
+		}
 		if (!rc) rc = run_assemble(pl);
 		if (rc) return rc;
 	}
@@ -2107,7 +2196,7 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 	// result copies run on the copy stream, ordered behind this plan's kernels only (later batches may
 	// already be queued on the compute stream)
 	cudaStream_t cs = ctx->copy_stream;
-	CK(ctx, cudaEventSynchronize(pl->done_ev));
+	CK(ctx, wait_event(pl->done_ev));
 	CK(ctx, cudaStreamWaitEvent(cs, pl->done_ev, 0));
 
 	// 1. counters: overflow-list length and winning tasks per class
@@ -2128,10 +2217,32 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 		pl->ev_cap = n_ov + 1024;
 		cudaError_t e = dalloc(ctx, (void**)&pl->d_events, (size_t)pl->ev_cap * sizeof(Event));
 		if (e != cudaSuccess) return set_err(ctx, DFB_ERR_NOMEM, "event buffer of %llu entries: %s", pl->ev_cap, cudaGetErrorString(e));
-		int rc = run_probe(pl);
-		if (!rc) rc = run_assemble(pl);
+		int rc;
+		if (pl->sweep_state_released)
+		{
+			// (a chunk of a pipelined batch gave its checkpoints back behind the probe sweep: both sweeps again)
+			pl->early_release = pl->sweep_state_released = false;
+			for (int c = 0; c < kNumClasses; c++)
+			{
+				ClassWork& cw = pl->cls[c];
+				if (!cw.n_jobs) continue;
+				const size_t n = (size_t)cw.n_jobs, gs = (size_t)kClasses[c].G * kClasses[c].S;
+				DALLOC(ctx, cw.d_ntg, n * gs * sizeof(uint32_t));
+				DALLOC(ctx, cw.d_rdq, n * gs * sizeof(uint32_t));
+				if (cw.ckpt_blocks > 0) DALLOC(ctx, cw.d_ckpt, cw.ckpt_words * sizeof(uint32_t));
+				cw.fp.ntg = cw.d_ntg;
+				cw.fp.rdq = cw.d_rdq;
+				cw.fp.ckpt = cw.d_ckpt;
+			}
+			rc = plan_run_impl(pl, nullptr);
+		}
+		else
+		{
+			rc = run_probe(pl);
+			if (!rc) rc = run_assemble(pl);
+			if (!rc) CK(ctx, cudaEventRecord(pl->done_ev, ctx->stream));
+		}
 		if (rc) return rc;
-		CK(ctx, cudaEventRecord(pl->done_ev, ctx->stream));
 		CK(ctx, cudaStreamWaitEvent(cs, pl->done_ev, 0));
 	}
 	int64_t n_slots = 0;
@@ -2170,11 +2281,12 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 	if (ctx->copied_ev)
 	{
 		CK(ctx, cudaEventRecord(ctx->copied_ev, cs));
-		CK(ctx, cudaEventSynchronize(ctx->copied_ev)); // sleeps through the transfer
+		CK(ctx, wait_event(ctx->copied_ev)); // (sleeps through the transfer)
 	}
 	CK(ctx, cudaStreamSynchronize(cs));
 	pl->stats.d2h_bytes = d2h;
 	pl->stats.probe_jobs = n_slots;
+	if (trace_on()) fprintf(stderr, "[dfb] fetch: %.1f MB device -> host\n", (double)d2h / 1e6);
 	tr.lap("split.fetch: d2h");
 
 	if (out_best && pl->n_tasks) memcpy(out_best, h_best, (size_t)pl->n_tasks * 4);
@@ -2380,7 +2492,12 @@ static int simple_align_pipelined(dfb_ctx* ctx, const dfb_simple_params* params,
                                   const dfb_seq_table* seqs, const int32_t* task_ref, const int32_t* task_seq,
                                   int64_t n_tasks, bool refs_monotone, int32_t* out_score)
 {
-	const int K = (int)std::max<int64_t>(2, std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks / 150000));
+	// chunks: a batch whose references come in task order (matealign: one window per task) uploads every byte once however
+	// it is cut, and is bound by the upload -- short chunks keep the wait for the first and the sweep of the last short;
+	// one whose references are named in any order re-uploads the reference table with every chunk: fewer, longer chunks
+	int64_t per_chunk = refs_monotone ? 80000 : 150000;
+	if (const char* e = getenv("DFB_SIMPLE_CHUNK_TASKS")) per_chunk = std::max<long long>(1000, atoll(e)); // tuning runs
+	const int K = (int)std::max<int64_t>(2, std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks / per_chunk));
 	std::vector<dfb_plan*> plans((size_t)K, nullptr), staged((size_t)K, nullptr);
 	std::vector<int64_t> t0((size_t)K + 1, 0);
 	{
@@ -2430,11 +2547,13 @@ static int simple_align_pipelined(dfb_ctx* ctx, const dfb_simple_params* params,
 		int arc = chunk_of(k, v);
 		if (arc) return arc;
 		const int64_t a = t0[(size_t)k], b = t0[(size_t)k + 1];
-		// (alternating upload streams: chunk k+1's copies do not queue behind chunk k's)
 		return split_build_enqueue(ctx, &sp, &v.refs, &v.seqs, task_ref + a, task_seq + a, nullptr, b - a, v.s_lo, k,
-		                           (k & 1) ? ctx->upload_stream2 : ctx->upload_stream, &staged[(size_t)k], true, v.r_lo);
+		                           device_build_upload_stream(ctx, k), &staged[(size_t)k], true, v.r_lo);
 	};
 	int rc = DFB_OK;
+	cudaEvent_t trace_base = nullptr; // DFB_TRACE: the device's side of the batch (see split_align_pipelined)
+	if (trace_on() && cudaEventCreate(&trace_base) == cudaSuccess) cudaEventRecord(trace_base, ctx->stream);
+	Trace trp;
 	if (device_build)
 	{
 		rc = upload(0);
@@ -2465,6 +2584,7 @@ static int simple_align_pipelined(dfb_ctx* ctx, const dfb_simple_params* params,
 		}
 		if (rc) break;
 		plans[(size_t)k] = pk;
+		if (trace_base) pk->timing = true;
 		// the next chunk's build kernels ride behind this chunk's sweep on the compute stream
 		dfb_plan* next = (k + 1 < K) ? staged[(size_t)k + 1] : nullptr;
 		const std::function<int()> hook = [&]() -> int { return next ? split_build_kernels(next) : DFB_OK; };
@@ -2482,6 +2602,19 @@ static int simple_align_pipelined(dfb_ctx* ctx, const dfb_simple_params* params,
 	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
 	if (!rc && e != cudaSuccess) rc = set_err(ctx, DFB_ERR_CUDA, "pipelined batch failed: %s", cudaGetErrorString(e));
 	if (!rc) rc = bounds_check_status(ctx);
+	trp.lap("simple pipelined: done");
+	if (trace_base)
+	{
+		for (int k = 0; k < K && !rc; k++)
+		{
+			float up = -1, a = -1, b2 = -1;
+			if (plans[(size_t)k]->pending.uploaded) cudaEventElapsedTime(&up, trace_base, plans[(size_t)k]->pending.uploaded);
+			cudaEventElapsedTime(&a, trace_base, plans[(size_t)k]->ev[0]);
+			cudaEventElapsedTime(&b2, trace_base, plans[(size_t)k]->ev[1]);
+			fprintf(stderr, "[dfb] device: chunk %d (%lld tasks) uploaded %.3f | sweep %.3f .. %.3f ms\n", k, (long long)plans[(size_t)k]->n_tasks, up, a, b2);
+		}
+		cudaEventDestroy(trace_base);
+	}
 	for (dfb_plan* sp2 : staged)
 		if (sp2)
 		{
@@ -2543,7 +2676,7 @@ static const int64_t kPipelineMinTasks = 1 << 18;
 
 static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, const dfb_seq_table* refs,
                                  const dfb_seq_table* reads, const int32_t* task_cluster, const int32_t* task_read,
-                                 const int32_t* task_min_score, int64_t n_tasks, int32_t* out_best)
+                                 const int32_t* task_min_score, int64_t n_tasks, int32_t* out_best, bool clusters_monotone)
 {
 	int K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min<int64_t>(dfb_ctx::kStageSlots, n_tasks), n_tasks / 330000));
 	if (const char* e = getenv("DFB_PIPELINE_CHUNKS")) // tuning runs
@@ -2588,7 +2721,18 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 		}
 	}
 	int rc = DFB_OK;
+	{
+		// the pinned buffer the chunks' results land in: sized for the largest chunk now (growing it chunk by chunk frees and
+		// pins it again each time, at 0.6 ms per MB either way)
+		int64_t largest = 0;
+		for (int k = 0; k < K; k++) largest = std::max(largest, t0[(size_t)k + 1] - t0[(size_t)k]);
+		ctx->h_out.ensure((size_t)largest * 72);
+	}
 	Trace trp;
+	// DFB_TRACE: the device's side of the batch -- when every chunk's uploads, first sweep and probe sweep + assembly
+	// ended, measured from an event recorded on the (idle) compute stream now
+	cudaEvent_t trace_base = nullptr;
+	if (trace_on() && cudaEventCreate(&trace_base) == cudaSuccess) cudaEventRecord(trace_base, ctx->stream);
 	// Where the job lists are built.  On the device: 31 ms of host CPU time per 2 M-task batch, but the build kernels sit
 	// on the compute stream (0.2 ms per chunk with their launch gaps).  On the host: 72 ms of CPU time over the context's
 	// workers, fully hidden under the GPU when the host has the threads -- 1.7 ms per batch faster then (A/B on one box,
@@ -2617,6 +2761,7 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	holder->ctx = ctx;
 	holder->split = true;
 	holder->n_tasks = n_tasks;
+	holder->stats.n_tasks = n_tasks;
 	if (holder->rows.cap < ctx->spare_rows.cap) holder->rows.swap(ctx->spare_rows);
 	if (holder->cols.cap < ctx->spare_cols.cap) holder->cols.swap(ctx->spare_cols);
 	holder->rows.n = holder->cols.n = 0;
@@ -2627,7 +2772,7 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	std::condition_variable cv;
 	int queued = 0;      // chunks handed to the GPU so far
 	bool abort = false;  // lane 1 failed: lane 2 stops after the chunks already queued
-	int fetch_rc = DFB_OK;
+	std::atomic<int> fetch_rc{DFB_OK}; // (lane 1 looks at it between chunks: nothing more is queued behind a failed fetch)
 	std::thread lane2([&] {
 		try
 		{
@@ -2661,30 +2806,47 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	// the job-build kernels of chunk k+1 ride on the compute stream between chunk k's two sweeps, so their counts are
 	// on the host before chunk k's probe sweep ends and the GPU never waits for this thread.
 	std::vector<dfb_plan*> staged((size_t)K, nullptr);
-	auto chunk_of = [&](int k, dfb_seq_table& view, int32_t& r_lo) -> int {
+	// a chunk sees views of both tables: its own reads and -- when the batch's clusters do not decrease, the order
+	// dosplitalign emits -- its own window pairs, so that every window is uploaded and packed once per batch (plus
+	// one shared cluster per chunk boundary) instead of once per chunk
+	struct View
+	{
+		dfb_seq_table reads, refs;
+		int32_t r_lo = 0, c_lo = 0;
+	};
+	auto chunk_of = [&](int k, View& v) -> int {
 		const int64_t a = t0[k], b = t0[k + 1];
 		if (b <= a) return set_err(ctx, DFB_ERR_STATE, "empty chunk in a pipelined batch");
-		r_lo = task_read[a];
+		v.r_lo = task_read[a];
 		const int32_t r_hi = task_read[b - 1] + 1;
-		if (r_lo < 0 || r_hi > reads->n) return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)a);
-		view = dfb_seq_table{reads->bytes, reads->off + r_lo, (int64_t)(r_hi - r_lo)};
+		if (v.r_lo < 0 || r_hi > reads->n) return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)a);
+		v.reads = dfb_seq_table{reads->bytes, reads->off + v.r_lo, (int64_t)(r_hi - v.r_lo)};
+		v.refs = *refs;
+		v.c_lo = 0;
+		if (clusters_monotone)
+		{
+			const int64_t c_lo = task_cluster[a], c_hi = (int64_t)task_cluster[b - 1] + 1;
+			if (c_lo < 0 || 2 * c_hi > refs->n)
+				return set_err(ctx, DFB_ERR_ARG, "task %lld: table index out of range", (long long)(c_lo < 0 ? a : b - 1));
+			v.c_lo = (int32_t)c_lo;
+			v.refs = dfb_seq_table{refs->bytes, refs->off + 2 * c_lo, 2 * (c_hi - c_lo)};
+		}
 		return DFB_OK;
 	};
 	auto upload = [&](int k) -> int {
-		dfb_seq_table view;
-		int32_t r_lo = 0;
-		int arc = chunk_of(k, view, r_lo);
+		View v;
+		int arc = chunk_of(k, v);
 		if (arc) return arc;
 		const int64_t a = t0[k], b = t0[k + 1];
-		return split_build_enqueue(ctx, params, refs, &view, task_cluster + a, task_read + a, task_min_score + a, b - a, r_lo, k,
-		                           (k & 1) ? ctx->upload_stream2 : ctx->upload_stream, &staged[(size_t)k]);
+		return split_build_enqueue(ctx, params, &v.refs, &v.reads, task_cluster + a, task_read + a, task_min_score + a, b - a, v.r_lo, k,
+		                           device_build_upload_stream(ctx, k), &staged[(size_t)k], false, v.c_lo);
 	};
 	if (device_build)
 	{
 		rc = upload(0);
 		if (!rc) rc = split_build_kernels(staged[0]); // (the GPU is idle: straight away)
 	}
-	for (int k = 0; k < K && !rc; k++)
+	for (int k = 0; k < K && !rc && !fetch_rc.load(); k++)
 	{
 		if (device_build && k + 1 < K && (rc = upload(k + 1))) break;
 		const int64_t a = t0[k], b = t0[k + 1];
@@ -2702,14 +2864,15 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 		}
 		if (rc == DFB_BUILD_ON_HOST)
 		{
-			dfb_seq_table view;
-			int32_t r_lo = 0;
-			if (!(rc = chunk_of(k, view, r_lo)))
-				rc = split_plan_create_impl(ctx, params, refs, &view, task_cluster + a, task_read + a, task_min_score + a, b - a, r_lo, k,
-				                            true, &pk);
+			View v;
+			if (!(rc = chunk_of(k, v)))
+				rc = split_plan_create_impl(ctx, params, &v.refs, &v.reads, task_cluster + a, task_read + a, task_min_score + a, b - a, v.r_lo, k,
+				                            true, &pk, v.c_lo);
 		}
 		if (rc) break;
 		pk->result_slot = k;
+		pk->early_release = true;
+		if (trace_base) pk->timing = true;
 		dfb_plan* next = (k + 1 < K) ? staged[(size_t)k + 1] : nullptr;
 		const std::function<int()> hook = [&]() -> int { return next ? split_build_kernels(next) : DFB_OK; };
 		rc = plan_run_impl(pk, &hook);
@@ -2734,7 +2897,7 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 	trp.lap("pipelined: lane 1 done");
 	lane2.join();
 	trp.lap("pipelined: lane 2 joined");
-	if (!rc) rc = fetch_rc;
+	if (!rc) rc = fetch_rc.load();
 	if (!rc)
 	{
 		holder->fetched = true;
@@ -2744,7 +2907,28 @@ static int split_align_pipelined(dfb_ctx* ctx, const dfb_split_params* params, c
 			holder->stats.events += plans[k]->stats.events;
 			holder->stats.probe_jobs += plans[k]->stats.probe_jobs;
 			holder->stats.d2h_bytes += plans[k]->stats.d2h_bytes;
+			holder->stats.h2d_bytes += plans[k]->stats.h2d_bytes;
+			holder->stats.cells += plans[k]->stats.cells;
+			holder->stats.fast_jobs += plans[k]->stats.fast_jobs;
+			holder->stats.generic_jobs += plans[k]->stats.generic_jobs;
+			holder->stats.kernel_launches += plans[k]->stats.kernel_launches;
+			holder->stats.raw_bytes += plans[k]->stats.raw_bytes;
+			holder->stats.packed_bytes += plans[k]->stats.packed_bytes;
 		}
+	}
+	if (trace_base)
+	{
+		for (int k = 0; k < K && !rc; k++)
+		{
+			float up = -1, a = -1, b = -1, c = -1;
+			if (plans[k]->pending.uploaded) cudaEventElapsedTime(&up, trace_base, plans[k]->pending.uploaded);
+			cudaEventElapsedTime(&a, trace_base, plans[k]->ev[0]);
+			cudaEventElapsedTime(&b, trace_base, plans[k]->ev[1]);
+			cudaEventElapsedTime(&c, trace_base, plans[k]->ev[2]);
+			fprintf(stderr, "[dfb] device: chunk %d (%lld tasks) uploaded %.3f | first sweep %.3f .. %.3f | probe + assembly .. %.3f ms\n", k,
+			        (long long)plans[k]->n_tasks, up, a, b, c);
+		}
+		cudaEventDestroy(trace_base);
 	}
 	for (int k = 0; k < K; k++)
 		if (plans[k]) dfb_plan_destroy(plans[k]);
@@ -2778,21 +2962,27 @@ static int dfb_split_align_batch_body(dfb_ctx* ctx, const dfb_split_params* para
 		if ((rc = check_table(ctx, refs, "refs")) || (rc = check_table_parallel(ctx, reads, "reads"))) return rc;
 		if (refs->n & 1) return set_err(ctx, DFB_ERR_ARG, "refs must hold two windows per cluster (n is odd)");
 		if (n_tasks > 0x7fffff00LL) return set_err(ctx, DFB_ERR_ARG, "too many tasks in one batch");
-		bool monotone = true;
+		bool monotone = true, clusters_monotone = true;
 		{
 			const int T = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->host_threads, n_tasks / 262144 + 1));
-			std::vector<char> ok((size_t)T, 1);
+			std::vector<char> ok((size_t)T, 1), okc((size_t)T, 1);
 			parallel_for(ctx->pool, T, [&](int tid) {
 				const int64_t a = std::max<int64_t>(1, n_tasks * tid / T), b = n_tasks * (tid + 1) / T;
-				bool m = true;
-				for (int64_t t = a; t < b && m; t++) m = task_read[t] >= task_read[t - 1];
+				bool m = true, mc = true;
+				for (int64_t t = a; t < b && m; t++)
+				{
+					m = task_read[t] >= task_read[t - 1];
+					mc = mc && task_cluster[t] >= task_cluster[t - 1];
+				}
 				ok[(size_t)tid] = m;
+				okc[(size_t)tid] = mc;
 			});
 			for (char c : ok) monotone = monotone && c;
+			for (char c : okc) clusters_monotone = clusters_monotone && c;
 		}
 		tre.lap("split: validated");
 		if (monotone)
-			return split_align_pipelined(ctx, params, refs, reads, task_cluster, task_read, task_min_score, n_tasks, out_best);
+			return split_align_pipelined(ctx, params, refs, reads, task_cluster, task_read, task_min_score, n_tasks, out_best, clusters_monotone);
 	}
 	dfb_plan* pl = nullptr;
 	int rc = dfb_split_plan_create(ctx, params, refs, reads, task_cluster, task_read, task_min_score, n_tasks, &pl);
@@ -2807,6 +2997,14 @@ static int dfb_split_align_batch_body(dfb_ctx* ctx, const dfb_split_params* para
 	// only the host-side rows are kept; the device buffers go back to the pool now
 	release_device(pl);
 	ctx->last_split = pl;
+	return DFB_OK;
+}
+
+extern "C" int dfb_split_result_stats(const dfb_ctx* ctx, dfb_plan_stats* stats)
+{
+	if (!ctx || !stats) return DFB_ERR_ARG;
+	if (!ctx->last_split) return set_err(ctx, DFB_ERR_STATE, "no split result on this context");
+	*stats = ctx->last_split->stats;
 	return DFB_OK;
 }
 

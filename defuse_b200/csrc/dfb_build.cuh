@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(DFB_BUILD_BLOCK) split_scatter_kernel(SplitBui
 	if (lane == leader) base = atomicAdd(&p.bin_fill[bin], (unsigned)__popc(same));
 	base = __shfl_sync(same, base, leader);
 	const unsigned int pos = p.bin_count[bin] + base + (unsigned)__popc(same & ((1u << lane) - 1u));
-	const long long c2 = 2 * (long long)p.task_cluster[t];
+	const long long c2 = 2 * ((long long)p.task_cluster[t] - p.ref_base);
 	const SeqDesc r1 = p.desc_a[c2], r2 = p.desc_a[c2 + 1], rdd = p.desc_b[(long long)p.task_read[t] - p.read_base];
 	JobPair jp;
 	jp.ref_w[0] = r1.word;

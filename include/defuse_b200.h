@@ -183,6 +183,10 @@ DFB_API int dfb_split_result_copy(const dfb_ctx* ctx, dfb_split_row* rows, int32
  * call on this context (or its destruction). */
 DFB_API int dfb_split_result_view(const dfb_ctx* ctx, const dfb_split_row** rows, int64_t* n_rows,
                                   const int32_t** cols, int64_t* n_cols);
+/* Accounting of the last dfb_split_align_batch on this context (bytes copied each way, arg-max columns, probe jobs):
+ * what the call itself moved -- a batch cut into chunks uploads every window once, a resident plan's statistics
+ * (dfb_plan_get_stats) do not describe it.  Timings are 0. */
+DFB_API int dfb_split_result_stats(const dfb_ctx* ctx, dfb_plan_stats* stats);
 
 /* ---- backtrace of chosen split alignments (GetAlignments(..., backtrace=true)) ------------- */
 

@@ -132,12 +132,15 @@ def split_workload(seed, n_clusters, tasks_per_cluster, L=100, R_lo=320, R_hi=36
             "cells": cells, "n_tasks": int(n_tasks), "L": int(L)}
 
 
-def local_workload(seed, n_refs, n_tasks, R=2001, L=100, sub=0.02, unrelated_frac=0.2):
+def local_workload(seed, n_refs, n_tasks, R=2001, L=100, sub=0.02, unrelated_frac=0.2, own_window=False):
     """localalign-shaped batch (config 2): n_refs references of R bases; each task picks one and a
-    L-base substring with substitutions, or an unrelated random sequence."""
+    L-base substring with substitutions, or an unrelated random sequence.  own_window: every task has its own
+    reference, in task order -- what matealign submits (one window cut per discordant mate, matealign.cpp: task_ref[k] = k)."""
     rng = np.random.default_rng(seed)
+    if own_window:
+        n_refs = n_tasks
     refs = ACGT[rng.integers(0, 4, (n_refs, R))]
-    task_ref = rng.integers(0, n_refs, n_tasks).astype(np.int32)
+    task_ref = np.arange(n_tasks, dtype=np.int32) if own_window else rng.integers(0, n_refs, n_tasks).astype(np.int32)
     start = rng.integers(0, R - L + 1, n_tasks)
     seqs = refs[task_ref[:, None], start[:, None] + np.arange(L)[None, :]]
     unrelated = rng.random(n_tasks) < unrelated_frac

@@ -190,9 +190,14 @@ def test_staged_plan_matches_one_call(oracle_mod, gpu_ctx):
     plan.close()
 
 
-def test_event_buffer_overflow_is_recovered(oracle_mod, gpu_ctx):
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_event_buffer_overflow_is_recovered(oracle_mod, gpu_ctx, monkeypatch, pipelined):
     """poly-A windows give ~R arg-max columns per row and ~L tie rows: far more than the default
-    event buffer share; the fetch must notice, re-size and re-sweep."""
+    event buffer share; the fetch must notice, re-size and re-sweep.  A chunk of a pipelined batch has given its
+    checkpoints back by then and runs both sweeps again."""
+    if pipelined:
+        monkeypatch.setenv("DFB_PIPELINE_MIN_TASKS", "16")
+        monkeypatch.setenv("DFB_DEVICE_BUILD", "1")
     polyA = b"A" * 700
     refs = [polyA, polyA]
     reads = [b"A" * 200] * 24
@@ -377,6 +382,17 @@ def test_pipelined_one_call_path(oracle_mod, gpu_ctx, monkeypatch):
     import defuse_b200 as d
     rng = np.random.default_rng(31)
     refs, reads, tc, trd = util.split_batch(rng, 40, 25, (0, 120), 60, 400, sub=0.02, indel=0.005, n_rate=0.01)
+    # clusters and reads both non-decreasing (dosplitalign's order): every chunk gets a view of the window table too,
+    # chunk boundaries fall inside clusters; both job-list builds, and a batch that starts at a later cluster
+    assert np.all(np.diff(tc) >= 0) and np.all(np.diff(trd) >= 0)
+    ms0 = np.array([d.split_min_score(len(reads[r])) for r in trd], np.int32)
+    for knob in ("DFB_DEVICE_BUILD", "DFB_HOST_BUILD"):
+        monkeypatch.setenv("DFB_PIPELINE_MIN_TASKS", "16")
+        monkeypatch.setenv(knob, "1")
+        _check_split(oracle_mod, gpu_ctx, refs, reads, tc, trd, ms0)
+        _check_split(oracle_mod, gpu_ctx, refs, reads, tc[333:], trd[333:], ms0[333:])
+        monkeypatch.delenv(knob)
+        monkeypatch.delenv("DFB_PIPELINE_MIN_TASKS")
     # several tasks per read (same read against neighbouring clusters), still non-decreasing
     tc = np.concatenate([tc, (tc + 1) % 40]).astype(np.int32)
     trd = np.concatenate([trd, trd]).astype(np.int32)
