@@ -209,6 +209,12 @@ struct dfb_ctx
 	cudaStream_t copy_stream = nullptr; // device->host result copies, ordered after a plan's kernels by an event
 	cudaStream_t upload_stream = nullptr; // uploads + packing of the next chunk of a pipelined batch
 	cudaStream_t upload_stream2 = nullptr; // device-built chunks alternate between the two: chunk k+1's uploads do not hold up chunk k's packing
+	// first-sweep state (checkpoints, probe targets, read symbols) of the chunk of a pipelined batch that is on the GPU:
+	// ONE buffer for all chunks and batches -- chunk k+1's first sweep is queued behind chunk k's probe sweep on the compute
+	// stream, so they never overlap --, grown when a chunk needs more.  (Allocated per chunk, a chunk slightly larger than
+	// the one before it grew the pool by gigabytes in the middle of a batch: 8 ms of idle GPU, profiles/r04f.)
+	uint8_t* sweep_arena = nullptr;
+	size_t sweep_arena_cap = 0;
 	cudaEvent_t copied_ev = nullptr;      // blocking-sync event behind the result copies of a fetch
 	// pageable caller buffers are staged through a small ring of pinned blocks by the context's workers (the driver's own
 	// staging copies with one thread and blocks the caller for the whole transfer)
@@ -429,6 +435,7 @@ extern "C" void dfb_ctx_destroy(dfb_ctx* ctx)
 		if (ev) cudaEventDestroy(ev);
 	ctx->h_out.release();
 	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+	if (ctx->sweep_arena) cudaFree(ctx->sweep_arena);
 	if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
 	if (ctx->upload_stream2) cudaStreamDestroy(ctx->upload_stream2);
 	if (ctx->copied_ev) cudaEventDestroy(ctx->copied_ev);
@@ -630,6 +637,7 @@ struct dfb_plan
 	// at dosplitalign's shape) back to the pool right behind their probe sweep, so that the next chunk's allocation reuses it
 	bool early_release = false;
 	bool sweep_state_released = false;
+	bool sweep_in_arena = false; // the three buffers live in ctx->sweep_arena (chunk of a pipelined batch): nothing to free
 	ClassWork cls[kNumClasses];
 	// generic path
 	int64_t n_gen_jobs = 0;
@@ -742,6 +750,7 @@ static void release_device(dfb_plan* plan)
 		dfree(ctx, cw.d_slot_task);
 		dfree(ctx, cw.d_slot_n);
 		dfree(ctx, cw.d_slot_ev);
+		if (plan->sweep_in_arena) cw.d_ntg = cw.d_rdq = cw.d_ckpt = nullptr;
 		dfree(ctx, cw.d_ntg);
 		dfree(ctx, cw.d_rdq);
 		dfree(ctx, cw.d_ckpt);
@@ -1076,6 +1085,8 @@ static int alloc_work(dfb_plan* pl, JobPair* d_jobs_base, GenJob* d_gen_base, co
 	dfb_ctx* ctx = pl->ctx;
 	DALLOC(ctx, pl->d_ctrl, kNumClasses * 4 * sizeof(int));
 	int64_t first = 0;
+	size_t arena_need = 0;
+	pl->sweep_in_arena = split && pl->early_release;
 	for (int c = 0; c < kNumClasses; c++)
 	{
 		ClassWork& cw = pl->cls[c];
@@ -1092,20 +1103,56 @@ static int alloc_work(dfb_plan* pl, JobPair* d_jobs_base, GenJob* d_gen_base, co
 			DALLOC(ctx, cw.d_slot_task, n * sizeof(int32_t));
 			DALLOC(ctx, cw.d_slot_n, n * sizeof(int));
 			DALLOC(ctx, cw.d_slot_ev, n * DFB_SLOT_EVENTS * sizeof(uint2));
-			DALLOC(ctx, cw.d_ntg, n * (size_t)kClasses[c].G * kClasses[c].S * sizeof(uint32_t));
-			DALLOC(ctx, cw.d_rdq, n * (size_t)kClasses[c].G * kClasses[c].S * sizeof(uint32_t));
 			DALLOC(ctx, cw.d_slot_rng, n * sizeof(uint32_t));
 			// checkpoints every CK = 4G steps of the wavefront (R + G - 1 steps)
 			const int G = kClasses[c].G, CK = 4 * G;
+			const size_t gs_bytes = n * (size_t)G * kClasses[c].S * sizeof(uint32_t);
 			cw.ckpt_blocks = (int)(((int64_t)cw.max_R + G - 2) / CK);
-			const size_t ck_bytes = n * (size_t)cw.ckpt_blocks * (size_t)(kClasses[c].S + 2) * G * sizeof(uint32_t);
-			if (cw.ckpt_blocks > 0 && ck_bytes <= (size_t)ctx->prop.totalGlobalMem / 4)
+			size_t ck_bytes = n * (size_t)cw.ckpt_blocks * (size_t)(kClasses[c].S + 2) * G * sizeof(uint32_t);
+			if (!(cw.ckpt_blocks > 0 && ck_bytes <= (size_t)ctx->prop.totalGlobalMem / 4))
 			{
-				DALLOC(ctx, cw.d_ckpt, ck_bytes);
-				cw.ckpt_words = ck_bytes / sizeof(uint32_t);
+				cw.ckpt_blocks = 0;
+				ck_bytes = 0;
+			}
+			cw.ckpt_words = ck_bytes / sizeof(uint32_t);
+			if (pl->sweep_in_arena)
+			{
+				// offsets now, pointers once the arena is known to hold every class
+				cw.d_ntg = (uint32_t*)(uintptr_t)arena_need;
+				arena_need = align_up(arena_need + gs_bytes, 256);
+				cw.d_rdq = (uint32_t*)(uintptr_t)arena_need;
+				arena_need = align_up(arena_need + gs_bytes, 256);
+				cw.d_ckpt = (uint32_t*)(uintptr_t)arena_need;
+				arena_need = align_up(arena_need + ck_bytes, 256);
 			}
 			else
-				cw.ckpt_blocks = 0;
+			{
+				DALLOC(ctx, cw.d_ntg, gs_bytes);
+				DALLOC(ctx, cw.d_rdq, gs_bytes);
+				if (ck_bytes) DALLOC(ctx, cw.d_ckpt, ck_bytes);
+			}
+		}
+	}
+	if (pl->sweep_in_arena)
+	{
+		if (arena_need > ctx->sweep_arena_cap)
+		{
+			// (stream-ordered on the compute stream like every use of it: the previous chunk's sweeps are done with the old
+			// buffer when it goes)
+			if (ctx->sweep_arena) cudaFreeAsync(ctx->sweep_arena, ctx->stream);
+			ctx->sweep_arena = nullptr;
+			ctx->sweep_arena_cap = 0;
+			const size_t want = arena_need + arena_need / 8;
+			CK(ctx, cudaMallocAsync((void**)&ctx->sweep_arena, want, ctx->stream));
+			ctx->sweep_arena_cap = want;
+		}
+		for (int c = 0; c < kNumClasses; c++)
+		{
+			ClassWork& cw = pl->cls[c];
+			if (!cw.n_jobs) continue;
+			cw.d_ntg = (uint32_t*)(ctx->sweep_arena + (uintptr_t)cw.d_ntg);
+			cw.d_rdq = (uint32_t*)(ctx->sweep_arena + (uintptr_t)cw.d_rdq);
+			cw.d_ckpt = cw.ckpt_words ? (uint32_t*)(ctx->sweep_arena + (uintptr_t)cw.d_ckpt) : nullptr;
 		}
 	}
 	if (pl->n_gen_jobs)
@@ -1379,6 +1426,7 @@ static int split_plan_create_impl(dfb_ctx* ctx, const dfb_split_params* params, 
 	if (!pl) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
 	pl->ctx = ctx;
 	pl->split = true;
+	pl->early_release = async; // (a chunk of a pipelined batch: its sweep state lives in the context's arena)
 	pl->sp = *params;
 	pl->n_tasks = n_tasks;
 	pl->stats.n_tasks = n_tasks;
@@ -1618,6 +1666,7 @@ static int split_build_enqueue(dfb_ctx* ctx, const dfb_split_params* params, con
 	if (!pl) return set_err(ctx, DFB_ERR_NOMEM, "out of host memory");
 	pl->ctx = ctx;
 	pl->split = !simple;
+	pl->early_release = !simple; // (always a chunk of a pipelined batch)
 	pl->sp = *params;
 	pl->n_tasks = n_tasks;
 	pl->stats.n_tasks = n_tasks;
@@ -2053,6 +2102,7 @@ static int plan_run_impl(dfb_plan* pl, const std::function<int()>* between_sweep
 			for (int c = 0; c < kNumClasses; c++)
 			{
 				ClassWork& cw = pl->cls[c];
+				if (pl->sweep_in_arena) cw.d_ckpt = cw.d_ntg = cw.d_rdq = nullptr; // (the next chunk takes the arena over)
 				dfree(ctx, cw.d_ckpt);
 				dfree(ctx, cw.d_ntg);
 				dfree(ctx, cw.d_rdq);
@@ -2221,7 +2271,7 @@ static int split_fetch_impl(dfb_plan* pl, int32_t* out_best, int64_t* n_rows, in
 		if (pl->sweep_state_released)
 		{
 			// (a chunk of a pipelined batch gave its checkpoints back behind the probe sweep: both sweeps again)
-			pl->early_release = pl->sweep_state_released = false;
+			pl->early_release = pl->sweep_state_released = pl->sweep_in_arena = false; // (buffers of its own this time)
 			for (int c = 0; c < kNumClasses; c++)
 			{
 				ClassWork& cw = pl->cls[c];
