@@ -387,10 +387,8 @@ def measure_sharded(aligner, args, rank, world, barrier):
         col_base = np.concatenate([[0], np.cumsum([len(c) for c in gathered["cols"]])])
         for r, g in enumerate(all_rows):
             g["col_begin"] += col_base[r]
-        merged = np.concatenate(all_rows)
         all_cols = np.concatenate(gathered["cols"])
-        order = np.argsort(merged["task"], kind="stable")   # rows of a task stay in their (ascending split row) order
-        merged = merged[order]
+        merged = sharding.merge_rows_by_task(n, all_rows)   # counting placement; rows of a task stay in their (ascending split row) order
         merge_ms = (time.perf_counter() - t0) * 1e3   # gather + merge into task order; the digest below is bookkeeping
         h = hashlib.sha1()
         h.update(best.tobytes())

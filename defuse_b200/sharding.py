@@ -69,3 +69,26 @@ def merge_by_task(n_tasks, parts):
             out = np.zeros((n_tasks,) + val.shape[1:], dtype=val.dtype)
         out[np.asarray(idx)] = val
     return out
+
+
+def merge_rows_by_task(n_tasks, row_parts):
+    """Row records of the shards (structured arrays with a `task` field in the BATCH's numbering, every part ordered by
+    task -- the order dfb_split_align_batch returns) -> one array in task order, the rows of a task in their part's
+    order.  Counting placement: rows per task, an exclusive scan, every part copied to its slots -- linear in the number
+    of rows, no sort (a task's rows all come from one part)."""
+    parts = [np.asarray(p) for p in row_parts if len(p)]
+    if not parts:
+        return np.zeros(0, dtype=np.asarray(row_parts[0]).dtype if len(row_parts) else np.int32)
+    counts = np.zeros(n_tasks + 1, dtype=np.int64)
+    for p in parts:
+        counts[1:] += np.bincount(p["task"], minlength=n_tasks)
+    first = np.cumsum(counts)  # first[t] = slot of task t's first row
+    out = np.empty(int(first[-1]), dtype=parts[0].dtype)
+    for p in parts:
+        task = p["task"].astype(np.int64)
+        # position of a row inside its task's run: its index minus the index of the run's first row
+        run_start = np.flatnonzero(np.concatenate([[True], task[1:] != task[:-1]]))
+        run_len = np.diff(np.concatenate([run_start, [len(task)]]))
+        within = np.arange(len(task)) - np.repeat(run_start, run_len)
+        out[first[task] + within] = p
+    return out

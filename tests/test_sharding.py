@@ -57,3 +57,26 @@ def test_gloo_world(world):
     p = subprocess.run(cmd, capture_output=True, env=env, timeout=300)
     assert p.returncode == 0, p.stderr.decode()[-3000:]
     assert ("OK world=%d" % world) in p.stdout.decode()
+
+
+def test_merge_rows_by_task_equals_stable_sort():
+    """Rows of the shards back into the batch's task order: the linear counting placement gives what a stable sort of
+    the concatenated parts gives (every part ordered by task, a task's rows all in one part)."""
+    rng = np.random.default_rng(5)
+    n_tasks = 5000
+    dt = np.dtype([("task", np.int32), ("read_split", np.int32), ("col_begin", np.int64)])
+    owner = rng.integers(0, 3, n_tasks)
+    n_rows = rng.integers(0, 4, n_tasks)
+    parts = []
+    for s in range(3):
+        tasks = np.repeat(np.flatnonzero(owner == s), n_rows[owner == s])
+        part = np.zeros(len(tasks), dt)
+        part["task"] = tasks
+        part["read_split"] = rng.integers(0, 100, len(tasks))
+        part["col_begin"] = np.arange(len(tasks)) + 1000 * s
+        parts.append(part)
+    got = sharding.merge_rows_by_task(n_tasks, parts)
+    cat = np.concatenate(parts)
+    want = cat[np.argsort(cat["task"], kind="stable")]
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+    assert len(sharding.merge_rows_by_task(n_tasks, [parts[0][:0], parts[1][:0]])) == 0
