@@ -968,7 +968,15 @@ static cudaError_t h2d_any(dfb_ctx* ctx, cudaStream_t up, void* dst, const void*
 		else if ((e = cudaEventSynchronize(ctx->ring_ev[slot])) != cudaSuccess) return e; // the block's last transfer is over
 		uint8_t* stage = (uint8_t*)ctx->h_ring.p + (size_t)slot * dfb_ctx::kRingBlock;
 		const uint8_t* from = (const uint8_t*)src + off;
-		const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->host_threads, n >> 20));
+		// (a thread per megabyte of the block; a thread per 512 or 256 KB -- DFB_STAGE_SHIFT=19 / 18 -- made the matealign shape
+		// from pageable arrays slower, 36 against 32 ms: call r04l)
+		static int shift = 0;
+		if (!shift)
+		{
+			const char* e = getenv("DFB_STAGE_SHIFT");
+			shift = (e && atoi(e) >= 12 && atoi(e) <= 24) ? atoi(e) : 20;
+		}
+		const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->host_threads, n >> shift));
 		parallel_for(ctx->pool, T, [&](int tid) {
 			const size_t a = n * (size_t)tid / (size_t)T, b = n * ((size_t)tid + 1) / (size_t)T;
 			memcpy(stage + a, from + a, b - a);

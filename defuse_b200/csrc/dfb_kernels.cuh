@@ -238,6 +238,14 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// 0xFFFF in every half of x whose bit 15 is set, 0 in the others (PRMT with sign replication: bytes 1, 1, 3, 3)
+__device__ __forceinline__ uint32_t spread_bit15(uint32_t x)
+{
+	uint32_t r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0u), "r"(0xBB99u));
+	return r;
+}
+
 // One arg-max column found by the probe sweep: the task's fixed region first, the overflow list after.
 __device__ __noinline__ void emit_probe_event(const FastParams& p, int item, int task, int h, int j, int col, int score)
 {
@@ -264,7 +272,9 @@ __device__ __noinline__ void emit_probe_event(const FastParams& p, int item, int
 // Decodes one ring block (8G reference columns of both halves) from the raw pool words cp.async left in shared memory
 // into 32-bit {half 1, half 0} symbol pairs.  Lane g owns columns 8g .. 8g+7 of the block and stores them in an order
 // rotated by the lane, so that the 32 lanes of the warp hit 32 different banks.  cw0 / cw1: pool word of ring column 0
-// in either half's reference (negative in front of the reference: those columns are padding).  Out of line: three call
+// in either half's reference (negative in front of the reference: those columns are padding).  The last G-1 columns of the
+// ring are stored a second time in front of it (ring[-1] = ring[RING-1] ...): lane g of the first sweep reads column u-g
+// at ring_lane[u mod RING] with ring_lane = ring - g and a warp-uniform index that needs no mask.  Out of line: three call
 // sites per kernel, and the instruction cache is what short probe rounds wait for.
 template <int G>
 __device__ __noinline__ void ring_decode_block(uint32_t* ring, const uint2* raw_slot, int blk, int cw0, int cw1, uint32_t R0, uint32_t R1,
@@ -295,7 +305,9 @@ __device__ __noinline__ void ring_decode_block(uint32_t* ring, const uint2* raw_
 		uint32_t f1 = (0x54474341u >> (8 * ((c1 >> (2 * nn)) & 3u))) & 0xFFu;
 		if (nn >= nv0) f0 = DFB_REF_PAD;
 		if (nn >= nv1) f1 = DFB_REF_PAD;
-		ring[(first + nn) & (RING - 1)] = f0 | (f1 << 16);
+		const uint32_t idx = (first + nn) & (RING - 1);
+		ring[idx] = f0 | (f1 << 16);
+		if (idx > (uint32_t)(RING - G)) ring[(int)idx - RING] = f0 | (f1 << 16); // mirror of the last G-1 columns
 	}
 	if (m0 | m1)
 	{
@@ -303,8 +315,10 @@ __device__ __noinline__ void ring_decode_block(uint32_t* ring, const uint2* raw_
 		uint16_t* ring16 = reinterpret_cast<uint16_t*>(ring);
 		for (int nn = 0; nn < 8; nn++)
 		{
-			if ((m0 >> nn) & 1u) ring16[2 * ((first + nn) & (RING - 1))] = __ldg(obytes + ((size_t)ref_w0 + (size_t)wi0) * 16 + bit0 + nn);
-			if ((m1 >> nn) & 1u) ring16[2 * ((first + nn) & (RING - 1)) + 1] = __ldg(obytes + ((size_t)ref_w1 + (size_t)wi1) * 16 + bit0 + nn);
+			const int idx = (int)((first + nn) & (RING - 1));
+			const int mirror = idx > RING - G ? idx - RING : idx; // (the same slot again when the column has no mirror)
+			if ((m0 >> nn) & 1u) ring16[2 * idx] = ring16[2 * mirror] = __ldg(obytes + ((size_t)ref_w0 + (size_t)wi0) * 16 + bit0 + nn);
+			if ((m1 >> nn) & 1u) ring16[2 * idx + 1] = ring16[2 * mirror + 1] = __ldg(obytes + ((size_t)ref_w1 + (size_t)wi1) * 16 + bit0 + nn);
 		}
 	}
 }
@@ -352,8 +366,9 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 	constexpr int CH = 8 * G;       // reference ring: block of CH columns, two blocks resident
 	constexpr int CK = 4 * G;       // checkpoint interval (steps): probe windows are whole CK blocks
 	constexpr int RING = 2 * CH;
-	// the groups of a warp read the same ring index in the same step: G words between their rings put them in different banks
-	constexpr int RING_STRIDE = RING + (NG > 1 ? G : 0);
+	// G words in front of every ring: the mirror of its last G-1 columns (ring_decode_block) -- and what puts the rings of a
+	// warp's groups, which read the same index in the same step, into different banks
+	constexpr int RING_STRIDE = RING + G;
 	constexpr int ROWS = G * S;
 	constexpr int RDW = (ROWS + 15) / 16;
 	constexpr int HG = G / 2;       // pool words of one half in a ring block
@@ -369,7 +384,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 	const int warp = threadIdx.x >> 5;
 	const int q = lane / G;
 	const int g = lane % G;
-	uint32_t* ring = s_ring[warp][q];
+	uint32_t* ring = s_ring[warp][q] + G;
 	uint32_t* rows = s_rows[warp][q];
 	uint16_t* rows16 = reinterpret_cast<uint16_t*>(rows);
 
@@ -499,9 +514,12 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		// one step of one lane: the next reference column against the S rows of the strip, with an activity test (lane g
 		// joins at step g and leaves after its last column) and the new column folded into the row state at once:
 		// head and tail steps
+		// (the boundary value of lane 0 comes in by a multiply-add on the FMA pipe, not by a select on the ALU pipe the
+		// sweep is bound by)
+		uint32_t lane_nz = g != 0 ? 1u : 0u, lane_add = g != 0 ? 0u : Bp;
+		asm volatile("" : "+r"(lane_nz), "+r"(lane_add)); // (opaque, or the compiler turns the multiply-add back into a select)
 		auto step = [&](const int u) {
-			uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G);
-			if (g == 0) recv = Bp;
+			const uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G) * lane_nz + lane_add;
 			const int b = u - g; // column
 			if ((unsigned)b < (unsigned)Rg)
 			{
@@ -529,12 +547,12 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 		};
 		// two steps of a lane whose columns are known to be in range (every lane has joined, none has left): no
 		// activity test, and one three-input maximum folds both columns into the row state (half the sink issues)
-		auto step_pair = [&](const int u) {
+		// (rp: this lane's two ring columns -- a pointer that walks the mirrored ring, no index arithmetic per step)
+		auto step_pair = [&](const uint32_t* rp) {
 			uint32_t Fe[S];
 			{
-				uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G);
-				if (g == 0) recv = Bp;
-				const uint32_t rf = ring[(u - g) & (RING - 1)];
+				const uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G) * lane_nz + lane_add;
+				const uint32_t rf = rp[0];
 				uint32_t left = recv;
 				uint32_t dg_in = prev;
 #pragma unroll
@@ -551,9 +569,8 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				Flast = left;
 			}
 			{
-				uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G);
-				if (g == 0) recv = Bp;
-				const uint32_t rf = ring[(u + 1 - g) & (RING - 1)];
+				const uint32_t recv = __shfl_up_sync(0xffffffffu, Flast, 1, G) * lane_nz + lane_add;
+				const uint32_t rf = rp[1];
 				uint32_t left = recv;
 				uint32_t dg_in = prev;
 #pragma unroll
@@ -606,29 +623,35 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 #pragma unroll 1
 			for (; u < u_head; u++) step(u);
 			const int u_pair_end = min(u_end, u_paired);
+			if (u + 1 < u_pair_end)
+			{
+				// (a checkpoint block never straddles the ring's end: RING = 4 CK)
+				const uint32_t* rp = ring - g + (u & (RING - 1));
+				const int n_pairs = (u_pair_end - u) >> 1;
+				const uint32_t* const rp_end = rp + 2 * n_pairs;
 #pragma unroll 1
-			for (; u + 1 < u_pair_end; u += 2) step_pair(u);
+				for (; rp != rp_end; rp += 2) step_pair(rp);
+				u += 2 * n_pairs;
+			}
 #pragma unroll 1
 			for (; u < u_end; u++) step(u);
 			if (MODE == MODE_SPLIT)
 			{
 				// end of a checkpoint block (or of the sweep), same step for all lanes: fold the block maxima into the
-				// row maxima and remember in which granules each row maximum occurs
-				// (branch-free: two DPX maxima with predicate outputs per row say, per half, whether the block maximum
-				// ties or beats the row maximum -- the block then joins or replaces the row's granule set)
-				const uint32_t bit_lo = 1u << (blkno >> p.gran_shift), bit_hi = bit_lo << 16;
+				// row maxima and remember in which granules each row maximum occurs: a block that ties the row maximum
+				// joins the row's granule set, one that beats it replaces the set.  No predicates (thirteen rows x four of
+				// them made ptxas spill predicates into a register, 17 ALU-pipe instructions per row): with
+				// xn = max(X, Y) both xn - X and xn - Y are non-negative in either half, so one 32-bit IADD3 per difference
+				// (+ 0x7FFF per half) leaves bit 15 of a half set exactly when the difference is positive, and a PRMT that
+				// replicates sign bits spreads it over the half -- 7 ALU-pipe instructions per row.
+				const uint32_t bit2 = (1u << (blkno >> p.gran_shift)) * 0x00010001u;
 #pragma unroll
 				for (int k = 0; k < S; k++)
 				{
-					bool ge_hi, ge_lo, old_ge_hi, old_ge_lo;
-					const uint32_t xn = __vibmax_s16x2(Y[k], X[k], &ge_hi, &ge_lo);   // ge: block maximum >= row maximum
-					(void)__vibmax_s16x2(X[k], Y[k], &old_ge_hi, &old_ge_lo);          // !old_ge: block maximum > row maximum
-					uint32_t inf = info[k];
-					if (!old_ge_lo) inf &= 0xFFFF0000u;
-					if (ge_lo) inf |= bit_lo;
-					if (!old_ge_hi) inf &= 0x0000FFFFu;
-					if (ge_hi) inf |= bit_hi;
-					info[k] = inf;
+					const uint32_t xn = __vmaxs2(X[k], Y[k]);
+					const uint32_t beat = spread_bit15(xn - X[k] + 0x7FFF7FFFu);  // 0xFFFF per half whose block maximum > row maximum
+					const uint32_t below = spread_bit15(xn - Y[k] + 0x7FFF7FFFu); // 0xFFFF per half whose block maximum < row maximum
+					info[k] = (info[k] & ~beat) | (bit2 & ~below);
 					X[k] = xn;
 					Y[k] = 0;
 				}
@@ -787,7 +810,9 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 	constexpr int CH = 8 * G;
 	constexpr int CK = 4 * G;
 	constexpr int RING = 2 * CH;
-	constexpr int RING_STRIDE = RING + (NG > 1 ? G : 0);
+	// G words in front of every ring: the mirror of its last G-1 columns (ring_decode_block) -- and what puts the rings of a
+	// warp's groups, which read the same index in the same step, into different banks
+	constexpr int RING_STRIDE = RING + G;
 	constexpr int HG = G / 2;
 	constexpr int PRE = 32; // ring columns in front of a round's first step (>= G-1, two whole pool words)
 	static_assert(G >= 8 && (G & (G - 1)) == 0 && G <= 32, "group size");
@@ -800,7 +825,7 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 	const int warp = threadIdx.x >> 5;
 	const int q = lane / G;
 	const int g = lane % G;
-	uint32_t* ring = s_ring[warp][q];
+	uint32_t* ring = s_ring[warp][q] + G;
 	uint2(*raw)[2][HG] = s_raw[warp][q];
 
 	const uint32_t B = p.bias;
