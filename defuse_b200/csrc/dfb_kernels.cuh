@@ -238,6 +238,14 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// (the PTX instruction itself: __byte_perm masks its selector first, one more ALU-pipe instruction per use)
+__device__ __forceinline__ uint32_t prmt(uint32_t lo, uint32_t hi, uint32_t selector)
+{
+	uint32_t r;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(selector));
+	return r;
+}
+
 // 0xFFFF in every half of x whose bit 15 is set, 0 in the others (PRMT with sign replication: bytes 1, 1, 3, 3)
 __device__ __forceinline__ uint32_t spread_bit15(uint32_t x)
 {
@@ -274,9 +282,10 @@ __device__ __noinline__ void emit_probe_event(const FastParams& p, int item, int
 // rotated by the lane, so that the 32 lanes of the warp hit 32 different banks.  cw0 / cw1: pool word of ring column 0
 // in either half's reference (negative in front of the reference: those columns are padding).  The last G-1 columns of the
 // ring are stored a second time in front of it (ring[-1] = ring[RING-1] ...): lane g of the first sweep reads column u-g
-// at ring_lane[u mod RING] with ring_lane = ring - g and a warp-uniform index that needs no mask.  Out of line: three call
+// at ring_lane[u mod RING] with ring_lane = ring - g and a warp-uniform index that needs no mask (MIRROR; the probe sweep
+// masks its index and does without).  Out of line: three call
 // sites per kernel, and the instruction cache is what short probe rounds wait for.
-template <int G>
+template <int G, bool MIRROR>
 __device__ __noinline__ void ring_decode_block(uint32_t* ring, const uint2* raw_slot, int blk, int cw0, int cw1, uint32_t R0, uint32_t R1,
                                                uint32_t ref_w0, uint32_t ref_w1, const uint8_t* __restrict__ obytes, int g,
                                                unsigned long long pool_words)
@@ -307,7 +316,7 @@ __device__ __noinline__ void ring_decode_block(uint32_t* ring, const uint2* raw_
 		if (nn >= nv1) f1 = DFB_REF_PAD;
 		const uint32_t idx = (first + nn) & (RING - 1);
 		ring[idx] = f0 | (f1 << 16);
-		if (idx > (uint32_t)(RING - G)) ring[(int)idx - RING] = f0 | (f1 << 16); // mirror of the last G-1 columns
+		if (MIRROR && idx > (uint32_t)(RING - G)) ring[(int)idx - RING] = f0 | (f1 << 16); // mirror of the last G-1 columns
 	}
 	if (m0 | m1)
 	{
@@ -316,7 +325,7 @@ __device__ __noinline__ void ring_decode_block(uint32_t* ring, const uint2* raw_
 		for (int nn = 0; nn < 8; nn++)
 		{
 			const int idx = (int)((first + nn) & (RING - 1));
-			const int mirror = idx > RING - G ? idx - RING : idx; // (the same slot again when the column has no mirror)
+			const int mirror = (MIRROR && idx > RING - G) ? idx - RING : idx; // (the same slot again when the column has no mirror)
 			if ((m0 >> nn) & 1u) ring16[2 * idx] = ring16[2 * mirror] = __ldg(obytes + ((size_t)ref_w0 + (size_t)wi0) * 16 + bit0 + nn);
 			if ((m1 >> nn) & 1u) ring16[2 * idx + 1] = ring16[2 * mirror + 1] = __ldg(obytes + ((size_t)ref_w1 + (size_t)wi1) * 16 + bit0 + nn);
 		}
@@ -377,7 +386,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 	static_assert(CH == 2 * CK, "the ring is refilled at the top of every second checkpoint block");
 
 	__shared__ uint32_t s_ring[4][NG][RING_STRIDE];
-	__shared__ uint32_t s_rows[4][NG][ROWS + 1];
+	__shared__ uint32_t s_rows[4][NG][RDW * 16 + 1]; // (whole 16-base words: the read staging stores without a row test)
 	__shared__ __align__(16) uint2 s_raw[4][NG][2][2][HG]; // [slot][half][word]: raw pool words of the ring blocks in flight (cp.async)
 
 	const int lane = threadIdx.x & 31;
@@ -420,18 +429,26 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 				const uint32_t widx = jp.read_w[h] + wi;
 				DFB_BC((uint32_t)wi * 16u >= len || widx < p.pool_words, 205);
 				if ((uint32_t)wi * 16u < len) pw = __ldg(p.pool + widx);
-#pragma unroll 4
+				// No per-base branches: every code is decoded -- a PRMT picks the NEGATED 16-bit symbol of the 2-bit code out
+				// of an 8-byte table; (-read + ref) mod 2^16 is 0 exactly on a match, so one VIADDMNMX.U16x2 (add, min with 1)
+				// yields the mismatch indicator in the sweep --, rows beyond the read are overwritten with the padding value,
+				// the exception plane patches its bytes afterwards (rare).
+				const int nv = min(16, max(0, (int)len - wi * 16)); // bases of this word inside the read
+				uint16_t* dst = rows16 + 2 * (wi * 16) + h;
+#pragma unroll
 				for (int n = 0; n < 16; n++)
 				{
-					const int pos = wi * 16 + n;
-					if (pos < ROWS)
-					{
-						uint32_t f = DFB_READ_PAD;
-						if ((uint32_t)pos < len) f = decode_base(pw, widx, n, p.obytes);
-						// stored negated: (-read + ref) mod 2^16 is 0 exactly on a match, so one
-						// VIADDMNMX.U16x2 (add, min with 1) yields the mismatch indicator
-						rows16[2 * pos + h] = (uint16_t)(0u - f);
-					}
+					const uint32_t code = (pw.x >> (2 * n)) & 3u;
+					// bytes 2c, 2c+1 of {0xFFBF (-'A'), 0xFFBD (-'C'), 0xFFB9 (-'G'), 0xFFAC (-'T')}
+					dst[2 * n] = (uint16_t)prmt(0xFFBDFFBFu, 0xFFACFFB9u, code * 0x22u + 0x10u);
+				}
+				for (int n = nv; n < 16; n++) dst[2 * n] = (uint16_t)(0u - DFB_READ_PAD); // (only a read's last word has any)
+				uint32_t ex = pw.y & (nv >= 16 ? 0xFFFFu : ((1u << nv) - 1u));
+				while (ex)
+				{
+					const int n = __ffs(ex) - 1;
+					ex &= ex - 1;
+					dst[2 * n] = (uint16_t)(0u - (uint32_t)__ldg(p.obytes + (size_t)widx * 16 + n));
 				}
 			}
 			__syncwarp();
@@ -479,7 +496,7 @@ __global__ void __launch_bounds__(128, FastOcc<S, MODE>::kMinBlocks) dp_fast_ker
 			cp_async_commit();
 		};
 		auto decode_block = [&](int blk) {
-			ring_decode_block<G>(ring, &raw[blk & 1][0][0], blk, 0, 0, R0, R1, jp.ref_w[0], jp.ref_w[1], p.obytes, g, p.pool_words);
+			ring_decode_block<G, true>(ring, &raw[blk & 1][0][0], blk, 0, 0, R0, R1, jp.ref_w[0], jp.ref_w[1], p.obytes, g, p.pool_words);
 		};
 		const int ring_blocks = min(2, (T + CH - 1) / CH); // ring columns this warp will read: T steps
 		issue_block(0);
@@ -909,7 +926,7 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 				cp_async_commit();
 			};
 			auto decode_block = [&](int blk) {
-				ring_decode_block<G>(ring, &raw[blk & 1][0][0], blk, c0 >> 4, c1 >> 4, R0, R1, jp.ref_w[0], jp.ref_w[1], p.obytes, g, p.pool_words);
+				ring_decode_block<G, false>(ring, &raw[blk & 1][0][0], blk, c0 >> 4, c1 >> 4, R0, R1, jp.ref_w[0], jp.ref_w[1], p.obytes, g, p.pool_words); // (the probe masks its ring index: no mirror)
 			};
 			__syncwarp(); // (the previous round's ring reads are over)
 			const int ring_blocks = min(2, (Tr + PRE + CH - 1) / CH);
