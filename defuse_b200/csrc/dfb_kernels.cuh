@@ -853,16 +853,26 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 	const int n_items = n_short + *p.hit_count_long;
 	const int j0 = g * S; // rows owned: j0+1 .. j0+S
 
+	auto claim = [&]() -> int {
+		int b = 0;
+		if (lane == 0) b = atomicAdd(p.cursor, NG);
+		return __shfl_sync(0xffffffffu, b, 0);
+	};
+	// queue position -> slot (one-round jobs were queued from the front, the others from the back)
+	auto slot_of = [&](int idx) -> int { return (idx >= n_short) ? p.n_jobs - 1 - (idx - n_short) : idx; };
 	for (;;)
 	{
-		int base = 0;
-		if (lane == 0) base = atomicAdd(p.cursor, NG);
-		base = __shfl_sync(0xffffffffu, base, 0);
+		const int base = claim();
 		if (base >= n_items) break;
 		const bool have = base + q < n_items;
-		// queue position -> slot (one-round jobs were queued from the front, the others from the back)
-		const int item = (base + q >= n_short) ? p.n_jobs - 1 - (base + q - n_short) : base + q;
+		const int item = slot_of(base + q);
 		int jid = 0;
+		uint32_t rng = 0;
+		if (have)
+		{
+			jid = p.hitq[item];
+			rng = p.slot_rng[item];
+		}
 		JobPair jp;
 		jp.ref_w[0] = jp.ref_w[1] = jp.read_w[0] = jp.read_w[1] = 0;
 		jp.R[0] = jp.R[1] = jp.L[0] = jp.L[1] = 0;
@@ -871,10 +881,8 @@ __global__ void __launch_bounds__(128, ProbeOcc<S>::kMinBlocks) dp_probe_kernel(
 		if (have)
 		{
 			DFB_BC(item >= 0 && item < p.n_jobs, 301);
-			jid = p.hitq[item];
 			DFB_BC(jid >= 0 && jid < p.n_jobs, 302);
 			jp = p.jobs[jid];
-			const uint32_t rng = p.slot_rng[item];
 			m0 = rng & 0xFFFFu;
 			m1 = rng >> 16;
 		}
