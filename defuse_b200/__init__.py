@@ -412,7 +412,7 @@ class SimpleAligner:
         host buffer out)."""
         task_ref, task_seq = _i32(task_ref), _i32(task_seq)
         if out is None:
-            out = np.zeros(task_ref.size, dtype=np.int32)
+            out = np.empty(task_ref.size, dtype=np.int32)   # (the call writes every entry)
         rt, st = refs.c_struct(), seqs.c_struct()
         self.ctx._check(self.ctx._lib.dfb_simple_align_batch(self.ctx._h, ctypes.byref(self.params), ctypes.byref(rt),
                                                              ctypes.byref(st), task_ref.ctypes.data, task_seq.ctypes.data,
@@ -431,6 +431,7 @@ class SplitReadAligner:
         self.params = _SplitParams(int(match), int(mismatch), int(gap), int(bool(end_gaps)), int(min_split_score))
         self.ctx = ctx or default_context()
         self._last = None
+        self._best_buf = None
 
     @staticmethod
     def _lens(refs, reads, task_cluster, task_read):
@@ -451,9 +452,17 @@ class SplitReadAligner:
     def align_batch(self, refs, reads, task_cluster, task_read, task_min_score, copy=True):
         """Batch of Align + GetAlignments(minScore, forceSplits=True, firstOnly=False) through
         dfb_split_align_batch; cluster c uses refs[2c] / refs[2c+1].  copy=False returns views into
-        library memory that stay valid until the next split call on this context."""
+        library memory (and, for `best`, into a buffer of this aligner) that stay valid until the next split call."""
         task_cluster, task_read, task_min_score = _i32(task_cluster), _i32(task_read), _i32(task_min_score)
-        best = np.zeros(task_cluster.size, dtype=np.int32)
+        n = task_cluster.size
+        if copy:
+            best = np.empty(n, dtype=np.int32)   # (the call writes every entry)
+        else:
+            # views all round: `best` too lives in a buffer of this aligner that the next call reuses -- a fresh 4 n-byte
+            # array per call is 2 000 page faults per 2 M tasks under the library's copies
+            if self._best_buf is None or self._best_buf.size < n:
+                self._best_buf = np.empty(max(n, 1), dtype=np.int32)
+            best = self._best_buf[:n]
         rt, st = refs.c_struct(), reads.c_struct()
         lib = self.ctx._lib
         self.ctx._check(lib.dfb_split_align_batch(self.ctx._h, ctypes.byref(self.params), ctypes.byref(rt), ctypes.byref(st),

@@ -277,7 +277,12 @@ static cudaError_t wait_event(cudaEvent_t ev)
 	for (int spins = 0;; spins++)
 	{
 		const cudaError_t q = cudaEventQuery(ev);
-		if (q != cudaErrorNotReady) return q;
+		if (q != cudaErrorNotReady)
+		{
+			// ("not ready" is an answer, not a failure: it must not be what a later cudaGetLastError() of this thread finds)
+			if (spins && q == cudaSuccess) (void)cudaGetLastError();
+			return q;
+		}
 		if (spins < 8) continue;
 		struct timespec ts = {0, 30000};
 		nanosleep(&ts, nullptr);
