@@ -305,29 +305,42 @@ __device__ __noinline__ void ring_decode_block(uint32_t* ring, const uint2* raw_
 	DFB_BC(nv0 == 0 || (unsigned long long)ref_w0 + (unsigned long long)wi0 < pool_words, 201);
 	DFB_BC(nv1 == 0 || (unsigned long long)ref_w1 + (unsigned long long)wi1 < pool_words, 202);
 	const int rot = g >> RSH;
-	const uint32_t first = (uint32_t)blk * CH + 16u * (g >> 1) + bit0;
+	// ring slot of the lane's first column: a multiple of 8, so + nn never wraps
+	const int base_idx = (int)(((uint32_t)blk * CH + 16u * (g >> 1) + bit0) & (RING - 1));
+	uint32_t* dst = ring + base_idx;
+	const int mirror_from = MIRROR ? RING - G - base_idx : 8; // columns nn > mirror_from have a mirror slot (RING words below)
+	// Both halves of a column with one PRMT: the 2-bit codes of the two references sit in the two halves of cc; the
+	// selector {code0, 4, code1, 4} picks {"ACGT"[code0], 0, "ACGT"[code1], 0} out of ("ACGT", 0).
+	const uint32_t cc = (c0 & 0xFFFFu) | (c1 << 16);
 #pragma unroll
 	for (int n = 0; n < 8; n++)
 	{
 		const int nn = (n + rot) & 7;
-		uint32_t f0 = (0x54474341u >> (8 * ((c0 >> (2 * nn)) & 3u))) & 0xFFu; // "ACGT"
-		uint32_t f1 = (0x54474341u >> (8 * ((c1 >> (2 * nn)) & 3u))) & 0xFFu;
-		if (nn >= nv0) f0 = DFB_REF_PAD;
-		if (nn >= nv1) f1 = DFB_REF_PAD;
-		const uint32_t idx = (first + nn) & (RING - 1);
-		ring[idx] = f0 | (f1 << 16);
-		if (MIRROR && idx > (uint32_t)(RING - G)) ring[(int)idx - RING] = f0 | (f1 << 16); // mirror of the last G-1 columns
+		const uint32_t x = (cc >> (2 * nn)) & 0x00030003u;
+		const uint32_t word = prmt(0x54474341u, 0u, x | (x >> 8) | 0x4040u);
+		dst[nn] = word;
+		if (MIRROR && nn > mirror_from) dst[nn - RING] = word;
+	}
+	uint16_t* dst16 = reinterpret_cast<uint16_t*>(dst);
+	if (nv0 < 8 || nv1 < 8)
+	{
+		// columns in front of a reference or at and past its end equal no read symbol (only the blocks at a reference's
+		// ends have any)
+		for (int nn = 0; nn < 8; nn++)
+		{
+			const int mirror = (MIRROR && nn > mirror_from) ? nn - RING : nn; // (the same slot again when the column has no mirror)
+			if (nn >= nv0) dst16[2 * nn] = dst16[2 * mirror] = (uint16_t)DFB_REF_PAD;
+			if (nn >= nv1) dst16[2 * nn + 1] = dst16[2 * mirror + 1] = (uint16_t)DFB_REF_PAD;
+		}
 	}
 	if (m0 | m1)
 	{
 		// exception plane (rare): the raw byte replaces the decoded code
-		uint16_t* ring16 = reinterpret_cast<uint16_t*>(ring);
 		for (int nn = 0; nn < 8; nn++)
 		{
-			const int idx = (int)((first + nn) & (RING - 1));
-			const int mirror = (MIRROR && idx > RING - G) ? idx - RING : idx; // (the same slot again when the column has no mirror)
-			if ((m0 >> nn) & 1u) ring16[2 * idx] = ring16[2 * mirror] = __ldg(obytes + ((size_t)ref_w0 + (size_t)wi0) * 16 + bit0 + nn);
-			if ((m1 >> nn) & 1u) ring16[2 * idx + 1] = ring16[2 * mirror + 1] = __ldg(obytes + ((size_t)ref_w1 + (size_t)wi1) * 16 + bit0 + nn);
+			const int mirror = (MIRROR && nn > mirror_from) ? nn - RING : nn;
+			if ((m0 >> nn) & 1u) dst16[2 * nn] = dst16[2 * mirror] = __ldg(obytes + ((size_t)ref_w0 + (size_t)wi0) * 16 + bit0 + nn);
+			if ((m1 >> nn) & 1u) dst16[2 * nn + 1] = dst16[2 * mirror + 1] = __ldg(obytes + ((size_t)ref_w1 + (size_t)wi1) * 16 + bit0 + nn);
 		}
 	}
 }
